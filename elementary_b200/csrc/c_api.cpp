@@ -1,0 +1,160 @@
+// c_api.cpp — extern "C" shim over eb::Engine; see include/elem_b200.h for the contract and the reference
+// interface each entry point replaces.
+#include "../../include/elem_b200.h"
+
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "graph_host.h"
+
+struct elem_b200_runtime {
+    eb::Engine* engine;
+    std::string scratch;
+};
+
+static thread_local std::string g_createError;
+
+extern "C" {
+
+int elem_b200_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+elem_b200_runtime* elem_b200_create(double sampleRate, int blockSize, int numVoices, int device) {
+    if (blockSize <= 0 || numVoices <= 0 || sampleRate <= 0) { g_createError = "bad argument"; return nullptr; }
+    // device == -1: plan-only runtime — the host logic (instruction interpreter, return codes, gc, graph
+    // compilation) runs without a GPU; every process/enqueue call fails with -1.  Used by the CPU test-suite.
+    if (device != -1) {
+        int n = elem_b200_device_count();
+        if (device < 0 || device >= n) { g_createError = "no such CUDA device (this library has no CPU fallback)"; return nullptr; }
+    }
+    try {
+        auto* rt = new elem_b200_runtime{new eb::Engine(sampleRate, blockSize, numVoices, device), {}};
+        if (!rt->engine->mixDevicePtr()) { g_createError = rt->engine->lastError(); delete rt->engine; delete rt; return nullptr; }
+        return rt;
+    } catch (const std::exception& e) {
+        g_createError = e.what();
+        return nullptr;
+    }
+}
+
+void elem_b200_destroy(elem_b200_runtime* rt) {
+    if (!rt) return;
+    delete rt->engine;
+    delete rt;
+}
+
+#define GUARD(expr)                                                   \
+    if (!rt) return eb::rc::BadArgument;                              \
+    try { return (expr); }                                            \
+    catch (const std::bad_alloc&) { return eb::rc::InvariantViolation; } \
+    catch (...) { return eb::rc::InvalidInstructionFormat; }
+
+int elem_b200_apply_instructions(elem_b200_runtime* rt, int voiceBegin, int voiceEnd, const char* json, size_t len) {
+    if (!json) return eb::rc::BadArgument;
+    GUARD(rt->engine->applyInstructions(voiceBegin, voiceEnd, json, len));
+}
+
+int elem_b200_set_property_per_voice(elem_b200_runtime* rt, int32_t nodeId, const char* key, const double* values, int voiceBegin, int count) {
+    if (!key || !values) return eb::rc::BadArgument;
+    GUARD(rt->engine->setPropertyPerVoice(nodeId, key, values, voiceBegin, count));
+}
+
+int elem_b200_process(elem_b200_runtime* rt, const float* const* in, size_t nIn, float* const* out, size_t nOut, size_t numSamples, void* /*userData*/) {
+    GUARD(rt->engine->process(in, nIn, out, nOut, numSamples));
+}
+
+int elem_b200_process_voices(elem_b200_runtime* rt, const float* in, size_t nIn, float* outVoices, float* mix, size_t nOut, size_t numSamples) {
+    GUARD(rt->engine->processVoices(in, nIn, outVoices, mix, nOut, numSamples));
+}
+
+int elem_b200_enqueue_block(elem_b200_runtime* rt, size_t nIn, size_t nOut, size_t numSamples, int flags) {
+    GUARD(rt->engine->enqueueBlock(nIn, nOut, numSamples, (flags & 1) != 0, (flags & 2) != 0, (flags & 4) != 0));
+}
+
+int elem_b200_synchronize(elem_b200_runtime* rt) { GUARD(rt->engine->synchronize()); }
+
+float* elem_b200_mix_device(elem_b200_runtime* rt) { return rt ? rt->engine->mixDevicePtr() : nullptr; }
+float* elem_b200_voice_out_device(elem_b200_runtime* rt) { return rt ? rt->engine->voiceOutDevicePtr() : nullptr; }
+float* elem_b200_voice_in_device(elem_b200_runtime* rt, size_t nIn) { return rt ? rt->engine->voiceInDevicePtr(nIn) : nullptr; }
+float* elem_b200_shared_in_device(elem_b200_runtime* rt, size_t nIn) { return rt ? rt->engine->sharedInDevicePtr(nIn) : nullptr; }
+void elem_b200_set_stream(elem_b200_runtime* rt, void* s) { if (rt) rt->engine->setStream(static_cast<cudaStream_t>(s)); }
+
+int elem_b200_add_shared_resource(elem_b200_runtime* rt, const char* name, const float* const* channels, size_t numChannels, size_t numSamples) {
+    if (!rt || !name) return 0;
+    try { return rt->engine->addSharedResource(name, channels, numChannels, numSamples); } catch (...) { return 0; }
+}
+
+void elem_b200_prune_shared_resources(elem_b200_runtime* rt) { if (rt) rt->engine->pruneSharedResources(); }
+
+int elem_b200_list_shared_resources(elem_b200_runtime* rt, char* buf, size_t cap) {
+    if (!rt) return 0;
+    auto names = rt->engine->listSharedResources();
+    std::string s;
+    for (auto& n : names) { s += n; s += '\n'; }
+    if (buf && cap) {
+        const size_t k = s.size() < cap - 1 ? s.size() : cap - 1;
+        std::memcpy(buf, s.data(), k);
+        buf[k] = 0;
+    }
+    return (int) names.size();
+}
+
+int elem_b200_gc(elem_b200_runtime* rt, int voice, int32_t* ids, size_t cap) {
+    if (!rt) return 0;
+    std::vector<int32_t> pruned;
+    rt->engine->gc(voice, pruned);
+    for (size_t i = 0; i < pruned.size() && i < cap; ++i) ids[i] = pruned[i];
+    return (int) pruned.size();
+}
+
+void elem_b200_reset(elem_b200_runtime* rt) { if (rt) rt->engine->reset(); }
+
+void elem_b200_process_queued_events(elem_b200_runtime*, elem_b200_event_cb, void*) {}
+
+int elem_b200_set_option(elem_b200_runtime* rt, const char* key, double value) {
+    if (!key) return eb::rc::BadArgument;
+    GUARD(rt->engine->setOption(key, value));
+}
+
+int elem_b200_describe(elem_b200_runtime* rt, char* buf, size_t cap) {
+    if (!rt) return 0;
+    const std::string s = rt->engine->describe();
+    if (buf && cap) {
+        const size_t k = s.size() < cap - 1 ? s.size() : cap - 1;
+        std::memcpy(buf, s.data(), k);
+        buf[k] = 0;
+    }
+    return (int) s.size() + 1;
+}
+
+uint64_t elem_b200_kernel_launches(elem_b200_runtime* rt) { return rt ? rt->engine->kernelLaunches() : 0; }
+
+const char* elem_b200_last_error(elem_b200_runtime* rt) {
+    if (!rt) return g_createError.c_str();
+    rt->scratch = rt->engine->lastError();
+    return rt->scratch.c_str();
+}
+
+const char* elem_b200_describe_return_code(int c) {   // Types.h:62-85
+    switch (c) {
+        case 0: return "Ok";
+        case 1: return "Node type not recognized";
+        case 2: return "Node not found";
+        case 3: return "Attempting to create a node that already exists";
+        case 4: return "Attempting to create a node type that already exists";
+        case 5: return "Invalid value type for the given node property";
+        case 6: return "Invalid value for the given node property";
+        case 7: return "Invariant violation";
+        case 8: return "Invalid instruction format";
+        case -1: return "CUDA error";
+        case -2: return "Bad argument";
+        default: return "Return code not recognized";
+    }
+}
+
+} // extern "C"

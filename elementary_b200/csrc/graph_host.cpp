@@ -1,0 +1,1211 @@
+// graph_host.cpp — see graph_host.h.  Reference behaviour mirrored here is cited inline as file:line of
+// /root/reference (runtime/elem/...).
+#include "graph_host.h"
+
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <functional>
+#include <list>
+#include <sstream>
+
+#include "convolve.h"
+#include "kernels.h"
+
+namespace eb {
+
+// ---------------------------------------------------------------------------------------------------------
+// GainFade mirror (helpers/GainFade.h)
+static double msToStep(double sr, double ms) { return ms > 1e-6 ? 1.0 / (sr * ms / 1000.0) : 1.0; }   // :10-12
+
+void GainFade::init(double sr) {            // GainFade(sr, 20, 20, 0.0, 1.0)  Core.h:80, GainFade.h:18-24
+    current = 0.0f; target = 1.0f; step = 0.0f; inStep = 0.0f; outStep = 0.0f;
+    setFadeInMs(sr, 20.0);
+    setFadeOutMs(sr, 20.0);
+}
+void GainFade::setFadeInMs(double sr, double ms) { inStep = (float) msToStep(sr, ms); updateStep(); }              // :74-77
+void GainFade::setFadeOutMs(double sr, double ms) { outStep = (float) ((double) -1.0f * msToStep(sr, ms)); updateStep(); }   // :79-82
+bool GainFade::settled() const { return std::fabs(target - current) <= 1e-6f; }                                     // :102-104
+void GainFade::advance(int n) {                                                                                  // :56-72
+    if (current == target) return;
+    float v = current + step * (float) n;
+    current = v < 0.0f ? 0.0f : (v > 1.0f ? 1.0f : v);
+}
+
+
+// ---------------------------------------------------------------------------------------------------------
+// Device-memory shims.  In "plan-only" mode (device == -1; used by the CPU test-suite to exercise the host
+// logic: instruction interpreter, return codes, gc, compilation) they fall back to host memory so that the
+// graph compiler can run without a GPU.  Plan-only engines can NOT render: every process call fails loudly.
+static void rawFree(void* p, bool plan) { if (!p) return; if (plan) std::free(p); else cudaFree(p); }
+
+cudaError_t Engine::dmalloc(void** p, size_t bytes) {
+    if (planOnly_) { *p = std::calloc(1, bytes ? bytes : 1); return *p ? cudaSuccess : cudaErrorMemoryAllocation; }
+    return cudaMalloc(p, bytes);
+}
+void Engine::dfree(void* p) { rawFree(p, planOnly_); }
+cudaError_t Engine::dmemset(void* p, int v, size_t bytes) {
+    if (planOnly_) { std::memset(p, v, bytes); return cudaSuccess; }
+    return cudaMemsetAsync(p, v, bytes, stream_);
+}
+cudaError_t Engine::dmemcpy(void* dst, const void* src, size_t bytes, cudaMemcpyKind kind) {
+    if (planOnly_) { std::memmove(dst, src, bytes); return cudaSuccess; }
+    return cudaMemcpyAsync(dst, src, bytes, kind, stream_);
+}
+cudaError_t Engine::dmemcpySync(void* dst, const void* src, size_t bytes, cudaMemcpyKind kind) {
+    if (planOnly_) { std::memmove(dst, src, bytes); return cudaSuccess; }
+    cudaError_t e = cudaMemcpyAsync(dst, src, bytes, kind, stream_);
+    if (e != cudaSuccess) return e;
+    return cudaStreamSynchronize(stream_);
+}
+void Engine::dsync() { if (!planOnly_ && stream_) cudaStreamSynchronize(stream_); }
+void Engine::dsetdev() { if (!planOnly_) cudaSetDevice(device_); }
+void Engine::setStream(cudaStream_t s) {
+    if (planOnly_) return;
+    if (ownStream_ && stream_) { cudaStreamSynchronize(stream_); cudaStreamDestroy(stream_); }
+    stream_ = s; ownStream_ = false;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+Program::~Program() {
+    if (dCode) rawFree(dCode, planOnly);
+    if (dStateMap) rawFree(dStateMap, planOnly);
+}
+
+struct TypeInfo { NodeKind kind; uint32_t fn; int stateRows; bool evenAlign; };
+
+// Registered builtin names: DefaultNodeTypes.h:53-143 (+ "convolve": wasm/Main.cpp:47).  Types that are out of
+// scope (seq*, sample*, mc.*, once, capture, fft, metro, time) are deliberately absent and yield
+// UnknownNodeType like any unregistered name (Runtime.h:304-305).
+static const std::unordered_map<std::string, TypeInfo>& typeTable() {
+    static const std::unordered_map<std::string, TypeInfo> t = {
+        {"in", {NodeKind::In, 0, 0, false}},
+        {"sin", {NodeKind::Unary, U_SIN, 0, false}}, {"cos", {NodeKind::Unary, U_COS, 0, false}},
+        {"tan", {NodeKind::Unary, U_TAN, 0, false}}, {"tanh", {NodeKind::Unary, U_TANH, 0, false}},
+        {"asinh", {NodeKind::Unary, U_ASINH, 0, false}}, {"ln", {NodeKind::Unary, U_LN, 0, false}},
+        {"log", {NodeKind::Unary, U_LOG10, 0, false}}, {"log2", {NodeKind::Unary, U_LOG2, 0, false}},
+        {"ceil", {NodeKind::Unary, U_CEIL, 0, false}}, {"floor", {NodeKind::Unary, U_FLOOR, 0, false}},
+        {"round", {NodeKind::Unary, U_ROUND, 0, false}}, {"sqrt", {NodeKind::Unary, U_SQRT, 0, false}},
+        {"exp", {NodeKind::Unary, U_EXP, 0, false}}, {"abs", {NodeKind::Unary, U_ABS, 0, false}},
+        {"le", {NodeKind::Binary, B_LE, 0, false}}, {"leq", {NodeKind::Binary, B_LEQ, 0, false}},
+        {"ge", {NodeKind::Binary, B_GE, 0, false}}, {"geq", {NodeKind::Binary, B_GEQ, 0, false}},
+        {"pow", {NodeKind::Binary, B_POW, 0, false}}, {"eq", {NodeKind::Binary, B_EQ, 0, false}},
+        {"and", {NodeKind::Binary, B_AND, 0, false}}, {"or", {NodeKind::Binary, B_OR, 0, false}},
+        {"add", {NodeKind::Reduce, R_ADD, 0, false}}, {"sub", {NodeKind::Reduce, R_SUB, 0, false}},
+        {"mul", {NodeKind::Reduce, R_MUL, 0, false}}, {"div", {NodeKind::Reduce, R_DIV, 0, false}},
+        {"mod", {NodeKind::Reduce, R_MOD, 0, false}}, {"min", {NodeKind::Reduce, R_MIN, 0, false}},
+        {"max", {NodeKind::Reduce, R_MAX, 0, false}},
+        {"root", {NodeKind::Root, 0, 0, false}}, {"const", {NodeKind::Const, 0, 0, false}},
+        {"sr", {NodeKind::Sr, 0, 0, false}},
+        {"phasor", {NodeKind::Phasor, 0, 1, false}}, {"sphasor", {NodeKind::SPhasor, 0, 2, false}},
+        {"counter", {NodeKind::Counter, 0, 1, false}}, {"accum", {NodeKind::Accum, 0, 2, false}},
+        {"latch", {NodeKind::Latch, 0, 2, false}}, {"maxhold", {NodeKind::MaxHold, 0, 3, false}},
+        {"rand", {NodeKind::Rand, 0, 1, false}},
+        {"delay", {NodeKind::Delay, 0, 1, false}}, {"sdelay", {NodeKind::SDelay, 0, 1, false}},
+        {"z", {NodeKind::Z, 0, 1, false}},
+        {"pole", {NodeKind::Pole, 0, 1, false}}, {"env", {NodeKind::Env, 0, 1, false}},
+        {"biquad", {NodeKind::Biquad, 0, 2, false}}, {"prewarp", {NodeKind::Prewarp, 0, 0, false}},
+        {"mm1p", {NodeKind::MM1p, 0, 2, true}}, {"svf", {NodeKind::Svf, 0, 4, true}},
+        {"svfshelf", {NodeKind::SvfShelf, 0, 4, true}},
+        {"tapIn", {NodeKind::TapIn, 0, 0, false}}, {"tapOut", {NodeKind::TapOut, 0, 0, false}},
+        {"table", {NodeKind::Table, 0, 0, false}},
+        {"blepsaw", {NodeKind::Blep, 0, 2, false}}, {"blepsquare", {NodeKind::Blep, 1, 2, false}},
+        {"bleptriangle", {NodeKind::Blep, 2, 2, false}},
+        {"convolve", {NodeKind::Convolve, 0, 0, false}},
+        {"meter", {NodeKind::PassThrough, 0, 0, false}}, {"scope", {NodeKind::PassThrough, 0, 0, false}},
+    };
+    return t;
+}
+
+static int bitceil(int n) {   // helpers/BitUtils.h:9
+    if ((n & (n - 1)) == 0) return n;
+    int o = 1;
+    while (o < n) o <<= 1;
+    return o;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+Engine::Engine(double sampleRate, int blockSize, int numVoices, int device)
+    : sr_(sampleRate), blockSize_(blockSize), numVoices_(numVoices), device_(device) {
+    if (numVoices_ < 1) numVoices_ = 1;
+    planOnly_ = device_ < 0;
+    if (!planOnly_) {
+        cuda(cudaSetDevice(device_), "cudaSetDevice");
+        cuda(cudaStreamCreateWithFlags(&stream_, cudaStreamNonBlocking), "cudaStreamCreate");
+    }
+    auto g = std::make_unique<Group>();
+    g->v0 = 0; g->nv = numVoices_; g->Vpad = (numVoices_ + 31) / 32 * 32;
+    groups_.push_back(std::move(g));
+    cuda(dmalloc((void**) &dMix_, sizeof(float) * MAX_OUT_CHANNELS * blockSize_), "cudaMalloc mix");
+    if (dMix_) cuda(dmemset(dMix_, 0, sizeof(float) * MAX_OUT_CHANNELS * blockSize_), "memset mix");
+}
+
+static void freeGroupStorage(Group& g, bool plan) {
+    for (auto& kv : g.nodes) {
+        if (kv.second.ring) rawFree(kv.second.ring, plan);
+        if (kv.second.tapPrivate) rawFree(kv.second.tapPrivate, plan);
+    }
+    for (auto& kv : g.tapShared) if (kv.second) rawFree(kv.second, plan);
+    if (g.dRows) rawFree(g.dRows, plan);
+}
+
+Engine::~Engine() {
+    dsetdev();
+    dsync();
+    for (auto& g : groups_) freeGroupStorage(*g, planOnly_);
+    groups_.clear();
+    for (auto& kv : resources_) if (kv.second->dChannel0) dfree(kv.second->dChannel0);
+    if (dMix_) dfree(dMix_);
+    if (dPartial_) dfree(dPartial_);
+    if (dOutVoice_) dfree(dOutVoice_);
+    if (dInVoice_) dfree(dInVoice_);
+    if (dInShared_) dfree(dInShared_);
+    if (hPinned_ && !planOnly_) cudaFreeHost(hPinned_);
+    if (ownStream_ && stream_) cudaStreamDestroy(stream_);
+}
+
+bool Engine::cuda(cudaError_t e, const char* what) {
+    if (e == cudaSuccess) return true;
+    lastError_ = std::string(what) + ": " + cudaGetErrorString(e);
+    return false;
+}
+
+int Engine::setOption(const char* key, double value) {
+    const std::string k(key);
+    if (k == "tile_samples") { if (value != 4 && value != 8) return rc::BadArgument; opt_.tileSamples = (int) value; }
+    else if (k == "tile_width") { opt_.tileWidth = (int) value; }
+    else if (k == "warps_per_cta") { opt_.warpsPerCta = (int) value; }
+    else if (k == "target_tiles") { opt_.targetTiles = (int) value; }
+    else return rc::BadArgument;
+    return rc::Ok;
+}
+
+std::string Engine::describe() const {
+    std::ostringstream os;
+    os << "{\"voices\":" << numVoices_ << ",\"groups\":[";
+    bool first = true;
+    for (auto& g : groups_) {
+        if (!first) os << ",";
+        first = false;
+        os << "{\"v0\":" << g->v0 << ",\"nv\":" << g->nv << ",\"tile_width\":" << g->tileWidth << ",\"nodes\":" << g->nodes.size();
+        if (g->pending || g->active) {
+            auto& p = g->pending ? g->pending : g->active;
+            os << ",\"slots\":" << p->nSlots << ",\"state_rows\":" << p->nStateRows << ",\"code_words\":" << p->code.size()
+               << ",\"roots\":" << p->rootIds.size();
+        }
+        os << "}";
+    }
+    os << "]}";
+    return os.str();
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// storage
+int Engine::allocRows(Group& g, int count, bool evenAlign, int& row) {
+    int start = g.rowsUsed;
+    if (evenAlign && (start & 1)) ++start;
+    const int need = start + count;
+    if (need > g.rowsCap) {
+        int cap = std::max(64, g.rowsCap * 2);
+        while (cap < need) cap *= 2;
+        float* nb = nullptr;
+        if (!cuda(dmalloc((void**) &nb, sizeof(float) * (size_t) cap * g.Vpad), "cudaMalloc rows")) return rc::CudaError;
+        if (!cuda(dmemset(nb, 0, sizeof(float) * (size_t) cap * g.Vpad), "memset rows")) return rc::CudaError;
+        if (g.dRows) {
+            if (!cuda(dmemcpy(nb, g.dRows, sizeof(float) * (size_t) g.rowsUsed * g.Vpad, cudaMemcpyDeviceToDevice), "copy rows")) return rc::CudaError;
+            dsync();
+            dfree(g.dRows);
+        }
+        g.dRows = nb;
+        g.rowsCap = cap;
+    }
+    row = start;
+    g.rowsUsed = need;
+    return rc::Ok;
+}
+
+int Engine::fillRowBits(Group& g, int row, int vb, int ve, uint32_t bits) {
+    if (row < 0) return rc::Ok;
+    const int n = ve - vb;
+    if (n <= 0) return rc::Ok;
+    uint32_t* p = reinterpret_cast<uint32_t*>(g.dRows + (size_t) row * g.Vpad + vb);
+    if (bits == 0) return cuda(dmemset(p, 0, sizeof(float) * n), "memset row") ? rc::Ok : rc::CudaError;
+    std::vector<uint32_t> tmp((size_t) n, bits);
+    if (!cuda(dmemcpy(p, tmp.data(), sizeof(uint32_t) * n, cudaMemcpyHostToDevice), "fill row")) return rc::CudaError;
+    dsync();   // tmp is pageable and dies here
+    return rc::Ok;
+}
+
+int Engine::fillRow(Group& g, int row, int vb, int ve, float value) {
+    uint32_t bits;
+    std::memcpy(&bits, &value, 4);
+    return fillRowBits(g, row, vb, ve, bits);
+}
+
+int Engine::ensureResourceOnDevice(Resource& r) {
+    if (r.dChannel0 || r.numSamples == 0) return rc::Ok;
+    if (!cuda(dmalloc((void**) &r.dChannel0, sizeof(float) * r.numSamples), "cudaMalloc resource")) return rc::CudaError;
+    if (!cuda(dmemcpySync(r.dChannel0, r.channels[0].data(), sizeof(float) * r.numSamples, cudaMemcpyHostToDevice), "upload resource")) return rc::CudaError;
+    return rc::Ok;
+}
+
+int Engine::addSharedResource(const char* name, const float* const* chans, size_t nCh, size_t nSamples) {
+    // insert-only: SharedResource.h:44-46 (emplace fails on an existing key)
+    if (resources_.count(name)) return 0;
+    auto r = std::make_shared<Resource>();
+    r->name = name;
+    r->numSamples = nSamples;
+    for (size_t c = 0; c < nCh; ++c) r->channels.emplace_back(chans[c], chans[c] + nSamples);   // copied in: AudioBufferResource.h:13-24
+    if (nCh == 0) r->numSamples = 0;
+    resources_[name] = r;
+    return 1;
+}
+
+void Engine::pruneSharedResources() {   // SharedResource.h:93-101: drop entries nobody else references
+    dsync();
+    for (auto it = resources_.begin(); it != resources_.end();) {
+        if (it->second.use_count() == 1) {
+            if (it->second->dChannel0) dfree(it->second->dChannel0);
+            it = resources_.erase(it);
+        } else ++it;
+    }
+}
+
+std::vector<std::string> Engine::listSharedResources() const {
+    std::vector<std::string> out;
+    for (auto& kv : resources_) out.push_back(kv.first);
+    return out;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// instruction interpreter
+static bool toInt32(const Value& v, int32_t& out) {
+    if (!v.isNumber()) return false;
+    out = static_cast<int32_t>(v.asNumber());   // Runtime.h:299
+    return true;
+}
+
+int Engine::createNode(Group& g, const Value& a1, const Value& a2) {   // Runtime.h:294-313
+    int32_t id;
+    if (!toInt32(a1, id) || !a2.isString()) return rc::InvalidInstructionFormat;
+    auto it = typeTable().find(a2.asString());
+    if (it == typeTable().end()) return rc::UnknownNodeType;
+    if (g.nodes.count(id)) return rc::NodeAlreadyExists;
+
+    Node n;
+    n.id = id;
+    n.kind = it->second.kind;
+    n.fn = it->second.fn;
+    n.typeName = a2.asString();
+    if (it->second.stateRows > 0) {
+        int r = allocRows(g, it->second.stateRows, it->second.evenAlign, n.stateRow);
+        if (r != rc::Ok) return r;
+    }
+    switch (n.kind) {
+        case NodeKind::Const: {   // Core.h:166 default 1
+            int r = allocRows(g, 1, false, n.paramRow);
+            if (r != rc::Ok) return r;
+            if ((r = fillRow(g, n.paramRow, 0, g.nv, 1.0f)) != rc::Ok) return r;
+        } break;
+        case NodeKind::Sr: {      // Core.h:173-180
+            int r = allocRows(g, 1, false, n.paramRow);
+            if (r != rc::Ok) return r;
+            if ((r = fillRow(g, n.paramRow, 0, g.nv, (float) sr_)) != rc::Ok) return r;
+        } break;
+        case NodeKind::Root: n.fade.init(sr_); n.channel = -1; break;          // Core.h:80-82
+        case NodeKind::Delay: n.size = blockSize_; n.ringDirty = true; break;  // Delays.h:56
+        case NodeKind::SDelay: n.length = blockSize_; n.size = bitceil(blockSize_ + blockSize_); n.ringDirty = true; break;   // Delays.h:183,197-198
+        default: break;
+    }
+    g.nodes.emplace(id, std::move(n));
+    return rc::Ok;
+}
+
+int Engine::appendChild(Group& g, const Value& a1, const Value& a2, const Value& a3) {   // Runtime.h:336-366
+    int32_t parent, child, chan;
+    if (!toInt32(a1, parent) || !toInt32(a2, child) || !toInt32(a3, chan)) return rc::InvalidInstructionFormat;
+    auto p = g.nodes.find(parent);
+    if (p == g.nodes.end()) return rc::NodeNotFound;
+    if (!g.nodes.count(child)) return rc::NodeNotFound;
+    p->second.inlets.push_back(Inlet{child, chan});
+    return rc::Ok;
+}
+
+int Engine::nodeSetProperty(Group& g, Node& n, const std::string& key, const Value& val, int vb, int ve) {
+    // vb/ve are group-relative voice bounds; only per-voice capable props honour a sub-range.
+    switch (n.kind) {
+        case NodeKind::Const:
+            if (key == "value") {   // Core.h:142-152
+                if (!val.isNumber()) return rc::InvalidPropertyType;
+                int r = fillRow(g, n.paramRow, vb, ve, (float) val.asNumber());
+                if (r != rc::Ok) return r;
+            }
+            break;
+        case NodeKind::Root:        // Core.h:33-64
+            if (key == "active") {
+                if (!val.isBool()) return rc::InvalidPropertyType;
+                if (val.asBool()) n.fade.fadeIn(); else n.fade.fadeOut();
+            }
+            if (key == "channel") {
+                if (!val.isNumber()) return rc::InvalidInstructionFormat;   // reference throws bad_variant_access here
+                n.channel = static_cast<int>(val.asNumber());
+            }
+            if (key == "fadeInMs") {
+                if (!val.isNumber()) return rc::InvalidPropertyType;
+                n.fade.setFadeInMs(sr_, val.asNumber());
+            }
+            if (key == "fadeOutMs") {
+                if (!val.isNumber()) return rc::InvalidPropertyType;
+                n.fade.setFadeOutMs(sr_, val.asNumber());
+            }
+            break;
+        case NodeKind::In:          // Math.h:95-105
+            if (key == "channel") {
+                if (!val.isNumber()) return rc::InvalidPropertyType;
+                n.channel = static_cast<int>(val.asNumber());
+            }
+            break;
+        case NodeKind::Svf:         // filters/SVF.h:30-46
+            if (key == "mode") {
+                if (!val.isString()) return rc::InvalidPropertyType;
+                const std::string& m = val.asString();
+                if (m == "lowpass") n.mode = 0; if (m == "bandpass") n.mode = 1; if (m == "highpass") n.mode = 2;
+                if (m == "notch") n.mode = 3; if (m == "allpass") n.mode = 4;
+            }
+            break;
+        case NodeKind::SvfShelf:    // filters/SVFShelf.h:30-44
+            if (key == "mode") {
+                if (!val.isString()) return rc::InvalidPropertyType;
+                const std::string& m = val.asString();
+                if (m == "lowshelf") n.mode = 0; if (m == "highshelf") n.mode = 1; if (m == "bell" || m == "peak") n.mode = 2;
+            }
+            break;
+        case NodeKind::MM1p:        // filters/MultiMode1p.h:50-65
+            if (key == "mode") {
+                if (!val.isString()) return rc::InvalidPropertyType;
+                const std::string& m = val.asString();
+                if (m == "lowpass") n.mode = 0; if (m == "highpass") n.mode = 2; if (m == "allpass") n.mode = 4;
+            }
+            break;
+        case NodeKind::Delay:       // Delays.h:59-76
+            if (key == "size") {
+                if (!val.isNumber()) return rc::InvalidPropertyType;
+                n.size = std::max(0, static_cast<int>(val.asNumber()));
+                n.ringDirty = true;
+            }
+            break;
+        case NodeKind::SDelay:      // Delays.h:188-206
+            if (key == "size") {
+                if (!val.isNumber()) return rc::InvalidPropertyType;
+                n.length = std::max(0, static_cast<int>(val.asNumber()));
+                n.size = bitceil(n.length + blockSize_);
+                n.ringDirty = true;
+            }
+            break;
+        case NodeKind::MaxHold:     // Core.h:292-303
+            if (key == "hold") {
+                if (!val.isNumber()) return rc::InvalidPropertyType;
+                const double h = sr_ * 0.001 * val.asNumber();
+                n.holdSamples = static_cast<uint32_t>(h);
+            }
+            break;
+        case NodeKind::Rand:        // Noise.h:13-23
+            if (key == "seed") {
+                if (!val.isNumber()) return rc::InvalidPropertyType;
+                int r = fillRowBits(g, n.stateRow, vb, ve, static_cast<uint32_t>(val.asNumber()));
+                if (r != rc::Ok) return r;
+            }
+            break;
+        case NodeKind::TapIn:
+        case NodeKind::TapOut:      // Feedback.h:24-38,71-85
+            if (key == "name") {
+                if (!val.isString()) return rc::InvalidPropertyType;
+                n.tapName = val.asString();
+            }
+            break;
+        case NodeKind::Table:       // Table.h:20-34
+        case NodeKind::Convolve:    // wasm/Convolve.h:35-56
+            if (key == "path") {
+                if (!val.isString()) return rc::InvalidPropertyType;
+                auto it = resources_.find(val.asString());
+                if (it == resources_.end()) return rc::InvalidPropertyValue;
+                n.resource = it->second;
+                n.resourceDirty = true;
+            }
+            break;
+        default: break;
+    }
+    n.props[key] = val;   // GraphNode.h:60-63
+    return rc::Ok;
+}
+
+int Engine::setProperty(Group& g, const Value& a1, const Value& a2, const Value& v, int vb, int ve) {   // Runtime.h:316-333
+    int32_t id;
+    if (!toInt32(a1, id) || !a2.isString()) return rc::InvalidInstructionFormat;
+    auto it = g.nodes.find(id);
+    if (it == g.nodes.end()) return rc::NodeNotFound;
+    return nodeSetProperty(g, it->second, a2.asString(), v, vb, ve);
+}
+
+int Engine::activateRoots(Group& g, const Value& roots) {   // Runtime.h:369-433
+    if (!roots.isArray()) return rc::InvalidInstructionFormat;
+    std::set<int32_t> active;
+    for (auto& v : roots.asArray()) {
+        int32_t id;
+        if (!toInt32(v, id)) return rc::InvalidInstructionFormat;
+        auto it = g.nodes.find(id);
+        if (it == g.nodes.end()) return rc::NodeNotFound;
+        if (it->second.kind == NodeKind::Root) {
+            nodeSetProperty(g, it->second, "active", Value::boolean(true), 0, g.nv);
+            active.insert(id);
+        }
+    }
+    for (int32_t id : g.currentRoots) {
+        auto it = g.nodes.find(id);
+        if (it == g.nodes.end() || it->second.kind != NodeKind::Root) continue;
+        Node& n = it->second;
+        if (!active.count(id)) nodeSetProperty(g, n, "active", Value::boolean(false), 0, g.nv);
+        if (n.fade.on() || !n.fade.settled()) active.insert(id);   // stillRunning(): Core.h:28-31
+    }
+    g.currentRoots.swap(active);
+    return rc::Ok;
+}
+
+int Engine::applyToGroup(Group& g, const std::vector<Value>& batch, int vb, int ve) {   // Runtime.h:170-218
+    bool shouldRebuild = false;
+    for (auto& next : batch) {
+        if (!next.isArray()) return rc::InvalidInstructionFormat;
+        auto& ar = next.asArray();
+        if (ar.empty() || !ar[0].isNumber()) return rc::InvalidInstructionFormat;
+        const int cmd = static_cast<int>(ar[0].asNumber());
+        int res = rc::Ok;
+        // the reference indexes ar[1..3] unchecked; a short instruction is undefined behaviour there, an
+        // InvalidInstructionFormat here.
+        auto need = [&](size_t n) { return ar.size() >= n; };
+        switch (cmd) {
+            case 0: res = need(3) ? createNode(g, ar[1], ar[2]) : rc::InvalidInstructionFormat; break;
+            case 3: res = need(4) ? setProperty(g, ar[1], ar[2], ar[3], vb, ve) : rc::InvalidInstructionFormat; break;
+            case 2: res = need(4) ? appendChild(g, ar[1], ar[2], ar[3]) : rc::InvalidInstructionFormat; break;
+            case 4:
+                res = need(2) ? activateRoots(g, ar[1]) : rc::InvalidInstructionFormat;
+                shouldRebuild = true;
+                break;
+            case 5:
+                if (shouldRebuild) {
+                    std::shared_ptr<Program> p;
+                    res = compile(g, g.active ? g.active->nIn : (g.pending ? g.pending->nIn : 0), p);
+                    if (res == rc::Ok) g.pending = p;   // rseqQueue.push(buildRenderSequence())
+                }
+                break;
+            default: break;
+        }
+        if (res != rc::Ok) return res;   // no rollback: Runtime.h:211-214
+    }
+    return rc::Ok;
+}
+
+bool Engine::isValueOnlyBatch(const std::vector<Value>& batch, int vb, int ve) {
+    // A batch made only of SET_PROPERTY on per-voice-capable props (const.value, rand.seed) never changes the
+    // structure of a group, so it may address any sub-range of voices without splitting the group.
+    for (auto& ins : batch) {
+        if (!ins.isArray()) return false;
+        auto& ar = ins.asArray();
+        if (ar.size() < 4 || !ar[0].isNumber() || static_cast<int>(ar[0].asNumber()) != 3) return false;
+        int32_t id;
+        if (!toInt32(ar[1], id) || !ar[2].isString() || !ar[3].isNumber()) return false;
+        for (auto& g : groups_) {
+            if (g->v0 >= ve || g->v0 + g->nv <= vb) continue;
+            auto it = g->nodes.find(id);
+            if (it == g->nodes.end()) return false;
+            const bool ok = (it->second.kind == NodeKind::Const && ar[2].asString() == "value") ||
+                            (it->second.kind == NodeKind::Rand && ar[2].asString() == "seed");
+            if (!ok) return false;
+        }
+    }
+    return true;
+}
+
+int Engine::splitGroupsAt(int v) {
+    if (v <= 0 || v >= numVoices_) return rc::Ok;
+    for (size_t i = 0; i < groups_.size(); ++i) {
+        Group& g = *groups_[i];
+        if (v <= g.v0 || v >= g.v0 + g.nv) continue;
+        // Only a group that owns no graph yet can be cut (its voices have no device state to migrate).
+        // Re-partitioning live voices is the "dynamic graph updates at voice scale" next-row.
+        if (!g.nodes.empty() || g.dRows) return fail(rc::InvariantViolation, "cannot split a voice group that already owns a graph; address whole groups or split before the first batch");
+        auto ng = std::make_unique<Group>();
+        ng->v0 = v; ng->nv = g.v0 + g.nv - v; ng->Vpad = (ng->nv + 31) / 32 * 32;
+        g.nv = v - g.v0; g.Vpad = (g.nv + 31) / 32 * 32;
+        groups_.insert(groups_.begin() + i + 1, std::move(ng));
+        return rc::Ok;
+    }
+    return rc::Ok;
+}
+
+int Engine::applyInstructions(int vb, int ve, const char* json, size_t len) {
+    dsetdev();
+    if (vb < 0) vb = 0;
+    if (ve < 0 || ve > numVoices_) ve = numVoices_;
+    if (vb >= ve) return fail(rc::BadArgument, "empty voice range");
+    Value doc;
+    try {
+        doc = parseJson(json, len);
+    } catch (const std::exception& e) {   // the reference throws here (JSON.h:146-154); the C ABI maps it to a code
+        return fail(rc::InvalidInstructionFormat, e.what());
+    }
+    if (!doc.isArray()) return fail(rc::InvalidInstructionFormat, "batch is not an array");
+    auto& batch = doc.asArray();
+
+    if (!isValueOnlyBatch(batch, vb, ve)) {
+        int r = splitGroupsAt(vb);
+        if (r != rc::Ok) return r;
+        if ((r = splitGroupsAt(ve)) != rc::Ok) return r;
+    }
+    for (auto& g : groups_) {
+        const int b = std::max(vb, g->v0), e = std::min(ve, g->v0 + g->nv);
+        if (b >= e) continue;
+        int r = applyToGroup(*g, batch, b - g->v0, e - g->v0);
+        if (r != rc::Ok) { if (lastError_.empty() || r > 0) lastError_ = "instruction failed"; return r; }
+    }
+    return rc::Ok;
+}
+
+int Engine::setPropertyPerVoice(int32_t nodeId, const char* key, const double* values, int vb, int count) {
+    // Vectorised SET_PROPERTY: values[i] goes to voice vb+i. Same semantics as `count`
+    // single-voice [3,id,key,value] batches, without `count` JSON parses.
+    dsetdev();
+    if (vb < 0 || count < 0 || vb + count > numVoices_) return fail(rc::BadArgument, "voice range out of bounds");
+    const std::string k(key);
+    for (auto& gp : groups_) {
+        Group& g = *gp;
+        const int b = std::max(vb, g.v0), e = std::min(vb + count, g.v0 + g.nv);
+        if (b >= e) continue;
+        auto it = g.nodes.find(nodeId);
+        if (it == g.nodes.end()) return rc::NodeNotFound;
+        Node& n = it->second;
+        int row;
+        std::vector<uint32_t> bits((size_t) (e - b));
+        if (n.kind == NodeKind::Const && k == "value") {
+            row = n.paramRow;
+            for (int v = b; v < e; ++v) { float f = (float) values[v - vb]; std::memcpy(&bits[v - b], &f, 4); }
+        } else if (n.kind == NodeKind::Rand && k == "seed") {
+            row = n.stateRow;
+            for (int v = b; v < e; ++v) bits[v - b] = static_cast<uint32_t>(values[v - vb]);
+        } else return fail(rc::InvalidPropertyType, "property is not per-voice capable");
+        if (!cuda(dmemcpy(g.dRows + (size_t) row * g.Vpad + (b - g.v0), bits.data(), sizeof(uint32_t) * bits.size(), cudaMemcpyHostToDevice), "per-voice prop upload")) return rc::CudaError;
+        dsync();
+        n.props[k] = Value::number(values[e - 1 - vb]);
+    }
+    return rc::Ok;
+}
+
+int Engine::gc(int voice, std::vector<int32_t>& pruned) {   // Runtime.h:221-272
+    pruned.clear();
+    for (auto& gp : groups_) {
+        Group& g = *gp;
+        if (voice < g.v0 || voice >= g.v0 + g.nv) continue;
+        std::set<int32_t> live;
+        if (g.active) live.insert(g.active->nodeIds.begin(), g.active->nodeIds.end());
+        if (g.pending) live.insert(g.pending->nodeIds.begin(), g.pending->nodeIds.end());
+        dsync();
+        for (auto it = g.nodes.begin(); it != g.nodes.end();) {
+            if (!live.count(it->first)) {
+                pruned.push_back(it->first);
+                if (it->second.ring) dfree(it->second.ring);
+                if (it->second.tapPrivate) dfree(it->second.tapPrivate);
+                it = g.nodes.erase(it);
+            } else ++it;
+        }
+    }
+    std::sort(pruned.begin(), pruned.end());
+    return rc::Ok;
+}
+
+void Engine::reset() {
+    // Runtime.h:449-458: only SampleNode does anything on reset() in the reference; no in-scope node does.
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// compile: sorted node list -> render program
+int Engine::chooseTileWidth(int nv) const {
+    if (opt_.tileWidth > 0) {
+        int L = 1;
+        while (L * 2 <= std::min(32, opt_.tileWidth)) L *= 2;
+        return L;
+    }
+    int L = 32;
+    while (L > 1 && (nv + L - 1) / L < opt_.targetTiles) L >>= 1;
+    return L;
+}
+
+void Engine::traverse(Group& g, std::set<int32_t>& visited, std::vector<int32_t>& order, int32_t n) {   // Runtime.h:503-518
+    if (visited.count(n)) return;
+    // A cycle would recurse forever in the reference; break it by marking the node before descending when we
+    // see it again on the stack (front ends never emit cycles).
+    static thread_local std::set<int32_t> onStack;
+    if (onStack.count(n)) return;
+    onStack.insert(n);
+    auto it = g.nodes.find(n);
+    if (it != g.nodes.end())
+        for (auto& in : it->second.inlets) traverse(g, visited, order, in.source);
+    onStack.erase(n);
+    order.push_back(n);
+    visited.insert(n);
+}
+
+struct Compiler {
+    Engine& E;
+    Group& g;
+    int nIn;
+    Program& prog;
+
+    struct PendingOp {
+        uint32_t opcode = 0, mode = 0, state = NO_STATE, aux0 = 0, aux1 = 0;
+        uint64_t ptr = 0;
+        int32_t outNode = 0;               // node whose output this op produces (0x7fffffff+k for temporaries)
+        std::vector<std::pair<uint32_t, int32_t>> operands;   // (kind, node id | param row)
+        bool isSeg = false;
+        int segRoot = 0;
+        size_t segEndOp = 0;
+    };
+    std::vector<PendingOp> ops;
+    std::vector<std::pair<int, int32_t>> promotes;   // (root index, tapOut node id)
+    int32_t tempCounter = 0;
+
+    int32_t newTemp() { return INT32_MIN + (++tempCounter); }
+
+    static void putDouble(PendingOp& op, double d) {
+        uint64_t b;
+        std::memcpy(&b, &d, 8);
+        op.aux0 = (uint32_t) b; op.aux1 = (uint32_t) (b >> 32);
+    }
+    static uint32_t fbits(float f) { uint32_t b; std::memcpy(&b, &f, 4); return b; }
+
+    std::pair<uint32_t, int32_t> operandFor(const Inlet& in) {
+        auto it = g.nodes.find(in.source);
+        if (it == g.nodes.end() || in.channel != 0) return {K_ZERO, 0};
+        const Node& c = it->second;
+        if (c.kind == NodeKind::Const || c.kind == NodeKind::Sr) return {K_PARAM, c.paramRow};
+        return {K_SLOT, c.id};
+    }
+
+    int emitNode(Node& n, int rootIndex);
+};
+
+int Compiler::emitNode(Node& n, int rootIndex) {
+    if (n.kind == NodeKind::Const || n.kind == NodeKind::Sr) return rc::Ok;   // folded into PARAM operands
+
+    const bool leaf = n.inlets.empty();
+    if (leaf && n.kind != NodeKind::Rand && n.kind != NodeKind::TapIn) prog.usesHostInputs = true;
+    // Inputs as the node's process() sees them: children, or — for a leaf — the host input channels
+    // (GraphRenderSequence.h:126-135).
+    std::vector<std::pair<uint32_t, int32_t>> inputs;
+    if (!leaf) {
+        for (auto& in : n.inlets) inputs.push_back(operandFor(in));
+    } else if (n.kind != NodeKind::In) {
+        for (int ch = 0; ch < nIn; ++ch) {
+            PendingOp ld;
+            ld.opcode = OP_LOADIN; ld.aux0 = (uint32_t) ch; ld.outNode = newTemp();
+            ops.push_back(ld);
+            inputs.push_back({K_SLOT, ld.outNode});
+            prog.usesHostInputs = true;
+        }
+    }
+    const int numCh = leaf ? nIn : (int) n.inlets.size();
+
+    PendingOp op;
+    op.outNode = n.id;
+    op.state = (n.stateRow >= 0) ? (uint32_t) n.stateRow : NO_STATE;   // rewritten to a smem index later
+    auto zeros = [&]() { op.opcode = OP_FILL0; op.state = NO_STATE; op.operands.clear(); };
+    auto take = [&](int k) { op.operands.assign(inputs.begin(), inputs.begin() + k); };
+
+    switch (n.kind) {
+        case NodeKind::In: {   // Math.h:107-122
+            const int ch = n.channel;
+            if (ch < 0 || ch >= numCh) { zeros(); break; }
+            if (leaf) { op.opcode = OP_LOADIN; op.aux0 = (uint32_t) ch; prog.usesHostInputs = true; }
+            else { op.opcode = OP_COPY; op.operands = {operandFor(n.inlets[ch])}; }
+        } break;
+        case NodeKind::Unary: if (numCh < 1) { zeros(); break; } op.opcode = OP_UNARY; op.mode = n.fn; take(1); break;
+        case NodeKind::Binary: if (numCh < 2) { zeros(); break; } op.opcode = OP_BINARY; op.mode = n.fn; take(2); break;
+        case NodeKind::Reduce:
+            if (numCh < 1) { zeros(); break; }
+            if (numCh > 255) return E.fail(rc::InvariantViolation, "more than 255 children on one node");
+            op.opcode = OP_REDUCE; op.mode = n.fn; take(numCh);
+            break;
+        case NodeKind::Root:
+            op.opcode = OP_ROOT; op.aux0 = (uint32_t) rootIndex;
+            if (numCh >= 1) take(1);
+            break;
+        case NodeKind::Phasor:
+            if (numCh < 1) { zeros(); break; }
+            op.opcode = OP_PHASOR; op.aux0 = fbits(1.0f / (float) E.sr_); take(1);   // Core.h:90
+            break;
+        case NodeKind::SPhasor:
+            if (numCh < 2) { zeros(); break; }
+            op.opcode = OP_SPHASOR; op.aux0 = fbits(1.0f / (float) E.sr_); take(2);
+            break;
+        case NodeKind::Counter: if (numCh < 1) { zeros(); break; } op.opcode = OP_COUNTER; take(1); break;
+        case NodeKind::Accum: if (numCh < 2) { zeros(); break; } op.opcode = OP_ACCUM; take(2); break;
+        case NodeKind::Latch: if (numCh < 2) { zeros(); break; } op.opcode = OP_LATCH; take(2); break;
+        case NodeKind::MaxHold: if (numCh < 2) { zeros(); break; } op.opcode = OP_MAXHOLD; op.aux0 = n.holdSamples; take(2); break;
+        case NodeKind::Rand: op.opcode = OP_RAND; break;
+        case NodeKind::Pole: if (numCh < 2) { zeros(); break; } op.opcode = OP_POLE; take(2); break;
+        case NodeKind::Env: if (numCh < 3) { zeros(); break; } op.opcode = OP_ENV; take(3); break;
+        case NodeKind::Biquad: if (numCh < 6) { zeros(); break; } op.opcode = OP_BIQUAD; take(6); break;
+        case NodeKind::Prewarp: if (numCh < 1) { zeros(); break; } op.opcode = OP_PREWARP; putDouble(op, 1.0 / E.sr_); take(1); break;
+        case NodeKind::MM1p: if (numCh < 2) { zeros(); break; } op.opcode = OP_MM1P; op.mode = (uint32_t) n.mode; take(2); break;
+        case NodeKind::Svf: if (numCh < 3) { zeros(); break; } op.opcode = OP_SVF; op.mode = (uint32_t) n.mode; putDouble(op, E.sr_); take(3); break;
+        case NodeKind::SvfShelf: if (numCh < 4) { zeros(); break; } op.opcode = OP_SVFSHELF; op.mode = (uint32_t) n.mode; putDouble(op, E.sr_); take(4); break;
+        case NodeKind::Z: if (numCh < 1) { zeros(); break; } op.opcode = OP_Z; take(1); break;
+        case NodeKind::Blep:
+            if (numCh < 1) { zeros(); break; }
+            op.opcode = OP_BLEP; op.mode = n.fn; op.aux0 = fbits((float) E.sr_); take(1);
+            break;
+        case NodeKind::PassThrough: if (numCh < 1) { zeros(); break; } op.opcode = OP_COPY; take(1); break;
+
+        case NodeKind::Delay: {   // Delays.h:92-106
+            const size_t tiles = (size_t) g.nTiles() * g.tileWidth;
+            if (n.ringDirty) {
+                E.dsync();
+                if (n.ring) { E.dfree(n.ring); n.ring = nullptr; }
+                n.ringFloats = (size_t) n.size * tiles;
+                if (n.ringFloats) {
+                    if (!E.cuda(E.dmalloc((void**) &n.ring, sizeof(float) * n.ringFloats), "cudaMalloc delay ring")) return rc::CudaError;
+                    if (!E.cuda(E.dmemset(n.ring, 0, sizeof(float) * n.ringFloats), "memset ring")) return rc::CudaError;
+                }
+                int r = E.fillRowBits(g, n.stateRow, 0, g.nv, 0);   // writeIndex = 0
+                if (r != rc::Ok) return r;
+                n.ringDirty = false;
+            }
+            if (numCh < 3) { zeros(); break; }
+            op.opcode = OP_DELAY; op.aux0 = (uint32_t) n.size; op.ptr = (uint64_t) (uintptr_t) n.ring; take(3);
+        } break;
+
+        case NodeKind::SDelay: {  // Delays.h:221-245
+            const size_t tiles = (size_t) g.nTiles() * g.tileWidth;
+            if (n.ringDirty) {
+                E.dsync();
+                if (n.ring) { E.dfree(n.ring); n.ring = nullptr; }
+                n.ringFloats = (size_t) n.size * tiles;
+                if (n.ringFloats) {
+                    if (!E.cuda(E.dmalloc((void**) &n.ring, sizeof(float) * n.ringFloats), "cudaMalloc sdelay ring")) return rc::CudaError;
+                    if (!E.cuda(E.dmemset(n.ring, 0, sizeof(float) * n.ringFloats), "memset ring")) return rc::CudaError;
+                }
+                int r = E.fillRowBits(g, n.stateRow, 0, g.nv, 0);
+                if (r != rc::Ok) return r;
+                n.ringDirty = false;
+            }
+            if (numCh < 1 || n.size == 0) { zeros(); break; }
+            op.opcode = OP_SDELAY; op.aux0 = (uint32_t) n.size; op.aux1 = (uint32_t) n.length; op.ptr = (uint64_t) (uintptr_t) n.ring; take(1);
+        } break;
+
+        case NodeKind::Table: {   // Table.h:44-57
+            if (numCh == 0 || !n.resource || n.resource->numSamples == 0) { zeros(); break; }
+            int r = E.ensureResourceOnDevice(*n.resource);
+            if (r != rc::Ok) return r;
+            op.opcode = OP_TABLE; op.aux0 = (uint32_t) n.resource->numSamples; op.ptr = (uint64_t) (uintptr_t) n.resource->dChannel0; take(1);
+        } break;
+
+        case NodeKind::TapIn:
+        case NodeKind::TapOut: {
+            const size_t floats = (size_t) g.nTiles() * g.tileWidth * E.blockSize_;
+            float* shared = nullptr;
+            if (!n.tapName.empty()) {   // Feedback.h:29-33: created on first request by either side
+                auto it = g.tapShared.find(n.tapName);
+                if (it == g.tapShared.end()) {
+                    if (!E.cuda(E.dmalloc((void**) &shared, sizeof(float) * floats), "cudaMalloc tap")) return rc::CudaError;
+                    if (!E.cuda(E.dmemset(shared, 0, sizeof(float) * floats), "memset tap")) return rc::CudaError;
+                    g.tapShared[n.tapName] = shared;
+                } else shared = it->second;
+            }
+            if (n.kind == NodeKind::TapIn) {
+                if (!shared) { zeros(); break; }
+                op.opcode = OP_TAPIN; op.ptr = (uint64_t) (uintptr_t) shared;
+            } else {
+                if (!n.tapPrivate) {
+                    if (!E.cuda(E.dmalloc((void**) &n.tapPrivate, sizeof(float) * floats), "cudaMalloc tapOut")) return rc::CudaError;
+                    if (!E.cuda(E.dmemset(n.tapPrivate, 0, sizeof(float) * floats), "memset tapOut")) return rc::CudaError;
+                }
+                if (shared) promotes.push_back({rootIndex, n.id});
+                if (numCh < 1) { zeros(); break; }
+                op.opcode = OP_TAPOUT; op.ptr = (uint64_t) (uintptr_t) n.tapPrivate; take(1);
+            }
+        } break;
+
+        case NodeKind::Convolve:
+            return E.fail(rc::InvariantViolation, "convolve inside a render program is handled by the convolution stage");
+
+        default: zeros(); break;
+    }
+    ops.push_back(std::move(op));
+    return rc::Ok;
+}
+
+int Engine::compile(Group& g, int nIn, std::shared_ptr<Program>& out) {
+    auto prog = std::make_shared<Program>();
+    prog->planOnly = planOnly_;
+    prog->nIn = nIn;
+    if (g.tileWidth == 0) g.tileWidth = chooseTileWidth(g.nv);
+
+    // Root order: Runtime.h:544-559 — iterate currentRoots ascending; active roots are pushed to the FRONT,
+    // inactive (fading out) ones to the back.
+    std::list<int32_t> sortedRoots;
+    for (int32_t id : g.currentRoots) {
+        auto it = g.nodes.find(id);
+        if (it == g.nodes.end() || it->second.kind != NodeKind::Root) continue;
+        auto ap = it->second.props.find("active");
+        const bool isActive = ap != it->second.props.end() && ap->second.isBool() && ap->second.asBool();
+        if (isActive) sortedRoots.push_front(id); else sortedRoots.push_back(id);
+    }
+    if (sortedRoots.size() > (size_t) MAX_ROOTS) return fail(rc::InvariantViolation, "more than 16 simultaneous roots");
+
+    Compiler C{*this, g, nIn, *prog};
+    std::set<int32_t> visited;
+    for (int32_t rid : sortedRoots) {
+        const int r = (int) prog->rootIds.size();
+        prog->rootIds.push_back(rid);
+        std::vector<int32_t> order;
+        traverse(g, visited, order, rid);
+        Compiler::PendingOp seg;
+        seg.isSeg = true; seg.opcode = OP_SEG; seg.segRoot = r;
+        const size_t segIdx = C.ops.size();
+        C.ops.push_back(seg);
+        for (int32_t nid : order) {
+            auto it = g.nodes.find(nid);
+            if (it == g.nodes.end()) continue;
+            prog->nodeIds.push_back(nid);
+            int rcode = C.emitNode(it->second, r);
+            if (rcode != rc::Ok) return rcode;
+        }
+        C.ops[segIdx].segEndOp = C.ops.size();
+    }
+
+    // ---- slot allocation by liveness (an output slot is never the slot of one of its own inputs) ----
+    std::unordered_map<int32_t, size_t> lastUse;
+    for (size_t i = 0; i < C.ops.size(); ++i)
+        for (auto& o : C.ops[i].operands)
+            if (o.first == K_SLOT) lastUse[o.second] = i;
+    std::unordered_map<int32_t, int> slotOf;
+    std::vector<int> freeSlots;
+    int nSlots = 0;
+    std::vector<int> outSlot(C.ops.size(), 0);
+    for (size_t i = 0; i < C.ops.size(); ++i) {
+        auto& op = C.ops[i];
+        if (op.isSeg) continue;
+        int s;
+        if (!freeSlots.empty()) { s = freeSlots.back(); freeSlots.pop_back(); }
+        else s = nSlots++;
+        if (s >= MAX_SLOTS) return fail(rc::InvariantViolation, "graph needs more than 255 live intermediates");
+        outSlot[i] = s;
+        slotOf[op.outNode] = s;
+        // free inputs whose last consumer is this op
+        for (auto& o : op.operands) {
+            if (o.first != K_SLOT) continue;
+            auto lu = lastUse.find(o.second);
+            auto so = slotOf.find(o.second);
+            if (lu != lastUse.end() && lu->second == i && so != slotOf.end()) {
+                freeSlots.push_back(so->second);
+                slotOf.erase(so);
+            }
+        }
+        // an output nobody reads (root buffers, dangling nodes) is dead immediately
+        if (!lastUse.count(op.outNode)) { freeSlots.push_back(s); slotOf.erase(op.outNode); }
+    }
+    // Second pass resolving operand slots needs the slot each producer had when it was alive: recompute.
+    {
+        std::unordered_map<int32_t, int> producerSlot;
+        for (size_t i = 0; i < C.ops.size(); ++i) if (!C.ops[i].isSeg) producerSlot[C.ops[i].outNode] = outSlot[i];
+        // producerSlot is unique per node because every node is produced exactly once per program.
+        // ---- state map: node state rows -> shared-memory state rows ----
+        std::unordered_map<uint32_t, uint32_t> smemIndexOfRow;
+        int nStateRows = 0;
+        auto mapState = [&](Node& n) -> uint32_t {
+            if (n.stateRow < 0) return NO_STATE;
+            auto it = smemIndexOfRow.find((uint32_t) n.stateRow);
+            if (it != smemIndexOfRow.end()) return it->second;
+            const auto& ti = typeTable().at(n.typeName);
+            if (ti.evenAlign && (nStateRows & 1)) {   // keep doubles 8-byte aligned in shared memory
+                prog->stateMap.push_back(STATE_PAD);
+                nStateRows += 1;
+            }
+            const uint32_t idx = (uint32_t) nStateRows;
+            if (ti.evenAlign) {
+                for (int k = 0; k < ti.stateRows; k += 2) prog->stateMap.push_back(((uint32_t) n.stateRow + k) | STATE_DOUBLE_FLAG);
+            } else {
+                for (int k = 0; k < ti.stateRows; ++k) prog->stateMap.push_back((uint32_t) n.stateRow + k);
+            }
+            nStateRows += ti.stateRows;
+            smemIndexOfRow[(uint32_t) n.stateRow] = idx;
+            return idx;
+        };
+
+        // ---- encode ----
+        std::vector<size_t> wordOffset(C.ops.size() + 1, 0);
+        for (size_t i = 0; i < C.ops.size(); ++i)
+            wordOffset[i + 1] = wordOffset[i] + OP_HEADER_WORDS + (C.ops[i].isSeg ? 0 : C.ops[i].operands.size());
+        for (size_t i = 0; i < C.ops.size(); ++i) {
+            auto& op = C.ops[i];
+            if (op.isSeg) {
+                prog->code.push_back(make_w0(OP_SEG, 0, 0, 0));
+                prog->code.push_back(NO_STATE);
+                prog->code.push_back((uint32_t) op.segRoot);
+                prog->code.push_back((uint32_t) (wordOffset[op.segEndOp] - wordOffset[i + 1]));
+                prog->code.push_back(0); prog->code.push_back(0);
+                continue;
+            }
+            uint32_t st = NO_STATE;
+            if (op.state != NO_STATE) {
+                auto it = g.nodes.find(op.outNode);
+                if (it != g.nodes.end()) st = mapState(it->second);
+            }
+            prog->code.push_back(make_w0(op.opcode, (uint32_t) op.operands.size(), (uint32_t) outSlot[i], op.mode));
+            prog->code.push_back(st);
+            prog->code.push_back(op.aux0);
+            prog->code.push_back(op.aux1);
+            prog->code.push_back((uint32_t) op.ptr);
+            prog->code.push_back((uint32_t) (op.ptr >> 32));
+            for (auto& o : op.operands) {
+                if (o.first == K_SLOT) {
+                    auto ps = producerSlot.find(o.second);
+                    if (ps == producerSlot.end()) prog->code.push_back(make_operand(K_ZERO, 0));
+                    else prog->code.push_back(make_operand(K_SLOT, (uint32_t) ps->second));
+                } else if (o.first == K_PARAM) prog->code.push_back(make_operand(K_PARAM, (uint32_t) o.second));
+                else prog->code.push_back(make_operand(K_ZERO, 0));
+            }
+        }
+        prog->code.push_back(make_w0(OP_END, 0, 0, 0));
+        for (auto& pr : C.promotes) {
+            Node& n = g.nodes.at(pr.second);
+            float* dst = g.tapShared[n.tapName];
+            const uint64_t sb = (uint64_t) (uintptr_t) n.tapPrivate, db = (uint64_t) (uintptr_t) dst;
+            prog->code.push_back(make_w0(OP_COPY, 0, 0, 0));
+            prog->code.push_back((uint32_t) pr.first);
+            prog->code.push_back((uint32_t) sb); prog->code.push_back((uint32_t) (sb >> 32));
+            prog->code.push_back((uint32_t) db); prog->code.push_back((uint32_t) (db >> 32));
+        }
+        prog->code.push_back(make_w0(OP_END, 0, 0, 0));
+        prog->nStateRows = (nStateRows + 1) & ~1;
+        prog->nSlots = std::max(1, nSlots);
+    }
+
+    // ---- upload ----
+    if (!cuda(dmalloc((void**) &prog->dCode, sizeof(uint32_t) * prog->code.size()), "cudaMalloc code")) return rc::CudaError;
+    if (!cuda(dmemcpySync(prog->dCode, prog->code.data(), sizeof(uint32_t) * prog->code.size(), cudaMemcpyHostToDevice), "upload code")) return rc::CudaError;
+    if (!prog->stateMap.empty()) {
+        if (!cuda(dmalloc((void**) &prog->dStateMap, sizeof(uint32_t) * prog->stateMap.size()), "cudaMalloc stateMap")) return rc::CudaError;
+        if (!cuda(dmemcpySync(prog->dStateMap, prog->stateMap.data(), sizeof(uint32_t) * prog->stateMap.size(), cudaMemcpyHostToDevice), "upload stateMap")) return rc::CudaError;
+    }
+    out = prog;
+    return rc::Ok;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// process
+int Engine::ensureBuffers(size_t nIn, size_t nOut, bool perVoiceIn, bool materialise) {
+    size_t tiles = 0;
+    for (auto& g : groups_) tiles += (size_t) g->nTiles();
+    const size_t pf = std::max<size_t>(1, tiles) * nOut * blockSize_;
+    if (pf > partialFloats_) {
+        dsync();
+        if (dPartial_) dfree(dPartial_);
+        if (!cuda(dmalloc((void**) &dPartial_, sizeof(float) * pf), "cudaMalloc partial")) return rc::CudaError;
+        dmemset(dPartial_, 0, sizeof(float) * pf);
+        partialFloats_ = pf;
+    }
+    if (materialise) {
+        const size_t of = (size_t) numVoices_ * nOut * blockSize_;
+        if (of > outVoiceFloats_) {
+            dsync();
+            if (dOutVoice_) dfree(dOutVoice_);
+            if (!cuda(dmalloc((void**) &dOutVoice_, sizeof(float) * of), "cudaMalloc voice out")) return rc::CudaError;
+            outVoiceFloats_ = of;
+        }
+    }
+    if (perVoiceIn && nIn) { if (!voiceInDevicePtr(nIn)) return rc::CudaError; }
+    else if (nIn) { if (!sharedInDevicePtr(nIn)) return rc::CudaError; }
+    return rc::Ok;
+}
+
+float* Engine::voiceInDevicePtr(size_t nIn) {
+    const size_t f = (size_t) numVoices_ * nIn * blockSize_;
+    if (f > inVoiceFloats_) {
+        dsync();
+        if (dInVoice_) dfree(dInVoice_);
+        dInVoice_ = nullptr;
+        if (!cuda(dmalloc((void**) &dInVoice_, sizeof(float) * f), "cudaMalloc voice in")) return nullptr;
+        dmemset(dInVoice_, 0, sizeof(float) * f);
+        inVoiceFloats_ = f;
+    }
+    return dInVoice_;
+}
+
+float* Engine::sharedInDevicePtr(size_t nIn) {
+    const size_t f = nIn * blockSize_;
+    if (f > inSharedFloats_) {
+        dsync();
+        if (dInShared_) dfree(dInShared_);
+        dInShared_ = nullptr;
+        if (!cuda(dmalloc((void**) &dInShared_, sizeof(float) * f), "cudaMalloc shared in")) return nullptr;
+        dmemset(dInShared_, 0, sizeof(float) * f);
+        inSharedFloats_ = f;
+    }
+    return dInShared_;
+}
+
+int Engine::enqueueBlock(size_t nIn, size_t nOut, size_t numSamples, bool perVoiceIn, bool materialise, bool mix) {
+    if (planOnly_) return fail(rc::CudaError, "plan-only runtime (no CUDA device): rendering is impossible, there is no CPU fallback");
+    dsetdev();
+    if (numSamples > (size_t) blockSize_ || nOut > (size_t) MAX_OUT_CHANNELS) return fail(rc::BadArgument, "numSamples > blockSize or too many output channels");
+
+    // Runtime::process: swap in the newest render sequence (Runtime.h:277-285); recompile when the number of
+    // host input channels a leaf node sees has changed.
+    for (auto& gp : groups_) {
+        Group& g = *gp;
+        if (g.pending) { g.active = g.pending; g.pending.reset(); }
+        if (g.active && g.active->nIn != (int) nIn) {
+            if (g.active->usesHostInputs) {   // leaf nodes see the host channels: GraphRenderSequence.h:126-135
+                std::shared_ptr<Program> p;
+                int r = compile(g, (int) nIn, p);
+                if (r != rc::Ok) return r;
+                g.active = p;
+            } else g.active->nIn = (int) nIn;
+        }
+    }
+    int r = ensureBuffers(nIn, nOut, perVoiceIn, materialise);
+    if (r != rc::Ok) return r;
+
+    int tileBase = 0;
+    for (auto& gp : groups_) {
+        Group& g = *gp;
+        const int nTiles = g.nTiles();
+        if (!g.active || nTiles == 0) {
+            // no render sequence yet: outputs are silence (Runtime.h:287-289 leaves the host buffers untouched;
+            // we define the voice's contribution as zero)
+            if (nTiles && mix) dmemset(dPartial_ + (size_t) tileBase * nOut * blockSize_, 0, sizeof(float) * (size_t) nTiles * nOut * blockSize_);
+            if (materialise && dOutVoice_) dmemset(dOutVoice_ + (size_t) g.v0 * nOut * blockSize_, 0, sizeof(float) * (size_t) g.nv * nOut * blockSize_);
+            tileBase += nTiles;
+            continue;
+        }
+        Program& p = *g.active;
+        LaunchParams P{};
+        P.code = p.dCode;
+        P.stateMap = p.dStateMap;
+        P.rows = g.dRows;
+        P.inShared = (!perVoiceIn && nIn) ? dInShared_ : nullptr;
+        P.inVoice = (perVoiceIn && nIn) ? dInVoice_ : nullptr;
+        P.outVoice = materialise ? dOutVoice_ : nullptr;
+        P.mixPartial = mix ? dPartial_ : nullptr;
+        P.nStateEntries = (int) p.stateMap.size();
+        P.nStateRows = p.nStateRows;
+        P.nSlots = p.nSlots;
+        P.Vpad = g.Vpad;
+        P.nv = g.nv;
+        P.voice0 = g.v0;
+        P.tileWidth = g.tileWidth;
+        P.numSamples = (int) numSamples;
+        P.blockSize = blockSize_;
+        P.nIn = (int) nIn;
+        P.nOut = (int) nOut;
+        P.inStride = blockSize_;
+        P.outStride = blockSize_;
+        P.tileBase = tileBase;
+        uint32_t runMask = 0;
+        for (size_t ri = 0; ri < p.rootIds.size(); ++ri) {
+            auto it = g.nodes.find(p.rootIds[ri]);
+            if (it == g.nodes.end()) continue;
+            Node& rn = it->second;
+            const bool stillRunning = rn.fade.on() || !rn.fade.settled();                     // Core.h:28-31
+            const bool chanOk = rn.channel >= 0 && (size_t) rn.channel < nOut;                // GraphRenderSequence.h:214-219
+            if (stillRunning && chanOk) runMask |= (1u << ri);
+            if (rn.fade.on()) runMask |= (1u << (16 + ri));                                   // promoteTapBuffers: :200-205
+            P.roots[ri] = RootDyn{rn.fade.current, rn.fade.step, rn.fade.target, rn.channel};
+        }
+        P.runMask = runMask;
+
+        // launch geometry: spread warps over the SMs first, then stack them
+        int wpc = opt_.warpsPerCta;
+        if (wpc <= 0) wpc = nTiles >= 148 * 8 ? 4 : (nTiles >= 148 * 4 ? 2 : 1);
+        const size_t perWarp = render_smem_bytes(opt_.tileSamples, p.nSlots, (int) nOut, p.nStateRows, 1, g.tileWidth);
+        while (wpc > 1 && perWarp * wpc > 200 * 1024) wpc >>= 1;
+        if (perWarp > 220 * 1024) return fail(rc::InvariantViolation, "graph state does not fit in shared memory");
+        if (!cuda(launch_render_block(P, opt_.tileSamples, wpc, stream_), "render kernel launch")) return rc::CudaError;
+        ++launches_;
+
+        for (size_t ri = 0; ri < p.rootIds.size(); ++ri) {
+            if (!(runMask & (1u << ri))) continue;
+            auto it = g.nodes.find(p.rootIds[ri]);
+            if (it != g.nodes.end()) it->second.fade.advance((int) numSamples);
+        }
+        tileBase += nTiles;
+    }
+    if (mix) {
+        if (tileBase > 0) {
+            if (!cuda(launch_mix_reduce(dPartial_, dMix_, tileBase, (int) nOut, blockSize_, (int) numSamples, stream_), "mix reduce launch")) return rc::CudaError;
+            ++launches_;
+        } else {
+            dmemset(dMix_, 0, sizeof(float) * nOut * blockSize_);
+        }
+    }
+    curNOut_ = nOut;
+    return rc::Ok;
+}
+
+int Engine::synchronize() {
+    if (planOnly_) return rc::Ok;
+    return cuda(cudaStreamSynchronize(stream_), "stream synchronize") ? rc::Ok : rc::CudaError;
+}
+
+int Engine::process(const float* const* in, size_t nIn, float* const* out, size_t nOut, size_t numSamples) {
+    if (planOnly_) return fail(rc::CudaError, "plan-only runtime (no CUDA device): rendering is impossible, there is no CPU fallback");
+    dsetdev();
+    if (numSamples > (size_t) blockSize_) return fail(rc::BadArgument, "numSamples > blockSize");
+    const size_t need = (nIn + nOut) * blockSize_;
+    if (need > pinnedFloats_) {
+        if (hPinned_) cudaFreeHost(hPinned_);
+        if (!cuda(cudaMallocHost(&hPinned_, sizeof(float) * need), "cudaMallocHost")) return rc::CudaError;
+        pinnedFloats_ = need;
+    }
+    if (nIn) {
+        float* d = sharedInDevicePtr(nIn);
+        if (!d) return rc::CudaError;
+        for (size_t c = 0; c < nIn; ++c) std::memcpy(hPinned_ + c * blockSize_, in[c], sizeof(float) * numSamples);
+        if (!cuda(dmemcpy(d, hPinned_, sizeof(float) * nIn * blockSize_, cudaMemcpyHostToDevice), "H2D inputs")) return rc::CudaError;
+    }
+    int r = enqueueBlock(nIn, nOut, numSamples, false, false, true);
+    if (r != rc::Ok) return r;
+    float* hOut = hPinned_ + nIn * blockSize_;
+    if (nOut) {
+        if (!cuda(dmemcpy(hOut, dMix_, sizeof(float) * nOut * blockSize_, cudaMemcpyDeviceToHost), "D2H mix")) return rc::CudaError;
+    }
+    if ((r = synchronize()) != rc::Ok) return r;
+    for (size_t c = 0; c < nOut; ++c) std::memcpy(out[c], hOut + c * blockSize_, sizeof(float) * numSamples);
+    return rc::Ok;
+}
+
+int Engine::processVoices(const float* in, size_t nIn, float* outVoices, float* mix, size_t nOut, size_t numSamples) {
+    if (planOnly_) return fail(rc::CudaError, "plan-only runtime (no CUDA device): rendering is impossible, there is no CPU fallback");
+    dsetdev();
+    if (numSamples > (size_t) blockSize_) return fail(rc::BadArgument, "numSamples > blockSize");
+    const bool perVoiceIn = in != nullptr && nIn > 0;
+    if (perVoiceIn) {
+        float* d = voiceInDevicePtr(nIn);
+        if (!d) return rc::CudaError;
+        // host layout [voice][nIn][numSamples] -> device [voice][nIn][blockSize]
+        if (!cuda(cudaMemcpy2DAsync(d, sizeof(float) * blockSize_, in, sizeof(float) * numSamples, sizeof(float) * numSamples,
+                                    (size_t) numVoices_ * nIn, cudaMemcpyHostToDevice, stream_), "H2D voice inputs")) return rc::CudaError;
+    }
+    int r = enqueueBlock(nIn, nOut, numSamples, perVoiceIn, outVoices != nullptr, mix != nullptr);
+    if (r != rc::Ok) return r;
+    if (outVoices) {
+        if (!cuda(cudaMemcpy2DAsync(outVoices, sizeof(float) * numSamples, dOutVoice_, sizeof(float) * blockSize_, sizeof(float) * numSamples,
+                                    (size_t) numVoices_ * nOut, cudaMemcpyDeviceToHost, stream_), "D2H voice outputs")) return rc::CudaError;
+    }
+    if (mix) {
+        if (!cuda(cudaMemcpy2DAsync(mix, sizeof(float) * numSamples, dMix_, sizeof(float) * blockSize_, sizeof(float) * numSamples,
+                                    nOut, cudaMemcpyDeviceToHost, stream_), "D2H mix")) return rc::CudaError;
+    }
+    return synchronize();
+}
+
+} // namespace eb

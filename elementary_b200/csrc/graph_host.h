@@ -1,0 +1,208 @@
+// graph_host.h — host side of the B200 engine: the part of elem::Runtime (runtime/elem/Runtime.h:40-577) that
+// is NOT the per-block walk: node table, instruction interpreter, DFS topological sort, root activation and
+// fades, garbage collection, shared resources — plus what is new here: voice groups, device storage and the
+// compilation of the sorted node list into a render program (program.h) for the fused kernel.
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <map>
+#include <memory>
+#include <set>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "program.h"
+#include "value.h"
+
+namespace eb {
+
+// Same numbering as elem::ReturnCode (runtime/elem/Types.h:51-60); negative values are ours (CUDA failures).
+namespace rc {
+constexpr int Ok = 0, UnknownNodeType = 1, NodeNotFound = 2, NodeAlreadyExists = 3, NodeTypeAlreadyExists = 4,
+              InvalidPropertyType = 5, InvalidPropertyValue = 6, InvariantViolation = 7, InvalidInstructionFormat = 8;
+constexpr int CudaError = -1, BadArgument = -2;
+}
+
+enum class NodeKind : uint8_t {
+    In, Unary, Binary, Reduce, Root, Const, Sr, Phasor, SPhasor, Counter, Accum, Latch, MaxHold, Rand,
+    Delay, SDelay, Z, Pole, Env, Biquad, Prewarp, MM1p, Svf, SvfShelf, TapIn, TapOut, Table, Blep, Convolve,
+    PassThrough   // analysis nodes (meter/scope/snapshot): audio passes through, events are out of scope
+};
+
+struct Inlet { int32_t source; int32_t channel; };
+
+// Float mirror of helpers/GainFade.h:16-121 (only what RootNode uses).
+struct GainFade {
+    float current = 0.0f, target = 1.0f, step = 0.0f, inStep = 0.0f, outStep = 0.0f;
+    void init(double sr);
+    void setFadeInMs(double sr, double ms);
+    void setFadeOutMs(double sr, double ms);
+    void fadeIn()  { target = 1.0f; updateStep(); }
+    void fadeOut() { target = 0.0f; updateStep(); }
+    bool on() const { return target > 0.5f; }
+    bool settled() const;
+    void advance(int numSamples);   // what GainFade::process does to currentGain after a block
+    void updateStep() { step = (current > target) ? outStep : inStep; }
+};
+
+struct Resource {
+    std::string name;
+    std::vector<std::vector<float>> channels;   // host copy (always float: AudioBufferResource.h:13-24)
+    float* dChannel0 = nullptr;                 // device copy of channel 0
+    size_t numSamples = 0;
+};
+
+struct ConvolverState;   // convolve.h
+
+struct Node {
+    int32_t id = 0;
+    NodeKind kind = NodeKind::Const;
+    uint32_t fn = 0;                 // UnaryFn / BinaryFn / ReduceFn / blep mode
+    std::string typeName;
+    std::vector<Inlet> inlets;
+    std::map<std::string, Value> props;
+
+    int paramRow = -1;               // const / sr: per-voice parameter row
+    int stateRow = -1;               // first scalar state row (even-aligned when it holds doubles)
+    int mode = 0;                    // svf / svfshelf / mm1p mode
+    int channel = 0;                 // in.channel, root.channel (-1 default for root)
+    GainFade fade;                   // root
+    int size = 0, length = 0;        // delay / sdelay
+    bool ringDirty = true;           // (re)allocate + zero + reset writeIndex at next compile (Delays.h:92-95)
+    float* ring = nullptr;
+    size_t ringFloats = 0;
+    uint32_t holdSamples = 0xFFFFFFFFu;   // maxhold
+    std::string tapName;
+    float* tapPrivate = nullptr;     // tapOut private delayBuffer
+    std::shared_ptr<Resource> resource;   // table / convolve
+    bool resourceDirty = false;
+    std::shared_ptr<ConvolverState> conv;
+};
+
+struct Program {
+    std::vector<uint32_t> code;
+    std::vector<uint32_t> stateMap;
+    int nStateRows = 0;
+    int nSlots = 1;
+    int nIn = 0;
+    bool usesHostInputs = false;
+    std::vector<int32_t> rootIds;         // root index -> node id
+    std::vector<int32_t> nodeIds;         // every node referenced (gc liveness)
+    uint32_t* dCode = nullptr;
+    uint32_t* dStateMap = nullptr;
+    bool planOnly = false;
+    // convolution stages: K1 stage k ends at codeOffsets[k+1]; between stages the convolvers run
+    struct Stage { uint32_t codeOffset; std::vector<int32_t> convolveNodes; };
+    std::vector<Stage> stages;
+    ~Program();
+};
+
+struct Group {
+    int v0 = 0, nv = 0, Vpad = 0;
+    int tileWidth = 0;                    // L, fixed at first compile
+    std::unordered_map<int32_t, Node> nodes;
+    std::set<int32_t> currentRoots;
+    float* dRows = nullptr;
+    int rowsCap = 0, rowsUsed = 0;
+    std::map<std::string, float*> tapShared;
+    std::shared_ptr<Program> pending, active;
+    int nTiles() const { return tileWidth ? (nv + tileWidth - 1) / tileWidth : 0; }
+};
+
+struct EngineOptions {
+    int tileSamples = 8;          // T
+    int tileWidth = 0;            // 0 = choose per group from the voice count
+    int warpsPerCta = 0;          // 0 = choose
+    int targetTiles = 2368;       // 148 SMs x 16 warps: shrink the tile width until this many warps exist
+};
+
+class Engine {
+public:
+    Engine(double sampleRate, int blockSize, int numVoices, int device);
+    ~Engine();
+
+    int applyInstructions(int voiceBegin, int voiceEnd, const char* json, size_t len);
+    int setPropertyPerVoice(int32_t nodeId, const char* key, const double* values, int voiceBegin, int count);
+    int addSharedResource(const char* name, const float* const* chans, size_t nCh, size_t nSamples);
+    void pruneSharedResources();
+    std::vector<std::string> listSharedResources() const;
+    int gc(int voice, std::vector<int32_t>& pruned);
+    void reset();
+
+    // Runtime::process shape: planar host buffers; inputs broadcast to every voice; out = mix bus.
+    int process(const float* const* in, size_t nIn, float* const* out, size_t nOut, size_t numSamples);
+    // Voice-major host buffers: in[voice][nIn][n] (may be null), out[voice][nOut][n] (may be null), mix (may be null).
+    int processVoices(const float* in, size_t nIn, float* outVoices, float* mix, size_t nOut, size_t numSamples);
+    // Device-resident: no host I/O, no synchronisation; used for throughput timing and by processVoices/process.
+    int enqueueBlock(size_t nIn, size_t nOut, size_t numSamples, bool perVoiceIn, bool materialise, bool mix);
+    int synchronize();
+
+    int setOption(const char* key, double value);
+    void setStream(cudaStream_t s);
+    float* mixDevicePtr() { return dMix_; }
+    float* voiceOutDevicePtr() { return dOutVoice_; }
+    float* voiceInDevicePtr(size_t nIn);
+    float* sharedInDevicePtr(size_t nIn);
+    const std::string& lastError() const { return lastError_; }
+    int numVoices() const { return numVoices_; }
+    int blockSize() const { return blockSize_; }
+    uint64_t kernelLaunches() const { return launches_; }
+    std::string describe() const;
+
+private:
+    double sr_;
+    int blockSize_, numVoices_, device_;
+    cudaStream_t stream_ = nullptr;
+    bool ownStream_ = true;
+    EngineOptions opt_;
+    std::vector<std::unique_ptr<Group>> groups_;
+    std::map<std::string, std::shared_ptr<Resource>> resources_;
+    std::string lastError_;
+    uint64_t launches_ = 0;
+
+    // I/O staging
+    float* dMix_ = nullptr;          // [MAX_OUT][blockSize]
+    float* dPartial_ = nullptr; size_t partialFloats_ = 0;
+    float* dOutVoice_ = nullptr; size_t outVoiceFloats_ = 0;
+    float* dInVoice_ = nullptr; size_t inVoiceFloats_ = 0;
+    float* dInShared_ = nullptr; size_t inSharedFloats_ = 0;
+    float* hPinned_ = nullptr; size_t pinnedFloats_ = 0;
+    size_t curNOut_ = 0;
+
+    bool planOnly_ = false;
+    bool cuda(cudaError_t e, const char* what);
+    cudaError_t dmalloc(void** p, size_t bytes);
+    void dfree(void* p);
+    cudaError_t dmemset(void* p, int v, size_t bytes);
+    cudaError_t dmemcpy(void* dst, const void* src, size_t bytes, cudaMemcpyKind kind);
+    cudaError_t dmemcpySync(void* dst, const void* src, size_t bytes, cudaMemcpyKind kind);
+    void dsync();
+    void dsetdev();
+    int fail(int code, const std::string& msg) { lastError_ = msg; return code; }
+
+    // instruction interpreter (Runtime.h:170-433)
+    int applyToGroup(Group& g, const std::vector<Value>& batch, int vb, int ve);
+    int createNode(Group& g, const Value& id, const Value& type);
+    int appendChild(Group& g, const Value& parent, const Value& child, const Value& chan);
+    int setProperty(Group& g, const Value& id, const Value& key, const Value& val, int vb, int ve);
+    int activateRoots(Group& g, const Value& roots);
+    int nodeSetProperty(Group& g, Node& n, const std::string& key, const Value& val, int vb, int ve);
+    bool isValueOnlyBatch(const std::vector<Value>& batch, int vb, int ve);
+    int splitGroupsAt(int v);
+
+    // storage
+    int allocRows(Group& g, int count, bool evenAlign, int& row);
+    int fillRow(Group& g, int row, int vb, int ve, float value);
+    int fillRowBits(Group& g, int row, int vb, int ve, uint32_t bits);
+    int ensureResourceOnDevice(Resource& r);
+
+    // compile (Runtime.h:521-577 + GraphRenderSequence.h:107-187)
+    int compile(Group& g, int nIn, std::shared_ptr<Program>& out);
+    void traverse(Group& g, std::set<int32_t>& visited, std::vector<int32_t>& order, int32_t n);
+    int chooseTileWidth(int nv) const;
+    int ensureBuffers(size_t nIn, size_t nOut, bool perVoiceIn, bool materialise);
+    friend struct Compiler;
+};
+
+} // namespace eb

@@ -1,0 +1,16 @@
+// kernels.h — host-callable launchers of the device kernels (render_kernel.cu, convolve_kernel.cu).
+#pragma once
+#include <cuda_runtime.h>
+#include <cstddef>
+#include "program.h"
+
+namespace eb {
+
+// K1: fused render-sequence kernel, one launch per voice group per block.
+size_t render_smem_bytes(int tileSamples, int nSlots, int nOut, int nStateRows, int warpsPerCta, int tileWidth);
+cudaError_t launch_render_block(const LaunchParams& P, int tileSamples, int warpsPerCta, cudaStream_t stream);
+
+// K2: deterministic reduction of per-tile partial mixes into the [nOut][blockSize] mix bus.
+cudaError_t launch_mix_reduce(const float* partial, float* out, int nTiles, int nOut, int blockSize, int numSamples, cudaStream_t stream);
+
+} // namespace eb

@@ -1,0 +1,113 @@
+// program.h — the compiled "render program" shared by the host graph compiler (graph_host.cpp) and the
+// fused device kernel (render_kernel.cu).
+//
+// The reference turns its node graph into a GraphRenderSequence: a topologically sorted list of closures,
+// each calling one GraphNode::process() over a whole block with one 2 KB buffer per node output
+// (runtime/elem/GraphRenderSequence.h:107-187,212-232; Runtime.h:521-577).  Here the same sorted list is
+// lowered to a flat array of 32-bit words that ONE kernel interprets, warp-uniformly, for every voice tile:
+//
+//   op := [w0 = opcode | nOperands<<8 | outSlot<<16 | mode<<24]
+//         [w1 = state index (row inside the warp's shared-memory state area) or 0xFFFFFFFF]
+//         [w2 = aux0] [w3 = aux1] [w4, w5 = 64-bit device pointer or two more aux words]
+//         [operand]*nOperands          operand = kind<<30 | index
+//
+// Node outputs live in shared-memory "slots" ([TILE samples][32 lanes] floats per warp, liveness-allocated by
+// the host), not in per-node block buffers; `const`/`sr` nodes never execute — their value is a per-voice
+// parameter row read straight from HBM.
+#pragma once
+#include <cstdint>
+
+namespace eb {
+
+enum Opcode : uint32_t {
+    OP_END = 0,
+    OP_SEG,        // root sub-sequence header: aux0 = root index, aux1 = words to skip when the root is not running
+    OP_FILL0,      // out = 0 (node lacked the inputs it needs: Core.h:125-126 and friends)
+    OP_COPY,       // out = in0 (IdentityNode with a child, tapOut pass-through)
+    OP_LOADIN,     // out = host input channel aux0 (IdentityNode leaf / leaf-node host inputs, GraphRenderSequence.h:126-135)
+    OP_UNARY,      // mode = UnaryFn                      (Math.h:9-28)
+    OP_BINARY,     // mode = BinaryFn                     (Math.h:30-57)
+    OP_REDUCE,     // mode = ReduceFn, left fold          (Math.h:59-89)
+    OP_PHASOR,     // Core.h:85-136 (WithReset=false)
+    OP_SPHASOR,    // Core.h:85-136 (WithReset=true)
+    OP_COUNTER,    // Core.h:183-215
+    OP_ACCUM,      // Core.h:218-248
+    OP_LATCH,      // Core.h:250-286
+    OP_MAXHOLD,    // Core.h:288-339
+    OP_RAND,       // Noise.h:9-43
+    OP_POLE,       // Filters.h:13-39
+    OP_ENV,        // Filters.h:46-79
+    OP_BIQUAD,     // Filters.h:87-120
+    OP_PREWARP,    // filters/MultiMode1p.h:9-37
+    OP_MM1P,       // filters/MultiMode1p.h:39-113
+    OP_SVF,        // filters/SVF.h:18-121
+    OP_SVFSHELF,   // filters/SVFShelf.h:20-126
+    OP_Z,          // Delays.h:15-39
+    OP_DELAY,      // Delays.h:51-169
+    OP_SDELAY,     // Delays.h:177-272
+    OP_TABLE,      // Table.h:16-76
+    OP_BLEP,       // Oscillators.h:19-94, mode = 0 saw / 1 square / 2 triangle
+    OP_TAPIN,      // Feedback.h:20-57
+    OP_TAPOUT,     // Feedback.h:59-131
+    OP_ROOT,       // Core.h:15-83 + helpers/GainFade.h:56-72, aux0 = root index, aux1 = output channel
+    OP_STOREBUF,   // stage boundary: in0 -> global per-voice block buffer (ptr), used around `convolve`
+    OP_LOADBUF,    // stage boundary: global per-voice block buffer (ptr) -> out
+    OP_COUNT_
+};
+
+enum UnaryFn : uint32_t { U_SIN = 0, U_COS, U_TAN, U_TANH, U_ASINH, U_LN, U_LOG10, U_LOG2, U_CEIL, U_FLOOR, U_ROUND, U_SQRT, U_EXP, U_ABS };
+enum BinaryFn : uint32_t { B_LE = 0, B_LEQ, B_GE, B_GEQ, B_POW, B_EQ, B_AND, B_OR };
+enum ReduceFn : uint32_t { R_ADD = 0, R_SUB, R_MUL, R_DIV, R_MOD, R_MIN, R_MAX };
+
+enum OperandKind : uint32_t { K_SLOT = 0, K_PARAM = 1, K_ZERO = 2 };
+
+constexpr uint32_t OP_HEADER_WORDS = 6;
+constexpr uint32_t NO_STATE = 0xFFFFFFFFu;
+constexpr uint32_t STATE_DOUBLE_FLAG = 0x80000000u;   // stateMap entry: two consecutive rows holding double[Vpad]
+constexpr uint32_t STATE_PAD = 0x7FFFFFFFu;           // stateMap entry: one unused shared-memory row (keeps doubles 8-byte aligned)
+constexpr int MAX_ROOTS = 16;
+constexpr int MAX_OUT_CHANNELS = 8;
+constexpr int MAX_SLOTS = 255;
+
+inline uint32_t make_w0(uint32_t opcode, uint32_t nOperands, uint32_t outSlot, uint32_t mode) {
+    return (opcode & 0xFF) | ((nOperands & 0xFF) << 8) | ((outSlot & 0xFF) << 16) | ((mode & 0xFF) << 24);
+}
+inline uint32_t make_operand(uint32_t kind, uint32_t index) { return (kind << 30) | (index & 0x3FFFFFFFu); }
+
+// Per-block dynamic root state (host mirrors GainFade, helpers/GainFade.h:56-72): the fade ramp of a block is a
+// pure function of (gain at block start, step, target), so it is passed by value with the launch.
+struct RootDyn {
+    float gain0;
+    float step;
+    float target;
+    int   channel;   // root "channel" prop; <0 or >= nOut => contributes nothing (GraphRenderSequence.h:214-219)
+};
+
+// One launch = one voice group (topology class).
+struct LaunchParams {
+    const uint32_t* code;        // program words (device)
+    const uint32_t* stateMap;    // [nStateEntries] global row index (| STATE_DOUBLE_FLAG)
+    float*          rows;        // group row storage: rows[row * Vpad + voice]
+    const float*    inShared;    // [nIn][inStride] host inputs shared by all voices (or null)
+    const float*    inVoice;     // [voice][nIn][inStride] per-voice inputs (or null)
+    float*          outVoice;    // [voice][nOut][outStride] per-voice outputs (or null = mix only)
+    float*          mixPartial;  // [tile][nOut][blockSize] per-tile partial mix (or null)
+    int nStateEntries;
+    int nStateRows;              // shared-memory state rows per warp
+    int nSlots;
+    int Vpad;
+    int nv;                      // voices in the group
+    int voice0;                  // first global voice index of the group (outVoice/inVoice indexing)
+    int tileWidth;               // L: voices per warp (power of two <= 32)
+    int numSamples;
+    int blockSize;
+    int nIn;
+    int nOut;
+    int inStride;
+    int outStride;
+    int tileBase;                // index of this group's first tile in mixPartial
+    uint32_t runMask;            // bit r set => root r's sub-sequence runs this block (RootNode::stillRunning)
+    RootDyn roots[MAX_ROOTS];
+};
+
+} // namespace eb

@@ -1,0 +1,268 @@
+"""Python mirror of ``elem::Runtime<float>`` over the C ABI of ``libelem_b200.so``.
+
+Same method names, argument meaning and error behaviour as the reference class
+(runtime/elem/Runtime.h:44-110): ``apply_instructions`` returns the reference's integer return codes
+(Types.h:51-60), ``process`` takes planar float32 inputs and fills planar outputs, shared resources are
+insert-only, ``gc`` returns the pruned node ids.  New here is the voice axis: one :class:`Runtime` holds
+``num_voices`` independent graph instances that render in one fused CUDA kernel per block.
+
+This module only *binds*: all work happens in the CUDA library (``include/elem_b200.h``).  There is no CPU
+fallback — if the shared library is missing it raises ImportError-like RuntimeError, and without a CUDA device
+``Runtime(...)`` raises, except for ``device=-1`` which builds a *plan-only* runtime (host logic and graph
+compilation only; every render call fails) used by the CPU test-suite.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import json
+import os
+from typing import Iterable, List, Optional, Sequence
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libelem_b200.so")
+
+_f32p = C.POINTER(C.c_float)
+_f32pp = C.POINTER(_f32p)
+
+RETURN_CODES = {
+    0: "Ok", 1: "UnknownNodeType", 2: "NodeNotFound", 3: "NodeAlreadyExists", 4: "NodeTypeAlreadyExists",
+    5: "InvalidPropertyType", 6: "InvalidPropertyValue", 7: "InvariantViolation", 8: "InvalidInstructionFormat",
+    -1: "CudaError", -2: "BadArgument",
+}
+
+FLAG_VOICE_IN, FLAG_VOICE_OUT, FLAG_MIX = 1, 2, 4
+
+_lib = None
+
+
+def load_library() -> C.CDLL:
+    """Load ``libelem_b200.so`` (built in-tree by ``__graft_entry__.build()``).  Fails loudly when missing."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(f"{LIB_PATH} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                           "(there is no CPU fallback)")
+    lib = C.CDLL(LIB_PATH)
+    lib.elem_b200_create.restype = C.c_void_p
+    lib.elem_b200_create.argtypes = [C.c_double, C.c_int, C.c_int, C.c_int]
+    lib.elem_b200_destroy.argtypes = [C.c_void_p]
+    lib.elem_b200_apply_instructions.restype = C.c_int
+    lib.elem_b200_apply_instructions.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_char_p, C.c_size_t]
+    lib.elem_b200_set_property_per_voice.restype = C.c_int
+    lib.elem_b200_set_property_per_voice.argtypes = [C.c_void_p, C.c_int32, C.c_char_p, C.POINTER(C.c_double), C.c_int, C.c_int]
+    lib.elem_b200_process.restype = C.c_int
+    lib.elem_b200_process.argtypes = [C.c_void_p, _f32pp, C.c_size_t, _f32pp, C.c_size_t, C.c_size_t, C.c_void_p]
+    lib.elem_b200_process_voices.restype = C.c_int
+    lib.elem_b200_process_voices.argtypes = [C.c_void_p, _f32p, C.c_size_t, _f32p, _f32p, C.c_size_t, C.c_size_t]
+    lib.elem_b200_enqueue_block.restype = C.c_int
+    lib.elem_b200_enqueue_block.argtypes = [C.c_void_p, C.c_size_t, C.c_size_t, C.c_size_t, C.c_int]
+    lib.elem_b200_synchronize.restype = C.c_int
+    lib.elem_b200_synchronize.argtypes = [C.c_void_p]
+    for name in ("elem_b200_mix_device", "elem_b200_voice_out_device"):
+        getattr(lib, name).restype = C.c_void_p
+        getattr(lib, name).argtypes = [C.c_void_p]
+    for name in ("elem_b200_voice_in_device", "elem_b200_shared_in_device"):
+        getattr(lib, name).restype = C.c_void_p
+        getattr(lib, name).argtypes = [C.c_void_p, C.c_size_t]
+    lib.elem_b200_set_stream.argtypes = [C.c_void_p, C.c_void_p]
+    lib.elem_b200_add_shared_resource.restype = C.c_int
+    lib.elem_b200_add_shared_resource.argtypes = [C.c_void_p, C.c_char_p, _f32pp, C.c_size_t, C.c_size_t]
+    lib.elem_b200_prune_shared_resources.argtypes = [C.c_void_p]
+    lib.elem_b200_list_shared_resources.restype = C.c_int
+    lib.elem_b200_list_shared_resources.argtypes = [C.c_void_p, C.c_char_p, C.c_size_t]
+    lib.elem_b200_gc.restype = C.c_int
+    lib.elem_b200_gc.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_int32), C.c_size_t]
+    lib.elem_b200_reset.argtypes = [C.c_void_p]
+    lib.elem_b200_process_queued_events.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.elem_b200_set_option.restype = C.c_int
+    lib.elem_b200_set_option.argtypes = [C.c_void_p, C.c_char_p, C.c_double]
+    lib.elem_b200_describe.restype = C.c_int
+    lib.elem_b200_describe.argtypes = [C.c_void_p, C.c_char_p, C.c_size_t]
+    lib.elem_b200_kernel_launches.restype = C.c_uint64
+    lib.elem_b200_kernel_launches.argtypes = [C.c_void_p]
+    lib.elem_b200_last_error.restype = C.c_char_p
+    lib.elem_b200_last_error.argtypes = [C.c_void_p]
+    lib.elem_b200_describe_return_code.restype = C.c_char_p
+    lib.elem_b200_describe_return_code.argtypes = [C.c_int]
+    lib.elem_b200_device_count.restype = C.c_int
+    _lib = lib
+    return lib
+
+
+def device_count() -> int:
+    return load_library().elem_b200_device_count()
+
+
+def describe_return_code(code: int) -> str:
+    return load_library().elem_b200_describe_return_code(code).decode()
+
+
+class DeviceArray:
+    """Zero-copy view of an engine-owned device buffer (``__cuda_array_interface__``), e.g. for
+    ``torch.as_tensor(rt.mix_device(), device='cuda')`` in the multi-GPU mix-bus reduce."""
+
+    def __init__(self, ptr: int, shape):
+        self.ptr, self.shape = ptr, tuple(shape)
+
+    @property
+    def __cuda_array_interface__(self):
+        return {"shape": self.shape, "typestr": "<f4", "data": (self.ptr, False), "version": 3, "strides": None}
+
+
+class Runtime:
+    """``elem::Runtime<float>`` with a voice axis.  See module docstring."""
+
+    def __init__(self, sample_rate: float = 48000.0, block_size: int = 512, num_voices: int = 1, device: int = 0,
+                 **options: float):
+        self._lib = load_library()
+        self.sample_rate, self.block_size, self.num_voices, self.device = float(sample_rate), int(block_size), int(num_voices), int(device)
+        h = self._lib.elem_b200_create(self.sample_rate, self.block_size, self.num_voices, self.device)
+        if not h:
+            raise RuntimeError("elem_b200_create failed: " + self._lib.elem_b200_last_error(None).decode())
+        self._h = C.c_void_p(h)
+        for k, v in options.items():
+            self.set_option(k, v)
+
+    def close(self) -> None:
+        if getattr(self, "_h", None):
+            self._lib.elem_b200_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- Runtime::applyInstructions (Runtime.h:48,170-218) ------------------------------------------------------
+    def apply_instructions(self, batch, voices: Optional[Sequence[int]] = None) -> int:
+        """Apply an instruction batch (list or JSON text) to voices ``[voices[0], voices[1])`` (default: all)."""
+        s = batch if isinstance(batch, (str, bytes)) else json.dumps(batch)
+        b = s.encode() if isinstance(s, str) else s
+        vb, ve = (0, -1) if voices is None else (int(voices[0]), int(voices[1]))
+        return self._lib.elem_b200_apply_instructions(self._h, vb, ve, b, len(b))
+
+    def set_property_per_voice(self, node_id: int, key: str, values, voice_begin: int = 0) -> int:
+        v = np.ascontiguousarray(np.asarray(values, dtype=np.float64))
+        return self._lib.elem_b200_set_property_per_voice(self._h, int(node_id), key.encode(),
+                                                          v.ctypes.data_as(C.POINTER(C.c_double)), int(voice_begin), v.size)
+
+    # -- Runtime::process (Runtime.h:51-57,275-290): out = mix bus over all voices -------------------------------
+    def process(self, inputs: Optional[np.ndarray], num_outputs: int, num_samples: Optional[int] = None) -> np.ndarray:
+        n = int(num_samples if num_samples is not None else self.block_size)
+        if inputs is None or len(inputs) == 0:
+            n_in, in_ptrs, keep = 0, None, None
+        else:
+            keep = np.ascontiguousarray(np.asarray(inputs, dtype=np.float32))
+            assert keep.ndim == 2 and keep.shape[1] >= n
+            n_in = keep.shape[0]
+            in_ptrs = (_f32p * n_in)(*[keep[i].ctypes.data_as(_f32p) for i in range(n_in)])
+        out = np.zeros((num_outputs, n), dtype=np.float32)
+        out_ptrs = (_f32p * max(1, num_outputs))(*[out[i].ctypes.data_as(_f32p) for i in range(num_outputs)])
+        rc = self._lib.elem_b200_process(self._h, in_ptrs, n_in, out_ptrs, num_outputs, n, None)
+        self._check(rc, "process")
+        return out
+
+    def process_voices(self, inputs: Optional[np.ndarray], num_outputs: int, num_samples: Optional[int] = None,
+                       want_voices: bool = True, want_mix: bool = True):
+        """Per-voice I/O: ``inputs`` is [voice, n_in, n] or None.  Returns (voices [voice, n_out, n] | None, mix [n_out, n] | None)."""
+        n = int(num_samples if num_samples is not None else self.block_size)
+        if inputs is None:
+            n_in, in_ptr, keep = 0, None, None
+        else:
+            keep = np.ascontiguousarray(np.asarray(inputs, dtype=np.float32))
+            assert keep.ndim == 3 and keep.shape[0] == self.num_voices and keep.shape[2] == n
+            n_in, in_ptr = keep.shape[1], keep.ctypes.data_as(_f32p)
+        ov = np.zeros((self.num_voices, num_outputs, n), dtype=np.float32) if want_voices else None
+        mix = np.zeros((num_outputs, n), dtype=np.float32) if want_mix else None
+        rc = self._lib.elem_b200_process_voices(self._h, in_ptr, n_in,
+                                                ov.ctypes.data_as(_f32p) if ov is not None else None,
+                                                mix.ctypes.data_as(_f32p) if mix is not None else None, num_outputs, n)
+        self._check(rc, "process_voices")
+        return ov, mix
+
+    def render_voices(self, n_blocks: int, num_outputs: int = 1, inputs: Optional[np.ndarray] = None):
+        """Run ``n_blocks`` blocks; returns (voices [voice, n_out, n_blocks*bs], mix [n_out, n_blocks*bs])."""
+        bs = self.block_size
+        vs, ms = [], []
+        for b in range(n_blocks):
+            inp = None if inputs is None else np.asarray(inputs)[:, :, b * bs:(b + 1) * bs]
+            v, m = self.process_voices(inp, num_outputs, bs)
+            vs.append(v)
+            ms.append(m)
+        return np.concatenate(vs, axis=2), np.concatenate(ms, axis=1)
+
+    # -- device-resident stepping -----------------------------------------------------------------------------
+    def enqueue_block(self, n_in: int = 0, n_out: int = 1, num_samples: Optional[int] = None, flags: int = FLAG_MIX) -> None:
+        n = int(num_samples if num_samples is not None else self.block_size)
+        self._check(self._lib.elem_b200_enqueue_block(self._h, n_in, n_out, n, flags), "enqueue_block")
+
+    def synchronize(self) -> None:
+        self._check(self._lib.elem_b200_synchronize(self._h), "synchronize")
+
+    def set_stream(self, cuda_stream_handle: int) -> None:
+        self._lib.elem_b200_set_stream(self._h, C.c_void_p(cuda_stream_handle))
+
+    def mix_device(self, n_out: int = 1) -> DeviceArray:
+        return DeviceArray(self._lib.elem_b200_mix_device(self._h), (n_out, self.block_size))
+
+    def voice_out_device(self, n_out: int = 1) -> DeviceArray:
+        return DeviceArray(self._lib.elem_b200_voice_out_device(self._h), (self.num_voices, n_out, self.block_size))
+
+    def voice_in_device(self, n_in: int) -> DeviceArray:
+        return DeviceArray(self._lib.elem_b200_voice_in_device(self._h, n_in), (self.num_voices, n_in, self.block_size))
+
+    def shared_in_device(self, n_in: int) -> DeviceArray:
+        return DeviceArray(self._lib.elem_b200_shared_in_device(self._h, n_in), (n_in, self.block_size))
+
+    # -- shared resources (Runtime.h:83-94) -----------------------------------------------------------------------
+    def add_shared_resource(self, name: str, data) -> bool:
+        a = np.ascontiguousarray(np.asarray(data, dtype=np.float32))
+        if a.ndim == 1:
+            a = a[None, :]
+        ptrs = (_f32p * a.shape[0])(*[a[i].ctypes.data_as(_f32p) for i in range(a.shape[0])])
+        return bool(self._lib.elem_b200_add_shared_resource(self._h, name.encode(), ptrs, a.shape[0], a.shape[1]))
+
+    def prune_shared_resources(self) -> None:
+        self._lib.elem_b200_prune_shared_resources(self._h)
+
+    def get_shared_resource_map_keys(self) -> List[str]:
+        buf = C.create_string_buffer(1 << 16)
+        self._lib.elem_b200_list_shared_resources(self._h, buf, len(buf))
+        return [s for s in buf.value.decode().split("\n") if s]
+
+    # -- gc / reset / events ------------------------------------------------------------------------------------
+    def gc(self, voice: int = 0) -> List[int]:
+        buf = (C.c_int32 * 65536)()
+        n = self._lib.elem_b200_gc(self._h, voice, buf, 65536)
+        return [buf[i] for i in range(min(n, 65536))]
+
+    def reset(self) -> None:
+        self._lib.elem_b200_reset(self._h)
+
+    def process_queued_events(self, callback=None) -> None:
+        self._lib.elem_b200_process_queued_events(self._h, None, None)
+
+    # -- introspection ------------------------------------------------------------------------------------------
+    def set_option(self, key: str, value: float) -> None:
+        self._check(self._lib.elem_b200_set_option(self._h, key.encode(), float(value)), f"set_option({key})")
+
+    def describe(self) -> dict:
+        n = self._lib.elem_b200_describe(self._h, None, 0)
+        buf = C.create_string_buffer(n + 16)
+        self._lib.elem_b200_describe(self._h, buf, len(buf))
+        return json.loads(buf.value.decode())
+
+    @property
+    def kernel_launches(self) -> int:
+        return int(self._lib.elem_b200_kernel_launches(self._h))
+
+    def last_error(self) -> str:
+        return self._lib.elem_b200_last_error(self._h).decode()
+
+    def _check(self, rc: int, what: str) -> None:
+        if rc != 0:
+            raise RuntimeError(f"{what} failed: rc={rc} ({RETURN_CODES.get(rc, '?')}): {self.last_error()}")

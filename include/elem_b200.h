@@ -1,0 +1,109 @@
+/* elem_b200.h — C ABI of the B200-native Elementary render engine (libelem_b200.so).
+ *
+ * Drop-in boundary for ONE path of elemaudio/elementary: elem::Runtime<float> — applyInstructions() /
+ * process() / gc() / shared resources — with the per-block graph walk executed by a fused sm_100a kernel for
+ * thousands of independent voices (graph instances) at once.  Every entry point below replaces the method of
+ * the reference class cited next to it (paths relative to the reference tree); the embind surface of
+ * wasm/Main.cpp:374-390 was the model.  Plain pointers and sizes only; the library owns all device memory and
+ * nothing device-side crosses this ABI except where a function says "device pointer".
+ *
+ * Conventions
+ *   - return value: 0 = Ok, 1..8 = elem::ReturnCode (runtime/elem/Types.h:51-60), negative = engine failure
+ *     (-1 CUDA error, -2 bad argument); elem_b200_last_error() gives the text.
+ *   - exceptions never cross the ABI: malformed JSON, which makes the reference throw (runtime/elem/JSON.h:
+ *     146-154, Value.h:89-92), returns 8 (InvalidInstructionFormat).
+ *   - threading: one control thread for everything except elem_b200_process*, which may run on one other
+ *     thread — the same contract as the reference (Runtime.h:329-332).
+ *   - audio buffers are planar, non-interleaved float32, borrowed for the duration of the call;
+ *     numSamples <= blockSize (Runtime.h:51-57).
+ *   - a "voice" is one independent instance of the reference Runtime: its own node table, state and outputs.
+ *     There is NO CPU fallback: without a CUDA device elem_b200_create returns NULL.
+ */
+#ifndef ELEM_B200_H
+#define ELEM_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct elem_b200_runtime elem_b200_runtime;
+
+/* Runtime<float>::Runtime(double sampleRate, int blockSize)  — runtime/elem/Runtime.h:44,158-166.
+ * New here: numVoices independent instances living on CUDA device `device`. */
+elem_b200_runtime* elem_b200_create(double sampleRate, int blockSize, int numVoices, int device);
+void elem_b200_destroy(elem_b200_runtime* rt);
+
+/* Runtime::applyInstructions(js::Array const&) — Runtime.h:48,170-218 — fed with the JSON text the JS
+ * reconciler emits (cli/Benchmark.cpp:40-43 does parseJSON + applyInstructions).  The batch is applied to
+ * every voice in [voiceBegin, voiceEnd) (voiceEnd < 0 = all).  A batch consisting only of SET_PROPERTY on
+ * per-voice capable props (const.value, rand.seed) may address any sub-range. */
+int elem_b200_apply_instructions(elem_b200_runtime* rt, int voiceBegin, int voiceEnd, const char* json, size_t len);
+
+/* Vectorised SET_PROPERTY: values[i] -> voice voiceBegin+i; equivalent to `count` single-voice
+ * [[3,nodeId,key,values[i]]] batches (Runtime.h:316-333) without `count` JSON parses. */
+int elem_b200_set_property_per_voice(elem_b200_runtime* rt, int32_t nodeId, const char* key,
+                                     const double* values, int voiceBegin, int count);
+
+/* Runtime::process(in, nIn, out, nOut, numSamples, userData) — Runtime.h:51-57,275-290.
+ * `in` channels are broadcast to every voice; out[c] receives the MIX BUS: the sum over all voices of what
+ * each voice's Runtime would have written to its out[c].  Host buffers; H2D/D2H copies are inside the call. */
+int elem_b200_process(elem_b200_runtime* rt, const float* const* in, size_t nIn,
+                      float* const* out, size_t nOut, size_t numSamples, void* userData);
+
+/* Voice-major variant for per-voice I/O and parity tests: in = [voice][nIn][numSamples] or NULL,
+ * outVoices = [voice][nOut][numSamples] or NULL, mix = [nOut][numSamples] or NULL (all host memory). */
+int elem_b200_process_voices(elem_b200_runtime* rt, const float* in, size_t nIn,
+                             float* outVoices, float* mix, size_t nOut, size_t numSamples);
+
+/* Device-resident stepping for throughput measurement and pipelines that keep audio in HBM: enqueue one block
+ * on the engine's stream (no host copies, no synchronisation).  flags: 1 = read per-voice inputs from
+ * elem_b200_voice_in_device(), 2 = materialise per-voice outputs, 4 = produce the mix bus. */
+int elem_b200_enqueue_block(elem_b200_runtime* rt, size_t nIn, size_t nOut, size_t numSamples, int flags);
+int elem_b200_synchronize(elem_b200_runtime* rt);
+float* elem_b200_mix_device(elem_b200_runtime* rt);                    /* device pointer [8][blockSize] */
+float* elem_b200_voice_out_device(elem_b200_runtime* rt);              /* device pointer [voice][nOut][blockSize] */
+float* elem_b200_voice_in_device(elem_b200_runtime* rt, size_t nIn);   /* device pointer [voice][nIn][blockSize] */
+float* elem_b200_shared_in_device(elem_b200_runtime* rt, size_t nIn);  /* device pointer [nIn][blockSize] */
+void elem_b200_set_stream(elem_b200_runtime* rt, void* cudaStream);    /* run on a caller-owned cudaStream_t */
+
+/* Runtime::addSharedResource(name, unique_ptr<SharedResource>) — Runtime.h:83,462-465;
+ * AudioBufferResource copies the samples (AudioBufferResource.h:13-24).  Returns 1 on success, 0 when the
+ * name already exists (SharedResource.h:44-46). */
+int elem_b200_add_shared_resource(elem_b200_runtime* rt, const char* name,
+                                  const float* const* channels, size_t numChannels, size_t numSamples);
+/* Runtime::pruneSharedResources() — Runtime.h:89,468-471 */
+void elem_b200_prune_shared_resources(elem_b200_runtime* rt);
+/* Runtime::getSharedResourceMapKeys() — Runtime.h:94,474-477.  Writes up to `cap` bytes of '\n'-separated
+ * names, returns the number of resources. */
+int elem_b200_list_shared_resources(elem_b200_runtime* rt, char* buf, size_t cap);
+
+/* Runtime::gc() — Runtime.h:76,221-272.  Collects for the voice group containing `voice`; writes up to `cap`
+ * pruned node ids (ascending), returns how many were pruned. */
+int elem_b200_gc(elem_b200_runtime* rt, int voice, int32_t* ids, size_t cap);
+/* Runtime::reset() — Runtime.h:70,449-458 */
+void elem_b200_reset(elem_b200_runtime* rt);
+/* Runtime::processQueuedEvents(cb) — Runtime.h:64,438-446.  No in-scope node emits events; the callback is
+ * never invoked.  Present so callers keep their per-block sequence (offline-renderer/index.ts:104-132). */
+typedef void (*elem_b200_event_cb)(const char* type, const char* jsonEvent, void* user);
+void elem_b200_process_queued_events(elem_b200_runtime* rt, elem_b200_event_cb cb, void* user);
+
+/* Tuning and introspection (no reference equivalent). Keys: "tile_samples" (4|8), "tile_width" (1..32, 0 =
+ * auto), "warps_per_cta", "target_tiles". Must be set before the first COMMIT of a voice group. */
+int elem_b200_set_option(elem_b200_runtime* rt, const char* key, double value);
+/* JSON description of voice groups and compiled programs; returns bytes needed. */
+int elem_b200_describe(elem_b200_runtime* rt, char* buf, size_t cap);
+/* Number of CUDA kernels this runtime has launched so far. */
+uint64_t elem_b200_kernel_launches(elem_b200_runtime* rt);
+const char* elem_b200_last_error(elem_b200_runtime* rt);
+/* ReturnCode::describe — runtime/elem/Types.h:62-85 */
+const char* elem_b200_describe_return_code(int code);
+/* Number of CUDA devices visible (0 = the library cannot run here). */
+int elem_b200_device_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ELEM_B200_H */

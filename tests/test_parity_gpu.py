@@ -1,0 +1,363 @@
+"""GPU parity: the CUDA path (through the C ABI) against the oracle on identical instruction batches.
+
+Criterion (north_star "1e-5 relative", read as SURVEY.md §8d prescribes): |gpu - ref| <= 1e-5 * max|ref| over
+the block + 1e-7.  Integer/index/selection nodes (latch, counter, maxhold, rand, z, sdelay, compare ops) must
+be bit-exact.  Every test renders from block 0, i.e. including the 20 ms root fade-in (960 samples @ 48 kHz).
+"""
+import math
+
+import numpy as np
+import pytest
+
+from elementary_b200 import Runtime, el, graphs
+from helpers import block_peak_tolerance_check, oracle_render
+
+pytestmark = pytest.mark.gpu
+
+SR, BS = 48000.0, 512
+
+
+def lcg_noise(n, seed, lo=-1.0, hi=1.0):
+    s = (seed * 2654435761 + 1) & 0xFFFFFFFF
+    out = np.empty(n, dtype=np.float32)
+    for i in range(n):
+        s = (s * 1664525 + 1013904223) & 0xFFFFFFFF
+        out[i] = lo + (hi - lo) * ((s >> 8) / float(1 << 24))
+    return out
+
+
+def run_gpu(batch, n_voices, n_blocks, n_out=1, inputs=None, voice_batches=None, resources=None, **opts):
+    rt = Runtime(SR, BS, n_voices, device=0, **opts)
+    for name, data in (resources or {}).items():
+        assert rt.add_shared_resource(name, data)
+    assert rt.apply_instructions(batch) == 0, rt.last_error()
+    if voice_batches is not None:
+        for v, b in enumerate(voice_batches):
+            if b:
+                assert rt.apply_instructions(b, voices=(v, v + 1)) == 0, rt.last_error()
+    got, mix = rt.render_voices(n_blocks, n_out, inputs)
+    return got, mix, rt
+
+
+def check(batch, n_voices=3, n_blocks=3, n_in=0, exact=False, resources=None, in_lo=-1.0, in_hi=1.0, n_out=1, **opts):
+    inputs = None
+    if n_in:
+        inputs = np.stack([np.stack([lcg_noise(n_blocks * BS, 100 * v + c, in_lo, in_hi) for c in range(n_in)])
+                           for v in range(n_voices)])
+    got, mix, rt = run_gpu(batch, n_voices, n_blocks, n_out, inputs, resources=resources, **opts)
+    ref = oracle_render(batch, n_blocks, n_out, SR, BS, inputs, voice_batches=[None] * n_voices, resources=resources)
+    if exact:
+        assert np.array_equal(got, ref), f"not bit exact: max diff {np.abs(got - ref).max()}"
+    else:
+        ok, worst, ex = block_peak_tolerance_check(got, ref, BS)
+        assert ok, f"worst err/tol {worst:.3g}, bit-exact fraction {ex:.4f}"
+    # mix bus == sum over voices (float64 reference sum, magnitude-scaled tolerance)
+    want = ref.astype(np.float64).sum(axis=0)
+    scale = np.abs(ref).astype(np.float64).sum(axis=0).max() + 1e-30
+    assert np.abs(mix - want).max() <= 1e-6 * scale + 1e-7
+    return got, ref
+
+
+IN0, IN1, IN2 = el.in_(0), el.in_(1), el.in_(2)
+
+UNARY = ["sin", "cos", "tan", "tanh", "asinh", "ceil", "floor", "round_", "exp", "abs_"]
+
+
+@pytest.mark.parametrize("name", UNARY)
+def test_unary(name):
+    check(el.render(getattr(el, name)(el.mul(3.0, IN0))), n_in=1, exact=name in ("ceil", "floor", "round_", "abs_"))
+
+
+@pytest.mark.parametrize("name", ["ln", "log", "log2", "sqrt"])
+def test_unary_positive_domain(name):
+    check(el.render(getattr(el, name)(IN0)), n_in=1, in_lo=0.01, in_hi=4.0, exact=name == "sqrt")
+
+
+@pytest.mark.parametrize("name", ["le", "leq", "ge", "geq", "eq", "and_", "or_"])
+def test_binary_compare(name):
+    a = el.round_(el.mul(2.0, IN0))
+    b = el.round_(el.mul(2.0, IN1))
+    check(el.render(getattr(el, name)(a, b)), n_in=2, exact=True)
+
+
+def test_pow():
+    check(el.render(el.pow_(el.mul(2.0, IN0), el.round_(el.mul(3.0, IN1)))), n_in=2)
+    check(el.render(el.pow_(el.abs_(IN0), IN1)), n_in=2)
+
+
+@pytest.mark.parametrize("name", ["add", "sub", "mul", "div", "mod", "min_", "max_"])
+def test_reduce(name):
+    f = getattr(el, name)
+    check(el.render(f(IN0, IN1, IN2, 0.37)), n_in=3, exact=name not in ("div", "mod") or True)
+
+
+def test_add_100_children():
+    # offline-renderer.test.js:78-95: a 100-child add of ones sums to 100
+    g = el.add(*[el.const(1.0, key=f"c{i}") for i in range(100)])
+    got, ref = check(el.render(g), n_voices=2, n_blocks=4, exact=True)
+    assert np.all(got[:, 0, 3 * BS:] == 100.0)
+
+
+def test_div_by_zero_is_zero():
+    check(el.render(el.div(IN0, el.round_(IN1))), n_in=2, exact=True)
+
+
+def test_phasor_cycle_saw_train():
+    check(el.render(el.phasor(440.0)), exact=True, n_blocks=6)
+    check(el.render(el.cycle(440.0)), n_blocks=8)
+    check(el.render(el.saw(110.0)), exact=True)
+    check(el.render(el.train(3000.0)), exact=True)
+    check(el.render(el.phasor(el.mul(2000.0, IN0))), n_in=1, exact=True)   # negative and audio-rate frequencies
+
+
+def test_cycle_440_anchor():
+    # SURVEY.md Appendix E anchors, generated from the compiled reference
+    got, _, _ = run_gpu(el.render(el.cycle(440.0)), 1, 8)
+    b0, b2 = got[0, 0, :BS], got[0, 0, 2 * BS:3 * BS]
+    assert b0[0] == 0.0 and abs(b0[1] - 5.99625273e-05) < 1e-9 and abs(b0[511] - (-0.487395674)) < 1e-5
+    assert abs(b2[0] - 0.653447926) < 1e-5 and abs(float((b2.astype(np.float64) ** 2).sum()) - 248.14756698) < 1e-2
+
+
+def test_sphasor_counter_accum_latch_maxhold():
+    gate = el.le(el.phasor(900.0), 0.3)
+    check(el.render(el.syncphasor(220.0, gate)), exact=True, n_blocks=4)
+    check(el.render(el.counter(gate)), exact=True)
+    check(el.render(el.accum(IN0, gate)), n_in=1, exact=True)
+    check(el.render(el.latch(gate, IN0)), n_in=1, exact=True)
+    check(el.render(el.maxhold({}, IN0, gate)), n_in=1, exact=True)
+    check(el.render(el.maxhold({"hold": 1.0}, IN0, 0.0)), n_in=1, exact=True)
+
+
+def test_rand_seeded():
+    check(el.render(el.rand(seed=12345)), exact=True)
+    check(el.render(el.noise(seed=7)), exact=True)
+
+
+def test_pole_env_biquad_z():
+    check(el.render(el.pole(0.95, IN0)), n_in=1)
+    check(el.render(el.pole(el.mul(0.9, IN1), IN0)), n_in=2)
+    check(el.render(el.env(0.9, 0.999, IN0)), n_in=1)
+    check(el.render(el.biquad(0.2, 0.4, 0.2, -0.5, 0.3, IN0)), n_in=1)
+    check(el.render(el.z(IN0)), n_in=1, exact=True)
+    check(el.render(el.smooth(el.tau2pole(0.01), IN0)), n_in=1)
+
+
+@pytest.mark.parametrize("mode", ["lowpass", "bandpass", "highpass", "notch", "allpass"])
+def test_svf(mode):
+    fc = el.add(1500.0, el.mul(1400.0, el.cycle(3.0)))
+    check(el.render(el.svf({"mode": mode}, fc, 1.5, IN0)), n_in=1, n_blocks=4)
+
+
+def test_svf_extreme_params_clamped():
+    check(el.render(el.svf({}, el.mul(40000.0, IN0), el.mul(30.0, IN1), IN2)), n_in=3)
+
+
+@pytest.mark.parametrize("mode", ["lowshelf", "highshelf", "bell"])
+def test_svfshelf(mode):
+    check(el.render(el.svfshelf({"mode": mode}, 900.0, 0.8, el.mul(12.0, IN1), IN0)), n_in=2)
+
+
+@pytest.mark.parametrize("mode", ["lowpass", "highpass", "allpass"])
+def test_mm1p_prewarp(mode):
+    check(el.render(el.mm1p({"mode": mode}, el.prewarp(el.add(2000.0, el.mul(1500.0, IN1))), IN0)), n_in=2)
+
+
+def test_delay_variants():
+    check(el.render(el.delay({"size": 4800}, 3001.5, 0.35, IN0)), n_in=1, n_blocks=12)       # first wrap at block 9
+    check(el.render(el.delay({"size": 100}, el.add(50.0, el.mul(49.0, IN1)), el.mul(1.5, IN2), IN0)), n_in=3, n_blocks=4)
+    check(el.render(el.delay({"size": 64}, 0.0, 0.9, IN0)), n_in=1, exact=True)               # zero length: write-through
+    check(el.render(el.delay({}, 17.25, 0.0, IN0)), n_in=1)                                  # default size = block size
+    check(el.render(el.sdelay({"size": 10}, IN0)), n_in=1, exact=True)
+    check(el.render(el.sdelay({"size": 3000}, IN0)), n_in=1, exact=True, n_blocks=8)
+    check(el.render(el.sdelay({"size": 0}, IN0)), n_in=1, exact=True)
+
+
+def test_table_lookup():
+    tab = np.sin(np.linspace(0, 2 * np.pi, 1000, dtype=np.float64)).astype(np.float32)
+    check(el.render(el.table({"path": "wt"}, el.phasor(441.0))), resources={"wt": tab}, n_blocks=4)
+    check(el.render(el.table({"path": "wt"}, el.mul(1.3, IN0))), resources={"wt": tab}, n_in=1)   # clamped to [0,1]
+
+
+@pytest.mark.parametrize("kind", ["blepsaw", "blepsquare", "bleptriangle"])
+def test_blep(kind):
+    check(el.render(getattr(el, kind)(el.add(1500.0, el.mul(1400.0, IN0)))), n_in=1, n_blocks=4)
+    check(el.render(getattr(el, kind)(440.0)), n_blocks=4)
+
+
+def test_taps_feedback_one_block_delay():
+    # tap.test.js:5-50 — ones in, tapOut(add(tapIn, in)): blocks read 1, 2, 3 after the fade-in
+    g = el.tap_out("test", el.add(el.tap_in("test"), IN0))
+    n_blocks = 14
+    inp = np.zeros((1, 1, n_blocks * BS), dtype=np.float32)
+    inp[:, :, 10 * BS:] = 1.0
+    got, _, _ = run_gpu(el.render(g), 1, n_blocks, inputs=inp)
+    ref = oracle_render(el.render(g), n_blocks, 1, SR, BS, inp[0])
+    assert np.array_equal(got, ref)
+    for k in range(3):
+        assert np.all(got[0, 0, (10 + k) * BS:(11 + k) * BS] == float(k + 1))
+
+
+def test_two_roots_shared_subgraph():
+    osc = el.cycle(330.0)
+    batch = el.render(el.mul(0.5, osc), el.tanh(el.mul(3.0, osc)))
+    check(batch, n_out=2, n_blocks=4)
+
+
+def test_sr_node_and_leaf_host_inputs():
+    check(el.render(el.div(el.sr(), 48000.0)), exact=True)
+    # a leaf `sin` node reads host channel 0 (GraphRenderSequence.h:126-135)
+    batch = [[0, 1, "root"], [0, 2, "sin"], [2, 1, 2, 0], [3, 1, "channel", 0], [4, [1]], [5]]
+    check(batch, n_in=1)
+
+
+def test_missing_inputs_give_zeros():
+    batch = [[0, 1, "root"], [0, 2, "svf"], [0, 3, "const"], [2, 2, 3, 0], [2, 1, 2, 0], [3, 1, "channel", 0], [4, [1]], [5]]
+    got, ref = check(batch, exact=True)
+    assert not got.any()
+
+
+SUBSYNTH_BLOCKS = 12
+
+
+@pytest.mark.parametrize("tile_width", [0, 1, 8, 32])
+def test_subsynth32_voices(tile_width):
+    n_voices = 45   # ragged against every tile width; covers all 40 distinct f0 values
+    vb = [graphs.subsynth32_voice_props(v) for v in range(n_voices)]
+    opts = {"tile_width": tile_width} if tile_width else {}
+    got, mix, rt = run_gpu(graphs.subsynth32(), n_voices, SUBSYNTH_BLOCKS, voice_batches=vb, **opts)
+    ref = oracle_render(graphs.subsynth32(), SUBSYNTH_BLOCKS, 1, SR, BS, voice_batches=vb)
+    ok, worst, ex = block_peak_tolerance_check(got, ref, BS)
+    assert ok, f"worst err/tol {worst:.3g}, bit-exact {ex:.4f}"
+    want = ref.astype(np.float64).sum(axis=0)
+    assert np.abs(mix - want).max() <= 1e-5 * np.abs(want).max()
+
+
+def test_subsynth32_anchor_f0_110():
+    got, _, _ = run_gpu(graphs.subsynth32(110.0), 1, 12)
+    b = got[0, 0].astype(np.float64)
+    assert abs(b[1] - (-5.93334116e-05)) < 1e-9
+    assert abs((b[2 * BS:3 * BS] ** 2).sum() - 226.292179392) < 5e-3
+    assert abs((b[11 * BS:12 * BS] ** 2).sum() - 828.648815053) < 2e-2
+
+
+def test_additive_voices():
+    n_voices, partials = 5, 64
+    vb = [graphs.additive64_voice_props(v, partials) for v in range(n_voices)]
+    got, mix, rt = run_gpu(graphs.additive64(110.0, partials), n_voices, 4, voice_batches=vb)
+    ref = oracle_render(graphs.additive64(110.0, partials), 4, 1, SR, BS, voice_batches=vb)
+    ok, worst, ex = block_peak_tolerance_check(got, ref, BS)
+    assert ok, f"worst err/tol {worst:.3g}, bit-exact {ex:.4f}"
+
+
+def test_plumbing_graph_two_channels():
+    check(graphs.plumbing(), n_out=2, n_blocks=4, n_voices=2)
+
+
+def test_short_and_varying_num_samples():
+    # numSamples may be smaller than blockSize and vary call to call (cli/Realtime.cpp:38-57)
+    from oracle import oracle as orc
+    from helpers import oracle_cls
+    batch = graphs.subsynth32(220.0)
+    rt = Runtime(SR, BS, 2, device=0)
+    assert rt.apply_instructions(batch) == 0
+    o = oracle_cls()(SR, BS)
+    assert o.apply(batch) == 0
+    for n in (512, 7, 100, 512, 1, 333, 512):
+        got, _ = rt.process_voices(None, 1, n)
+        ref = o.process(None, 1, n)
+        tol = 1e-5 * np.abs(ref).max() + 1e-7
+        assert np.abs(got[0] - ref).max() <= tol and np.array_equal(got[0], got[1])
+
+
+def test_reference_goldens_delay_sdelay_table_maxhold():
+    # jest snapshots of js/packages/offline-renderer/__tests__ (delays/vfs/maxhold .test.js.snap)
+    def run(graph, inp, resources=None, sr=SR):
+        rt = Runtime(sr, BS, 1, device=0)
+        for k, v in (resources or {}).items():
+            rt.add_shared_resource(k, v)
+        assert rt.apply_instructions(el.render(graph)) == 0
+        z = np.zeros((1, 1, BS), dtype=np.float32)
+        for _ in range(10):
+            rt.process_voices(z, 1, BS)
+        x = np.zeros((1, 1, BS), dtype=np.float32)
+        x[0, 0, :len(inp)] = inp
+        got, _ = rt.process_voices(x, 1, BS)
+        return got[0, 0, :len(inp)]
+
+    assert np.array_equal(run(el.delay({"size": 10}, 0.5, 0, IN0), [1, 2, 3, 4]), [0, 0.5, 1, 1.5])
+    assert np.array_equal(run(el.delay({"size": 10}, 0, 0, IN0), [1, 2, 3, 4]), [1, 2, 3, 4])
+    sd_in = [1, 2, 3, 4, 4, 3, 2, 1] + [0] * 16
+    assert np.array_equal(run(el.sdelay({"size": 10}, IN0), sd_in), [0] * 10 + [1, 2, 3, 4, 4, 3, 2, 1] + [0] * 6)
+    assert np.array_equal(run(el.table({"path": "/v/increment"}, IN0), [0, 0.25, 0.5, 0.75, 1],
+                              {"/v/increment": np.array([1, 2, 3, 4, 5], dtype=np.float32)}), [1, 2, 3, 4, 5])
+    assert np.array_equal(run(el.maxhold({}, IN0, 0), [1, 2, 3, 4, 3, 2, 1]), [1, 2, 3, 4, 4, 4, 4])
+    mh_in = [1, 2, 3, 4, 3, 2, 1] + [1] * 41
+    # the jest suite runs at the OfflineRenderer default of 44.1 kHz: hold = 1 ms = 44 samples
+    assert np.array_equal(run(el.maxhold({"hold": 1}, IN0, 0), mh_in, sr=44100.0), [1, 2, 3] + [4] * 44 + [1])
+
+
+def test_const_math_goldens():
+    # offline-renderer.test.js:5-23: el.mul(2,3) settles at 6 once the fade is over
+    got, _, _ = run_gpu(el.render(el.mul(2, 3)), 1, 11)
+    assert np.all(got[0, 0, 10 * BS:] == 6.0)
+
+
+def test_root_fade_ramp():
+    # const 1 -> root: block 0 = i/960 ramp, block 1 reaches 1, then 1
+    got, _, _ = run_gpu(el.render(el.const(1.0)), 1, 3)
+    x = got[0, 0]
+    assert x[0] == 0.0 and abs(x[1] - 0.00104166672) < 1e-10 and abs(x[511] - 0.53229171) < 1e-7
+    assert abs(x[512] - 0.533333361) < 1e-7 and x[1023] == 1.0 and np.all(x[1024:] == 1.0)
+
+
+def test_graph_update_crossfade_and_gc():
+    # render A, run, render B (A's root fades out while B fades in), run; parity against the oracle throughout
+    from helpers import oracle_cls
+    r = el.Renderer()
+    a = r.render(el.cycle(220.0))
+    b = r.render(el.mul(0.5, el.saw(330.0)))
+    rt = Runtime(SR, BS, 2, device=0)
+    o = oracle_cls()(SR, BS)
+    assert rt.apply_instructions(a) == 0 and o.apply(a) == 0
+    outs_g, outs_r = [], []
+    for _ in range(4):
+        outs_g.append(rt.process_voices(None, 1, BS)[0][0]); outs_r.append(o.process(None, 1, BS))
+    assert rt.apply_instructions(b) == 0 and o.apply(b) == 0
+    for _ in range(6):
+        outs_g.append(rt.process_voices(None, 1, BS)[0][0]); outs_r.append(o.process(None, 1, BS))
+    g, rr = np.concatenate(outs_g, axis=1), np.concatenate(outs_r, axis=1)
+    ok, worst, ex = block_peak_tolerance_check(g, rr, BS)
+    assert ok, f"worst err/tol {worst:.3g}"
+    if hasattr(o, "gc"):
+        assert sorted(rt.gc()) == sorted(o.gc())
+
+
+def test_heterogeneous_voice_groups():
+    # different graphs on different voice ranges of one runtime (config 5 in miniature)
+    rt = Runtime(SR, BS, 6, device=0)
+    batches = [graphs.random_graph(seed, 24) for seed in range(3)]
+    for i, b in enumerate(batches):
+        assert rt.apply_instructions(b, voices=(2 * i, 2 * i + 2)) == 0, rt.last_error()
+    got, mix = rt.render_voices(6, 1)
+    for i, b in enumerate(batches):
+        ref = oracle_render(b, 6, 1, SR, BS)
+        for v in (2 * i, 2 * i + 1):
+            ok, worst, ex = block_peak_tolerance_check(got[v], ref[0], BS)
+            assert ok, f"graph {i}: worst err/tol {worst:.3g}"
+
+
+def test_process_mix_api_shared_inputs():
+    # Runtime::process shape: inputs broadcast to all voices, output = mix bus
+    n_voices = 37
+    batch = el.render(el.mul(IN0, el.cycle(el.const(200.0, key="f"))))
+    rt = Runtime(SR, BS, n_voices, device=0)
+    assert rt.apply_instructions(batch) == 0
+    fid = el.const(0, key="f").id()
+    freqs = 100.0 + 10.0 * np.arange(n_voices)
+    assert rt.set_property_per_voice(fid, "value", freqs) == 0
+    x = lcg_noise(3 * BS, 5)[None, :]
+    outs = np.concatenate([rt.process(x[:, b * BS:(b + 1) * BS], 1, BS) for b in range(3)], axis=1)
+    vb = [[[3, fid, "value", float(f)]] for f in freqs]
+    ref = oracle_render(batch, 3, 1, SR, BS, x, voice_batches=vb)
+    want = ref.astype(np.float64).sum(axis=0)
+    assert np.abs(outs - want).max() <= 1e-5 * np.abs(want).max()
