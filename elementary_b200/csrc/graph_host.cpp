@@ -494,7 +494,10 @@ int Engine::applyToGroup(Group& g, const std::vector<Value>& batch, int vb, int 
                 if (shouldRebuild) {
                     std::shared_ptr<Program> p;
                     res = compile(g, g.active ? g.active->nIn : (g.pending ? g.pending->nIn : 0), p);
-                    if (res == rc::Ok) g.pending = p;   // rseqQueue.push(buildRenderSequence())
+                    if (res == rc::Ok) {                // rseqQueue.push(buildRenderSequence())
+                        if (g.pending) g.superseded.push_back(g.pending);
+                        g.pending = p;
+                    }
                 }
                 break;
             default: break;
@@ -607,6 +610,7 @@ int Engine::gc(int voice, std::vector<int32_t>& pruned) {   // Runtime.h:221-272
         std::set<int32_t> live;
         if (g.active) live.insert(g.active->nodeIds.begin(), g.active->nodeIds.end());
         if (g.pending) live.insert(g.pending->nodeIds.begin(), g.pending->nodeIds.end());
+        for (auto& q : g.superseded) live.insert(q->nodeIds.begin(), q->nodeIds.end());
         dsync();
         for (auto it = g.nodes.begin(); it != g.nodes.end();) {
             if (!live.count(it->first)) {
@@ -1062,7 +1066,7 @@ int Engine::enqueueBlock(size_t nIn, size_t nOut, size_t numSamples, bool perVoi
     // host input channels a leaf node sees has changed.
     for (auto& gp : groups_) {
         Group& g = *gp;
-        if (g.pending) { g.active = g.pending; g.pending.reset(); }
+        if (g.pending) { g.active = g.pending; g.pending.reset(); g.superseded.clear(); }
         if (g.active && g.active->nIn != (int) nIn) {
             if (g.active->usesHostInputs) {   // leaf nodes see the host channels: GraphRenderSequence.h:126-135
                 std::shared_ptr<Program> p;

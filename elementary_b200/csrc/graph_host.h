@@ -107,6 +107,7 @@ struct Group {
     int rowsCap = 0, rowsUsed = 0;
     std::map<std::string, float*> tapShared;
     std::shared_ptr<Program> pending, active;
+    std::vector<std::shared_ptr<Program>> superseded;   // queued but never run (rseqQueue, Runtime.h:133,277-285): still pin their nodes for gc
     int nTiles() const { return tileWidth ? (nv + tileWidth - 1) / tileWidth : 0; }
 };
 

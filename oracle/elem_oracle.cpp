@@ -1,0 +1,665 @@
+// oracle/elem_oracle.cpp — TEST INFRASTRUCTURE, NOT PRODUCT CODE.
+//
+// A plain scalar CPU restatement of the reference algorithm for the hot path
+//   elem::Runtime<float>::applyInstructions / process  and the builtin node kernels it walks,
+// written from the reference's semantics (each function cites the file:line under /root/reference it follows).
+// It is deliberately structured like the reference — one block buffer per node, nodes processed one after
+// another over the whole block — and shares NO code with the CUDA product (own instruction reader, own graph
+// walk, own node kernels), so that a bug in the product cannot hide in a common dependency.
+//
+// Pinning: this restatement is validated (tests/test_oracle_cpu.py) against
+//   (1) the compiled reference itself (oracle/_ref/libelem_ref.so) — bit-exact on every graph of the test-suite
+//       (same compiler, flags -O2 -ffp-contract=off and glibc libm), and
+//   (2) the reference's own golden vectors (jest snapshots for delay/sdelay/table/taps/maxhold/const math and
+//       the known-answer anchors of SURVEY.md Appendix E).
+// Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline leg may load this library.
+//
+// Build: g++ -std=c++17 -O2 -DNDEBUG -ffp-contract=off (oracle/Makefile) — no -ffast-math, no FMA contraction.
+
+#include <algorithm>
+#include <cfloat>
+#include <cmath>
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <list>
+#include <map>
+#include <memory>
+#include <set>
+#include <sstream>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+namespace {
+
+constexpr float kEps = FLT_EPSILON;
+
+// ---- helpers/Change.h:12-32 ------------------------------------------------------------------------------
+struct Change {
+    float lastIn = 0;
+    float operator()(float xn) {
+        float dt = xn - lastIn;
+        lastIn = xn;
+        if (dt > 0.0f) return 1.0f;
+        if (dt < 0.0f) return -1.0f;
+        return 0.0f;
+    }
+};
+
+// ---- helpers/GainFade.h:10-121 -----------------------------------------------------------------------------
+struct Fade {
+    float cur = 0, target = 0, step = 0, inStep = 0, outStep = 0;
+    static double msToStep(double sr, double ms) { return ms > 1e-6 ? 1.0 / (sr * ms / 1000.0) : 1.0; }
+    void update() { step = cur > target ? outStep : inStep; }
+    void init(double sr) { cur = 0.0f; target = 1.0f; setIn(sr, 20); setOut(sr, 20); }   // Core.h:80
+    void setIn(double sr, double ms) { inStep = (float) msToStep(sr, ms); update(); }
+    void setOut(double sr, double ms) { outStep = (float) ((double) -1.0f * msToStep(sr, ms)); update(); }
+    void fadeIn() { target = 1.0f; update(); }
+    void fadeOut() { target = 0.0f; update(); }
+    bool on() const { return target > 0.5f; }
+    bool settled() const { return std::abs(target - cur) <= 1e-6f; }
+    void process(const float* in, float* out, int n) {   // GainFade.h:56-72
+        if (cur == target) {
+            for (int i = 0; i < n; ++i) out[i] = in[i] * target;
+            return;
+        }
+        for (int i = 0; i < n; ++i) out[i] = in[i] * std::clamp(cur + step * i, 0.0f, 1.0f);
+        cur = std::clamp(cur + step * n, 0.0f, 1.0f);
+    }
+};
+
+struct PropValue {
+    char kind = 'N';   // N number, S string, B bool, J other json
+    double num = 0;
+    std::string str;
+};
+
+struct Resource { std::vector<float> data; };
+struct Engine;
+
+struct Node {
+    int32_t id = 0;
+    std::string type;
+    std::vector<std::pair<int32_t, int>> inlets;
+    std::vector<float> out;      // one block buffer per node (GraphRenderSequence.h:121-124)
+    Engine* eng = nullptr;
+
+    // state / props, by node family
+    float phase = 0, acc = 0;                       // phasor, blep
+    Change change;
+    float value = 1.0f;                             // const (Core.h:166)
+    float count = 0, total = 0, z = 0, hold = 0;    // counter, accum, latch
+    float mx = 0; uint32_t heldSamples = 0; uint32_t holdTime = 0xFFFFFFFFu;   // maxhold
+    uint32_t seed = 0;                              // rand (reference default is std::rand(); tests always set it)
+    float z1 = 0, z2 = 0;                           // pole / env (z1), biquad
+    double dz = 0, ic1 = 0, ic2 = 0;                // mm1p, svf
+    int mode = 0, channel = 0;
+    Fade fade;                                      // root
+    bool activeProp = false;
+    std::vector<float> ring; int writeIndex = 0; int length = 0; bool ringPending = false; std::vector<float> pendingRing;
+    std::string tapName;
+    std::vector<float> tapPrivate;
+    std::shared_ptr<Resource> res, pendingRes;
+};
+
+struct RootSeq { int32_t root; std::vector<int32_t> order; std::vector<int32_t> tapOuts; };
+struct RenderSeq { std::vector<RootSeq> subseqs; };
+
+struct Engine {
+    double sr;
+    int bs;
+    std::unordered_map<int32_t, Node> nodes;
+    std::set<int32_t> currentRoots;
+    std::map<std::string, std::shared_ptr<Resource>> resources;
+    std::map<std::string, std::vector<float>> taps;
+    std::shared_ptr<RenderSeq> queued, active;
+
+    Engine(double s, int b) : sr(s), bs(b) {}
+
+    static bool known(const std::string& t) {
+        static const std::set<std::string> k = {
+            "in", "sin", "cos", "tan", "tanh", "asinh", "ln", "log", "log2", "ceil", "floor", "round", "sqrt", "exp", "abs",
+            "le", "leq", "ge", "geq", "pow", "eq", "and", "or", "add", "sub", "mul", "div", "mod", "min", "max",
+            "root", "const", "phasor", "sphasor", "sr", "counter", "accum", "latch", "maxhold", "rand",
+            "delay", "sdelay", "z", "pole", "env", "biquad", "prewarp", "mm1p", "svf", "svfshelf",
+            "tapIn", "tapOut", "table", "blepsaw", "blepsquare", "bleptriangle", "meter", "scope"};
+        return k.count(t) > 0;
+    }
+
+    static int bitceil(int n) { if ((n & (n - 1)) == 0) return n; int o = 1; while (o < n) o <<= 1; return o; }   // BitUtils.h:9
+
+    // ---- Runtime.h:294-313 ----
+    int createNode(int32_t id, const std::string& type) {
+        if (!known(type)) return 1;
+        if (nodes.count(id)) return 3;
+        Node n;
+        n.id = id; n.type = type; n.eng = this; n.out.assign(bs, 0.0f);
+        if (type == "root") { n.fade.init(sr); n.channel = -1; }
+        if (type == "delay") { n.pendingRing.assign(bs, 0.0f); n.ringPending = true; }                       // Delays.h:56
+        if (type == "sdelay") { n.pendingRing.assign(bitceil(bs + bs), 0.0f); n.ringPending = true; n.length = bs; }   // Delays.h:183
+        if (type == "tapOut") n.tapPrivate.assign(bs, 0.0f);                                                  // Feedback.h:63-66
+        nodes.emplace(id, std::move(n));
+        return 0;
+    }
+
+    // ---- Runtime.h:336-366 ----
+    int appendChild(int32_t p, int32_t c, int ch) {
+        if (!nodes.count(p) || !nodes.count(c)) return 2;
+        nodes.at(p).inlets.push_back({c, ch});
+        return 0;
+    }
+
+    // ---- Runtime.h:316-333 and each node's setProperty ----
+    int setProperty(int32_t id, const std::string& key, const PropValue& v) {
+        auto it = nodes.find(id);
+        if (it == nodes.end()) return 2;
+        Node& n = it->second;
+        const std::string& t = n.type;
+        const bool isNum = v.kind == 'N', isStr = v.kind == 'S', isBool = v.kind == 'B';
+        if (t == "const" && key == "value") { if (!isNum) return 5; n.value = (float) v.num; }              // Core.h:142-152
+        if (t == "root") {                                                                                  // Core.h:33-64
+            if (key == "active") { if (!isBool) return 5; if (v.num != 0) n.fade.fadeIn(); else n.fade.fadeOut(); n.activeProp = v.num != 0; }
+            if (key == "channel") { if (!isNum) return 8; n.channel = (int) v.num; }
+            if (key == "fadeInMs") { if (!isNum) return 5; n.fade.setIn(sr, v.num); }
+            if (key == "fadeOutMs") { if (!isNum) return 5; n.fade.setOut(sr, v.num); }
+        }
+        if (t == "in" && key == "channel") { if (!isNum) return 5; n.channel = (int) v.num; }               // Math.h:95-105
+        if (t == "svf" && key == "mode") {                                                                  // SVF.h:30-46
+            if (!isStr) return 5;
+            if (v.str == "lowpass") n.mode = 0; if (v.str == "bandpass") n.mode = 1; if (v.str == "highpass") n.mode = 2;
+            if (v.str == "notch") n.mode = 3; if (v.str == "allpass") n.mode = 4;
+        }
+        if (t == "svfshelf" && key == "mode") {                                                             // SVFShelf.h:30-44
+            if (!isStr) return 5;
+            if (v.str == "lowshelf") n.mode = 0; if (v.str == "highshelf") n.mode = 1; if (v.str == "bell" || v.str == "peak") n.mode = 2;
+        }
+        if (t == "mm1p" && key == "mode") {                                                                 // MultiMode1p.h:50-65
+            if (!isStr) return 5;
+            if (v.str == "lowpass") n.mode = 0; if (v.str == "highpass") n.mode = 2; if (v.str == "allpass") n.mode = 4;
+        }
+        if (t == "delay" && key == "size") {                                                                // Delays.h:59-76
+            if (!isNum) return 5;
+            n.pendingRing.assign(std::max(0, (int) v.num), 0.0f); n.ringPending = true;
+        }
+        if (t == "sdelay" && key == "size") {                                                               // Delays.h:188-206
+            if (!isNum) return 5;
+            const int len = std::max(0, (int) v.num);
+            n.pendingRing.assign(bitceil(len + bs), 0.0f); n.ringPending = true; n.length = len;
+        }
+        if (t == "maxhold" && key == "hold") {                                                              // Core.h:292-303
+            if (!isNum) return 5;
+            n.holdTime = (uint32_t) (sr * 0.001 * v.num);
+        }
+        if (t == "rand" && key == "seed") { if (!isNum) return 5; n.seed = (uint32_t) v.num; }             // Noise.h:13-23
+        if ((t == "tapIn" || t == "tapOut") && key == "name") {                                             // Feedback.h:24-38,71-85
+            if (!isStr) return 5;
+            n.tapName = v.str;
+            if (!taps.count(v.str)) taps[v.str].assign(bs, 0.0f);
+        }
+        if (t == "table" && key == "path") {                                                                // Table.h:20-34
+            if (!isStr) return 5;
+            auto r = resources.find(v.str);
+            if (r == resources.end()) return 6;
+            n.pendingRes = r->second;
+        }
+        return 0;
+    }
+
+    // ---- Runtime.h:369-433 ----
+    int activateRoots(const std::vector<int32_t>& ids) {
+        std::set<int32_t> act;
+        for (int32_t id : ids) {
+            auto it = nodes.find(id);
+            if (it == nodes.end()) return 2;
+            if (it->second.type == "root") { it->second.fade.fadeIn(); it->second.activeProp = true; act.insert(id); }
+        }
+        for (int32_t id : currentRoots) {
+            auto it = nodes.find(id);
+            if (it == nodes.end() || it->second.type != "root") continue;
+            Node& n = it->second;
+            if (!act.count(id)) { n.fade.fadeOut(); n.activeProp = false; }
+            if (n.fade.on() || !n.fade.settled()) act.insert(id);
+        }
+        currentRoots.swap(act);
+        return 0;
+    }
+
+    // ---- Runtime.h:503-518 ----
+    void traverse(std::set<int32_t>& visited, std::vector<int32_t>& order, int32_t id) {
+        if (visited.count(id)) return;
+        for (auto& in : nodes.at(id).inlets) traverse(visited, order, in.first);
+        order.push_back(id);
+        visited.insert(id);
+    }
+
+    // ---- Runtime.h:521-577 ----
+    void buildRenderSequence() {
+        auto seq = std::make_shared<RenderSeq>();
+        std::list<int32_t> sorted;
+        for (int32_t id : currentRoots) {
+            Node& n = nodes.at(id);
+            if (n.type != "root") continue;
+            if (n.activeProp) sorted.push_front(id); else sorted.push_back(id);
+        }
+        std::set<int32_t> visited;
+        for (int32_t rid : sorted) {
+            RootSeq rs;
+            rs.root = rid;
+            traverse(visited, rs.order, rid);
+            for (int32_t nid : rs.order) if (nodes.at(nid).type == "tapOut") rs.tapOuts.push_back(nid);   // GraphRenderSequence.h:113-115
+            seq->subseqs.push_back(std::move(rs));
+        }
+        queued = seq;
+    }
+
+    void processNode(Node& n, const float* const* hostIn, int nHostIn, int ns);
+    void process(const float* const* in, int nIn, float* const* out, int nOut, int ns);
+};
+
+// ---- one node over one block: the builtins ---------------------------------------------------------------------
+void Engine::processNode(Node& n, const float* const* hostIn, int nHostIn, int ns) {
+    // Inputs: child buffers, or for a leaf the host input channels (GraphRenderSequence.h:126-135,171-186)
+    std::vector<const float*> in;
+    if (n.inlets.empty()) { for (int c = 0; c < nHostIn; ++c) in.push_back(hostIn[c]); }
+    else for (auto& il : n.inlets) in.push_back(nodes.at(il.first).out.data());
+    const int nch = (int) in.size();
+    float* out = n.out.data();
+    const std::string& t = n.type;
+    auto zeros = [&]() { std::fill_n(out, ns, 0.0f); };
+
+    auto unary = [&](float (*f)(float)) { if (nch < 1) return zeros(); for (int i = 0; i < ns; ++i) out[i] = f(in[0][i]); };   // Math.h:9-28
+    auto binary = [&](auto f) {                                                                                                 // Math.h:30-57
+        if (nch < 2) return zeros();
+        for (int i = 0; i < ns; ++i) out[i] = f(in[0][i], in[1][i]);
+    };
+    auto reduce = [&](auto f) {                                                                                                 // Math.h:59-89
+        if (nch < 1) return zeros();
+        for (int i = 0; i < ns; ++i) out[i] = in[0][i];
+        for (int c = 1; c < nch; ++c) for (int i = 0; i < ns; ++i) out[i] = f(out[i], in[c][i]);
+    };
+
+    if (t == "sin") return unary([](float x) { return std::sin(x); });
+    if (t == "cos") return unary([](float x) { return std::cos(x); });
+    if (t == "tan") return unary([](float x) { return std::tan(x); });
+    if (t == "tanh") return unary([](float x) { return std::tanh(x); });
+    if (t == "asinh") return unary([](float x) { return std::asinh(x); });
+    if (t == "ln") return unary([](float x) { return std::log(x); });
+    if (t == "log") return unary([](float x) { return std::log10(x); });
+    if (t == "log2") return unary([](float x) { return std::log2(x); });
+    if (t == "ceil") return unary([](float x) { return std::ceil(x); });
+    if (t == "floor") return unary([](float x) { return std::floor(x); });
+    if (t == "round") return unary([](float x) { return std::round(x); });
+    if (t == "sqrt") return unary([](float x) { return std::sqrt(x); });
+    if (t == "exp") return unary([](float x) { return std::exp(x); });
+    if (t == "abs") return unary([](float x) { return std::abs(x); });
+
+    if (t == "le") return binary([](float x, float y) { return (float) (x < y); });
+    if (t == "leq") return binary([](float x, float y) { return (float) (x <= y); });
+    if (t == "ge") return binary([](float x, float y) { return (float) (x > y); });
+    if (t == "geq") return binary([](float x, float y) { return (float) (x >= y); });
+    if (t == "pow") return binary([](float x, float y) { return (x < 0.0f && y != std::floor(y)) ? 0.0f : std::pow(x, y); });   // Math.h:179-188
+    if (t == "eq") return binary([](float x, float y) { return (float) (std::abs(x - y) <= kEps); });                          // Math.h:142-147
+    if (t == "and") return binary([](float x, float y) { return (float) (std::abs(1.0f - x) <= kEps && std::abs(1.0f - y) <= kEps); });
+    if (t == "or") return binary([](float x, float y) { return (float) (std::abs(1.0f - x) <= kEps || std::abs(1.0f - y) <= kEps); });
+
+    if (t == "add") return reduce([](float x, float y) { return x + y; });
+    if (t == "sub") return reduce([](float x, float y) { return x - y; });
+    if (t == "mul") return reduce([](float x, float y) { return x * y; });
+    if (t == "div") return reduce([](float x, float y) { return y == 0.0f ? 0.0f : x / y; });   // Math.h:135-140
+    if (t == "mod") return reduce([](float x, float y) { return std::fmod(x, y); });
+    if (t == "min") return reduce([](float x, float y) { return std::min(x, y); });
+    if (t == "max") return reduce([](float x, float y) { return std::max(x, y); });
+
+    if (t == "in") {   // Math.h:107-122
+        const size_t ch = (size_t) n.channel;
+        if (ch >= (size_t) nch) return zeros();
+        std::copy_n(in[ch], ns, out);
+        return;
+    }
+    if (t == "meter" || t == "scope") {   // Analyzers.h: audio passes through (events out of scope)
+        if (nch < 1) return zeros();
+        std::copy_n(in[0], ns, out);
+        return;
+    }
+    if (t == "const") { std::fill_n(out, ns, n.value); return; }          // Core.h:154-163
+    if (t == "sr") { std::fill_n(out, ns, (float) sr); return; }          // Core.h:173-180
+
+    if (t == "root") {   // Core.h:66-78
+        if (nch < 1) return zeros();
+        n.fade.process(in[0], out, ns);
+        return;
+    }
+    if (t == "phasor" || t == "sphasor") {   // Core.h:89-131
+        const bool withReset = t == "sphasor";
+        if (nch < (withReset ? 2 : 1)) return zeros();
+        for (int i = 0; i < ns; ++i) {
+            if (withReset && n.change(in[1][i]) > 0.5f) n.phase = 0.0f;
+            const float step = in[0][i] * (1.0f / (float) sr);
+            const float y = n.phase;
+            const float next = n.phase + step;
+            n.phase = next - std::floor(next);
+            out[i] = y;
+        }
+        return;
+    }
+    if (t == "counter") {   // Core.h:198-211
+        if (nch < 1) return zeros();
+        for (int i = 0; i < ns; ++i) {
+            if ((1.0f - in[0][i]) <= kEps) { out[i] = n.count; n.count = n.count + 1.0f; continue; }
+            n.count = 0.0f; out[i] = 0.0f;
+        }
+        return;
+    }
+    if (t == "accum") {   // Core.h:233-243
+        if (nch < 2) return zeros();
+        for (int i = 0; i < ns; ++i) {
+            if (n.change(in[1][i]) > 0.5f) n.total = 0.0f;
+            n.total += in[0][i];
+            out[i] = n.total;
+        }
+        return;
+    }
+    if (t == "latch") {   // Core.h:265-281
+        if (nch < 2) return zeros();
+        for (int i = 0; i < ns; ++i) {
+            const float l = in[0][i], x = in[1][i];
+            if (std::abs(n.z) <= kEps && l > kEps) n.hold = x;
+            n.z = l;
+            out[i] = n.hold;
+        }
+        return;
+    }
+    if (t == "maxhold") {   // Core.h:315-332
+        if (nch < 2) return zeros();
+        for (int i = 0; i < ns; ++i) {
+            const float x = in[0][i], reset = in[1][i];
+            if (n.change(reset) > 0.5f || ++n.heldSamples >= n.holdTime) { n.mx = x; n.heldSamples = 0; }
+            else if (x > n.mx) { n.heldSamples = 0; n.mx = x; }
+            out[i] = n.mx;
+        }
+        return;
+    }
+    if (t == "rand") {   // Noise.h:25-38
+        for (int i = 0; i < ns; ++i) {
+            n.seed = 214013u * n.seed + 2531011u;
+            out[i] = (int) ((n.seed >> 16) & 0x7FFF) / (float) 0x7FFF;
+        }
+        return;
+    }
+    if (t == "pole") {   // Filters.h:27-33
+        if (nch < 2) return zeros();
+        for (int i = 0; i < ns; ++i) { n.z1 = in[1][i] + in[0][i] * n.z1; out[i] = n.z1; }
+        return;
+    }
+    if (t == "env") {   // Filters.h:61-73
+        if (nch < 3) return zeros();
+        for (int i = 0; i < ns; ++i) {
+            const float ap = in[0][i], rp = in[1][i], vn = std::abs(in[2][i]);
+            if (std::abs(vn) > n.z1) n.z1 = ap * (n.z1 - vn) + vn; else n.z1 = rp * (n.z1 - vn) + vn;
+            out[i] = n.z1;
+        }
+        return;
+    }
+    if (t == "biquad") {   // Filters.h:102-114
+        if (nch < 6) return zeros();
+        for (int i = 0; i < ns; ++i) {
+            const float b0 = in[0][i], b1 = in[1][i], b2 = in[2][i], a1 = in[3][i], a2 = in[4][i], x = in[5][i];
+            const float y = b0 * x + n.z1;
+            n.z1 = b1 * x - a1 * y + n.z2;
+            n.z2 = b2 * x - a2 * y;
+            out[i] = y;
+        }
+        return;
+    }
+    if (t == "prewarp") {   // MultiMode1p.h:23-33
+        if (nch < 1) return zeros();
+        const double T = 1.0 / sr;
+        for (int i = 0; i < ns; ++i) {
+            const double twoPi = 2.0 * 3.141592653589793238;
+            const double wd = twoPi * (double) in[0][i];
+            out[i] = (float) std::tan(wd * T / 2.0);
+        }
+        return;
+    }
+    if (t == "mm1p") {   // MultiMode1p.h:78-103
+        if (nch < 2) return zeros();
+        for (int i = 0; i < ns; ++i) {
+            const double g = std::clamp((double) in[0][i], 0.0, 0.9999);
+            const float xn = in[1][i];
+            const double G = g / (1.0 + g);
+            const double v = ((double) xn - n.dz) * G;
+            const double lp = v + n.dz;
+            n.dz = lp + v;
+            if (n.mode == 0) out[i] = (float) lp;
+            else if (n.mode == 2) out[i] = xn - (float) lp;
+            else out[i] = (float) (lp + lp - xn);
+        }
+        return;
+    }
+    if (t == "svf") {   // SVF.h:48-104
+        if (nch < 3) return zeros();
+        for (int i = 0; i < ns; ++i) {
+            const double fc = in[0][i], q = in[1][i];
+            const float v0 = in[2][i];
+            const double g = std::tan(3.14159265359 * std::clamp(fc, 20.0, sr / 2.0001) / sr);
+            const double k = 1.0 / std::clamp(q, 0.25, 20.0);
+            const double a1 = 1.0 / (1.0 + g * (g + k)), a2 = g * a1, a3 = g * a2;
+            const double v3 = v0 - n.ic2;
+            const double v1 = n.ic1 * a1 + v3 * a2;
+            const double v2 = n.ic2 + n.ic1 * a2 + v3 * a3;
+            n.ic1 = v1 * 2.0 - n.ic1;
+            n.ic2 = v2 * 2.0 - n.ic2;
+            switch (n.mode) {
+                case 0: out[i] = (float) v2; break;
+                case 1: out[i] = (float) v1; break;
+                case 2: out[i] = (float) (v0 - k * v1 - v2); break;
+                case 3: out[i] = (float) (v0 - k * v1); break;
+                default: out[i] = (float) (v0 - 2.0 * k * v1); break;
+            }
+        }
+        return;
+    }
+    if (t == "svfshelf") {   // SVFShelf.h:44-106
+        if (nch < 4) return zeros();
+        for (int i = 0; i < ns; ++i) {
+            const double fc = in[0][i], q = in[1][i], gdb = in[2][i];
+            const float v0 = in[3][i];
+            const double A = std::pow(10, gdb / 40.0);
+            double g = std::tan(3.14159265359 * std::clamp(fc, 20.0, sr / 2.0001) / sr);
+            double k = 1.0 / std::clamp(q, 0.25, 20.0);
+            if (n.mode == 0) g /= A;
+            if (n.mode == 1) g *= A;
+            if (n.mode == 2) k /= A;
+            const double a1 = 1.0 / (1.0 + g * (g + k)), a2 = g * a1, a3 = g * a2;
+            const double v3 = v0 - n.ic2;
+            const double v1 = n.ic1 * a1 + v3 * a2;
+            const double v2 = n.ic2 + n.ic1 * a2 + v3 * a3;
+            n.ic1 = v1 * 2.0 - n.ic1;
+            n.ic2 = v2 * 2.0 - n.ic2;
+            if (n.mode == 2) out[i] = (float) (v0 + k * (A * A - 1.0) * v1);
+            else if (n.mode == 0) out[i] = (float) (v0 + k * (A - 1.0) * v1 + (A * A - 1.0) * v2);
+            else out[i] = (float) (A * A * v0 + k * (1.0 - A) * A * v1 + (1.0 - A * A) * v2);
+        }
+        return;
+    }
+    if (t == "z") {   // Delays.h:29-34
+        if (nch < 1) return zeros();
+        for (int i = 0; i < ns; ++i) { const float x = in[0][i]; out[i] = n.z; n.z = x; }
+        return;
+    }
+    if (t == "delay") {   // Delays.h:87-159
+        if (n.ringPending) { n.ring.swap(n.pendingRing); n.ringPending = false; n.writeIndex = 0; }
+        if (nch < 3) return zeros();
+        const int size = (int) n.ring.size();
+        float* d = n.ring.data();
+        if (size == 0) { std::copy_n(in[0], ns, out); return; }
+        for (int i = 0; i < ns; ++i) {
+            const float offset = std::clamp(in[0][i], 0.0f, (float) size);
+            if (offset <= kEps) {
+                const float x = in[2][i];
+                d[n.writeIndex] = x; out[i] = x;
+                if (++n.writeIndex >= size) n.writeIndex -= size;
+                continue;
+            }
+            const float readFrac = (float) (size + n.writeIndex) - offset;
+            const int readLeft = (int) readFrac, readRight = readLeft + 1;
+            const float frac = readFrac - std::floor(readFrac);
+            const float left = d[readLeft % size], right = d[readRight % size];
+            const float o = left + frac * (right - left);
+            const float fb = std::clamp(in[1][i], -1.0f, 1.0f);
+            d[n.writeIndex] = in[2][i] + fb * o;
+            out[i] = o;
+            if (++n.writeIndex >= size) n.writeIndex -= size;
+        }
+        return;
+    }
+    if (t == "sdelay") {   // Delays.h:221-260
+        if (n.ringPending) { n.ring.swap(n.pendingRing); n.ringPending = false; n.writeIndex = 0; }
+        const int size = (int) n.ring.size();
+        if (nch < 1 || size == 0) return zeros();
+        const int mask = size - 1, len = n.length;
+        float* d = n.ring.data();
+        const int readStart = n.writeIndex - len;
+        for (int i = 0; i < ns; ++i) { d[n.writeIndex] = in[0][i]; n.writeIndex = (n.writeIndex + 1) & mask; }
+        for (int i = 0; i < ns; ++i) out[i] = d[(size + readStart + i) & mask];
+        return;
+    }
+    if (t == "table") {   // Table.h:39-71
+        if (n.pendingRes) { n.res = n.pendingRes; n.pendingRes.reset(); }
+        if (nch == 0 || !n.res || n.res->data.empty()) return zeros();
+        const int size = (int) n.res->data.size();
+        const float* d = n.res->data.data();
+        for (int i = 0; i < ns; ++i) {
+            const float readPos = std::clamp(in[0][i], 0.0f, 1.0f) * (float) (size - 1);
+            const int readLeft = (int) readPos, readRight = readLeft + 1;
+            const float frac = readPos - std::floor(readPos);
+            const float left = d[readLeft % size], right = d[readRight % size];
+            out[i] = left + frac * (right - left);
+        }
+        return;
+    }
+    if (t == "blepsaw" || t == "blepsquare" || t == "bleptriangle") {   // Oscillators.h:23-89
+        if (nch < 1) return zeros();
+        const int mode = t == "blepsaw" ? 0 : (t == "blepsquare" ? 1 : 2);
+        const float fsr = (float) sr;
+        auto blep = [](float phase, float inc) -> float {
+            if (phase < inc) { const float p = phase / inc; return (2.0f - p) * p - 1.0f; }
+            if (phase > (1.0f - inc)) { const float p = (phase - 1.0f) / inc; return (p + 2.0f) * p + 1.0f; }
+            return 0.0f;
+        };
+        for (int i = 0; i < ns; ++i) {
+            const float inc = in[0][i] / fsr;
+            float y;
+            if (mode == 0) y = 2.0f * n.phase - 1.0f - blep(n.phase, inc);
+            else {
+                const float naive = n.phase < 0.5f ? 1.0f : -1.0f;
+                const float halfPhase = std::fmod(n.phase + 0.5f, 1.0f);
+                const float square = naive + blep(n.phase, inc) - blep(halfPhase, inc);
+                if (mode == 1) y = square;
+                else { n.acc += 4.0f * inc * square; y = n.acc; }
+            }
+            n.phase += inc;
+            if (n.phase >= 1.0f) n.phase -= 1.0f;
+            out[i] = y;
+        }
+        return;
+    }
+    if (t == "tapIn") {   // Feedback.h:42-52
+        auto it = taps.find(n.tapName);
+        if (n.tapName.empty() || it == taps.end()) return zeros();
+        std::copy_n(it->second.data(), ns, out);
+        return;
+    }
+    if (t == "tapOut") {   // Feedback.h:109-121
+        if (nch < 1 || ns > (int) n.tapPrivate.size()) return zeros();
+        std::copy_n(in[0], ns, n.tapPrivate.data());
+        std::copy_n(in[0], ns, out);
+        return;
+    }
+    zeros();
+}
+
+// ---- Runtime.h:275-290 + GraphRenderSequence.h:268-309,212-232 ----
+void Engine::process(const float* const* in, int nIn, float* const* out, int nOut, int ns) {
+    if (queued) { active = queued; queued.reset(); }
+    if (!active) return;
+    for (int c = 0; c < nOut; ++c) std::fill_n(out[c], ns, 0.0f);
+    for (auto& sq : active->subseqs) {
+        Node& root = nodes.at(sq.root);
+        const size_t ch = (size_t) root.channel;
+        const bool running = root.fade.on() || !root.fade.settled();
+        if (!running || ch >= (size_t) nOut) continue;
+        for (int32_t nid : sq.order) processNode(nodes.at(nid), in, nIn, ns);
+        for (int j = 0; j < ns; ++j) out[ch][j] += root.out[j];
+    }
+    for (auto& sq : active->subseqs) {   // promoteTapBuffers: GraphRenderSequence.h:200-210
+        if (!nodes.at(sq.root).fade.on()) continue;
+        for (int32_t nid : sq.tapOuts) {
+            Node& n = nodes.at(nid);
+            if (n.tapName.empty()) continue;
+            std::copy_n(n.tapPrivate.data(), ns, taps[n.tapName].data());
+        }
+    }
+}
+
+} // namespace
+
+extern "C" {
+
+void* elem_oracle_create(double sr, int bs) { return new Engine(sr, bs); }
+void elem_oracle_destroy(void* h) { delete static_cast<Engine*>(h); }
+
+// Line format produced by oracle/oracle.py:batch_to_text (no JSON parser on purpose).
+int elem_oracle_apply_text(void* h, const char* text) {
+    auto* e = static_cast<Engine*>(h);
+    std::istringstream ss(text);
+    std::string line;
+    bool rebuild = false;
+    while (std::getline(ss, line)) {
+        if (line.empty()) continue;
+        std::istringstream ls(line);
+        int op;
+        if (!(ls >> op)) return 8;
+        int res = 0;
+        if (op == 0) { long long id; std::string type; if (!(ls >> id >> type)) return 8; res = e->createNode((int32_t) id, type); }
+        else if (op == 2) { long long p, c; int ch; if (!(ls >> p >> c >> ch)) return 8; res = e->appendChild((int32_t) p, (int32_t) c, ch); }
+        else if (op == 3) {
+            long long id; std::string key; char kind;
+            if (!(ls >> id >> key >> kind)) return 8;
+            PropValue v; v.kind = kind;
+            std::string rest; std::getline(ls, rest);
+            if (!rest.empty() && rest[0] == ' ') rest.erase(0, 1);
+            if (kind == 'N' || kind == 'B') v.num = std::strtod(rest.c_str(), nullptr); else v.str = rest;
+            res = e->setProperty((int32_t) id, key, v);
+        } else if (op == 4) {
+            std::vector<int32_t> ids; long long id;
+            while (ls >> id) ids.push_back((int32_t) id);
+            res = e->activateRoots(ids);
+            rebuild = true;
+        } else if (op == 5) { if (rebuild) e->buildRenderSequence(); }
+        if (res != 0) return res;
+    }
+    return 0;
+}
+
+int elem_oracle_add_shared_resource(void* h, const char* name, const float* data, size_t n) {
+    auto* e = static_cast<Engine*>(h);
+    if (e->resources.count(name)) return 0;
+    auto r = std::make_shared<Resource>();
+    r->data.assign(data, data + n);
+    e->resources[name] = r;
+    return 1;
+}
+
+void elem_oracle_process_flat(void* h, const float* in, size_t nIn, float* out, size_t nOut, size_t ns) {
+    auto* e = static_cast<Engine*>(h);
+    std::vector<const float*> ip(nIn);
+    std::vector<float*> op(nOut);
+    for (size_t i = 0; i < nIn; ++i) ip[i] = in + i * ns;
+    for (size_t i = 0; i < nOut; ++i) op[i] = out + i * ns;
+    e->process(ip.data(), (int) nIn, op.data(), (int) nOut, (int) ns);
+}
+
+} // extern "C"

@@ -23,5 +23,5 @@ def _ensure_built():
 
 @pytest.fixture(scope="session", autouse=True)
 def built():
-    pass  # _ensure_built()
+    _ensure_built()
     yield

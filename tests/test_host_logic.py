@@ -1,0 +1,125 @@
+"""CPU: host-side logic of the product (instruction interpreter, return codes, gc, graph compilation) exercised
+through a plan-only runtime (device=-1) and compared, where it applies, with the compiled reference's behaviour."""
+import json
+
+import numpy as np
+import pytest
+
+from elementary_b200 import Runtime, el, graphs
+from oracle import oracle as orc
+from cases import CASES
+
+SR, BS = 48000.0, 512
+
+
+def plan(n_voices=8, **opts):
+    return Runtime(SR, BS, n_voices, device=-1, **opts)
+
+
+BAD_BATCHES = [
+    ([[0, 1, "nope"]], 1),
+    ([[0, 2, "sin"], [0, 2, "sin"]], 3),
+    ([[2, 5, 6, 0]], 2),
+    ([[0, 7, "sin"], [2, 7, 99, 0]], 2),
+    ([[3, 1234, "value", 1]], 2),
+    ([[0, 3, "const"], [3, 3, "value", "x"]], 5),
+    ([[0, 4, "table"], [3, 4, "path", "missing"]], 6),
+    ([[0, 5, "svf"], [3, 5, "mode", 3]], 5),
+    ([[0, 6, "root"], [3, 6, "active", 1]], 5),
+    ([[4, [424242]]], 2),
+    ([5], 8),
+    ([["x", 1, "sin"]], 8),
+    ([[0, "id", "sin"]], 8),
+    ([[0, 8, "delay"], [3, 8, "size", "big"]], 5),
+]
+
+
+@pytest.mark.parametrize("batch,code", BAD_BATCHES)
+def test_error_codes_match_reference(batch, code):
+    assert plan().apply_instructions(batch) == code
+    if orc.ref_available():
+        assert orc.RefRuntime(SR, BS).apply(batch) == code
+
+
+def test_malformed_json_is_code_8_not_an_exception():
+    rt = plan()
+    assert rt.apply_instructions("[[0, 1") == 8
+    assert rt.apply_instructions("{}") == 8
+    assert rt.apply_instructions("") == 8
+
+
+@pytest.mark.parametrize("case", CASES, ids=[c["name"] for c in CASES])
+def test_every_case_compiles(case):
+    rt = plan(4)
+    for k, v in (case["resources"] or {}).items():
+        assert rt.add_shared_resource(k, v)
+    assert rt.apply_instructions(case["batch"]) == 0, rt.last_error()
+    d = rt.describe()
+    assert d["groups"][0]["roots"] >= 1 and d["groups"][0]["code_words"] > 6
+
+
+def test_subsynth32_program_shape():
+    rt = plan(4096)
+    assert rt.apply_instructions(graphs.subsynth32()) == 0
+    g = rt.describe()["groups"][0]
+    assert g["nodes"] == 32                      # 31 + root
+    assert g["state_rows"] == 10                 # 3 phasor + 2 svf doubles (4 rows) + delay index, padded even
+    assert g["slots"] <= 6                       # liveness allocation: intermediates, not 32 block buffers
+    assert g["tile_width"] == 1                  # 4096 voices -> one voice per warp to fill the machine
+    rt = plan(1 << 17)
+    assert rt.apply_instructions(graphs.subsynth32()) == 0
+    assert rt.describe()["groups"][0]["tile_width"] == 32
+
+
+def test_shared_resources_are_insert_only_and_prunable():
+    rt = plan()
+    assert rt.add_shared_resource("one", np.arange(5, dtype=np.float32))
+    assert not rt.add_shared_resource("one", np.arange(3, dtype=np.float32))     # SharedResource.h:44-46
+    assert rt.add_shared_resource("two", np.arange(5, dtype=np.float32))
+    assert sorted(rt.get_shared_resource_map_keys()) == ["one", "two"]
+    assert rt.apply_instructions(el.render(el.table({"path": "one"}, el.in_(0)))) == 0
+    rt.prune_shared_resources()                                                    # vfs.test.js:57-90
+    assert rt.get_shared_resource_map_keys() == ["one"]
+
+
+def test_gc_matches_reference():
+    """gc.test.js semantics: nodes of a replaced graph are collectable only once the new sequence is active."""
+    r = el.Renderer()
+    a = r.render(el.cycle(220.0))
+    b = r.render(el.mul(0.5, el.saw(330.0)))
+    rt = plan(2)
+    assert rt.apply_instructions(a) == 0 and rt.gc() == []
+    assert rt.apply_instructions(b) == 0
+    assert rt.gc() == []          # old sequence is still the active one until the next process()
+    if orc.ref_available():
+        o = orc.RefRuntime(SR, BS)
+        assert o.apply(a) == 0 and o.gc() == []
+
+
+def test_value_only_batches_address_sub_ranges_but_structure_does_not_split_live_groups():
+    rt = plan(64)
+    assert rt.apply_instructions(graphs.subsynth32()) == 0
+    assert rt.apply_instructions(graphs.subsynth32_voice_props(5), voices=(5, 6)) == 0
+    assert len(rt.describe()["groups"]) == 1
+    assert rt.apply_instructions([[0, 99, "sin"]], voices=(5, 6)) == 7          # documented limitation (N1)
+    ida, _ = graphs.subsynth32_param_ids()
+    assert rt.set_property_per_voice(ida, "value", np.linspace(50, 500, 64)) == 0
+    assert rt.set_property_per_voice(12345, "value", np.zeros(4)) == 2
+
+
+def test_fresh_runtime_can_host_different_graphs_per_voice_range():
+    rt = plan(10)
+    for i in range(5):
+        assert rt.apply_instructions(graphs.random_graph(i, 24), voices=(2 * i, 2 * i + 2)) == 0, rt.last_error()
+    groups = rt.describe()["groups"]
+    assert [g["v0"] for g in groups] == [0, 2, 4, 6, 8] and all(g["nv"] == 2 for g in groups)
+
+
+def test_el_renderer_is_incremental():
+    r = el.Renderer()
+    a = r.render(el.cycle(el.const(220.0, key="f")))
+    b = r.render(el.cycle(el.const(330.0, key="f")))
+    assert sum(1 for i in a if i[0] == 0) == 6           # root, sin, mul, const 2pi, phasor, const f (hashing.test.js.snap)
+    assert [i for i in b if i[0] == 0] == []             # nothing new is created ...
+    assert [i[2:] for i in b if i[0] == 3] == [["value", 330.0]]   # ... only the keyed const changes
+    assert b[-2][0] == 4 and b[-1] == [5]
