@@ -134,6 +134,11 @@ int elem_b200_describe(elem_b200_runtime* rt, char* buf, size_t cap) {
 
 uint64_t elem_b200_kernel_launches(elem_b200_runtime* rt) { return rt ? rt->engine->kernelLaunches() : 0; }
 
+double elem_b200_take_kernel_time_ms(elem_b200_runtime* rt, uint64_t* count) {
+    if (!rt) { if (count) *count = 0; return 0.0; }
+    return rt->engine->takeKernelTimeMs(count);
+}
+
 const char* elem_b200_last_error(elem_b200_runtime* rt) {
     if (!rt) return g_createError.c_str();
     rt->scratch = rt->engine->lastError();

@@ -161,6 +161,8 @@ Engine::~Engine() {
     if (dInVoice_) dfree(dInVoice_);
     if (dInShared_) dfree(dInShared_);
     if (hPinned_ && !planOnly_) cudaFreeHost(hPinned_);
+    for (auto& ev : timedEvents_) { cudaEventDestroy(ev.first); cudaEventDestroy(ev.second); }
+    for (auto& ev : eventPool_) { cudaEventDestroy(ev.first); cudaEventDestroy(ev.second); }
     if (ownStream_ && stream_) cudaStreamDestroy(stream_);
 }
 
@@ -176,6 +178,7 @@ int Engine::setOption(const char* key, double value) {
     else if (k == "tile_width") { opt_.tileWidth = (int) value; }
     else if (k == "warps_per_cta") { opt_.warpsPerCta = (int) value; }
     else if (k == "target_tiles") { opt_.targetTiles = (int) value; }
+    else if (k == "time_kernels") { timeKernels_ = value != 0 && !planOnly_; }
     else return rc::BadArgument;
     return rc::Ok;
 }
@@ -1133,7 +1136,14 @@ int Engine::enqueueBlock(size_t nIn, size_t nOut, size_t numSamples, bool perVoi
         const size_t perWarp = render_smem_bytes(opt_.tileSamples, p.nSlots, (int) nOut, p.nStateRows, 1, g.tileWidth);
         while (wpc > 1 && perWarp * wpc > 200 * 1024) wpc >>= 1;
         if (perWarp > 220 * 1024) return fail(rc::InvariantViolation, "graph state does not fit in shared memory");
+        std::pair<cudaEvent_t, cudaEvent_t> ev{nullptr, nullptr};
+        if (timeKernels_) {
+            if (!eventPool_.empty()) { ev = eventPool_.back(); eventPool_.pop_back(); }
+            else { cudaEventCreate(&ev.first); cudaEventCreate(&ev.second); }
+            cudaEventRecord(ev.first, stream_);
+        }
         if (!cuda(launch_render_block(P, opt_.tileSamples, wpc, stream_), "render kernel launch")) return rc::CudaError;
+        if (timeKernels_) { cudaEventRecord(ev.second, stream_); timedEvents_.push_back(ev); }
         ++launches_;
 
         for (size_t ri = 0; ri < p.rootIds.size(); ++ri) {
@@ -1153,6 +1163,20 @@ int Engine::enqueueBlock(size_t nIn, size_t nOut, size_t numSamples, bool perVoi
     }
     curNOut_ = nOut;
     return rc::Ok;
+}
+
+double Engine::takeKernelTimeMs(uint64_t* count) {
+    if (planOnly_) { if (count) *count = 0; return 0.0; }
+    cudaStreamSynchronize(stream_);
+    double total = 0.0;
+    for (auto& ev : timedEvents_) {
+        float ms = 0.0f;
+        if (cudaEventElapsedTime(&ms, ev.first, ev.second) == cudaSuccess) total += ms;
+        eventPool_.push_back(ev);
+    }
+    if (count) *count = timedEvents_.size();
+    timedEvents_.clear();
+    return total;
 }
 
 int Engine::synchronize() {

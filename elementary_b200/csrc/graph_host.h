@@ -149,6 +149,9 @@ public:
     int numVoices() const { return numVoices_; }
     int blockSize() const { return blockSize_; }
     uint64_t kernelLaunches() const { return launches_; }
+    // Sum of the device durations (ms) of the K1 render kernels launched since the last call, measured with
+    // CUDA events recorded on the launching stream (option "time_kernels" = 1). Synchronises the stream.
+    double takeKernelTimeMs(uint64_t* count);
     std::string describe() const;
 
 private:
@@ -161,6 +164,8 @@ private:
     std::map<std::string, std::shared_ptr<Resource>> resources_;
     std::string lastError_;
     uint64_t launches_ = 0;
+    bool timeKernels_ = false;
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> timedEvents_, eventPool_;
 
     // I/O staging
     float* dMix_ = nullptr;          // [MAX_OUT][blockSize]

@@ -91,12 +91,16 @@ typedef void (*elem_b200_event_cb)(const char* type, const char* jsonEvent, void
 void elem_b200_process_queued_events(elem_b200_runtime* rt, elem_b200_event_cb cb, void* user);
 
 /* Tuning and introspection (no reference equivalent). Keys: "tile_samples" (4|8), "tile_width" (1..32, 0 =
- * auto), "warps_per_cta", "target_tiles". Must be set before the first COMMIT of a voice group. */
+ * auto), "warps_per_cta", "target_tiles", "time_kernels" (0|1). Must be set before the first COMMIT of a voice group. */
 int elem_b200_set_option(elem_b200_runtime* rt, const char* key, double value);
 /* JSON description of voice groups and compiled programs; returns bytes needed. */
 int elem_b200_describe(elem_b200_runtime* rt, char* buf, size_t cap);
 /* Number of CUDA kernels this runtime has launched so far. */
 uint64_t elem_b200_kernel_launches(elem_b200_runtime* rt);
+/* With option "time_kernels" = 1 every K1 render-kernel launch is bracketed by CUDA events on the launching
+ * stream; this returns the summed device time (ms) of the launches since the previous call and their count.
+ * Synchronises the stream. */
+double elem_b200_take_kernel_time_ms(elem_b200_runtime* rt, uint64_t* count);
 const char* elem_b200_last_error(elem_b200_runtime* rt);
 /* ReturnCode::describe — runtime/elem/Types.h:62-85 */
 const char* elem_b200_describe_return_code(int code);
