@@ -157,7 +157,8 @@ def run_b200(args, rank, local_rank, world):
     voices = args.voices
     stream = torch.cuda.Stream()
     with torch.cuda.stream(stream):
-        rt = build_runtime(voices, local_rank, rank, stream.cuda_stream, time_kernels=1)
+        extra = {"tile_width": args.tile_width} if args.tile_width else {}
+        rt = build_runtime(voices, local_rank, rank, stream.cuda_stream, time_kernels=1, **extra)
         mix = torch.as_tensor(rt.mix_device(1), device=f"cuda:{local_rank}")
         flush = torch.empty(256 << 20, dtype=torch.uint8, device=f"cuda:{local_rank}")
         host_mix = torch.empty((1, BS), dtype=torch.float32).pin_memory()
@@ -276,6 +277,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--voices", type=int, default=VOICES_PER_GPU, help="voices per GPU (default: the BASELINE config)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--tile-width", type=int, default=0, help="override the voices-per-warp heuristic (exploration only)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))

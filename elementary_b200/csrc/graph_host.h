@@ -112,7 +112,6 @@ struct Group {
 };
 
 struct EngineOptions {
-    int tileSamples = 8;          // T
     int tileWidth = 0;            // 0 = choose per group from the voice count
     int warpsPerCta = 0;          // 0 = choose
     int targetTiles = 2368;       // 148 SMs x 16 warps: shrink the tile width until this many warps exist

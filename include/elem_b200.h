@@ -90,7 +90,7 @@ void elem_b200_reset(elem_b200_runtime* rt);
 typedef void (*elem_b200_event_cb)(const char* type, const char* jsonEvent, void* user);
 void elem_b200_process_queued_events(elem_b200_runtime* rt, elem_b200_event_cb cb, void* user);
 
-/* Tuning and introspection (no reference equivalent). Keys: "tile_samples" (4|8), "tile_width" (1..32, 0 =
+/* Tuning and introspection (no reference equivalent). Keys: "tile_width" (1..32, 0 =
  * auto), "warps_per_cta", "target_tiles", "time_kernels" (0|1). Must be set before the first COMMIT of a voice group. */
 int elem_b200_set_option(elem_b200_runtime* rt, const char* key, double value);
 /* JSON description of voice groups and compiled programs; returns bytes needed. */
