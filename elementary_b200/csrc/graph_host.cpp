@@ -70,6 +70,7 @@ void Engine::setStream(cudaStream_t s) {
 Program::~Program() {
     if (dCode) rawFree(dCode, planOnly);
     if (dStateMap) rawFree(dStateMap, planOnly);
+    if (dParamMap) rawFree(dParamMap, planOnly);
 }
 
 struct TypeInfo { NodeKind kind; uint32_t fn; int stateRows; bool evenAlign; };
@@ -80,21 +81,21 @@ struct TypeInfo { NodeKind kind; uint32_t fn; int stateRows; bool evenAlign; };
 static const std::unordered_map<std::string, TypeInfo>& typeTable() {
     static const std::unordered_map<std::string, TypeInfo> t = {
         {"in", {NodeKind::In, 0, 0, false}},
-        {"sin", {NodeKind::Unary, U_SIN, 0, false}}, {"cos", {NodeKind::Unary, U_COS, 0, false}},
-        {"tan", {NodeKind::Unary, U_TAN, 0, false}}, {"tanh", {NodeKind::Unary, U_TANH, 0, false}},
-        {"asinh", {NodeKind::Unary, U_ASINH, 0, false}}, {"ln", {NodeKind::Unary, U_LN, 0, false}},
-        {"log", {NodeKind::Unary, U_LOG10, 0, false}}, {"log2", {NodeKind::Unary, U_LOG2, 0, false}},
-        {"ceil", {NodeKind::Unary, U_CEIL, 0, false}}, {"floor", {NodeKind::Unary, U_FLOOR, 0, false}},
-        {"round", {NodeKind::Unary, U_ROUND, 0, false}}, {"sqrt", {NodeKind::Unary, U_SQRT, 0, false}},
-        {"exp", {NodeKind::Unary, U_EXP, 0, false}}, {"abs", {NodeKind::Unary, U_ABS, 0, false}},
-        {"le", {NodeKind::Binary, B_LE, 0, false}}, {"leq", {NodeKind::Binary, B_LEQ, 0, false}},
-        {"ge", {NodeKind::Binary, B_GE, 0, false}}, {"geq", {NodeKind::Binary, B_GEQ, 0, false}},
-        {"pow", {NodeKind::Binary, B_POW, 0, false}}, {"eq", {NodeKind::Binary, B_EQ, 0, false}},
-        {"and", {NodeKind::Binary, B_AND, 0, false}}, {"or", {NodeKind::Binary, B_OR, 0, false}},
-        {"add", {NodeKind::Reduce, R_ADD, 0, false}}, {"sub", {NodeKind::Reduce, R_SUB, 0, false}},
-        {"mul", {NodeKind::Reduce, R_MUL, 0, false}}, {"div", {NodeKind::Reduce, R_DIV, 0, false}},
-        {"mod", {NodeKind::Reduce, R_MOD, 0, false}}, {"min", {NodeKind::Reduce, R_MIN, 0, false}},
-        {"max", {NodeKind::Reduce, R_MAX, 0, false}},
+        {"sin", {NodeKind::Unary, F_SIN, 0, false}}, {"cos", {NodeKind::Unary, F_COS, 0, false}},
+        {"tan", {NodeKind::Unary, F_TAN, 0, false}}, {"tanh", {NodeKind::Unary, F_TANH, 0, false}},
+        {"asinh", {NodeKind::Unary, F_ASINH, 0, false}}, {"ln", {NodeKind::Unary, F_LN, 0, false}},
+        {"log", {NodeKind::Unary, F_LOG10, 0, false}}, {"log2", {NodeKind::Unary, F_LOG2, 0, false}},
+        {"ceil", {NodeKind::Unary, F_CEIL, 0, false}}, {"floor", {NodeKind::Unary, F_FLOOR, 0, false}},
+        {"round", {NodeKind::Unary, F_ROUND, 0, false}}, {"sqrt", {NodeKind::Unary, F_SQRT, 0, false}},
+        {"exp", {NodeKind::Unary, F_EXP, 0, false}}, {"abs", {NodeKind::Unary, F_ABS, 0, false}},
+        {"le", {NodeKind::Binary, F_LE, 0, false}}, {"leq", {NodeKind::Binary, F_LEQ, 0, false}},
+        {"ge", {NodeKind::Binary, F_GE, 0, false}}, {"geq", {NodeKind::Binary, F_GEQ, 0, false}},
+        {"pow", {NodeKind::Binary, F_POW, 0, false}}, {"eq", {NodeKind::Binary, F_EQ, 0, false}},
+        {"and", {NodeKind::Binary, F_AND, 0, false}}, {"or", {NodeKind::Binary, F_OR, 0, false}},
+        {"add", {NodeKind::Reduce, F_ADD, 0, false}}, {"sub", {NodeKind::Reduce, F_SUB, 0, false}},
+        {"mul", {NodeKind::Reduce, F_MUL, 0, false}}, {"div", {NodeKind::Reduce, F_DIV, 0, false}},
+        {"mod", {NodeKind::Reduce, F_MOD, 0, false}}, {"min", {NodeKind::Reduce, F_MIN, 0, false}},
+        {"max", {NodeKind::Reduce, F_MAX, 0, false}},
         {"root", {NodeKind::Root, 0, 0, false}}, {"const", {NodeKind::Const, 0, 0, false}},
         {"sr", {NodeKind::Sr, 0, 0, false}},
         {"phasor", {NodeKind::Phasor, 0, 1, false}}, {"sphasor", {NodeKind::SPhasor, 0, 2, false}},
@@ -177,6 +178,7 @@ int Engine::setOption(const char* key, double value) {
     if (k == "tile_width") { opt_.tileWidth = (int) value; }
     else if (k == "warps_per_cta") { opt_.warpsPerCta = (int) value; }
     else if (k == "target_tiles") { opt_.targetTiles = (int) value; }
+    else if (k == "fuse_chains") { opt_.fuseChains = value != 0; }
     else if (k == "time_kernels") { timeKernels_ = value != 0 && !planOnly_; }
     else return rc::BadArgument;
     return rc::Ok;
@@ -192,7 +194,7 @@ std::string Engine::describe() const {
         os << "{\"v0\":" << g->v0 << ",\"nv\":" << g->nv << ",\"tile_width\":" << g->tileWidth << ",\"nodes\":" << g->nodes.size();
         if (g->pending || g->active) {
             auto& p = g->pending ? g->pending : g->active;
-            os << ",\"slots\":" << p->nSlots << ",\"state_rows\":" << p->nStateRows << ",\"code_words\":" << p->code.size()
+            os << ",\"slots\":" << p->nSlots << ",\"state_rows\":" << p->nStateRows << ",\"params\":" << p->paramMap.size() << ",\"ops\":" << p->nOps << ",\"code_words\":" << p->code.size()
                << ",\"roots\":" << p->rootIds.size();
         }
         os << "}";
@@ -670,6 +672,10 @@ struct Compiler {
         uint64_t ptr = 0;
         int32_t outNode = 0;               // node whose output this op produces (0x7fffffff+k for temporaries)
         std::vector<std::pair<uint32_t, int32_t>> operands;   // (kind, node id | param row)
+        struct Step { uint32_t fn; uint32_t kind; int32_t ref; };   // OP_CHAIN: acc = fn(acc, operand) / fn(acc)
+        std::vector<Step> steps;
+        int segment = 0;                   // root sub-sequence the op belongs to
+        bool dead = false;                 // absorbed into a later chain
         bool isSeg = false;
         int segRoot = 0;
         size_t segEndOp = 0;
@@ -732,12 +738,19 @@ int Compiler::emitNode(Node& n, int rootIndex) {
             if (leaf) { op.opcode = OP_LOADIN; op.aux0 = (uint32_t) ch; prog.usesHostInputs = true; }
             else { op.opcode = OP_COPY; op.operands = {operandFor(n.inlets[ch])}; }
         } break;
-        case NodeKind::Unary: if (numCh < 1) { zeros(); break; } op.opcode = OP_UNARY; op.mode = n.fn; take(1); break;
-        case NodeKind::Binary: if (numCh < 2) { zeros(); break; } op.opcode = OP_BINARY; op.mode = n.fn; take(2); break;
-        case NodeKind::Reduce:
+        // Math.h:9-89 — element-wise nodes become one-node chains; fuseChains() merges runs of them
+        case NodeKind::Unary:
             if (numCh < 1) { zeros(); break; }
-            if (numCh > 255) return E.fail(rc::InvariantViolation, "more than 255 children on one node");
-            op.opcode = OP_REDUCE; op.mode = n.fn; take(numCh);
+            op.opcode = OP_CHAIN; take(1); op.steps.push_back({n.fn, K_ZERO, 0});
+            break;
+        case NodeKind::Binary:
+            if (numCh < 2) { zeros(); break; }
+            op.opcode = OP_CHAIN; take(1); op.steps.push_back({n.fn, inputs[1].first, inputs[1].second});
+            break;
+        case NodeKind::Reduce:   // left fold over the children in order (Math.h:71-84)
+            if (numCh < 1) { zeros(); break; }
+            op.opcode = OP_CHAIN; take(1);
+            for (int j = 1; j < numCh; ++j) op.steps.push_back({n.fn, inputs[j].first, inputs[j].second});
             break;
         case NodeKind::Root:
             op.opcode = OP_ROOT; op.aux0 = (uint32_t) rootIndex;
@@ -874,30 +887,171 @@ int Engine::compile(Group& g, int nIn, std::shared_ptr<Program>& out) {
         std::vector<int32_t> order;
         traverse(g, visited, order, rid);
         Compiler::PendingOp seg;
-        seg.isSeg = true; seg.opcode = OP_SEG; seg.segRoot = r;
+        seg.isSeg = true; seg.opcode = OP_SEG; seg.segRoot = r; seg.segment = r;
         const size_t segIdx = C.ops.size();
         C.ops.push_back(seg);
         for (int32_t nid : order) {
             auto it = g.nodes.find(nid);
             if (it == g.nodes.end()) continue;
             prog->nodeIds.push_back(nid);
+            const size_t before = C.ops.size();
             int rcode = C.emitNode(it->second, r);
             if (rcode != rc::Ok) return rcode;
+            for (size_t k = before; k < C.ops.size(); ++k) C.ops[k].segment = r;
         }
         C.ops[segIdx].segEndOp = C.ops.size();
+    }
+    auto& ops = C.ops;
+    using Step = Compiler::PendingOp::Step;
+
+    auto forEachSlotUse = [](const Compiler::PendingOp& op, const std::function<void(int32_t)>& f) {
+        for (auto& o : op.operands) if (o.first == K_SLOT) f(o.second);
+        for (auto& st : op.steps) if (!chain_fn_is_unary(st.fn) && st.kind == K_SLOT) f(st.ref);
+    };
+
+    // ---- chain fusion -------------------------------------------------------------------------------------
+    // An element-wise node whose output has exactly one use, by a later element-wise node of the same root
+    // sub-sequence, is folded into its consumer: as the head of the consumer's chain when it is the first
+    // operand, or — for the other operands of a fold — by ending the producer's chain with the reversed step
+    // fn(running value, acc).  Every node is still evaluated exactly once, with the same operand values in the
+    // same left-fold order (Math.h:71-84), so results are bit-identical; only the evaluation ORDER of
+    // independent stateless nodes changes, and the intermediates stay in registers.
+    if (opt_.fuseChains) {
+        std::unordered_map<int32_t, int> uses;
+        for (auto& op : ops) if (!op.isSeg) forEachSlotUse(op, [&](int32_t id) { ++uses[id]; });
+        std::unordered_map<int32_t, size_t> producer;   // value id -> index of the (still open) chain producing it
+        std::vector<Compiler::PendingOp> outOps;
+        std::vector<size_t> segHeaderAt(prog->rootIds.size(), 0);
+        int32_t& tempCounter = C.tempCounter;
+        for (size_t i = 0; i < ops.size(); ++i) {
+            Compiler::PendingOp op = ops[i];
+            if (op.isSeg) { segHeaderAt[op.segRoot] = outOps.size(); outOps.push_back(op); continue; }
+            if (op.opcode != OP_CHAIN) { outOps.push_back(op); continue; }
+            auto absorbable = [&](uint32_t kind, int32_t ref) -> long {
+                if (kind != K_SLOT) return -1;
+                auto u = uses.find(ref);
+                if (u == uses.end() || u->second != 1) return -1;
+                auto p = producer.find(ref);
+                if (p == producer.end()) return -1;
+                const auto& pop = outOps[p->second];
+                if (pop.dead || pop.opcode != OP_CHAIN || pop.segment != op.segment) return -1;
+                return (long) p->second;
+            };
+            // head: the first operand's producer continues into this chain
+            Compiler::PendingOp cur = op;
+            cur.steps.clear();
+            {
+                long pi = absorbable(op.operands[0].first, op.operands[0].second);
+                if (pi >= 0) {
+                    cur.operands = outOps[pi].operands;
+                    cur.steps = outOps[pi].steps;
+                    outOps[pi].dead = true;
+                }
+            }
+            for (const Step& st : op.steps) {
+                long pi = chain_fn_is_unary(st.fn) ? -1 : absorbable(st.kind, st.ref);
+                if (pi < 0 || cur.steps.size() + outOps[pi].steps.size() > 200) { cur.steps.push_back(st); continue; }
+                // flush the running value to a temporary, then restart from the absorbed producer and finish
+                // with the reversed step: value = fn(running, producer)
+                uint32_t runKind = cur.operands[0].first;
+                int32_t runRef = cur.operands[0].second;
+                if (!cur.steps.empty()) {
+                    Compiler::PendingOp flushed = cur;
+                    flushed.outNode = INT32_MIN + (++tempCounter);
+                    flushed.state = NO_STATE;
+                    outOps.push_back(flushed);
+                    runKind = K_SLOT; runRef = flushed.outNode;
+                }
+                cur.operands = outOps[pi].operands;
+                cur.steps = outOps[pi].steps;
+                outOps[pi].dead = true;
+                cur.steps.push_back({st.fn | CHAIN_REVERSED, runKind, runRef});
+            }
+            if (cur.steps.size() > 120) {   // keep every op's operand block within 255 words
+                // split: flush the first 100 steps into a temporary and continue from it
+                while (cur.steps.size() > 120) {
+                    Compiler::PendingOp head = cur;
+                    head.steps.assign(cur.steps.begin(), cur.steps.begin() + 100);
+                    head.outNode = INT32_MIN + (++tempCounter);
+                    outOps.push_back(head);
+                    cur.operands = {{K_SLOT, head.outNode}};
+                    cur.steps.erase(cur.steps.begin(), cur.steps.begin() + 100);
+                }
+            }
+            producer[cur.outNode] = outOps.size();
+            outOps.push_back(cur);
+        }
+        // drop absorbed ops, fix segment ends
+        std::vector<Compiler::PendingOp> compact;
+        std::vector<size_t> segStart(prog->rootIds.size(), 0);
+        for (auto& op : outOps) {
+            if (op.dead) continue;
+            if (op.isSeg) segStart[op.segRoot] = compact.size();
+            compact.push_back(op);
+        }
+        for (size_t r = 0; r < segStart.size(); ++r) {
+            size_t end = compact.size();
+            for (size_t k = segStart[r] + 1; k < compact.size(); ++k) if (compact[k].isSeg) { end = k; break; }
+            compact[segStart[r]].segEndOp = end;
+        }
+        ops.swap(compact);
+
+        // ---- re-schedule each root sub-sequence to shorten live ranges -----------------------------------------
+        // Depth-first from the sinks of the segment, visiting the operand with the larger sub-tree first
+        // (Sethi-Ullman order).  Any topological order gives the same results — every op is a function of its
+        // operand values and its own private state only — but this one keeps a 64-partial additive voice at 3
+        // live slots instead of 65.
+        std::vector<Compiler::PendingOp> sched;
+        size_t i0 = 0;
+        while (i0 < ops.size()) {
+            const size_t segBegin = i0;                       // ops[segBegin] is the OP_SEG header
+            const size_t segEnd = ops[segBegin].segEndOp;
+            std::unordered_map<int32_t, size_t> prodIdx;      // value id -> op index inside this segment
+            for (size_t k = segBegin + 1; k < segEnd; ++k) prodIdx[ops[k].outNode] = k;
+            std::vector<std::vector<size_t>> deps(segEnd - segBegin);
+            std::vector<int> consumers(segEnd - segBegin, 0);
+            for (size_t k = segBegin + 1; k < segEnd; ++k)
+                forEachSlotUse(ops[k], [&](int32_t id) {
+                    auto p = prodIdx.find(id);
+                    if (p != prodIdx.end() && p->second != k) { deps[k - segBegin].push_back(p->second); ++consumers[p->second - segBegin]; }
+                });
+            std::vector<long> weight(segEnd - segBegin, -1);
+            std::function<long(size_t)> subtree = [&](size_t k) -> long {
+                long& w = weight[k - segBegin];
+                if (w >= 0) return w;
+                w = 1;
+                for (size_t d : deps[k - segBegin]) w += subtree(d);
+                return w;
+            };
+            std::vector<char> done(segEnd - segBegin, 0);
+            const size_t headerAt = sched.size();
+            sched.push_back(ops[segBegin]);
+            std::function<void(size_t)> emit = [&](size_t k) {
+                if (done[k - segBegin]) return;
+                done[k - segBegin] = 1;
+                std::vector<size_t> ds = deps[k - segBegin];
+                std::stable_sort(ds.begin(), ds.end(), [&](size_t a, size_t b) { return subtree(a) > subtree(b); });
+                for (size_t d : ds) emit(d);
+                sched.push_back(ops[k]);
+            };
+            for (size_t k = segBegin + 1; k < segEnd; ++k) if (consumers[k - segBegin] == 0) emit(k);
+            for (size_t k = segBegin + 1; k < segEnd; ++k) emit(k);   // anything unreachable (cannot happen) keeps its place
+            sched[headerAt].segEndOp = sched.size();
+            i0 = segEnd;
+        }
+        ops.swap(sched);
     }
 
     // ---- slot allocation by liveness (an output slot is never the slot of one of its own inputs) ----
     std::unordered_map<int32_t, size_t> lastUse;
-    for (size_t i = 0; i < C.ops.size(); ++i)
-        for (auto& o : C.ops[i].operands)
-            if (o.first == K_SLOT) lastUse[o.second] = i;
+    for (size_t i = 0; i < ops.size(); ++i)
+        if (!ops[i].isSeg) forEachSlotUse(ops[i], [&](int32_t id) { lastUse[id] = i; });
     std::unordered_map<int32_t, int> slotOf;
     std::vector<int> freeSlots;
     int nSlots = 0;
-    std::vector<int> outSlot(C.ops.size(), 0);
-    for (size_t i = 0; i < C.ops.size(); ++i) {
-        auto& op = C.ops[i];
+    std::vector<int> outSlot(ops.size(), 0);
+    for (size_t i = 0; i < ops.size(); ++i) {
+        auto& op = ops[i];
         if (op.isSeg) continue;
         int s;
         if (!freeSlots.empty()) { s = freeSlots.back(); freeSlots.pop_back(); }
@@ -906,23 +1060,21 @@ int Engine::compile(Group& g, int nIn, std::shared_ptr<Program>& out) {
         outSlot[i] = s;
         slotOf[op.outNode] = s;
         // free inputs whose last consumer is this op
-        for (auto& o : op.operands) {
-            if (o.first != K_SLOT) continue;
-            auto lu = lastUse.find(o.second);
-            auto so = slotOf.find(o.second);
+        forEachSlotUse(op, [&](int32_t id) {
+            auto lu = lastUse.find(id);
+            auto so = slotOf.find(id);
             if (lu != lastUse.end() && lu->second == i && so != slotOf.end()) {
                 freeSlots.push_back(so->second);
                 slotOf.erase(so);
             }
-        }
+        });
         // an output nobody reads (root buffers, dangling nodes) is dead immediately
         if (!lastUse.count(op.outNode)) { freeSlots.push_back(s); slotOf.erase(op.outNode); }
     }
-    // Second pass resolving operand slots needs the slot each producer had when it was alive: recompute.
     {
-        std::unordered_map<int32_t, int> producerSlot;
-        for (size_t i = 0; i < C.ops.size(); ++i) if (!C.ops[i].isSeg) producerSlot[C.ops[i].outNode] = outSlot[i];
-        // producerSlot is unique per node because every node is produced exactly once per program.
+        std::unordered_map<int32_t, int> producerSlot;   // every value is produced exactly once per program
+        for (size_t i = 0; i < ops.size(); ++i) if (!ops[i].isSeg) producerSlot[ops[i].outNode] = outSlot[i];
+
         // ---- state map: node state rows -> shared-memory state rows ----
         std::unordered_map<uint32_t, uint32_t> smemIndexOfRow;
         int nStateRows = 0;
@@ -945,19 +1097,41 @@ int Engine::compile(Group& g, int nIn, std::shared_ptr<Program>& out) {
             smemIndexOfRow[(uint32_t) n.stateRow] = idx;
             return idx;
         };
+        // ---- parameter map: global parameter rows -> shared-memory parameter rows (row 0 = zeros) ----
+        std::unordered_map<int32_t, uint32_t> smemParamOfRow;
+        auto encodeOperand = [&](uint32_t kind, int32_t ref) -> uint32_t {
+            if (kind == K_SLOT) {
+                auto ps = producerSlot.find(ref);
+                if (ps == producerSlot.end()) return make_operand(K_PARAM, 0);   // never produced: reads as zero
+                return make_operand(K_SLOT, (uint32_t) ps->second);
+            }
+            if (kind == K_PARAM) {
+                auto it = smemParamOfRow.find(ref);
+                if (it == smemParamOfRow.end()) {
+                    prog->paramMap.push_back((uint32_t) ref);
+                    it = smemParamOfRow.emplace(ref, (uint32_t) prog->paramMap.size()).first;   // 1-based
+                }
+                return make_operand(K_PARAM, it->second);
+            }
+            return make_operand(K_PARAM, 0);
+        };
 
         // ---- encode ----
-        std::vector<size_t> wordOffset(C.ops.size() + 1, 0);
-        for (size_t i = 0; i < C.ops.size(); ++i)
-            wordOffset[i + 1] = wordOffset[i] + OP_HEADER_WORDS + (C.ops[i].isSeg ? 0 : C.ops[i].operands.size());
-        for (size_t i = 0; i < C.ops.size(); ++i) {
-            auto& op = C.ops[i];
+        auto opWords = [&](const Compiler::PendingOp& op) -> size_t {
+            if (op.isSeg) return OP_HEADER_WORDS;
+            size_t n = op.operands.size() + 2 * op.steps.size();
+            return OP_HEADER_WORDS + ((n + 3) & ~(size_t) 3);
+        };
+        std::vector<size_t> wordOffset(ops.size() + 1, 0);
+        for (size_t i = 0; i < ops.size(); ++i) wordOffset[i + 1] = wordOffset[i] + opWords(ops[i]);
+        for (size_t i = 0; i < ops.size(); ++i) {
+            auto& op = ops[i];
             if (op.isSeg) {
                 prog->code.push_back(make_w0(OP_SEG, 0, 0, 0));
                 prog->code.push_back(NO_STATE);
                 prog->code.push_back((uint32_t) op.segRoot);
                 prog->code.push_back((uint32_t) (wordOffset[op.segEndOp] - wordOffset[i + 1]));
-                prog->code.push_back(0); prog->code.push_back(0);
+                for (int k = 0; k < 4; ++k) prog->code.push_back(0);
                 continue;
             }
             uint32_t st = NO_STATE;
@@ -965,34 +1139,41 @@ int Engine::compile(Group& g, int nIn, std::shared_ptr<Program>& out) {
                 auto it = g.nodes.find(op.outNode);
                 if (it != g.nodes.end()) st = mapState(it->second);
             }
-            prog->code.push_back(make_w0(op.opcode, (uint32_t) op.operands.size(), (uint32_t) outSlot[i], op.mode));
+            const size_t nOperandWords = opWords(op) - OP_HEADER_WORDS;
+            if (nOperandWords > 255) return fail(rc::InvariantViolation, "operand block of one op exceeds 255 words");
+            prog->code.push_back(make_w0(op.opcode, (uint32_t) nOperandWords, (uint32_t) outSlot[i], op.mode));
             prog->code.push_back(st);
             prog->code.push_back(op.aux0);
             prog->code.push_back(op.aux1);
             prog->code.push_back((uint32_t) op.ptr);
             prog->code.push_back((uint32_t) (op.ptr >> 32));
-            for (auto& o : op.operands) {
-                if (o.first == K_SLOT) {
-                    auto ps = producerSlot.find(o.second);
-                    if (ps == producerSlot.end()) prog->code.push_back(make_operand(K_ZERO, 0));
-                    else prog->code.push_back(make_operand(K_SLOT, (uint32_t) ps->second));
-                } else if (o.first == K_PARAM) prog->code.push_back(make_operand(K_PARAM, (uint32_t) o.second));
-                else prog->code.push_back(make_operand(K_ZERO, 0));
+            prog->code.push_back((uint32_t) (op.opcode == OP_CHAIN ? op.steps.size() : op.operands.size()));
+            prog->code.push_back(0);
+            size_t written = 0;
+            for (auto& o : op.operands) { prog->code.push_back(encodeOperand(o.first, o.second)); ++written; }
+            for (auto& stp : op.steps) {
+                prog->code.push_back(stp.fn);
+                prog->code.push_back(chain_fn_is_unary(stp.fn) ? 0u : encodeOperand(stp.kind, stp.ref));
+                written += 2;
             }
+            for (; written < nOperandWords; ++written) prog->code.push_back(0);
         }
-        prog->code.push_back(make_w0(OP_END, 0, 0, 0));
+        for (int k = 0; k < 8; ++k) prog->code.push_back(k == 0 ? make_w0(OP_END, 0, 0, 0) : 0u);
         for (auto& pr : C.promotes) {
             Node& n = g.nodes.at(pr.second);
             float* dst = g.tapShared[n.tapName];
             const uint64_t sb = (uint64_t) (uintptr_t) n.tapPrivate, db = (uint64_t) (uintptr_t) dst;
-            prog->code.push_back(make_w0(OP_COPY, 0, 0, 0));
+            prog->code.push_back(make_w0(OP_PROMOTE, 0, 0, 0));
             prog->code.push_back((uint32_t) pr.first);
             prog->code.push_back((uint32_t) sb); prog->code.push_back((uint32_t) (sb >> 32));
             prog->code.push_back((uint32_t) db); prog->code.push_back((uint32_t) (db >> 32));
+            prog->code.push_back(0); prog->code.push_back(0);
         }
-        prog->code.push_back(make_w0(OP_END, 0, 0, 0));
+        for (int k = 0; k < 8; ++k) prog->code.push_back(k == 0 ? make_w0(OP_END, 0, 0, 0) : 0u);
         prog->nStateRows = (nStateRows + 1) & ~1;
         prog->nSlots = std::max(1, nSlots);
+        prog->nOps = 0;
+        for (auto& op : ops) if (!op.isSeg) ++prog->nOps;
     }
 
     // ---- upload ----
@@ -1001,6 +1182,10 @@ int Engine::compile(Group& g, int nIn, std::shared_ptr<Program>& out) {
     if (!prog->stateMap.empty()) {
         if (!cuda(dmalloc((void**) &prog->dStateMap, sizeof(uint32_t) * prog->stateMap.size()), "cudaMalloc stateMap")) return rc::CudaError;
         if (!cuda(dmemcpySync(prog->dStateMap, prog->stateMap.data(), sizeof(uint32_t) * prog->stateMap.size(), cudaMemcpyHostToDevice), "upload stateMap")) return rc::CudaError;
+    }
+    if (!prog->paramMap.empty()) {
+        if (!cuda(dmalloc((void**) &prog->dParamMap, sizeof(uint32_t) * prog->paramMap.size()), "cudaMalloc paramMap")) return rc::CudaError;
+        if (!cuda(dmemcpySync(prog->dParamMap, prog->paramMap.data(), sizeof(uint32_t) * prog->paramMap.size(), cudaMemcpyHostToDevice), "upload paramMap")) return rc::CudaError;
     }
     out = prog;
     return rc::Ok;
@@ -1097,6 +1282,8 @@ int Engine::enqueueBlock(size_t nIn, size_t nOut, size_t numSamples, bool perVoi
         LaunchParams P{};
         P.code = p.dCode;
         P.stateMap = p.dStateMap;
+        P.paramMap = p.dParamMap;
+        P.nParams = (int) p.paramMap.size();
         P.rows = g.dRows;
         P.inShared = (!perVoiceIn && nIn) ? dInShared_ : nullptr;
         P.inVoice = (perVoiceIn && nIn) ? dInVoice_ : nullptr;
@@ -1132,7 +1319,7 @@ int Engine::enqueueBlock(size_t nIn, size_t nOut, size_t numSamples, bool perVoi
         // launch geometry: spread warps over the SMs first, then stack them
         int wpc = opt_.warpsPerCta;
         if (wpc <= 0) wpc = nTiles >= 148 * 8 ? 4 : (nTiles >= 148 * 4 ? 2 : 1);
-        const size_t perWarp = render_smem_bytes(p.nSlots, (int) nOut, p.nStateRows, 1, g.tileWidth);
+        const size_t perWarp = render_smem_bytes(p.nSlots, (int) nOut, p.nStateRows, (int) p.paramMap.size(), 1, g.tileWidth);
         while (wpc > 1 && perWarp * wpc > 200 * 1024) wpc >>= 1;
         if (perWarp > 220 * 1024) return fail(rc::InvariantViolation, "graph state does not fit in shared memory");
         std::pair<cudaEvent_t, cudaEvent_t> ev{nullptr, nullptr};

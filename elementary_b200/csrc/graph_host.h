@@ -83,6 +83,8 @@ struct Node {
 struct Program {
     std::vector<uint32_t> code;
     std::vector<uint32_t> stateMap;
+    std::vector<uint32_t> paramMap;       // shared-memory parameter row i+1 <- global row paramMap[i]
+    int nOps = 0;
     int nStateRows = 0;
     int nSlots = 1;
     int nIn = 0;
@@ -91,6 +93,7 @@ struct Program {
     std::vector<int32_t> nodeIds;         // every node referenced (gc liveness)
     uint32_t* dCode = nullptr;
     uint32_t* dStateMap = nullptr;
+    uint32_t* dParamMap = nullptr;
     bool planOnly = false;
     // convolution stages: K1 stage k ends at codeOffsets[k+1]; between stages the convolvers run
     struct Stage { uint32_t codeOffset; std::vector<int32_t> convolveNodes; };
@@ -114,7 +117,8 @@ struct Group {
 struct EngineOptions {
     int tileWidth = 0;            // 0 = choose per group from the voice count
     int warpsPerCta = 0;          // 0 = choose
-    int targetTiles = 2368;       // 148 SMs x 16 warps: shrink the tile width until this many warps exist
+    int targetTiles = 2048;       // shrink the tile width until about this many warps exist (measured optimum, profiles/)
+    bool fuseChains = true;       // fold runs of element-wise nodes into one OP_CHAIN
 };
 
 class Engine {

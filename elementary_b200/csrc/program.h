@@ -6,14 +6,17 @@
 // (runtime/elem/GraphRenderSequence.h:107-187,212-232; Runtime.h:521-577).  Here the same sorted list is
 // lowered to a flat array of 32-bit words that ONE kernel interprets, warp-uniformly, for every voice tile:
 //
-//   op := [w0 = opcode | nOperands<<8 | outSlot<<16 | mode<<24]
-//         [w1 = state index (row inside the warp's shared-memory state area) or 0xFFFFFFFF]
-//         [w2 = aux0] [w3 = aux1] [w4, w5 = 64-bit device pointer or two more aux words]
-//         [operand]*nOperands          operand = kind<<30 | index
+//   op := header (8 words, 16-byte aligned so it is fetched with two 128-bit loads)
+//           [w0 = opcode | nWords<<8 | outSlot<<16 | mode<<24]   nWords = operand words that follow (padded to x4)
+//           [w1 = state index (row inside the warp's shared-memory state area) or 0xFFFFFFFF]
+//           [w2 = aux0] [w3 = aux1] [w4, w5 = 64-bit device pointer] [w6 = logical operand / step count] [w7 = 0]
+//         operand words            operand = kind<<30 | index
 //
-// Node outputs live in shared-memory "slots" ([TILE samples][32 lanes] floats per warp, liveness-allocated by
-// the host), not in per-node block buffers; `const`/`sr` nodes never execute — their value is a per-voice
-// parameter row read straight from HBM.
+// Node outputs live in shared-memory "slots" ([T samples][L voices] floats per warp, liveness-allocated by the
+// host), not in per-node block buffers.  `const`/`sr` nodes never execute: their per-voice value is a parameter
+// row, staged once per block into the warp's shared-memory parameter area and read like a slot with stride 0.
+// Runs of stateless element-wise nodes (sin, mul, add, le, ...) whose intermediate has a single consumer are
+// fused by the host into one OP_CHAIN: the intermediate never leaves registers.
 #pragma once
 #include <cstdint>
 
@@ -23,11 +26,9 @@ enum Opcode : uint32_t {
     OP_END = 0,
     OP_SEG,        // root sub-sequence header: aux0 = root index, aux1 = words to skip when the root is not running
     OP_FILL0,      // out = 0 (node lacked the inputs it needs: Core.h:125-126 and friends)
-    OP_COPY,       // out = in0 (IdentityNode with a child, tapOut pass-through)
+    OP_COPY,       // out = in0 (IdentityNode with a child, analysis pass-through)
     OP_LOADIN,     // out = host input channel aux0 (IdentityNode leaf / leaf-node host inputs, GraphRenderSequence.h:126-135)
-    OP_UNARY,      // mode = UnaryFn                      (Math.h:9-28)
-    OP_BINARY,     // mode = BinaryFn                     (Math.h:30-57)
-    OP_REDUCE,     // mode = ReduceFn, left fold          (Math.h:59-89)
+    OP_CHAIN,      // acc = operand0; then w6 steps (fn word, operand word): unary/binary/reducing math (Math.h:9-89)
     OP_PHASOR,     // Core.h:85-136 (WithReset=false)
     OP_SPHASOR,    // Core.h:85-136 (WithReset=true)
     OP_COUNTER,    // Core.h:183-215
@@ -49,19 +50,28 @@ enum Opcode : uint32_t {
     OP_BLEP,       // Oscillators.h:19-94, mode = 0 saw / 1 square / 2 triangle
     OP_TAPIN,      // Feedback.h:20-57
     OP_TAPOUT,     // Feedback.h:59-131
-    OP_ROOT,       // Core.h:15-83 + helpers/GainFade.h:56-72, aux0 = root index, aux1 = output channel
+    OP_ROOT,       // Core.h:15-83 + helpers/GainFade.h:56-72, aux0 = root index
     OP_STOREBUF,   // stage boundary: in0 -> global per-voice block buffer (ptr), used around `convolve`
     OP_LOADBUF,    // stage boundary: global per-voice block buffer (ptr) -> out
+    OP_PROMOTE,    // after the first OP_END: tap promotion record (w1 = root index, w2/w3 = src, w4/w5 = dst)
     OP_COUNT_
 };
 
-enum UnaryFn : uint32_t { U_SIN = 0, U_COS, U_TAN, U_TANH, U_ASINH, U_LN, U_LOG10, U_LOG2, U_CEIL, U_FLOOR, U_ROUND, U_SQRT, U_EXP, U_ABS };
-enum BinaryFn : uint32_t { B_LE = 0, B_LEQ, B_GE, B_GEQ, B_POW, B_EQ, B_AND, B_OR };
-enum ReduceFn : uint32_t { R_ADD = 0, R_SUB, R_MUL, R_DIV, R_MOD, R_MIN, R_MAX };
+// Chain step function codes (one table for the unary, binary and reducing node families of Math.h).
+enum ChainFn : uint32_t {
+    // unary: DefaultNodeTypes.h:54-67
+    F_SIN = 0, F_COS, F_TAN, F_TANH, F_ASINH, F_LN, F_LOG10, F_LOG2, F_CEIL, F_FLOOR, F_ROUND, F_SQRT, F_EXP, F_ABS,
+    // binary reducing: DefaultNodeTypes.h:80-86
+    F_ADD = 16, F_SUB, F_MUL, F_DIV, F_MOD, F_MIN, F_MAX,
+    // binary: DefaultNodeTypes.h:70-77
+    F_LE = 32, F_LEQ, F_GE, F_GEQ, F_POW, F_EQ, F_AND, F_OR,
+};
+constexpr uint32_t CHAIN_REVERSED = 0x100;   // step computes fn(operand, acc) instead of fn(acc, operand)
+inline bool chain_fn_is_unary(uint32_t fn) { return (fn & 0xFF) < 16; }
 
 enum OperandKind : uint32_t { K_SLOT = 0, K_PARAM = 1, K_ZERO = 2 };
 
-constexpr uint32_t OP_HEADER_WORDS = 6;
+constexpr uint32_t OP_HEADER_WORDS = 8;
 constexpr uint32_t NO_STATE = 0xFFFFFFFFu;
 constexpr uint32_t STATE_DOUBLE_FLAG = 0x80000000u;   // stateMap entry: two consecutive rows holding double[Vpad]
 constexpr uint32_t STATE_PAD = 0x7FFFFFFFu;           // stateMap entry: one unused shared-memory row (keeps doubles 8-byte aligned)
@@ -69,8 +79,8 @@ constexpr int MAX_ROOTS = 16;
 constexpr int MAX_OUT_CHANNELS = 8;
 constexpr int MAX_SLOTS = 255;
 
-inline uint32_t make_w0(uint32_t opcode, uint32_t nOperands, uint32_t outSlot, uint32_t mode) {
-    return (opcode & 0xFF) | ((nOperands & 0xFF) << 8) | ((outSlot & 0xFF) << 16) | ((mode & 0xFF) << 24);
+inline uint32_t make_w0(uint32_t opcode, uint32_t nWords, uint32_t outSlot, uint32_t mode) {
+    return (opcode & 0xFF) | ((nWords & 0xFF) << 8) | ((outSlot & 0xFF) << 16) | ((mode & 0xFF) << 24);
 }
 inline uint32_t make_operand(uint32_t kind, uint32_t index) { return (kind << 30) | (index & 0x3FFFFFFFu); }
 
@@ -85,8 +95,9 @@ struct RootDyn {
 
 // One launch = one voice group (topology class).
 struct LaunchParams {
-    const uint32_t* code;        // program words (device)
-    const uint32_t* stateMap;    // [nStateEntries] global row index (| STATE_DOUBLE_FLAG)
+    const uint32_t* code;        // program words (device, 16-byte aligned)
+    const uint32_t* stateMap;    // [nStateEntries] global row index (| STATE_DOUBLE_FLAG) or STATE_PAD
+    const uint32_t* paramMap;    // [nParams] global row index of shared-memory parameter row i+1 (row 0 is zeros)
     float*          rows;        // group row storage: rows[row * Vpad + voice]
     const float*    inShared;    // [nIn][inStride] host inputs shared by all voices (or null)
     const float*    inVoice;     // [voice][nIn][inStride] per-voice inputs (or null)
@@ -94,6 +105,7 @@ struct LaunchParams {
     float*          mixPartial;  // [tile][nOut][blockSize] per-tile partial mix (or null)
     int nStateEntries;
     int nStateRows;              // shared-memory state rows per warp
+    int nParams;                 // parameter rows per warp (excluding the zero row)
     int nSlots;
     int Vpad;
     int nv;                      // voices in the group
@@ -106,7 +118,7 @@ struct LaunchParams {
     int inStride;
     int outStride;
     int tileBase;                // index of this group's first tile in mixPartial
-    uint32_t runMask;            // bit r set => root r's sub-sequence runs this block (RootNode::stillRunning)
+    uint32_t runMask;            // bit r: root r's sub-sequence runs this block; bit 16+r: root r promotes its taps
     RootDyn roots[MAX_ROOTS];
 };
 

@@ -65,10 +65,23 @@ def test_subsynth32_program_shape():
     assert g["nodes"] == 32                      # 31 + root
     assert g["state_rows"] == 10                 # 3 phasor + 2 svf doubles (4 rows) + delay index, padded even
     assert g["slots"] <= 6                       # liveness allocation: intermediates, not 32 block buffers
-    assert g["tile_width"] == 1                  # 4096 voices -> one voice per warp to fill the machine
+    assert g["ops"] == 11                        # 19 executable nodes fused into 11 ops (chains of element-wise math)
+    assert g["params"] == 13                     # the 13 consts of SURVEY.md §8d, staged per block in shared memory
+    assert g["tile_width"] == 2                  # 4096 voices -> 2 voices per warp (2048 warps) to fill the machine
     rt = plan(1 << 17)
     assert rt.apply_instructions(graphs.subsynth32()) == 0
     assert rt.describe()["groups"][0]["tile_width"] == 32
+
+
+def test_additive_voice_is_scheduled_into_a_handful_of_slots():
+    rt = plan(64)
+    assert rt.apply_instructions(graphs.additive64()) == 0
+    g = rt.describe()["groups"][0]
+    assert g["nodes"] == 387 and g["state_rows"] == 64 and g["params"] == 129
+    assert g["slots"] <= 4                       # Sethi-Ullman order + incremental fold: not 65 live block buffers
+    rt = plan(64, fuse_chains=0)
+    assert rt.apply_instructions(graphs.additive64()) == 0
+    assert rt.describe()["groups"][0]["slots"] == 65
 
 
 def test_shared_resources_are_insert_only_and_prunable():
