@@ -158,6 +158,9 @@ def run_b200(args, rank, local_rank, world):
     stream = torch.cuda.Stream()
     with torch.cuda.stream(stream):
         extra = {"tile_width": args.tile_width} if args.tile_width else {}
+        for kv in args.opt:
+            k, v = kv.split("=")
+            extra[k] = float(v)
         rt = build_runtime(voices, local_rank, rank, stream.cuda_stream, time_kernels=1, **extra)
         mix = torch.as_tensor(rt.mix_device(1), device=f"cuda:{local_rank}")
         flush = torch.empty(256 << 20, dtype=torch.uint8, device=f"cuda:{local_rank}")
@@ -278,6 +281,7 @@ def main():
     ap.add_argument("--voices", type=int, default=VOICES_PER_GPU, help="voices per GPU (default: the BASELINE config)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--tile-width", type=int, default=0, help="override the voices-per-warp heuristic (exploration only)")
+    ap.add_argument("--opt", action="append", default=[], help="extra runtime option key=value (exploration only)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))

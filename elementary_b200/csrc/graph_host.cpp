@@ -178,6 +178,7 @@ int Engine::setOption(const char* key, double value) {
     if (k == "tile_width") { opt_.tileWidth = (int) value; }
     else if (k == "warps_per_cta") { opt_.warpsPerCta = (int) value; }
     else if (k == "target_tiles") { opt_.targetTiles = (int) value; }
+    else if (k == "niter") { opt_.niter = (int) value; }
     else if (k == "fuse_chains") { opt_.fuseChains = value != 0; }
     else if (k == "time_kernels") { timeKernels_ = value != 0 && !planOnly_; }
     else return rc::BadArgument;
@@ -1319,7 +1320,7 @@ int Engine::enqueueBlock(size_t nIn, size_t nOut, size_t numSamples, bool perVoi
         // launch geometry: spread warps over the SMs first, then stack them
         int wpc = opt_.warpsPerCta;
         if (wpc <= 0) wpc = nTiles >= 148 * 8 ? 4 : (nTiles >= 148 * 4 ? 2 : 1);
-        const size_t perWarp = render_smem_bytes(p.nSlots, (int) nOut, p.nStateRows, (int) p.paramMap.size(), 1, g.tileWidth);
+        const size_t perWarp = render_smem_bytes(p.nSlots, (int) nOut, p.nStateRows, (int) p.paramMap.size(), 1, g.tileWidth, opt_.niter);
         while (wpc > 1 && perWarp * wpc > 200 * 1024) wpc >>= 1;
         if (perWarp > 220 * 1024) return fail(rc::InvariantViolation, "graph state does not fit in shared memory");
         std::pair<cudaEvent_t, cudaEvent_t> ev{nullptr, nullptr};
@@ -1328,7 +1329,7 @@ int Engine::enqueueBlock(size_t nIn, size_t nOut, size_t numSamples, bool perVoi
             else { cudaEventCreate(&ev.first); cudaEventCreate(&ev.second); }
             cudaEventRecord(ev.first, stream_);
         }
-        if (!cuda(launch_render_block(P, wpc, stream_), "render kernel launch")) return rc::CudaError;
+        if (!cuda(launch_render_block(P, wpc, opt_.niter, stream_), "render kernel launch")) return rc::CudaError;
         if (timeKernels_) { cudaEventRecord(ev.second, stream_); timedEvents_.push_back(ev); }
         ++launches_;
 

@@ -118,6 +118,7 @@ struct EngineOptions {
     int tileWidth = 0;            // 0 = choose per group from the voice count
     int warpsPerCta = 0;          // 0 = choose
     int targetTiles = 2048;       // shrink the tile width until about this many warps exist (measured optimum, profiles/)
+    int niter = 0;                // 0 = default elements-per-lane per tile; 4 selects the T = 4 variant for L = 32
     bool fuseChains = true;       // fold runs of element-wise nodes into one OP_CHAIN
 };
 

@@ -7,9 +7,9 @@
 namespace eb {
 
 // K1: fused render-sequence kernel, one launch per voice group per block.
-int render_niter_for(int tileWidth);   // elements per lane per sample tile (E = 32*NITER = L*T)
-size_t render_smem_bytes(int nSlots, int nOut, int nStateRows, int nParams, int warpsPerCta, int tileWidth);
-cudaError_t launch_render_block(const LaunchParams& P, int warpsPerCta, cudaStream_t stream);
+int render_niter_for(int tileWidth, int niterOverride);   // elements per lane per sample tile (E = 32*NITER = L*T)
+size_t render_smem_bytes(int nSlots, int nOut, int nStateRows, int nParams, int warpsPerCta, int tileWidth, int niterOverride);
+cudaError_t launch_render_block(const LaunchParams& P, int warpsPerCta, int niterOverride, cudaStream_t stream);
 
 // K2: deterministic reduction of per-tile partial mixes into the [nOut][blockSize] mix bus.
 cudaError_t launch_mix_reduce(const float* partial, float* out, int nTiles, int nOut, int blockSize, int numSamples, cudaStream_t stream);

@@ -68,6 +68,21 @@ __device__ __forceinline__ double bits_to_double(uint32_t lo, uint32_t hi) {
     return __longlong_as_double((long long) ((uint64_t) lo | ((uint64_t) hi << 32)));
 }
 
+// Cold or bulky libm entry points are kept out of line: the kernel is one big interpreter and its instruction
+// footprint decides how often warps stall on instruction fetch (ncu: stall_no_instruction).  sinf/tanhf and the
+// cheap rounding/abs/sqrt ops stay inline.
+__device__ __noinline__ double tan_f64(double x) { return tan(x); }
+__device__ __noinline__ double pow_f64(double x, double y) { return pow(x, y); }
+__device__ __noinline__ float cos_f32(float x) { return cosf(x); }
+__device__ __noinline__ float tan_f32(float x) { return tanf(x); }
+__device__ __noinline__ float asinh_f32(float x) { return asinhf(x); }
+__device__ __noinline__ float log_f32(float x) { return logf(x); }
+__device__ __noinline__ float log10_f32(float x) { return log10f(x); }
+__device__ __noinline__ float log2_f32(float x) { return log2f(x); }
+__device__ __noinline__ float exp_f32(float x) { return expf(x); }
+__device__ __noinline__ float pow_f32(float x, float y) { return powf(x, y); }
+__device__ __noinline__ float fmod_f32(float x, float y) { return fmodf(x, y); }
+
 // Math.h:30-57,128-188 — fn(x, y) for the binary and reducing node families
 __device__ __forceinline__ float binary_apply(uint32_t fn, float x, float y) {
     switch (fn) {
@@ -75,14 +90,14 @@ __device__ __forceinline__ float binary_apply(uint32_t fn, float x, float y) {
         case F_SUB: return x - y;
         case F_MUL: return x * y;
         case F_DIV: return (y == 0.0f) ? 0.0f : x / y;
-        case F_MOD: return fmodf(x, y);
+        case F_MOD: return fmod_f32(x, y);
         case F_MIN: return stdmin(x, y);
         case F_MAX: return stdmax(x, y);
         case F_LE:  return (x < y) ? 1.0f : 0.0f;
         case F_LEQ: return (x <= y) ? 1.0f : 0.0f;
         case F_GE:  return (x > y) ? 1.0f : 0.0f;
         case F_GEQ: return (x >= y) ? 1.0f : 0.0f;
-        case F_POW: return (x < 0.0f && y != floorf(y)) ? 0.0f : powf(x, y);
+        case F_POW: return (x < 0.0f && y != floorf(y)) ? 0.0f : pow_f32(x, y);
         case F_EQ:  return (fabsf(x - y) <= kEps) ? 1.0f : 0.0f;
         case F_AND: return (fabsf(1.0f - x) <= kEps && fabsf(1.0f - y) <= kEps) ? 1.0f : 0.0f;
         default:    return (fabsf(1.0f - x) <= kEps || fabsf(1.0f - y) <= kEps) ? 1.0f : 0.0f;
@@ -95,7 +110,10 @@ __host__ __device__ constexpr int ilog2(int x) { return x <= 1 ? 0 : 1 + ilog2(x
 
 // =========================================================================================================
 template <int NITER, int LOGL>
-__global__ void __launch_bounds__(128, 4) render_block_kernel(const __grid_constant__ LaunchParams P) {
+// Occupancy target (measured, profiles/r01_d_occupancy_ab.txt): the full-width geometry (L = 32, every lane a voice)
+// is issue-latency bound and gains 20 % from 64-register / 8-CTA occupancy; the narrow geometries run few warps
+// anyway and prefer the 128-register budget.
+__global__ void __launch_bounds__(128, (LOGL == 5) ? 8 : 4) render_block_kernel(const __grid_constant__ LaunchParams P) {
     constexpr int L = 1 << LOGL;          // voices per warp
     constexpr int E = 32 * NITER;         // elements per sample tile
     constexpr int T = E >> LOGL;          // samples per tile
@@ -222,18 +240,18 @@ __global__ void __launch_bounds__(128, 4) render_block_kernel(const __grid_const
                     if (fn < 16) {
                         switch (fn) {
                             case F_SIN:   FOR_K(k) acc[k] = sinf(acc[k]); break;
-                            case F_COS:   FOR_K(k) acc[k] = cosf(acc[k]); break;
-                            case F_TAN:   FOR_K(k) acc[k] = tanf(acc[k]); break;
+                            case F_COS:   FOR_K(k) acc[k] = cos_f32(acc[k]); break;
+                            case F_TAN:   FOR_K(k) acc[k] = tan_f32(acc[k]); break;
                             case F_TANH:  FOR_K(k) acc[k] = tanhf(acc[k]); break;
-                            case F_ASINH: FOR_K(k) acc[k] = asinhf(acc[k]); break;
-                            case F_LN:    FOR_K(k) acc[k] = logf(acc[k]); break;
-                            case F_LOG10: FOR_K(k) acc[k] = log10f(acc[k]); break;
-                            case F_LOG2:  FOR_K(k) acc[k] = log2f(acc[k]); break;
+                            case F_ASINH: FOR_K(k) acc[k] = asinh_f32(acc[k]); break;
+                            case F_LN:    FOR_K(k) acc[k] = log_f32(acc[k]); break;
+                            case F_LOG10: FOR_K(k) acc[k] = log10_f32(acc[k]); break;
+                            case F_LOG2:  FOR_K(k) acc[k] = log2_f32(acc[k]); break;
                             case F_CEIL:  FOR_K(k) acc[k] = ceilf(acc[k]); break;
                             case F_FLOOR: FOR_K(k) acc[k] = floorf(acc[k]); break;
                             case F_ROUND: FOR_K(k) acc[k] = roundf(acc[k]); break;
                             case F_SQRT:  FOR_K(k) acc[k] = sqrtf(acc[k]); break;
-                            case F_EXP:   FOR_K(k) acc[k] = expf(acc[k]); break;
+                            case F_EXP:   FOR_K(k) acc[k] = exp_f32(acc[k]); break;
                             default:      FOR_K(k) acc[k] = fabsf(acc[k]); break;
                         }
                     } else {
@@ -430,7 +448,7 @@ __global__ void __launch_bounds__(128, 4) render_block_kernel(const __grid_const
                 FOR_K(k) {
                     const double twoPi = 2.0 * 3.141592653589793238;
                     const double wd = twoPi * (double) LDE(fc, k);
-                    out[k * 32] = (float) tan(wd * Ts / 2.0);
+                    out[k * 32] = (float) tan_f64(wd * Ts / 2.0);
                 }
             } break;
 
@@ -467,7 +485,7 @@ __global__ void __launch_bounds__(128, 4) render_block_kernel(const __grid_const
                 // all lanes, one element per slice
                 double ga[NITER], a1a[NITER], ka[NITER];
                 FOR_K(k) {
-                    const double g = tan(3.14159265359 * clampd((double) LDE(fc, k), 20.0, fmax) / sr);
+                    const double g = tan_f64(3.14159265359 * clampd((double) LDE(fc, k), 20.0, fmax) / sr);
                     const double kq = 1.0 / clampd((double) LDE(q, k), 0.25, 20.0);
                     ga[k] = g; ka[k] = kq;
                     a1a[k] = 1.0 / (1.0 + g * (g + kq));
@@ -528,8 +546,8 @@ __global__ void __launch_bounds__(128, 4) render_block_kernel(const __grid_const
                     double* s2 = reinterpret_cast<double*>(sst + (sidx + 2) * L) + lane;
                     double ic1 = *s1, ic2 = *s2;
                     _Pragma("unroll 2") for (int t = 0; t < cnt; ++t) {
-                        const double A = pow(10.0, (double) LDT(gdb, t) / 40.0);
-                        double g = tan(3.14159265359 * clampd((double) LDT(fc, t), 20.0, fmax) / sr);
+                        const double A = pow_f64(10.0, (double) LDT(gdb, t) / 40.0);
+                        double g = tan_f64(3.14159265359 * clampd((double) LDT(fc, t), 20.0, fmax) / sr);
                         double kq = 1.0 / clampd((double) LDT(q, t), 0.25, 20.0);
                         if (mode == 0) g /= A;
                         if (mode == 1) g *= A;
@@ -686,7 +704,7 @@ __global__ void __launch_bounds__(128, 4) render_block_kernel(const __grid_const
                             y = 2.0f * phase - 1.0f - blep(phase, inc);
                         } else {
                             const float naive = (phase < 0.5f) ? 1.0f : -1.0f;
-                            const float halfPhase = fmodf(phase + 0.5f, 1.0f);
+                            const float halfPhase = fmod_f32(phase + 0.5f, 1.0f);
                             const float square = naive + blep(phase, inc) - blep(halfPhase, inc);
                             if (mode == 1) y = square;
                             else { acc += 4.0f * inc * square; y = acc; }
@@ -856,14 +874,16 @@ __global__ void __launch_bounds__(1024) mix_reduce_kernel(const float* __restric
 // =========================================================================================================
 // host-side launchers (called from graph_host.cpp)
 
-int render_niter_for(int tileWidth) {
-    // E = L*T elements per sample tile: 256 when the tile is wide enough (T = 256/L >= 8), else T = 32 samples.
+int render_niter_for(int tileWidth, int niterOverride) {
+    // E = L*T = 32*NITER elements per sample tile.  Default: 256 elements when the tile is wide enough (T = 256/L),
+    // else T = 32 samples.  L = 32 may also run with NITER = 4 (T = 4): smaller code and register footprint.
+    if (tileWidth == 32 && niterOverride == 4) return 4;
     if (tileWidth >= 8) return 8;
     return tileWidth;   // L = 4 -> 4, 2 -> 2, 1 -> 1
 }
 
-size_t render_smem_bytes(int nSlots, int nOut, int nStateRows, int nParams, int warpsPerCta, int tileWidth) {
-    const int E = 32 * render_niter_for(tileWidth);
+size_t render_smem_bytes(int nSlots, int nOut, int nStateRows, int nParams, int warpsPerCta, int tileWidth, int niterOverride) {
+    const int E = 32 * render_niter_for(tileWidth, niterOverride);
     const size_t perWarp = ((size_t) (nSlots + nOut) * E + (size_t) (nStateRows + nParams + 1) * tileWidth + 3) & ~(size_t) 3;
     return (size_t) warpsPerCta * perWarp * sizeof(float);
 }
@@ -876,15 +896,16 @@ static cudaError_t launch_impl(const LaunchParams& P, int grid, int threads, siz
     return cudaGetLastError();
 }
 
-cudaError_t launch_render_block(const LaunchParams& P, int warpsPerCta, cudaStream_t stream) {
+cudaError_t launch_render_block(const LaunchParams& P, int warpsPerCta, int niterOverride, cudaStream_t stream) {
     const int L = P.tileWidth;
     const int nTiles = (P.nv + L - 1) / L;
     if (nTiles <= 0) return cudaSuccess;
     const int grid = (nTiles + warpsPerCta - 1) / warpsPerCta;
     const int threads = warpsPerCta * 32;
-    const size_t smem = render_smem_bytes(P.nSlots, P.nOut, P.nStateRows, P.nParams, warpsPerCta, L);
+    const size_t smem = render_smem_bytes(P.nSlots, P.nOut, P.nStateRows, P.nParams, warpsPerCta, L, niterOverride);
     switch (L) {
-        case 32: return launch_impl<8, 5>(P, grid, threads, smem, stream);
+        case 32: return render_niter_for(32, niterOverride) == 4 ? launch_impl<4, 5>(P, grid, threads, smem, stream)
+                                                                  : launch_impl<8, 5>(P, grid, threads, smem, stream);
         case 16: return launch_impl<8, 4>(P, grid, threads, smem, stream);
         case 8:  return launch_impl<8, 3>(P, grid, threads, smem, stream);
         case 4:  return launch_impl<4, 2>(P, grid, threads, smem, stream);

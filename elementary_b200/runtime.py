@@ -21,7 +21,7 @@ from typing import Iterable, List, Optional, Sequence
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libelem_b200.so")
+LIB_PATH = os.environ.get("ELEM_B200_LIB") or os.path.join(_HERE, "libelem_b200.so")   # env override: A/B builds only
 
 _f32p = C.POINTER(C.c_float)
 _f32pp = C.POINTER(_f32p)
