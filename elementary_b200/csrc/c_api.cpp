@@ -139,6 +139,11 @@ double elem_b200_take_kernel_time_ms(elem_b200_runtime* rt, uint64_t* count) {
     return rt->engine->takeKernelTimeMs(count);
 }
 
+double elem_b200_last_convolve_time_ms(elem_b200_runtime* rt, uint64_t* count) {
+    if (!rt) { if (count) *count = 0; return 0.0; }
+    return rt->engine->lastConvolveTimeMs(count);
+}
+
 const char* elem_b200_last_error(elem_b200_runtime* rt) {
     if (!rt) return g_createError.c_str();
     rt->scratch = rt->engine->lastError();

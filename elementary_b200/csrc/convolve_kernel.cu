@@ -1,3 +1,208 @@
-// convolve_kernel.cu — K3 placeholder (filled in below in this round).
+// convolve_kernel.cu — K3: uniformly partitioned FFT convolution, hand-written shared-memory FFT + complex MAC.
+// No cuFFT, no tensor cores: this is a streaming frequency-domain delay line, bound by the HBM reads of the input
+// spectra (see convolve.h for the algorithmic bytes).
+//
+// One CTA (256 threads) serves CONV_CH_PER_CTA = 4 channels so that every IR spectrum value fetched from L2 is used
+// four times.  Per call:
+//   1. append the new samples to the partition's input buffer, zero-pad to 1024 (FFTConvolver.cpp:157-164)
+//   2. real FFT 1024 = complex Stockham radix-2 FFT 512 in shared memory + split post-pass  (replaces OouraFFT::fft,
+//      AudioFFT.cpp:132-155; float arithmetic instead of the reference's double)
+//   3. if the input buffer was empty: Ypre = sum_{i>=1} H_i * X_{cur+i}   (FFTConvolver.cpp:168-177,
+//      ComplexMultiplyAccumulate Utilities.cpp:66-117)
+//   4. Y = Ypre + X_cur * H_0 (:178-179); inverse real FFT (:182); out = y[fill..] + overlap[fill..] (:185)
+//   5. when the partition is complete: overlap = y[512..1024) (:194), the host rotates `cur` (:200)
 #include "convolve.h"
-namespace eb {}
+
+namespace eb {
+
+namespace {
+
+__device__ __forceinline__ float2 cmul(float2 a, float2 b) { return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); }
+__device__ __forceinline__ float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
+__device__ __forceinline__ float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
+__device__ __forceinline__ float2 cconj(float2 a) { return make_float2(a.x, -a.y); }
+
+constexpr int CH = CONV_CH_PER_CTA;
+constexpr int N2 = 512;   // complex FFT length
+
+// 9 Stockham radix-2 stages over CH independent 512-point transforms; 256 threads = one butterfly per thread per
+// channel per stage.  Returns the buffer holding the result (always `b` for 9 stages).
+template <bool INVERSE>
+__device__ __forceinline__ void fft512(float2 (*a)[N2], float2 (*b)[N2], const float2* tw, int tid) {
+    float2 (*src)[N2] = a;
+    float2 (*dst)[N2] = b;
+#pragma unroll 1
+    for (int ns = 1; ns < N2; ns <<= 1) {
+        const int k = tid & (ns - 1);
+        float2 w = tw[k * (N2 / ns)];
+        if (INVERSE) w.y = -w.y;
+        const int j0 = ((tid - k) << 1) + k;
+#pragma unroll
+        for (int c = 0; c < CH; ++c) {
+            const float2 u = src[c][tid];
+            const float2 v = cmul(w, src[c][tid + N2 / 2]);
+            dst[c][j0] = cadd(u, v);
+            dst[c][j0 + ns] = csub(u, v);
+        }
+        __syncthreads();
+        float2 (*t)[N2] = src; src = dst; dst = t;
+    }
+}
+
+} // namespace
+
+__global__ void __launch_bounds__(256) convolve_chunk_kernel(
+    const float* __restrict__ in, float* __restrict__ out, int stride, int offset, int n, int fill, int cur, int S, int nv,
+    const float2* __restrict__ H, float2* __restrict__ fdl, float2* __restrict__ ypre,
+    float* __restrict__ overlap, float* __restrict__ inbuf, const float2* __restrict__ twg) {
+    __shared__ float2 A[CH][N2];
+    __shared__ float2 B[CH][N2];
+    __shared__ float2 tw[N2];
+    __shared__ float2 nyq[CH];    // bin 512 of the current spectrum / product
+
+    const int tid = threadIdx.x;
+    const int ch0 = blockIdx.x * CH;
+
+    tw[tid] = twg[tid];
+    tw[tid + 256] = twg[tid + 256];
+
+    // 1. append the chunk to the partition input buffer and load it as 512 complex points (even, odd), zero-padded
+#pragma unroll
+    for (int c = 0; c < CH; ++c) {
+        const int ch = ch0 + c;
+        if (ch < nv) {
+            float* ib = inbuf + (size_t) ch * CONV_BLOCK;
+            for (int i = tid; i < n; i += 256) ib[fill + i] = in[(size_t) ch * stride + offset + i];
+        }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int c = 0; c < CH; ++c) {
+        const int ch = ch0 + c;
+        float2 z = make_float2(0.0f, 0.0f);
+        if (ch < nv) z = reinterpret_cast<const float2*>(inbuf + (size_t) ch * CONV_BLOCK)[tid];
+        A[c][tid] = z;
+        A[c][tid + 256] = make_float2(0.0f, 0.0f);
+    }
+    __syncthreads();
+
+    // 2. forward transform: Z = FFT512(z) lands in B; split into the 513 bins of the real FFT (written to A / nyq)
+    fft512<false>(A, B, tw, tid);
+#pragma unroll
+    for (int c = 0; c < CH; ++c) {
+        const int ch = ch0 + c;
+        float2* slot = fdl + ((size_t) ch * S + cur) * CONV_BINS;
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int k = tid + h * 256;
+            const float2 zk = B[c][k];
+            const float2 zn = cconj(B[c][(N2 - k) & (N2 - 1)]);
+            const float2 e = make_float2(0.5f * (zk.x + zn.x), 0.5f * (zk.y + zn.y));
+            const float2 d = csub(zk, zn);
+            const float2 o = make_float2(0.5f * d.y, -0.5f * d.x);      // -0.5i * (zk - zn)
+            const float2 x = cadd(e, cmul(tw[k], o));
+            A[c][k] = x;
+            if (ch < nv) slot[k] = x;
+            if (k == 0) {                                                 // bin 512: E[0] - O[0]
+                const float2 xn = csub(e, o);
+                nyq[c] = xn;
+                if (ch < nv) slot[N2] = xn;
+            }
+        }
+    }
+    __syncthreads();
+
+    // 3./4. frequency-domain delay line: Y[b] = sum_i H_i[b] * X_{cur+i}[b]; the older partitions only once per block
+    for (int b = tid; b < CONV_BINS; b += 256) {
+        float2 acc[CH];
+        if (fill == 0) {
+#pragma unroll
+            for (int c = 0; c < CH; ++c) acc[c] = make_float2(0.0f, 0.0f);
+#pragma unroll 4
+            for (int i = 1; i < S; ++i) {
+                const float2 h = __ldg(H + (size_t) i * CONV_BINS + b);
+                int slotIdx = cur + i;
+                if (slotIdx >= S) slotIdx -= S;
+#pragma unroll
+                for (int c = 0; c < CH; ++c) {
+                    const int ch = ch0 + c;
+                    if (ch < nv) {
+                        const float2 x = fdl[((size_t) ch * S + slotIdx) * CONV_BINS + b];
+                        acc[c] = cadd(acc[c], cmul(h, x));
+                    }
+                }
+            }
+#pragma unroll
+            for (int c = 0; c < CH; ++c) if (ch0 + c < nv) ypre[(size_t) (ch0 + c) * CONV_BINS + b] = acc[c];
+        } else {
+#pragma unroll
+            for (int c = 0; c < CH; ++c) acc[c] = (ch0 + c < nv) ? ypre[(size_t) (ch0 + c) * CONV_BINS + b] : make_float2(0.0f, 0.0f);
+        }
+        const float2 h0 = __ldg(H + b);
+#pragma unroll
+        for (int c = 0; c < CH; ++c) {
+            const float2 x = (b < N2) ? A[c][b] : nyq[c];
+            const float2 y = cadd(acc[c], cmul(x, h0));
+            if (b < N2) B[c][b] = y; else nyq[c] = y;
+        }
+    }
+    __syncthreads();
+
+    // inverse split: Zi[k] = E[k] + i*O[k] from Y[k], conj(Y[512-k])  (reads B / nyq, writes A)
+#pragma unroll
+    for (int c = 0; c < CH; ++c) {
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int k = tid + h * 256;
+            const float2 yk = B[c][k];
+            const float2 yn = cconj(k == 0 ? nyq[c] : B[c][N2 - k]);
+            const float2 e = make_float2(0.5f * (yk.x + yn.x), 0.5f * (yk.y + yn.y));
+            const float2 d = make_float2(0.5f * (yk.x - yn.x), 0.5f * (yk.y - yn.y));
+            const float2 o = cmul(d, cconj(tw[k]));
+            A[c][k] = make_float2(e.x - o.y, e.y + o.x);                 // e + i*o
+        }
+    }
+    __syncthreads();
+    fft512<true>(A, B, tw, tid);   // result in B: z[j] * 512
+
+    // 5. overlap-add output for the samples of this chunk; save the second half when the partition is complete
+    const float scale = 1.0f / 512.0f;
+#pragma unroll
+    for (int c = 0; c < CH; ++c) {
+        const int ch = ch0 + c;
+        if (ch >= nv) continue;
+        const float* y = reinterpret_cast<const float*>(&B[c][0]);      // y[2j] = re z[j], y[2j+1] = im z[j]
+        float* ov = overlap + (size_t) ch * CONV_BLOCK;
+        for (int i = tid; i < n; i += 256) out[(size_t) ch * stride + offset + i] = y[fill + i] * scale + ov[fill + i];
+    }
+    if (fill + n == CONV_BLOCK) {
+        __syncthreads();
+#pragma unroll
+        for (int c = 0; c < CH; ++c) {
+            const int ch = ch0 + c;
+            if (ch >= nv) continue;
+            const float* y = reinterpret_cast<const float*>(&B[c][0]);
+            float* ov = overlap + (size_t) ch * CONV_BLOCK;
+            float* ib = inbuf + (size_t) ch * CONV_BLOCK;
+            for (int i = tid; i < CONV_BLOCK; i += 256) { ov[i] = y[CONV_BLOCK + i] * scale; ib[i] = 0.0f; }
+        }
+    }
+}
+
+cudaError_t convolver_process_chunk(ConvolverState& st, const float* in, float* out, int stride, int offset, int n, cudaStream_t stream) {
+    if (st.planOnly) return cudaErrorNotSupported;
+    if (st.partitions == 0) {   // empty (fully trimmed) IR: silence (FFTConvolver.cpp:149-153)
+        return cudaMemset2DAsync(out + offset, sizeof(float) * stride, 0, sizeof(float) * n, st.nv, stream);
+    }
+    const int grid = (st.nv + CONV_CH_PER_CTA - 1) / CONV_CH_PER_CTA;
+    convolve_chunk_kernel<<<grid, 256, 0, stream>>>(in, out, stride, offset, n, st.fill, st.cur, st.partitions, st.nv,
+                                                    st.dH, st.dFdl, st.dYpre, st.dOverlap, st.dInBuf, st.dTw);
+    st.fill += n;
+    if (st.fill == CONV_BLOCK) {
+        st.fill = 0;
+        st.cur = (st.cur > 0) ? st.cur - 1 : st.partitions - 1;   // FFTConvolver.cpp:200
+    }
+    return cudaGetLastError();
+}
+
+} // namespace eb

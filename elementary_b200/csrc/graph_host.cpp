@@ -71,6 +71,7 @@ Program::~Program() {
     if (dCode) rawFree(dCode, planOnly);
     if (dStateMap) rawFree(dStateMap, planOnly);
     if (dParamMap) rawFree(dParamMap, planOnly);
+    for (float* p : blockBuffers) rawFree(p, planOnly);
 }
 
 struct TypeInfo { NodeKind kind; uint32_t fn; int stateRows; bool evenAlign; };
@@ -853,8 +854,18 @@ int Compiler::emitNode(Node& n, int rootIndex) {
             }
         } break;
 
-        case NodeKind::Convolve:
-            return E.fail(rc::InvariantViolation, "convolve inside a render program is handled by the convolution stage");
+        case NodeKind::Convolve: {   // wasm/Convolve.h:58-85: zeros without an input or a loaded IR
+            if (numCh == 0 || !n.resource) { zeros(); break; }
+            if (n.resourceDirty || !n.conv) {   // a new `path` makes a fresh convolver (Convolve.h:45-51)
+                auto cs = std::make_shared<ConvolverState>();
+                const auto& ch0 = n.resource->channels.empty() ? std::vector<float>() : n.resource->channels[0];
+                std::string err;
+                if (!convolver_init(*cs, ch0.data(), ch0.size(), g.nv, E.planOnly_, E.stream_, err)) return E.fail(rc::CudaError, err);
+                n.conv = cs;
+                n.resourceDirty = false;
+            }
+            op.opcode = 0xF0; take(1);   // OP_HOST_CONV: lowered to STOREBUF + K3 + LOADBUF by the stage pass
+        } break;
 
         default: zeros(); break;
     }
@@ -1043,63 +1054,178 @@ int Engine::compile(Group& g, int nIn, std::shared_ptr<Program>& out) {
         ops.swap(sched);
     }
 
-    // ---- slot allocation by liveness (an output slot is never the slot of one of its own inputs) ----
-    std::unordered_map<int32_t, size_t> lastUse;
-    for (size_t i = 0; i < ops.size(); ++i)
-        if (!ops[i].isSeg) forEachSlotUse(ops[i], [&](int32_t id) { lastUse[id] = i; });
-    std::unordered_map<int32_t, int> slotOf;
-    std::vector<int> freeSlots;
-    int nSlots = 0;
-    std::vector<int> outSlot(ops.size(), 0);
-    for (size_t i = 0; i < ops.size(); ++i) {
-        auto& op = ops[i];
-        if (op.isSeg) continue;
-        int s;
-        if (!freeSlots.empty()) { s = freeSlots.back(); freeSlots.pop_back(); }
-        else s = nSlots++;
-        if (s >= MAX_SLOTS) return fail(rc::InvariantViolation, "graph needs more than 255 live intermediates");
-        outSlot[i] = s;
-        slotOf[op.outNode] = s;
-        // free inputs whose last consumer is this op
-        forEachSlotUse(op, [&](int32_t id) {
-            auto lu = lastUse.find(id);
-            auto so = slotOf.find(id);
-            if (lu != lastUse.end() && lu->second == i && so != slotOf.end()) {
-                freeSlots.push_back(so->second);
-                slotOf.erase(so);
-            }
-        });
-        // an output nobody reads (root buffers, dangling nodes) is dead immediately
-        if (!lastUse.count(op.outNode)) { freeSlots.push_back(s); slotOf.erase(op.outNode); }
-    }
-    {
-        std::unordered_map<int32_t, int> producerSlot;   // every value is produced exactly once per program
-        for (size_t i = 0; i < ops.size(); ++i) if (!ops[i].isSeg) producerSlot[ops[i].outNode] = outSlot[i];
-
-        // ---- state map: node state rows -> shared-memory state rows ----
-        std::unordered_map<uint32_t, uint32_t> smemIndexOfRow;
-        int nStateRows = 0;
-        auto mapState = [&](Node& n) -> uint32_t {
-            if (n.stateRow < 0) return NO_STATE;
-            auto it = smemIndexOfRow.find((uint32_t) n.stateRow);
-            if (it != smemIndexOfRow.end()) return it->second;
-            const auto& ti = typeTable().at(n.typeName);
-            if (ti.evenAlign && (nStateRows & 1)) {   // keep doubles 8-byte aligned in shared memory
-                prog->stateMap.push_back(STATE_PAD);
-                nStateRows += 1;
-            }
-            const uint32_t idx = (uint32_t) nStateRows;
-            if (ti.evenAlign) {
-                for (int k = 0; k < ti.stateRows; k += 2) prog->stateMap.push_back(((uint32_t) n.stateRow + k) | STATE_DOUBLE_FLAG);
-            } else {
-                for (int k = 0; k < ti.stateRows; ++k) prog->stateMap.push_back((uint32_t) n.stateRow + k);
-            }
-            nStateRows += ti.stateRows;
-            smemIndexOfRow[(uint32_t) n.stateRow] = idx;
-            return idx;
+    // ---- stages: a `convolve` node is a whole-block operation (K3) that cannot live inside the sample-tiled
+    // interpreter, so the program is cut into K1 stages around it.  Values that cross a stage boundary travel
+    // through per-voice block buffers in HBM (OP_STOREBUF / OP_LOADBUF); root ops always run in the last stage.
+    constexpr uint32_t OP_HOST_CONV = 0xF0;   // host-only pseudo opcode emitted for Convolve nodes
+    std::vector<std::vector<Compiler::PendingOp>> stageOps;
+    bool hasConv = false;
+    for (auto& op : ops) if (op.opcode == OP_HOST_CONV) hasConv = true;
+    if (!hasConv) {
+        stageOps.push_back(ops);
+    } else {
+        std::unordered_map<int32_t, int> stageOfValue;       // stage in which the value becomes available to K1
+        std::unordered_map<int32_t, const Compiler::PendingOp*> producerOp;
+        int lastStage = 0;
+        std::vector<int> stageOfOp(ops.size(), 0);
+        for (size_t i = 0; i < ops.size(); ++i) {
+            auto& op = ops[i];
+            if (op.isSeg) continue;
+            int st = 0;
+            forEachSlotUse(op, [&](int32_t id) { auto it = stageOfValue.find(id); if (it != stageOfValue.end()) st = std::max(st, it->second); });
+            stageOfOp[i] = st;
+            stageOfValue[op.outNode] = (op.opcode == OP_HOST_CONV) ? st + 1 : st;
+            lastStage = std::max(lastStage, stageOfValue[op.outNode]);
+        }
+        for (size_t i = 0; i < ops.size(); ++i) if (!ops[i].isSeg && ops[i].opcode == OP_ROOT) stageOfOp[i] = lastStage;
+        const int nStages = lastStage + 1;
+        const size_t blockFloats = (size_t) g.Vpad * blockSize_;
+        auto newBlockBuffer = [&]() -> float* {
+            float* p = nullptr;
+            if (!cuda(dmalloc((void**) &p, sizeof(float) * blockFloats), "cudaMalloc stage buffer")) return nullptr;
+            dmemset(p, 0, sizeof(float) * blockFloats);
+            prog->blockBuffers.push_back(p);
+            return p;
         };
-        // ---- parameter map: global parameter rows -> shared-memory parameter rows (row 0 = zeros) ----
-        std::unordered_map<int32_t, uint32_t> smemParamOfRow;
+        // buffers: one per convolve node (in, out) and one per ordinary value that crosses stages
+        std::unordered_map<int32_t, float*> spillOf;         // value id -> HBM block buffer holding it
+        prog->stages.resize(nStages);
+        for (size_t i = 0; i < ops.size(); ++i) {
+            auto& op = ops[i];
+            if (op.isSeg || op.opcode != OP_HOST_CONV) continue;
+            Node& n = g.nodes.at(op.outNode);
+            float* inB = newBlockBuffer(); float* outB = newBlockBuffer();
+            if (!inB || !outB) return rc::CudaError;
+            prog->stages[stageOfOp[i]].convolves.push_back({n.id, inB, outB});
+            spillOf[op.outNode] = outB;
+            op.ptr = (uint64_t) (uintptr_t) inB;
+        }
+        // which values are read in a later stage than the one that produces them?
+        std::unordered_map<int32_t, int> producedIn;
+        for (size_t i = 0; i < ops.size(); ++i) if (!ops[i].isSeg) producedIn[ops[i].outNode] = (ops[i].opcode == OP_HOST_CONV) ? -1 : stageOfOp[i];
+        for (size_t i = 0; i < ops.size(); ++i) {
+            if (ops[i].isSeg) continue;
+            forEachSlotUse(ops[i], [&](int32_t id) {
+                auto p = producedIn.find(id);
+                if (p == producedIn.end() || p->second < 0) return;
+                if (p->second < stageOfOp[i] && !spillOf.count(id)) spillOf[id] = nullptr;   // allocate below
+            });
+        }
+        for (auto& kv : spillOf) if (!kv.second) { kv.second = newBlockBuffer(); if (!kv.second) return rc::CudaError; }
+
+        stageOps.assign(nStages, {});
+        for (int st = 0; st < nStages; ++st) {
+            auto& out = stageOps[st];
+            size_t i = 0;
+            while (i < ops.size()) {
+                const size_t segBegin = i, segEnd = ops[i].segEndOp;
+                const size_t headerAt = out.size();
+                out.push_back(ops[segBegin]);
+                std::unordered_map<int32_t, int32_t> loaded;   // value id -> temp id loaded in this stage+segment
+                for (size_t k = segBegin + 1; k < segEnd; ++k) {
+                    if (stageOfOp[k] != st) continue;
+                    Compiler::PendingOp op = ops[k];
+                    // reload operands that were produced in an earlier stage (or by a convolver)
+                    auto fix = [&](uint32_t& kind, int32_t& ref) {
+                        if (kind != K_SLOT) return;
+                        auto p = producedIn.find(ref);
+                        if (p == producedIn.end()) return;
+                        if (p->second >= 0 && p->second >= st) return;
+                        auto l = loaded.find(ref);
+                        if (l == loaded.end()) {
+                            Compiler::PendingOp ld;
+                            ld.opcode = OP_LOADBUF; ld.segment = op.segment; ld.outNode = INT32_MIN + (++C.tempCounter);
+                            ld.ptr = (uint64_t) (uintptr_t) spillOf.at(ref);
+                            out.push_back(ld);
+                            l = loaded.emplace(ref, ld.outNode).first;
+                        }
+                        ref = l->second;
+                    };
+                    for (auto& o : op.operands) fix(o.first, o.second);
+                    for (auto& stp : op.steps) if (!chain_fn_is_unary(stp.fn)) fix(stp.kind, stp.ref);
+                    if (op.opcode == OP_HOST_CONV) {          // stage the convolver input
+                        op.opcode = OP_STOREBUF; op.state = NO_STATE; op.outNode = INT32_MIN + (++C.tempCounter);
+                        out.push_back(op);
+                        continue;
+                    }
+                    out.push_back(op);
+                    auto sp = spillOf.find(op.outNode);
+                    if (sp != spillOf.end()) {                // the value is needed by a later stage
+                        Compiler::PendingOp stb;
+                        stb.opcode = OP_STOREBUF; stb.segment = op.segment; stb.outNode = INT32_MIN + (++C.tempCounter);
+                        stb.operands = {{K_SLOT, op.outNode}};
+                        stb.ptr = (uint64_t) (uintptr_t) sp->second;
+                        out.push_back(stb);
+                    }
+                }
+                out[headerAt].segEndOp = out.size();
+                i = segEnd;
+            }
+        }
+    }
+
+    // ---- per stage: slot allocation by liveness (an output slot is never the slot of one of its own inputs),
+    //      then encoding ----
+    std::unordered_map<uint32_t, uint32_t> smemIndexOfRow;
+    int nStateRows = 0;
+    auto mapState = [&](Node& n) -> uint32_t {
+        if (n.stateRow < 0) return NO_STATE;
+        auto it = smemIndexOfRow.find((uint32_t) n.stateRow);
+        if (it != smemIndexOfRow.end()) return it->second;
+        const auto& ti = typeTable().at(n.typeName);
+        if (ti.evenAlign && (nStateRows & 1)) {   // keep doubles 8-byte aligned in shared memory
+            prog->stateMap.push_back(STATE_PAD);
+            nStateRows += 1;
+        }
+        const uint32_t idx = (uint32_t) nStateRows;
+        if (ti.evenAlign) {
+            for (int k = 0; k < ti.stateRows; k += 2) prog->stateMap.push_back(((uint32_t) n.stateRow + k) | STATE_DOUBLE_FLAG);
+        } else {
+            for (int k = 0; k < ti.stateRows; ++k) prog->stateMap.push_back((uint32_t) n.stateRow + k);
+        }
+        nStateRows += ti.stateRows;
+        smemIndexOfRow[(uint32_t) n.stateRow] = idx;
+        return idx;
+    };
+    std::unordered_map<int32_t, uint32_t> smemParamOfRow;
+    int nSlotsMax = 1;
+    prog->nOps = 0;
+    if (prog->stages.empty()) prog->stages.resize(1);
+    for (size_t stg = 0; stg < stageOps.size(); ++stg) {
+        auto& sops = stageOps[stg];
+        prog->stages[stg].codeOffset = (uint32_t) prog->code.size();
+
+        std::unordered_map<int32_t, size_t> lastUse;
+        for (size_t i = 0; i < sops.size(); ++i)
+            if (!sops[i].isSeg) forEachSlotUse(sops[i], [&](int32_t id) { lastUse[id] = i; });
+        std::unordered_map<int32_t, int> slotOf;
+        std::vector<int> freeSlots;
+        int nSlots = 0;
+        std::vector<int> outSlot(sops.size(), 0);
+        for (size_t i = 0; i < sops.size(); ++i) {
+            auto& op = sops[i];
+            if (op.isSeg) continue;
+            int s;
+            if (!freeSlots.empty()) { s = freeSlots.back(); freeSlots.pop_back(); }
+            else s = nSlots++;
+            if (s >= MAX_SLOTS) return fail(rc::InvariantViolation, "graph needs more than 255 live intermediates");
+            outSlot[i] = s;
+            slotOf[op.outNode] = s;
+            forEachSlotUse(op, [&](int32_t id) {   // free inputs whose last consumer is this op
+                auto lu = lastUse.find(id);
+                auto so = slotOf.find(id);
+                if (lu != lastUse.end() && lu->second == i && so != slotOf.end()) {
+                    freeSlots.push_back(so->second);
+                    slotOf.erase(so);
+                }
+            });
+            // an output nobody reads (root buffers, dangling nodes) is dead immediately
+            if (!lastUse.count(op.outNode)) { freeSlots.push_back(s); slotOf.erase(op.outNode); }
+        }
+        nSlotsMax = std::max(nSlotsMax, nSlots);
+
+        std::unordered_map<int32_t, int> producerSlot;   // every value is produced exactly once per stage
+        for (size_t i = 0; i < sops.size(); ++i) if (!sops[i].isSeg) producerSlot[sops[i].outNode] = outSlot[i];
         auto encodeOperand = [&](uint32_t kind, int32_t ref) -> uint32_t {
             if (kind == K_SLOT) {
                 auto ps = producerSlot.find(ref);
@@ -1116,17 +1242,15 @@ int Engine::compile(Group& g, int nIn, std::shared_ptr<Program>& out) {
             }
             return make_operand(K_PARAM, 0);
         };
-
-        // ---- encode ----
         auto opWords = [&](const Compiler::PendingOp& op) -> size_t {
             if (op.isSeg) return OP_HEADER_WORDS;
             size_t n = op.operands.size() + 2 * op.steps.size();
             return OP_HEADER_WORDS + ((n + 3) & ~(size_t) 3);
         };
-        std::vector<size_t> wordOffset(ops.size() + 1, 0);
-        for (size_t i = 0; i < ops.size(); ++i) wordOffset[i + 1] = wordOffset[i] + opWords(ops[i]);
-        for (size_t i = 0; i < ops.size(); ++i) {
-            auto& op = ops[i];
+        std::vector<size_t> wordOffset(sops.size() + 1, 0);
+        for (size_t i = 0; i < sops.size(); ++i) wordOffset[i + 1] = wordOffset[i] + opWords(sops[i]);
+        for (size_t i = 0; i < sops.size(); ++i) {
+            auto& op = sops[i];
             if (op.isSeg) {
                 prog->code.push_back(make_w0(OP_SEG, 0, 0, 0));
                 prog->code.push_back(NO_STATE);
@@ -1135,6 +1259,7 @@ int Engine::compile(Group& g, int nIn, std::shared_ptr<Program>& out) {
                 for (int k = 0; k < 4; ++k) prog->code.push_back(0);
                 continue;
             }
+            ++prog->nOps;
             uint32_t st = NO_STATE;
             if (op.state != NO_STATE) {
                 auto it = g.nodes.find(op.outNode);
@@ -1160,22 +1285,22 @@ int Engine::compile(Group& g, int nIn, std::shared_ptr<Program>& out) {
             for (; written < nOperandWords; ++written) prog->code.push_back(0);
         }
         for (int k = 0; k < 8; ++k) prog->code.push_back(k == 0 ? make_w0(OP_END, 0, 0, 0) : 0u);
-        for (auto& pr : C.promotes) {
-            Node& n = g.nodes.at(pr.second);
-            float* dst = g.tapShared[n.tapName];
-            const uint64_t sb = (uint64_t) (uintptr_t) n.tapPrivate, db = (uint64_t) (uintptr_t) dst;
-            prog->code.push_back(make_w0(OP_PROMOTE, 0, 0, 0));
-            prog->code.push_back((uint32_t) pr.first);
-            prog->code.push_back((uint32_t) sb); prog->code.push_back((uint32_t) (sb >> 32));
-            prog->code.push_back((uint32_t) db); prog->code.push_back((uint32_t) (db >> 32));
-            prog->code.push_back(0); prog->code.push_back(0);
+        if (stg + 1 == stageOps.size()) {   // tap promotion records live behind the last stage only
+            for (auto& pr : C.promotes) {
+                Node& n = g.nodes.at(pr.second);
+                float* dst = g.tapShared[n.tapName];
+                const uint64_t sb = (uint64_t) (uintptr_t) n.tapPrivate, db = (uint64_t) (uintptr_t) dst;
+                prog->code.push_back(make_w0(OP_PROMOTE, 0, 0, 0));
+                prog->code.push_back((uint32_t) pr.first);
+                prog->code.push_back((uint32_t) sb); prog->code.push_back((uint32_t) (sb >> 32));
+                prog->code.push_back((uint32_t) db); prog->code.push_back((uint32_t) (db >> 32));
+                prog->code.push_back(0); prog->code.push_back(0);
+            }
         }
         for (int k = 0; k < 8; ++k) prog->code.push_back(k == 0 ? make_w0(OP_END, 0, 0, 0) : 0u);
-        prog->nStateRows = (nStateRows + 1) & ~1;
-        prog->nSlots = std::max(1, nSlots);
-        prog->nOps = 0;
-        for (auto& op : ops) if (!op.isSeg) ++prog->nOps;
     }
+    prog->nStateRows = (nStateRows + 1) & ~1;
+    prog->nSlots = nSlotsMax;
 
     // ---- upload ----
     if (!cuda(dmalloc((void**) &prog->dCode, sizeof(uint32_t) * prog->code.size()), "cudaMalloc code")) return rc::CudaError;
@@ -1323,15 +1448,45 @@ int Engine::enqueueBlock(size_t nIn, size_t nOut, size_t numSamples, bool perVoi
         const size_t perWarp = render_smem_bytes(p.nSlots, (int) nOut, p.nStateRows, (int) p.paramMap.size(), 1, g.tileWidth, opt_.niter);
         while (wpc > 1 && perWarp * wpc > 200 * 1024) wpc >>= 1;
         if (perWarp > 220 * 1024) return fail(rc::InvariantViolation, "graph state does not fit in shared memory");
-        std::pair<cudaEvent_t, cudaEvent_t> ev{nullptr, nullptr};
-        if (timeKernels_) {
-            if (!eventPool_.empty()) { ev = eventPool_.back(); eventPool_.pop_back(); }
-            else { cudaEventCreate(&ev.first); cudaEventCreate(&ev.second); }
-            cudaEventRecord(ev.first, stream_);
+        const size_t nStages = std::max<size_t>(1, p.stages.size());
+        for (size_t stg = 0; stg < nStages; ++stg) {
+            const bool last = stg + 1 == nStages;
+            P.code = p.dCode + (p.stages.empty() ? 0 : p.stages[stg].codeOffset);
+            P.outVoice = (last && materialise) ? dOutVoice_ : nullptr;   // outputs and taps belong to the last stage
+            P.mixPartial = (last && mix) ? dPartial_ : nullptr;
+            std::pair<cudaEvent_t, cudaEvent_t> ev{nullptr, nullptr};
+            if (timeKernels_) {
+                if (!eventPool_.empty()) { ev = eventPool_.back(); eventPool_.pop_back(); }
+                else { cudaEventCreate(&ev.first); cudaEventCreate(&ev.second); }
+                cudaEventRecord(ev.first, stream_);
+            }
+            if (!cuda(launch_render_block(P, wpc, opt_.niter, stream_), "render kernel launch")) return rc::CudaError;
+            if (timeKernels_) { cudaEventRecord(ev.second, stream_); timedEvents_.push_back(ev); }
+            ++launches_;
+            if (p.stages.empty()) continue;
+            // K3: the convolvers fed by this stage (ConvolutionNode::process, wasm/Convolve.h:58-85); a call longer
+            // than what is left of the current 512-sample partition is cut like FFTConvolver.cpp:155-203 does
+            for (auto& cv : p.stages[stg].convolves) {
+                auto it = g.nodes.find(cv.node);
+                if (it == g.nodes.end() || !it->second.conv) continue;
+                ConvolverState& cs = *it->second.conv;
+                int offset = 0;
+                while (offset < (int) numSamples) {
+                    const int n = cs.partitions == 0 ? (int) numSamples - offset
+                                                     : std::min((int) numSamples - offset, CONV_BLOCK - cs.fill);
+                    std::pair<cudaEvent_t, cudaEvent_t> ev3{nullptr, nullptr};
+                    if (timeKernels_) {
+                        if (!eventPool_.empty()) { ev3 = eventPool_.back(); eventPool_.pop_back(); }
+                        else { cudaEventCreate(&ev3.first); cudaEventCreate(&ev3.second); }
+                        cudaEventRecord(ev3.first, stream_);
+                    }
+                    if (!cuda(convolver_process_chunk(cs, cv.in, cv.out, blockSize_, offset, n, stream_), "convolver launch")) return rc::CudaError;
+                    if (timeKernels_) { cudaEventRecord(ev3.second, stream_); timedConvEvents_.push_back(ev3); }
+                    ++launches_;
+                    offset += n;
+                }
+            }
         }
-        if (!cuda(launch_render_block(P, wpc, opt_.niter, stream_), "render kernel launch")) return rc::CudaError;
-        if (timeKernels_) { cudaEventRecord(ev.second, stream_); timedEvents_.push_back(ev); }
-        ++launches_;
 
         for (size_t ri = 0; ri < p.rootIds.size(); ++ri) {
             if (!(runMask & (1u << ri))) continue;
@@ -1363,6 +1518,13 @@ double Engine::takeKernelTimeMs(uint64_t* count) {
     }
     if (count) *count = timedEvents_.size();
     timedEvents_.clear();
+    lastConvMs_ = 0.0; lastConvCount_ = timedConvEvents_.size();
+    for (auto& ev : timedConvEvents_) {
+        float ms = 0.0f;
+        if (cudaEventElapsedTime(&ms, ev.first, ev.second) == cudaSuccess) lastConvMs_ += ms;
+        eventPool_.push_back(ev);
+    }
+    timedConvEvents_.clear();
     return total;
 }
 

@@ -95,9 +95,11 @@ struct Program {
     uint32_t* dStateMap = nullptr;
     uint32_t* dParamMap = nullptr;
     bool planOnly = false;
-    // convolution stages: K1 stage k ends at codeOffsets[k+1]; between stages the convolvers run
-    struct Stage { uint32_t codeOffset; std::vector<int32_t> convolveNodes; };
+    // K1 stages: stage k interprets code[stages[k].codeOffset ...]; after it the convolvers of that stage run (K3)
+    struct Conv { int32_t node; float* in; float* out; };
+    struct Stage { uint32_t codeOffset = 0; std::vector<Conv> convolves; };
     std::vector<Stage> stages;
+    std::vector<float*> blockBuffers;     // [Vpad][blockSize] HBM buffers carrying values across stages
     ~Program();
 };
 
@@ -156,6 +158,8 @@ public:
     // Sum of the device durations (ms) of the K1 render kernels launched since the last call, measured with
     // CUDA events recorded on the launching stream (option "time_kernels" = 1). Synchronises the stream.
     double takeKernelTimeMs(uint64_t* count);
+    // K3 time/count gathered by the same takeKernelTimeMs() call
+    double lastConvolveTimeMs(uint64_t* count) const { if (count) *count = lastConvCount_; return lastConvMs_; }
     std::string describe() const;
 
 private:
@@ -169,7 +173,8 @@ private:
     std::string lastError_;
     uint64_t launches_ = 0;
     bool timeKernels_ = false;
-    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> timedEvents_, eventPool_;
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> timedEvents_, timedConvEvents_, eventPool_;
+    double lastConvMs_ = 0.0; uint64_t lastConvCount_ = 0;
 
     // I/O staging
     float* dMix_ = nullptr;          // [MAX_OUT][blockSize]

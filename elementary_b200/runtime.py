@@ -85,6 +85,8 @@ def load_library() -> C.CDLL:
     lib.elem_b200_kernel_launches.argtypes = [C.c_void_p]
     lib.elem_b200_take_kernel_time_ms.restype = C.c_double
     lib.elem_b200_take_kernel_time_ms.argtypes = [C.c_void_p, C.POINTER(C.c_uint64)]
+    lib.elem_b200_last_convolve_time_ms.restype = C.c_double
+    lib.elem_b200_last_convolve_time_ms.argtypes = [C.c_void_p, C.POINTER(C.c_uint64)]
     lib.elem_b200_last_error.restype = C.c_char_p
     lib.elem_b200_last_error.argtypes = [C.c_void_p]
     lib.elem_b200_describe_return_code.restype = C.c_char_p
@@ -266,6 +268,12 @@ class Runtime:
         """(summed device ms of the K1 launches since the last call, number of launches); needs time_kernels=1."""
         n = C.c_uint64(0)
         ms = self._lib.elem_b200_take_kernel_time_ms(self._h, C.byref(n))
+        return float(ms), int(n.value)
+
+    def last_convolve_time_ms(self):
+        """(summed device ms of the K3 launches, count) gathered by the latest take_kernel_time_ms()."""
+        n = C.c_uint64(0)
+        ms = self._lib.elem_b200_last_convolve_time_ms(self._h, C.byref(n))
         return float(ms), int(n.value)
 
     def last_error(self) -> str:

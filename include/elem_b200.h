@@ -101,6 +101,8 @@ uint64_t elem_b200_kernel_launches(elem_b200_runtime* rt);
  * stream; this returns the summed device time (ms) of the launches since the previous call and their count.
  * Synchronises the stream. */
 double elem_b200_take_kernel_time_ms(elem_b200_runtime* rt, uint64_t* count);
+/* Same for the K3 convolver launches, as gathered by the most recent elem_b200_take_kernel_time_ms() call. */
+double elem_b200_last_convolve_time_ms(elem_b200_runtime* rt, uint64_t* count);
 const char* elem_b200_last_error(elem_b200_runtime* rt);
 /* ReturnCode::describe — runtime/elem/Types.h:62-85 */
 const char* elem_b200_describe_return_code(int code);
