@@ -132,19 +132,24 @@ def random_graph(seed: int, nodes: int = 64) -> List[list]:
     uid[0] += 1
     pool.append(el.sub(el.mul(kconst(2.0), el.rand(seed=(seed * 7919 + uid[0]) & 0x7FFFFFFF, key=f"g{seed}r{uid[0]}")), kconst(1.0)))
 
-    def count(n: el.Node, seen: set) -> int:
+    def reachable(n: el.Node, seen: set) -> None:
         if n.id() in seen:
-            return 0
+            return
         seen.add(n.id())
-        return 1 + sum(count(c, seen) for c in n.children)
+        for c in n.children:
+            reachable(c, seen)
+
+    def output_graph() -> el.Node:
+        return el.tanh(el.mul(kconst(0.25), el.add(*pool[-4:])))
 
     ops = ["sin", "tanh", "add", "sub", "mul", "min", "max", "pole", "svf", "biquad", "z", "sdelay", "delay",
            "phasor", "rand", "abs", "mm1p"]
     while True:
         seen: set = set()
-        total = sum(count(n, seen) for n in pool[-8:])
-        total = len(seen)
-        if total >= nodes - 2:
+        saved = uid[0]
+        reachable(output_graph(), seen)
+        uid[0] = saved                      # the probe must not consume const keys
+        if len(seen) + 1 >= nodes:          # + the root
             break
         op = r.pick(ops)
         a = r.pick(pool)
@@ -184,5 +189,4 @@ def random_graph(seed: int, nodes: int = 64) -> List[list]:
             n = el.rand(seed=(seed * 104729 + uid[0]) & 0x7FFFFFFF, key=f"g{seed}r{uid[0]}")
         pool.append(n)
 
-    out = el.mul(kconst(0.25), el.add(*pool[-4:]))
-    return el.render(el.tanh(out))
+    return el.render(output_graph())

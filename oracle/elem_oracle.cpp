@@ -70,6 +70,180 @@ struct Fade {
     }
 };
 
+
+// ---- wasm/FFTConvolver restated ------------------------------------------------------------------------------
+// Real FFT with float I/O computed in double (AudioFFT.cpp:132-176 does the same with Ooura's rdft; any exact
+// double-precision DFT gives the same values to ~1e-16, i.e. identical floats except on rounding ties).
+struct RealFFT {
+    size_t n = 0;
+    std::vector<double> cosT, sinT;
+    void init(size_t size) {
+        n = size;
+        cosT.resize(n / 2); sinT.resize(n / 2);
+        for (size_t k = 0; k < n / 2; ++k) { cosT[k] = std::cos(2.0 * M_PI * (double) k / (double) n); sinT[k] = std::sin(2.0 * M_PI * (double) k / (double) n); }
+    }
+    void transform(std::vector<double>& re, std::vector<double>& im, bool inverse) const {
+        for (size_t i = 1, j = 0; i < n; ++i) {
+            size_t bit = n >> 1;
+            for (; j & bit; bit >>= 1) j ^= bit;
+            j ^= bit;
+            if (i < j) { std::swap(re[i], re[j]); std::swap(im[i], im[j]); }
+        }
+        for (size_t len = 2; len <= n; len <<= 1) {
+            const size_t step = n / len;
+            for (size_t i = 0; i < n; i += len)
+                for (size_t k = 0; k < len / 2; ++k) {
+                    const double wr = cosT[k * step], wi = inverse ? sinT[k * step] : -sinT[k * step];
+                    const double xr = re[i + k + len / 2] * wr - im[i + k + len / 2] * wi;
+                    const double xi = re[i + k + len / 2] * wi + im[i + k + len / 2] * wr;
+                    re[i + k + len / 2] = re[i + k] - xr; im[i + k + len / 2] = im[i + k] - xi;
+                    re[i + k] += xr; im[i + k] += xi;
+                }
+        }
+    }
+    void fft(const float* data, float* ore, float* oim) const {       // AudioFFT::fft: n reals -> n/2+1 bins
+        std::vector<double> re(data, data + n), im(n, 0.0);
+        transform(re, im, false);
+        for (size_t k = 0; k <= n / 2; ++k) { ore[k] = (float) re[k]; oim[k] = (float) im[k]; }
+    }
+    void ifft(float* data, const float* ire, const float* iim) const { // AudioFFT::ifft: n/2+1 bins -> n reals (normalised)
+        std::vector<double> re(n), im(n);
+        for (size_t k = 0; k <= n / 2; ++k) { re[k] = ire[k]; im[k] = iim[k]; }
+        for (size_t k = n / 2 + 1; k < n; ++k) { re[k] = ire[n - k]; im[k] = -(double) iim[n - k]; }
+        transform(re, im, true);
+        for (size_t i = 0; i < n; ++i) data[i] = (float) (re[i] / (double) n);
+    }
+};
+
+struct Spectrum { std::vector<float> re, im; void resize(size_t n) { re.assign(n, 0.0f); im.assign(n, 0.0f); } };
+
+// Utilities.cpp:66-117 (scalar branch)
+static void cmac(Spectrum& r, const Spectrum& a, const Spectrum& b) {
+    for (size_t i = 0; i < r.re.size(); ++i) {
+        r.re[i] += a.re[i] * b.re[i] - a.im[i] * b.im[i];
+        r.im[i] += a.re[i] * b.im[i] + a.im[i] * b.re[i];
+    }
+}
+
+static size_t nextPow2(size_t v) { size_t p = 1; while (p < v) p *= 2; return p; }   // Utilities.h:288-296
+
+// FFTConvolver.cpp:85-204 — uniformly partitioned overlap-add convolution with zero latency
+struct FFTConv {
+    size_t blockSize = 0, segSize = 0, segCount = 0, bins = 0, current = 0, fill = 0;
+    std::vector<Spectrum> segs, segsIR;
+    std::vector<float> fftBuffer, overlap, inputBuffer;
+    Spectrum pre, conv;
+    RealFFT fft;
+
+    void init(size_t bs, const float* ir, size_t irLen) {                          // :85-144
+        *this = FFTConv();
+        if (bs == 0) return;
+        while (irLen > 0 && std::fabs(ir[irLen - 1]) < 0.000001f) --irLen;         // :94-98
+        if (irLen == 0) return;
+        blockSize = nextPow2(bs);
+        segSize = 2 * blockSize;
+        segCount = (size_t) std::ceil((float) irLen / (float) blockSize);
+        bins = segSize / 2 + 1;
+        fft.init(segSize);
+        fftBuffer.assign(segSize, 0.0f);
+        segs.resize(segCount); segsIR.resize(segCount);
+        for (size_t i = 0; i < segCount; ++i) {
+            segs[i].resize(bins); segsIR[i].resize(bins);
+            const size_t remaining = irLen - i * blockSize;
+            const size_t sizeCopy = remaining >= blockSize ? blockSize : remaining;
+            std::fill(fftBuffer.begin(), fftBuffer.end(), 0.0f);                   // CopyAndPad
+            std::copy_n(ir + i * blockSize, sizeCopy, fftBuffer.begin());
+            fft.fft(fftBuffer.data(), segsIR[i].re.data(), segsIR[i].im.data());
+        }
+        pre.resize(bins); conv.resize(bins);
+        overlap.assign(blockSize, 0.0f);
+        inputBuffer.assign(blockSize, 0.0f);
+    }
+
+    void process(const float* input, float* output, size_t len) {                  // :147-204
+        if (segCount == 0) { std::fill_n(output, len, 0.0f); return; }
+        size_t processed = 0;
+        while (processed < len) {
+            const bool wasEmpty = fill == 0;
+            const size_t processing = std::min(len - processed, blockSize - fill);
+            const size_t pos = fill;
+            std::copy_n(input + processed, processing, inputBuffer.begin() + pos);
+            std::fill(fftBuffer.begin(), fftBuffer.end(), 0.0f);
+            std::copy_n(inputBuffer.begin(), blockSize, fftBuffer.begin());
+            fft.fft(fftBuffer.data(), segs[current].re.data(), segs[current].im.data());
+            if (wasEmpty) {
+                pre.resize(bins);
+                for (size_t i = 1; i < segCount; ++i) cmac(pre, segsIR[i], segs[(current + i) % segCount]);
+            }
+            conv = pre;
+            cmac(conv, segs[current], segsIR[0]);
+            fft.ifft(fftBuffer.data(), conv.re.data(), conv.im.data());
+            for (size_t i = 0; i < processing; ++i) output[processed + i] = fftBuffer[pos + i] + overlap[pos + i];   // Sum
+            fill += processing;
+            if (fill == blockSize) {
+                std::fill(inputBuffer.begin(), inputBuffer.end(), 0.0f);
+                fill = 0;
+                std::copy_n(fftBuffer.begin() + blockSize, blockSize, overlap.begin());
+                current = current > 0 ? current - 1 : segCount - 1;
+            }
+            processed += processing;
+        }
+    }
+};
+
+// TwoStageFFTConvolver.cpp:74-237 — head (short blocks) + two tail stages whose results are delayed by one / two
+// tail blocks; the tail convolution runs inline (doBackgroundProcessing, :234-237)
+struct TwoStageConv {
+    size_t headBlock = 0, tailBlock = 0, tailInputFill = 0, precalculatedPos = 0;
+    FFTConv head, tail0, tail;
+    std::vector<float> tailOutput0, tailPre0, tailOutput, tailPre, tailInput, bgInput;
+
+    void init(size_t hb, size_t tb, const float* ir, size_t irLen) {               // :74-135
+        *this = TwoStageConv();
+        if (hb == 0 || tb == 0) return;
+        if (hb > tb) std::swap(hb, tb);
+        while (irLen > 0 && std::fabs(ir[irLen - 1]) < 0.000001f) --irLen;
+        if (irLen == 0) return;
+        headBlock = nextPow2(hb); tailBlock = nextPow2(tb);
+        head.init(headBlock, ir, std::min(irLen, tailBlock));
+        if (irLen > tailBlock) {
+            tail0.init(headBlock, ir + tailBlock, std::min(irLen - tailBlock, tailBlock));
+            tailOutput0.assign(tailBlock, 0.0f); tailPre0.assign(tailBlock, 0.0f);
+        }
+        if (irLen > 2 * tailBlock) {
+            tail.init(tailBlock, ir + 2 * tailBlock, irLen - 2 * tailBlock);
+            tailOutput.assign(tailBlock, 0.0f); tailPre.assign(tailBlock, 0.0f); bgInput.assign(tailBlock, 0.0f);
+        }
+        if (!tailPre0.empty() || !tailPre.empty()) tailInput.assign(tailBlock, 0.0f);
+    }
+
+    void process(const float* input, float* output, size_t len) {                  // :138-220
+        head.process(input, output, len);
+        if (tailInput.empty()) return;
+        size_t processed = 0;
+        while (processed < len) {
+            const size_t processing = std::min(len - processed, headBlock - (tailInputFill % headBlock));
+            if (!tailPre0.empty()) for (size_t i = 0; i < processing; ++i) output[processed + i] += tailPre0[precalculatedPos + i];
+            if (!tailPre.empty()) for (size_t i = 0; i < processing; ++i) output[processed + i] += tailPre[precalculatedPos + i];
+            precalculatedPos += processing;
+            std::copy_n(input + processed, processing, tailInput.begin() + tailInputFill);
+            tailInputFill += processing;
+            if (!tailPre0.empty() && tailInputFill % headBlock == 0) {
+                const size_t off = tailInputFill - headBlock;
+                tail0.process(tailInput.data() + off, tailOutput0.data() + off, headBlock);
+                if (tailInputFill == tailBlock) tailPre0.swap(tailOutput0);
+            }
+            if (!tailPre.empty() && tailInputFill == tailBlock) {
+                tailPre.swap(tailOutput);
+                bgInput = tailInput;
+                tail.process(bgInput.data(), tailOutput.data(), tailBlock);
+            }
+            if (tailInputFill == tailBlock) { tailInputFill = 0; precalculatedPos = 0; }
+            processed += processing;
+        }
+    }
+};
+
 struct PropValue {
     char kind = 'N';   // N number, S string, B bool, J other json
     double num = 0;
@@ -102,6 +276,7 @@ struct Node {
     std::string tapName;
     std::vector<float> tapPrivate;
     std::shared_ptr<Resource> res, pendingRes;
+    std::shared_ptr<TwoStageConv> conv, pendingConv;   // convolve (wasm/Convolve.h)
 };
 
 struct RootSeq { int32_t root; std::vector<int32_t> order; std::vector<int32_t> tapOuts; };
@@ -124,7 +299,7 @@ struct Engine {
             "le", "leq", "ge", "geq", "pow", "eq", "and", "or", "add", "sub", "mul", "div", "mod", "min", "max",
             "root", "const", "phasor", "sphasor", "sr", "counter", "accum", "latch", "maxhold", "rand",
             "delay", "sdelay", "z", "pole", "env", "biquad", "prewarp", "mm1p", "svf", "svfshelf",
-            "tapIn", "tapOut", "table", "blepsaw", "blepsquare", "bleptriangle", "meter", "scope"};
+            "tapIn", "tapOut", "table", "blepsaw", "blepsquare", "bleptriangle", "meter", "scope", "convolve"};
         return k.count(t) > 0;
     }
 
@@ -197,6 +372,14 @@ struct Engine {
             if (!isStr) return 5;
             n.tapName = v.str;
             if (!taps.count(v.str)) taps[v.str].assign(bs, 0.0f);
+        }
+        if (t == "convolve" && key == "path") {                                                             // wasm/Convolve.h:35-56
+            if (!isStr) return 5;
+            auto r = resources.find(v.str);
+            if (r == resources.end()) return 6;
+            auto co = std::make_shared<TwoStageConv>();
+            co->init(512, 4096, r->second->data.data(), r->second->data.size());
+            n.pendingConv = co;
         }
         if (t == "table" && key == "path") {                                                                // Table.h:20-34
             if (!isStr) return 5;
@@ -564,6 +747,12 @@ void Engine::processNode(Node& n, const float* const* hostIn, int nHostIn, int n
             if (n.phase >= 1.0f) n.phase -= 1.0f;
             out[i] = y;
         }
+        return;
+    }
+    if (t == "convolve") {   // wasm/Convolve.h:58-85
+        if (n.pendingConv) { n.conv = n.pendingConv; n.pendingConv.reset(); }
+        if (nch == 0 || !n.conv) return zeros();
+        n.conv->process(in[0], out, (size_t) ns);
         return;
     }
     if (t == "tapIn") {   // Feedback.h:42-52

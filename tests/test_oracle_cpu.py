@@ -108,3 +108,50 @@ def test_return_codes(cls):
     assert r.apply([[2, 5, 6, 0]]) == 2                         # NodeNotFound
     assert r.apply([[0, 3, "const"], [3, 3, "value", "x"]]) == 5   # InvalidPropertyType
     assert r.apply([[0, 4, "table"], [3, 4, "path", "missing"]]) == 6   # InvalidPropertyValue
+
+
+# ---- convolve (wasm/Convolve.h + wasm/FFTConvolver): the restatement uses its own double-precision FFT instead of
+# Ooura's, so agreement with the compiled reference is to float rounding (1 ulp), not bit-for-bit; both are pinned
+# against an exact double-precision convolution exactly like the reference's own self-test does
+# (wasm/FFTConvolver/test/Test.cpp:82-140, 58 cases against a naive O(N*M) convolution).
+@pytest.mark.parametrize("cls", _checkers(), ids=lambda c: c.__name__)
+@pytest.mark.parametrize("taps,blocks", [(1, 4), (300, 6), (512, 6), (513, 6), (4096, 20), (4097, 22), (9000, 30), (16384, 40)])
+def test_convolve_against_exact_convolution(cls, taps, blocks):
+    ir = np.asarray(graphs.lcg_ir(16384)[:taps], dtype=np.float32) * 2.0
+    rng = np.random.RandomState(taps)
+    x = ((rng.rand(1, blocks * BS) - 0.5) * 0.5).astype(np.float32)
+    r = cls(SR, BS)
+    assert r.add_shared_resource("ir", ir) and r.apply(graphs.convolve_channel("ir")) == 0
+    got = r.render(blocks, 1, BS, x)[0]
+    want = np.convolve(x[0].astype(np.float64), ir.astype(np.float64))[: blocks * BS]
+    peak = np.abs(want).max()
+    assert np.abs(got[2 * BS:] - want[2 * BS:]).max() <= 1e-6 * peak      # after the 20 ms root fade-in
+
+
+@needs_ref
+@pytest.mark.parametrize("taps", [300, 5000, 16384])
+def test_convolve_port_matches_reference_to_float_rounding(taps):
+    ir = np.asarray(graphs.lcg_ir(16384)[:taps], dtype=np.float32)
+    rng = np.random.RandomState(3)
+    x = ((rng.rand(1, 36 * BS) - 0.5) * 0.5).astype(np.float32)
+    outs = []
+    for cls in (orc.PortRuntime, orc.RefRuntime):
+        r = cls(SR, BS)
+        assert r.add_shared_resource("ir", ir) and r.apply(graphs.convolve_channel("ir")) == 0
+        outs.append(r.render(36, 1, BS, x))
+    assert np.abs(outs[0] - outs[1]).max() <= 5e-7 * np.abs(outs[1]).max()
+
+
+@pytest.mark.parametrize("cls", _checkers(), ids=lambda c: c.__name__)
+def test_convolve_varying_call_lengths_is_still_a_plain_convolution(cls):
+    ir = np.asarray(graphs.lcg_ir(2000), dtype=np.float32) * 2.0
+    r = cls(SR, BS)
+    assert r.add_shared_resource("ir", ir) and r.apply(graphs.convolve_channel("ir")) == 0
+    rng = np.random.RandomState(9)
+    xs, ys = [], []
+    for n in [512, 512, 512, 7, 100, 512, 405, 1, 333, 512, 512]:
+        x = ((rng.rand(1, n) - 0.5) * 0.5).astype(np.float32)
+        xs.append(x[0]); ys.append(r.process(x, 1, n)[0])
+    x, y = np.concatenate(xs), np.concatenate(ys)
+    want = np.convolve(x.astype(np.float64), ir.astype(np.float64))[: len(x)]
+    assert np.abs(y[1536:] - want[1536:]).max() <= 1e-6 * np.abs(want).max()
