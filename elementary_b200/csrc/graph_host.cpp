@@ -163,6 +163,7 @@ Engine::~Engine() {
     if (dInVoice_) dfree(dInVoice_);
     if (dInShared_) dfree(dInShared_);
     if (hPinned_ && !planOnly_) cudaFreeHost(hPinned_);
+    for (auto& kv : batch_) { if (kv.second.dDescs) dfree(kv.second.dDescs); if (kv.second.dTileStart) dfree(kv.second.dTileStart); }
     for (auto& ev : timedEvents_) { cudaEventDestroy(ev.first); cudaEventDestroy(ev.second); }
     for (auto& ev : eventPool_) { cudaEventDestroy(ev.first); cudaEventDestroy(ev.second); }
     if (ownStream_ && stream_) cudaStreamDestroy(stream_);
@@ -180,6 +181,7 @@ int Engine::setOption(const char* key, double value) {
     else if (k == "warps_per_cta") { opt_.warpsPerCta = (int) value; }
     else if (k == "target_tiles") { opt_.targetTiles = (int) value; }
     else if (k == "niter") { opt_.niter = (int) value; }
+    else if (k == "batch_groups") { opt_.batchGroups = value != 0; }
     else if (k == "fuse_chains") { opt_.fuseChains = value != 0; }
     else if (k == "time_kernels") { timeKernels_ = value != 0 && !planOnly_; }
     else return rc::BadArgument;
@@ -1393,6 +1395,7 @@ int Engine::enqueueBlock(size_t nIn, size_t nOut, size_t numSamples, bool perVoi
     if (r != rc::Ok) return r;
 
     int tileBase = 0;
+    std::map<int, std::vector<LaunchParams>> buckets;   // tile width -> single-stage groups launched together
     for (auto& gp : groups_) {
         Group& g = *gp;
         const int nTiles = g.nTiles();
@@ -1449,6 +1452,11 @@ int Engine::enqueueBlock(size_t nIn, size_t nOut, size_t numSamples, bool perVoi
         while (wpc > 1 && perWarp * wpc > 200 * 1024) wpc >>= 1;
         if (perWarp > 220 * 1024) return fail(rc::InvariantViolation, "graph state does not fit in shared memory");
         const size_t nStages = std::max<size_t>(1, p.stages.size());
+        if (nStages == 1 && groups_.size() > 1 && opt_.batchGroups) {
+            // heterogeneous voice groups: collect single-stage groups per tile geometry and launch each bucket once
+            P.code = p.dCode + (p.stages.empty() ? 0 : p.stages[0].codeOffset);
+            buckets[g.tileWidth].push_back(P);
+        } else
         for (size_t stg = 0; stg < nStages; ++stg) {
             const bool last = stg + 1 == nStages;
             P.code = p.dCode + (p.stages.empty() ? 0 : p.stages[stg].codeOffset);
@@ -1494,6 +1502,49 @@ int Engine::enqueueBlock(size_t nIn, size_t nOut, size_t numSamples, bool perVoi
             if (it != g.nodes.end()) it->second.fade.advance((int) numSamples);
         }
         tileBase += nTiles;
+    }
+    for (auto& kv : buckets) {
+        auto& descs = kv.second;
+        const int L = kv.first;
+        std::vector<int> tileStart(descs.size());
+        int total = 0, maxSlots = 1, maxState = 0, maxParams = 0;
+        for (size_t i = 0; i < descs.size(); ++i) {
+            tileStart[i] = total;
+            total += (descs[i].nv + L - 1) / L;
+            maxSlots = std::max(maxSlots, descs[i].nSlots);
+            maxState = std::max(maxState, descs[i].nStateRows);
+            maxParams = std::max(maxParams, descs[i].nParams);
+        }
+        // descriptors change only while roots fade or when graphs change: re-upload only then
+        BatchBuffers& bb = batch_[L];
+        const size_t dbytes = descs.size() * sizeof(LaunchParams), tbytes = tileStart.size() * sizeof(int);
+        if (bb.capGroups < descs.size()) {
+            dsync();
+            if (bb.dDescs) dfree(bb.dDescs);
+            if (bb.dTileStart) dfree(bb.dTileStart);
+            bb.capGroups = descs.size() * 2;
+            if (!cuda(dmalloc((void**) &bb.dDescs, bb.capGroups * sizeof(LaunchParams)), "cudaMalloc group descriptors")) return rc::CudaError;
+            if (!cuda(dmalloc((void**) &bb.dTileStart, bb.capGroups * sizeof(int)), "cudaMalloc tile table")) return rc::CudaError;
+            bb.lastDescs.clear();
+        }
+        if (bb.lastDescs.size() != dbytes || std::memcmp(bb.lastDescs.data(), descs.data(), dbytes) != 0) {
+            if (!cuda(cudaMemcpyAsync(bb.dDescs, descs.data(), dbytes, cudaMemcpyHostToDevice, stream_), "upload group descriptors")) return rc::CudaError;
+            if (!cuda(cudaMemcpyAsync(bb.dTileStart, tileStart.data(), tbytes, cudaMemcpyHostToDevice, stream_), "upload tile table")) return rc::CudaError;
+            bb.lastDescs.assign(reinterpret_cast<const char*>(descs.data()), reinterpret_cast<const char*>(descs.data()) + dbytes);
+        }
+        int wpc = opt_.warpsPerCta;
+        if (wpc <= 0) wpc = total >= 148 * 8 ? 4 : (total >= 148 * 4 ? 2 : 1);
+        while (wpc > 1 && render_smem_bytes(maxSlots, (int) nOut, maxState, maxParams, wpc, L, 0) > 200 * 1024) wpc >>= 1;
+        std::pair<cudaEvent_t, cudaEvent_t> ev{nullptr, nullptr};
+        if (timeKernels_) {
+            if (!eventPool_.empty()) { ev = eventPool_.back(); eventPool_.pop_back(); }
+            else { cudaEventCreate(&ev.first); cudaEventCreate(&ev.second); }
+            cudaEventRecord(ev.first, stream_);
+        }
+        if (!cuda(launch_render_groups(bb.dDescs, bb.dTileStart, (int) descs.size(), total, L, maxSlots, (int) nOut, maxState, maxParams, wpc, stream_),
+                  "render groups kernel launch")) return rc::CudaError;
+        if (timeKernels_) { cudaEventRecord(ev.second, stream_); timedEvents_.push_back(ev); }
+        ++launches_;
     }
     if (mix) {
         if (tileBase > 0) {

@@ -121,6 +121,7 @@ struct EngineOptions {
     int warpsPerCta = 0;          // 0 = choose
     int targetTiles = 2048;       // shrink the tile width until about this many warps exist (measured optimum, profiles/)
     int niter = 0;                // 0 = default elements-per-lane per tile; 4 selects the T = 4 variant for L = 32
+    bool batchGroups = true;      // launch all single-stage voice groups of one tile geometry together
     bool fuseChains = true;       // fold runs of element-wise nodes into one OP_CHAIN
 };
 
@@ -184,6 +185,8 @@ private:
     float* dInShared_ = nullptr; size_t inSharedFloats_ = 0;
     float* hPinned_ = nullptr; size_t pinnedFloats_ = 0;
     size_t curNOut_ = 0;
+    struct BatchBuffers { LaunchParams* dDescs = nullptr; int* dTileStart = nullptr; size_t capGroups = 0; std::vector<char> lastDescs; };
+    std::map<int, BatchBuffers> batch_;   // per tile width
 
     bool planOnly_ = false;
     bool cuda(cudaError_t e, const char* what);

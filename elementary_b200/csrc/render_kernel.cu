@@ -109,11 +109,9 @@ __host__ __device__ constexpr int ilog2(int x) { return x <= 1 ? 0 : 1 + ilog2(x
 } // namespace
 
 // =========================================================================================================
+// The whole per-tile interpreter; instantiated by the two thin __global__ wrappers at the end of this section.
 template <int NITER, int LOGL>
-// Occupancy target (measured, profiles/r01_d_occupancy_ab.txt): the full-width geometry (L = 32, every lane a voice)
-// is issue-latency bound and gains 20 % from 64-register / 8-CTA occupancy; the narrow geometries run few warps
-// anyway and prefer the 128-register budget.
-__global__ void __launch_bounds__(128, (LOGL == 5) ? 8 : 4) render_block_kernel(const __grid_constant__ LaunchParams P) {
+__device__ __forceinline__ void render_tile(const LaunchParams& P, const int tile, const int perWarp) {
     constexpr int L = 1 << LOGL;          // voices per warp
     constexpr int E = 32 * NITER;         // elements per sample tile
     constexpr int T = E >> LOGL;          // samples per tile
@@ -121,12 +119,8 @@ __global__ void __launch_bounds__(128, (LOGL == 5) ? 8 : 4) render_block_kernel(
     constexpr int PER = 32 >> LOGL;       // samples of one voice inside one 32-element slice
     extern __shared__ __align__(16) float smem[];
 
-    const int warpsPerCta = blockDim.x >> 5;
     const int warpInCta = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
-    const int nTiles = (P.nv + L - 1) >> LOGL;
-    const int tile = blockIdx.x * warpsPerCta + warpInCta;
-    if (tile >= nTiles) return;           // whole warp leaves together
 
     const int vlane = lane & (L - 1);     // the voice column this lane works for
     const int voice = tile * L + vlane;   // may be a padding voice (>= nv): it owns storage but is never output
@@ -134,7 +128,6 @@ __global__ void __launch_bounds__(128, (LOGL == 5) ? 8 : 4) render_block_kernel(
     const bool owner = lane < L;          // this lane runs the recurrences of `voice`
     const int tlane = lane >> LOGL;       // sample index of this lane's element inside slice 0
 
-    const int perWarp = ((P.nSlots + P.nOut) * E + (P.nStateRows + P.nParams + 1) * L + 3) & ~3;
     float* const slots = smem + (size_t) warpInCta * perWarp;
     float* const outacc = slots + P.nSlots * E;
     float* const sst = outacc + P.nOut * E;
@@ -851,6 +844,35 @@ __global__ void __launch_bounds__(128, (LOGL == 5) ? 8 : 4) render_block_kernel(
 #undef FOR_OWNER
 }
 
+// Occupancy target (measured, profiles/r01_d_occupancy_ab.txt): the full-width geometry (L = 32, every lane a voice)
+// is issue-latency bound and gains 20 % from 64-register / 8-CTA occupancy; the narrow geometries run few warps
+// anyway and prefer the 128-register budget.
+#define EB_BOUNDS __launch_bounds__(128, (LOGL == 5) ? 8 : 4)
+
+// One voice group per launch: the descriptor travels in the constant bank.
+template <int NITER, int LOGL>
+__global__ void EB_BOUNDS render_block_kernel(const __grid_constant__ LaunchParams P, const int perWarp) {
+    const int tile = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (tile >= ((P.nv + (1 << LOGL) - 1) >> LOGL)) return;   // whole warp leaves together
+    render_tile<NITER, LOGL>(P, tile, perWarp);
+}
+
+// Many voice groups (different graphs) of the same tile geometry in ONE launch: warp w finds its group by binary
+// search in the tile prefix table and reads that group's descriptor from global memory.  This is what makes
+// thousands of small heterogeneous graphs (BASELINE config 5) run concurrently instead of one launch each.
+template <int NITER, int LOGL>
+__global__ void EB_BOUNDS render_groups_kernel(const LaunchParams* __restrict__ descs, const int* __restrict__ tileStart,
+                                                const int nGroups, const int totalTiles, const int perWarp) {
+    const int w = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (w >= totalTiles) return;
+    int lo = 0, hi = nGroups - 1;                      // largest g with tileStart[g] <= w
+    while (lo < hi) {
+        const int mid = (lo + hi + 1) >> 1;
+        if (__ldg(tileStart + mid) <= w) lo = mid; else hi = mid - 1;
+    }
+    render_tile<NITER, LOGL>(descs[lo], w - __ldg(tileStart + lo), perWarp);
+}
+
 // ---- deterministic reduction of the per-tile partial mixes: out[ch][s] = sum over tiles in fixed order ----
 __global__ void __launch_bounds__(1024) mix_reduce_kernel(const float* __restrict__ partial, float* __restrict__ out,
                                                           int nTiles, int nOut, int blockSize, int numSamples) {
@@ -892,7 +914,17 @@ template <int NITER, int LOGL>
 static cudaError_t launch_impl(const LaunchParams& P, int grid, int threads, size_t smem, cudaStream_t stream) {
     cudaError_t e = cudaFuncSetAttribute(render_block_kernel<NITER, LOGL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
     if (e != cudaSuccess) return e;
-    render_block_kernel<NITER, LOGL><<<grid, threads, smem, stream>>>(P);
+    render_block_kernel<NITER, LOGL><<<grid, threads, smem, stream>>>(P, (int) (smem / sizeof(float) / (threads / 32)));
+    return cudaGetLastError();
+}
+
+template <int NITER, int LOGL>
+static cudaError_t launch_groups_impl(const LaunchParams* descs, const int* tileStart, int nGroups, int totalTiles,
+                                      int grid, int threads, size_t smem, cudaStream_t stream) {
+    cudaError_t e = cudaFuncSetAttribute(render_groups_kernel<NITER, LOGL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
+    if (e != cudaSuccess) return e;
+    render_groups_kernel<NITER, LOGL><<<grid, threads, smem, stream>>>(descs, tileStart, nGroups, totalTiles,
+                                                                          (int) (smem / sizeof(float) / (threads / 32)));
     return cudaGetLastError();
 }
 
@@ -911,6 +943,23 @@ cudaError_t launch_render_block(const LaunchParams& P, int warpsPerCta, int nite
         case 4:  return launch_impl<4, 2>(P, grid, threads, smem, stream);
         case 2:  return launch_impl<2, 1>(P, grid, threads, smem, stream);
         default: return launch_impl<1, 0>(P, grid, threads, smem, stream);
+    }
+}
+
+// descs / tileStart are DEVICE pointers; maxSlots etc. are the maxima over the groups (uniform shared-memory carve-up).
+cudaError_t launch_render_groups(const LaunchParams* descs, const int* tileStart, int nGroups, int totalTiles, int tileWidth,
+                                 int maxSlots, int nOut, int maxStateRows, int maxParams, int warpsPerCta, cudaStream_t stream) {
+    if (totalTiles <= 0) return cudaSuccess;
+    const int grid = (totalTiles + warpsPerCta - 1) / warpsPerCta;
+    const int threads = warpsPerCta * 32;
+    const size_t smem = render_smem_bytes(maxSlots, nOut, maxStateRows, maxParams, warpsPerCta, tileWidth, 0);
+    switch (tileWidth) {
+        case 32: return launch_groups_impl<8, 5>(descs, tileStart, nGroups, totalTiles, grid, threads, smem, stream);
+        case 16: return launch_groups_impl<8, 4>(descs, tileStart, nGroups, totalTiles, grid, threads, smem, stream);
+        case 8:  return launch_groups_impl<8, 3>(descs, tileStart, nGroups, totalTiles, grid, threads, smem, stream);
+        case 4:  return launch_groups_impl<4, 2>(descs, tileStart, nGroups, totalTiles, grid, threads, smem, stream);
+        case 2:  return launch_groups_impl<2, 1>(descs, tileStart, nGroups, totalTiles, grid, threads, smem, stream);
+        default: return launch_groups_impl<1, 0>(descs, tileStart, nGroups, totalTiles, grid, threads, smem, stream);
     }
 }
 
