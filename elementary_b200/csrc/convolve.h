@@ -19,22 +19,23 @@ namespace eb {
 constexpr int CONV_BLOCK = 512;          // partition / head block size (Convolve.h:49: init(512, 4096, ...))
 constexpr int CONV_FFT = 1024;           // segment size 2*B (FFTConvolver.cpp:107)
 constexpr int CONV_BINS = 513;           // ComplexSize(1024)
-constexpr int CONV_CH_PER_CTA = 4;       // channels sharing one pass over the IR spectra
+constexpr int CONV_PACKED_BINS = 512;    // stored spectra: bin 0 = (Re X[0], Re X[512]) — both bins are purely real
+constexpr int CONV_CH_PER_CTA = 2;       // channels sharing one pass over the IR spectra (measured: profiles/r01_g_*)
 
 struct ConvolverState {
     int partitions = 0;                  // S
     int nv = 0;                          // channels (voices of the group)
     int cur = 0;                         // FDL slot of the block being filled (decrements per block: FFTConvolver.cpp:200)
     int fill = 0;                        // samples already in the current partition's input buffer (:157-162)
-    float2* dH = nullptr;                // [S][513]   IR partition spectra
-    float2* dFdl = nullptr;              // [nv][S][513] input spectra ring (frequency-domain delay line)
-    float2* dYpre = nullptr;             // [nv][513]  sum over the older partitions, valid while fill > 0 (:168-177)
+    float2* dH = nullptr;                // [S][512]   IR partition spectra (packed)
+    float2* dFdl = nullptr;              // [nv][S][512] input spectra ring (frequency-domain delay line)
+    float2* dYpre = nullptr;             // [nv][512]  sum over the older partitions, valid while fill > 0 (:168-177)
     float* dOverlap = nullptr;           // [nv][512]
     float* dInBuf = nullptr;             // [nv][512]
     float2* dTw = nullptr;               // [512] exp(-2*pi*i*m/1024)
     bool planOnly = false;
     ~ConvolverState();
-    size_t bytesPerChannel() const { return (size_t) partitions * CONV_BINS * 8 + CONV_BINS * 8 + 2 * CONV_BLOCK * 4; }
+    size_t bytesPerChannel() const { return (size_t) partitions * CONV_PACKED_BINS * 8 + CONV_PACKED_BINS * 8 + 2 * CONV_BLOCK * 4; }
 };
 
 // Build the device state for `nv` channels sharing one impulse response. Returns false and fills `err` on failure.
@@ -47,8 +48,8 @@ cudaError_t convolver_process_chunk(ConvolverState& st, const float* in, float* 
 // Algorithmic HBM bytes of one full 512-sample block for one channel.
 inline size_t convolver_algorithmic_bytes_per_channel_block(int partitions) {
     return (size_t) 2 * CONV_BLOCK * 4                         // input read + output write
-         + (size_t) (partitions - 1) * CONV_BINS * 8           // older input spectra read
-         + (size_t) CONV_BINS * 8                              // newest spectrum written
+         + (size_t) (partitions - 1) * CONV_PACKED_BINS * 8    // older input spectra read
+         + (size_t) CONV_PACKED_BINS * 8                       // newest spectrum written
          + (size_t) 2 * CONV_BLOCK * 4;                        // overlap read + write
 }
 

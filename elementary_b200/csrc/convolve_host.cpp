@@ -61,7 +61,7 @@ bool convolver_init(ConvolverState& st, const float* ir, size_t irLen, int nv, b
     if (st.partitions == 0) return true;
     const int S = st.partitions;
 
-    std::vector<float2> H((size_t) S * CONV_BINS);
+    std::vector<float2> H((size_t) S * CONV_PACKED_BINS);
     std::vector<std::complex<double>> buf(CONV_FFT);
     for (int i = 0; i < S; ++i) {
         for (int k = 0; k < CONV_FFT; ++k) {
@@ -69,7 +69,8 @@ bool convolver_init(ConvolverState& st, const float* ir, size_t irLen, int nv, b
             buf[k] = (k < CONV_BLOCK && idx < irLen) ? std::complex<double>((double) ir[idx], 0.0) : std::complex<double>(0.0, 0.0);
         }
         fftDouble(buf);
-        for (int b = 0; b < CONV_BINS; ++b) H[(size_t) i * CONV_BINS + b] = make_float2((float) buf[b].real(), (float) buf[b].imag());
+        for (int b = 1; b < CONV_PACKED_BINS; ++b) H[(size_t) i * CONV_PACKED_BINS + b] = make_float2((float) buf[b].real(), (float) buf[b].imag());
+        H[(size_t) i * CONV_PACKED_BINS] = make_float2((float) buf[0].real(), (float) buf[CONV_BLOCK].real());   // packed (H[0], H[512])
     }
     std::vector<float2> tw(512);
     for (int m = 0; m < 512; ++m) {
@@ -79,8 +80,8 @@ bool convolver_init(ConvolverState& st, const float* ir, size_t irLen, int nv, b
 
     if (!allocDev((void**) &st.dH, H.size() * sizeof(float2), planOnly, stream, err)) return false;
     if (!allocDev((void**) &st.dTw, tw.size() * sizeof(float2), planOnly, stream, err)) return false;
-    if (!allocDev((void**) &st.dFdl, (size_t) nv * S * CONV_BINS * sizeof(float2), planOnly, stream, err)) return false;
-    if (!allocDev((void**) &st.dYpre, (size_t) nv * CONV_BINS * sizeof(float2), planOnly, stream, err)) return false;
+    if (!allocDev((void**) &st.dFdl, (size_t) nv * S * CONV_PACKED_BINS * sizeof(float2), planOnly, stream, err)) return false;
+    if (!allocDev((void**) &st.dYpre, (size_t) nv * CONV_PACKED_BINS * sizeof(float2), planOnly, stream, err)) return false;
     if (!allocDev((void**) &st.dOverlap, (size_t) nv * CONV_BLOCK * sizeof(float), planOnly, stream, err)) return false;
     if (!allocDev((void**) &st.dInBuf, (size_t) nv * CONV_BLOCK * sizeof(float), planOnly, stream, err)) return false;
     if (planOnly) {

@@ -23,6 +23,7 @@ __device__ __forceinline__ float2 csub(float2 a, float2 b) { return make_float2(
 __device__ __forceinline__ float2 cconj(float2 a) { return make_float2(a.x, -a.y); }
 
 constexpr int CH = CONV_CH_PER_CTA;
+constexpr int NB = CONV_PACKED_BINS;   // 512: bin 0 carries (Re X[0], Re X[512]) — both are purely real
 constexpr int N2 = 512;   // complex FFT length
 
 // 9 Stockham radix-2 stages over CH independent 512-point transforms; 256 threads = one butterfly per thread per
@@ -58,7 +59,6 @@ __global__ void __launch_bounds__(256) convolve_chunk_kernel(
     __shared__ float2 A[CH][N2];
     __shared__ float2 B[CH][N2];
     __shared__ float2 tw[N2];
-    __shared__ float2 nyq[CH];    // bin 512 of the current spectrum / product
 
     const int tid = threadIdx.x;
     const int ch0 = blockIdx.x * CH;
@@ -86,12 +86,12 @@ __global__ void __launch_bounds__(256) convolve_chunk_kernel(
     }
     __syncthreads();
 
-    // 2. forward transform: Z = FFT512(z) lands in B; split into the 513 bins of the real FFT (written to A / nyq)
+    // 2. forward transform: Z = FFT512(z) lands in B; split into the bins of the real FFT, bin 512 packed into bin 0 (written to A)
     fft512<false>(A, B, tw, tid);
 #pragma unroll
     for (int c = 0; c < CH; ++c) {
         const int ch = ch0 + c;
-        float2* slot = fdl + ((size_t) ch * S + cur) * CONV_BINS;
+        float2* slot = fdl + ((size_t) ch * S + cur) * NB;
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
             const int k = tid + h * 256;
@@ -100,66 +100,70 @@ __global__ void __launch_bounds__(256) convolve_chunk_kernel(
             const float2 e = make_float2(0.5f * (zk.x + zn.x), 0.5f * (zk.y + zn.y));
             const float2 d = csub(zk, zn);
             const float2 o = make_float2(0.5f * d.y, -0.5f * d.x);      // -0.5i * (zk - zn)
-            const float2 x = cadd(e, cmul(tw[k], o));
+            float2 x = cadd(e, cmul(tw[k], o));
+            if (k == 0) x = make_float2(e.x + o.x, e.x - o.x);          // packed: (X[0], X[512]) = (E0 + O0, E0 - O0), both real
             A[c][k] = x;
             if (ch < nv) slot[k] = x;
-            if (k == 0) {                                                 // bin 512: E[0] - O[0]
-                const float2 xn = csub(e, o);
-                nyq[c] = xn;
-                if (ch < nv) slot[N2] = xn;
-            }
         }
     }
     __syncthreads();
 
-    // 3./4. frequency-domain delay line: Y[b] = sum_i H_i[b] * X_{cur+i}[b]; the older partitions only once per block
-    for (int b = tid; b < CONV_BINS; b += 256) {
+    // 3./4. frequency-domain delay line: Y[b] = sum_i H_i[b] * X_{cur+i}[b]; the older partitions only once per block.
+    // Bin 0 is the packed pair of real bins and multiplies component-wise.
+#pragma unroll
+    for (int hh = 0; hh < 2; ++hh) {
+        const int b = tid + hh * 256;
         float2 acc[CH];
         if (fill == 0) {
 #pragma unroll
             for (int c = 0; c < CH; ++c) acc[c] = make_float2(0.0f, 0.0f);
 #pragma unroll 4
             for (int i = 1; i < S; ++i) {
-                const float2 h = __ldg(H + (size_t) i * CONV_BINS + b);
+                const float2 h = __ldg(H + (size_t) i * NB + b);
                 int slotIdx = cur + i;
                 if (slotIdx >= S) slotIdx -= S;
 #pragma unroll
                 for (int c = 0; c < CH; ++c) {
                     const int ch = ch0 + c;
                     if (ch < nv) {
-                        const float2 x = fdl[((size_t) ch * S + slotIdx) * CONV_BINS + b];
-                        acc[c] = cadd(acc[c], cmul(h, x));
+                        const float2 x = fdl[((size_t) ch * S + slotIdx) * NB + b];
+                        acc[c] = (b == 0) ? make_float2(acc[c].x + h.x * x.x, acc[c].y + h.y * x.y) : cadd(acc[c], cmul(h, x));
                     }
                 }
             }
 #pragma unroll
-            for (int c = 0; c < CH; ++c) if (ch0 + c < nv) ypre[(size_t) (ch0 + c) * CONV_BINS + b] = acc[c];
+            for (int c = 0; c < CH; ++c) if (ch0 + c < nv) ypre[(size_t) (ch0 + c) * NB + b] = acc[c];
         } else {
 #pragma unroll
-            for (int c = 0; c < CH; ++c) acc[c] = (ch0 + c < nv) ? ypre[(size_t) (ch0 + c) * CONV_BINS + b] : make_float2(0.0f, 0.0f);
+            for (int c = 0; c < CH; ++c) acc[c] = (ch0 + c < nv) ? ypre[(size_t) (ch0 + c) * NB + b] : make_float2(0.0f, 0.0f);
         }
         const float2 h0 = __ldg(H + b);
 #pragma unroll
         for (int c = 0; c < CH; ++c) {
-            const float2 x = (b < N2) ? A[c][b] : nyq[c];
-            const float2 y = cadd(acc[c], cmul(x, h0));
-            if (b < N2) B[c][b] = y; else nyq[c] = y;
+            const float2 x = A[c][b];
+            B[c][b] = (b == 0) ? make_float2(acc[c].x + x.x * h0.x, acc[c].y + x.y * h0.y) : cadd(acc[c], cmul(x, h0));
         }
     }
     __syncthreads();
 
-    // inverse split: Zi[k] = E[k] + i*O[k] from Y[k], conj(Y[512-k])  (reads B / nyq, writes A)
+    // inverse split: Zi[k] = E[k] + i*O[k] from Y[k], conj(Y[512-k])  (reads B, writes A)
 #pragma unroll
     for (int c = 0; c < CH; ++c) {
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
             const int k = tid + h * 256;
             const float2 yk = B[c][k];
-            const float2 yn = cconj(k == 0 ? nyq[c] : B[c][N2 - k]);
-            const float2 e = make_float2(0.5f * (yk.x + yn.x), 0.5f * (yk.y + yn.y));
-            const float2 d = make_float2(0.5f * (yk.x - yn.x), 0.5f * (yk.y - yn.y));
-            const float2 o = cmul(d, cconj(tw[k]));
-            A[c][k] = make_float2(e.x - o.y, e.y + o.x);                 // e + i*o
+            float2 z;
+            if (k == 0) {                                                 // packed (Y0, Y512): E0 = (Y0+Y512)/2, O0 = (Y0-Y512)/2
+                z = make_float2(0.5f * (yk.x + yk.y), 0.5f * (yk.x - yk.y));
+            } else {
+                const float2 yn = cconj(B[c][N2 - k]);
+                const float2 e = make_float2(0.5f * (yk.x + yn.x), 0.5f * (yk.y + yn.y));
+                const float2 d = make_float2(0.5f * (yk.x - yn.x), 0.5f * (yk.y - yn.y));
+                const float2 o = cmul(d, cconj(tw[k]));
+                z = make_float2(e.x - o.y, e.y + o.x);                    // e + i*o
+            }
+            A[c][k] = z;
         }
     }
     __syncthreads();
