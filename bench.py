@@ -224,6 +224,9 @@ def run_b200(args, rank, local_rank, world):
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dev_ms, e2e_ms = float(t[0]), float(t[1])
+        if world > 1:
+            dist.barrier()
+            dist.destroy_process_group()
 
     if rank != 0:
         return
@@ -262,10 +265,10 @@ def run_b200(args, rank, local_rank, world):
                 "ms_per_step": e2e_ms / args.steps, "api": "elem_b200_process (host out buffers)" if world == 1 else "elem_b200_enqueue_block + NCCL all_reduce + D2H of the mix bus"},
         "gpu_launches": int(launches),
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": None, "peak_kind": f"of {peak_kind}", "kernel": "render_block_kernel<8>",
+                     "traffic": None, "peak_kind": f"of {peak_kind}", "kernel": "render_block_kernel<NITER,LOGL> (K1)",
                      "kernel_ms": k1_avg_ms, "kernel_launches_timed": k1_n,
                      "algorithmic_bytes_per_launch": algo_bytes,
-                     "note": "K1 is FP64/latency-bound at 4096 voices (one voice per warp); see DESIGN.md §4"},
+                     "note": "K1 is instruction-issue bound, not HBM bound (intermediates never leave the SM); see DESIGN.md section 4"},
         "clocks": clocks,
         "cpu_baseline": cpu,
     }

@@ -1054,6 +1054,33 @@ int Engine::compile(Group& g, int nIn, std::shared_ptr<Program>& out) {
             i0 = segEnd;
         }
         ops.swap(sched);
+
+        // ---- group independent constant-frequency phasors into runs ----------------------------------------------
+        // A phasor fed by a parameter depends on nothing, so it may run anywhere in its segment.  With L < 32 voices
+        // per warp only L lanes work in a recurrence; a run of R <= 32/L such phasors is executed by R lane groups
+        // in one serial loop (render_kernel.cu, OP_PHASOR with aux1 = R).  Followers are pulled forward to sit
+        // right behind the leader; the look-ahead is bounded so live ranges stay short.
+        bool staged = false;   // programs cut into stages (convolve) insert spill ops between ops: keep them ungrouped
+        for (auto& op : ops) if (op.opcode == 0xF0) staged = true;
+        const int maxRun = staged ? 1 : std::min(8, 32 / std::max(1, g.tileWidth));
+        auto isParamPhasor = [](const Compiler::PendingOp& op) {
+            return !op.isSeg && op.opcode == OP_PHASOR && op.operands.size() == 1 && op.operands[0].first != K_SLOT;
+        };
+        for (size_t i = 0; i < ops.size(); ++i) {
+            if (!isParamPhasor(ops[i]) || ops[i].aux1 != 0 || ops[i].mode == 1) continue;
+            size_t segEnd = ops.size();
+            for (size_t k = i + 1; k < ops.size(); ++k) if (ops[k].isSeg) { segEnd = k; break; }
+            uint32_t run = 1;
+            for (size_t j = i + 1; j < segEnd && j < i + 1 + (size_t) 4 * maxRun && (int) run < maxRun; ++j) {
+                if (!isParamPhasor(ops[j]) || ops[j].mode == 1) continue;
+                Compiler::PendingOp follower = ops[j];
+                follower.mode = 1;                     // marks "member of a run" (never dispatched on its own)
+                ops.erase(ops.begin() + (long) j);
+                ops.insert(ops.begin() + (long) (i + run), follower);
+                ++run;
+            }
+            ops[i].aux1 = run;                         // run length, 1 = a lone constant-frequency phasor
+        }
     }
 
     // ---- stages: a `convolve` node is a whole-block operation (K3) that cannot live inside the sample-tiled

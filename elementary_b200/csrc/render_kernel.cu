@@ -31,6 +31,7 @@
 #include <cfloat>
 #include <cmath>
 #include <cstdint>
+#include <type_traits>
 #include "program.h"
 #include "kernels.h"
 
@@ -270,17 +271,38 @@ __device__ __forceinline__ void render_tile(const LaunchParams& P, const int til
             } break;
 
             case OP_PHASOR: {   // Core.h:89-97: step = f * (1/sr) in float; phase = next - floor(next)
-                const Opnd f = decode(__ldg(opnds));
                 const float rsr = __uint_as_float(aux0);
-                if (owner) {
-                    float phase = sst[sidx * L + lane];
-                    FOR_OWNER(t) {
-                        const float step = LDT(f, t) * rsr;
-                        outT[t * L] = phase;
-                        const float next = phase + step;
-                        phase = next - floorf(next);
+                if (aux1 >= 1) {
+                    // A run of aux1 independent constant-frequency phasors (grouped by the host): lane group g = lane/L
+                    // runs phasor g of the run, so up to 32/L recurrences advance in one serial loop.
+                    constexpr int OPW = OP_HEADER_WORDS + 4;
+                    const int gi = lane >> LOGL;
+                    if (gi < (int) aux1) {
+                        const uint32_t* mine = pc - OPW + gi * OPW;
+                        const uint32_t mw0 = __ldg(mine), msidx = __ldg(mine + 1), mop = __ldg(mine + OP_HEADER_WORDS);
+                        float* const o = slots + ((mw0 >> 16) & 0xFF) * E + vlane;
+                        const float step = spar[(mop & 0x3FFFFFFFu) * L + vlane] * rsr;
+                        float phase = sst[msidx * L + vlane];
+                        FOR_OWNER(t) {
+                            o[t * L] = phase;
+                            const float next = phase + step;
+                            phase = next - floorf(next);
+                        }
+                        sst[msidx * L + vlane] = phase;
                     }
-                    sst[sidx * L + lane] = phase;
+                    pc += (aux1 - 1) * OPW;
+                } else {
+                    const Opnd f = decode(__ldg(opnds));
+                    if (owner) {
+                        float phase = sst[sidx * L + lane];
+                        FOR_OWNER(t) {
+                            const float step = LDT(f, t) * rsr;
+                            outT[t * L] = phase;
+                            const float next = phase + step;
+                            phase = next - floorf(next);
+                        }
+                        sst[sidx * L + lane] = phase;
+                    }
                 }
             } break;
 
@@ -475,13 +497,16 @@ __device__ __forceinline__ void render_tile(const LaunchParams& P, const int til
                 const double sr = bits_to_double(aux0, aux1);
                 const double fmax = sr / 2.0001;
                 // phase 1 — coefficients (updateCoeffs, SVF.h:72-80) are a pure function of (fc, q) per sample:
-                // all lanes, one element per slice
-                double ga[NITER], a1a[NITER], ka[NITER];
+                // all lanes, one element per slice.  ga holds g for L = 32 (a2, a3 are then formed by the lane itself)
+                // and a2 otherwise (a3 goes through a3a), so that the serial part of narrow tiles is as short as possible.
+                double ga[NITER], a1a[NITER], ka[NITER], a3a[(L == 32) ? 1 : NITER];
                 FOR_K(k) {
                     const double g = tan_f64(3.14159265359 * clampd((double) LDE(fc, k), 20.0, fmax) / sr);
                     const double kq = 1.0 / clampd((double) LDE(q, k), 0.25, 20.0);
-                    ga[k] = g; ka[k] = kq;
+                    ka[k] = kq;
                     a1a[k] = 1.0 / (1.0 + g * (g + kq));
+                    if (L == 32) ga[k] = g;
+                    else { const double a2 = g * a1a[k]; ga[k] = a2; a3a[k] = g * a2; }
                 }
                 // phase 2 — the tick recurrence (SVF.h:48-70), serial per voice; every lane walks the loop so the
                 // coefficients can be fetched from the lane that computed them (sample t = k*PER + j of voice v
@@ -491,36 +516,44 @@ __device__ __forceinline__ void render_tile(const LaunchParams& P, const int til
                     ic1 = reinterpret_cast<const double*>(sst + sidx * L)[lane];
                     ic2 = reinterpret_cast<const double*>(sst + (sidx + 2) * L)[lane];
                 }
-                FOR_K(k) {
-                    _Pragma("unroll") for (int j = 0; j < PER; ++j) {
-                        const int t = k * PER + j;
-                        if (t < cnt) {     // warp-uniform
-                            const int src = j * L + vlane;
-                            const double g = (L == 32) ? ga[k] : __shfl_sync(FULL, ga[k], src);
-                            const double a1 = (L == 32) ? a1a[k] : __shfl_sync(FULL, a1a[k], src);
-                            const double kq = (L == 32) ? ka[k] : __shfl_sync(FULL, ka[k], src);
-                            if (owner) {
-                                const double a2 = g * a1;
-                                const double a3 = g * a2;
-                                const float v0 = LDT(x, t);
-                                const double v3 = (double) v0 - ic2;
-                                const double v1 = ic1 * a1 + v3 * a2;
-                                const double v2 = ic2 + ic1 * a2 + v3 * a3;
-                                ic1 = v1 * 2.0 - ic1;
-                                ic2 = v2 * 2.0 - ic2;
-                                float y;
-                                switch (mode) {
-                                    case 0: y = (float) v2; break;
-                                    case 1: y = (float) v1; break;
-                                    case 2: y = (float) ((double) v0 - kq * v1 - v2); break;
-                                    case 3: y = (float) ((double) v0 - kq * v1); break;
-                                    default: y = (float) ((double) v0 - 2.0 * kq * v1); break;
+                auto tickLoop = [&](auto lowpassTag) {
+                    constexpr bool LOWPASS = decltype(lowpassTag)::value;
+                    FOR_K(k) {
+                        _Pragma("unroll") for (int j = 0; j < PER; ++j) {
+                            const int t = k * PER + j;
+                            if (t < cnt) {     // warp-uniform
+                                const int src = j * L + vlane;
+                                double a1, a2, a3, kq = 0.0;
+                                if (L == 32) { a1 = a1a[k]; a2 = ga[k] * a1; a3 = ga[k] * a2; kq = ka[k]; }
+                                else {
+                                    a1 = __shfl_sync(FULL, a1a[k], src);
+                                    a2 = __shfl_sync(FULL, ga[k], src);
+                                    a3 = __shfl_sync(FULL, a3a[(L == 32) ? 0 : k], src);
+                                    if (!LOWPASS) kq = __shfl_sync(FULL, ka[k], src);
                                 }
-                                outT[t * L] = y;
+                                if (owner) {
+                                    const float v0 = LDT(x, t);
+                                    const double v3 = (double) v0 - ic2;
+                                    const double v1 = ic1 * a1 + v3 * a2;
+                                    const double v2 = ic2 + ic1 * a2 + v3 * a3;
+                                    ic1 = v1 * 2.0 - ic1;
+                                    ic2 = v2 * 2.0 - ic2;
+                                    float y;
+                                    if (LOWPASS) y = (float) v2;
+                                    else switch (mode) {
+                                        case 0: y = (float) v2; break;
+                                        case 1: y = (float) v1; break;
+                                        case 2: y = (float) ((double) v0 - kq * v1 - v2); break;
+                                        case 3: y = (float) ((double) v0 - kq * v1); break;
+                                        default: y = (float) ((double) v0 - 2.0 * kq * v1); break;
+                                    }
+                                    outT[t * L] = y;
+                                }
                             }
                         }
                     }
-                }
+                };
+                if (mode == 0) tickLoop(std::true_type{}); else tickLoop(std::false_type{});
                 if (owner) {
                     reinterpret_cast<double*>(sst + sidx * L)[lane] = ic1;
                     reinterpret_cast<double*>(sst + (sidx + 2) * L)[lane] = ic2;

@@ -78,7 +78,10 @@ def test_additive_voice_is_scheduled_into_a_handful_of_slots():
     assert rt.apply_instructions(graphs.additive64()) == 0
     g = rt.describe()["groups"][0]
     assert g["nodes"] == 387 and g["state_rows"] == 64 and g["params"] == 129
-    assert g["slots"] <= 4                       # Sethi-Ullman order + incremental fold: not 65 live block buffers
+    assert g["slots"] <= 11                      # Sethi-Ullman order + incremental fold (+7 for runs of 8 fused phasors): not 65
+    big = plan(1 << 17)
+    assert big.apply_instructions(graphs.additive64()) == 0
+    assert big.describe()["groups"][0]["slots"] <= 4   # full-width tiles do not group phasors
     rt = plan(64, fuse_chains=0)
     assert rt.apply_instructions(graphs.additive64()) == 0
     assert rt.describe()["groups"][0]["slots"] == 65

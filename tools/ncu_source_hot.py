@@ -9,11 +9,10 @@ hi = next(i for i, r in enumerate(rows) if r and r[0] == "Line No")
 hdr = rows[hi]
 li, si = hdr.index("Line No"), hdr.index("Source")
 src_lines = {}
-try:
-    for i, l in enumerate(open("elementary_b200/csrc/render_kernel.cu"), 1):
-        src_lines[str(i)] = l.strip()[:110]
-except OSError:
-    pass
+src_out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "cuda"], capture_output=True, text=True).stdout
+for r in csv.reader(io.StringIO(src_out)):   # the source embedded in the report (not the file on disk, which may have moved on)
+    if len(r) >= 2 and r[0].isdigit():
+        src_lines[r[0]] = r[1].strip()[:110]
 ii = hdr.index("Instructions Executed"); sa = hdr.index("# Samples")
 tot_i = tot_s = 0
 agg = collections.defaultdict(lambda: [0, 0])
