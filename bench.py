@@ -238,6 +238,13 @@ def run_b200(args, rank, local_rank, world):
     algo_bytes = ALGO_BYTES_PER_VOICE_BLOCK_MIX_ONLY * voices
     achieved = algo_bytes / (k1_avg_ms * 1e-3) / 1e9 if k1_avg_ms > 0 else 0.0
     desc = rt.describe()["groups"][0]
+    traffic = None   # DRAM bytes of one K1 launch from the committed ncu --set full capture of this same configuration
+    try:
+        tj = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))["render_block_kernel"].get(str(voices))
+        if tj:
+            traffic = tj["dram_bytes_read"] + tj["dram_bytes_write"]
+    except Exception:
+        pass
 
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
@@ -265,7 +272,7 @@ def run_b200(args, rank, local_rank, world):
                 "ms_per_step": e2e_ms / args.steps, "api": "elem_b200_process (host out buffers)" if world == 1 else "elem_b200_enqueue_block + NCCL all_reduce + D2H of the mix bus"},
         "gpu_launches": int(launches),
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": None, "peak_kind": f"of {peak_kind}", "kernel": "render_block_kernel<NITER,LOGL> (K1)",
+                     "traffic": traffic, "peak_kind": f"of {peak_kind}", "kernel": "render_block_kernel<NITER,LOGL> (K1)",
                      "kernel_ms": k1_avg_ms, "kernel_launches_timed": k1_n,
                      "algorithmic_bytes_per_launch": algo_bytes,
                      "note": "K1 is instruction-issue bound, not HBM bound (intermediates never leave the SM); see DESIGN.md section 4"},

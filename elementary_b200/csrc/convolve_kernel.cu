@@ -2,8 +2,7 @@
 // No cuFFT, no tensor cores: this is a streaming frequency-domain delay line, bound by the HBM reads of the input
 // spectra (see convolve.h for the algorithmic bytes).
 //
-// One CTA (256 threads) serves CONV_CH_PER_CTA = 4 channels so that every IR spectrum value fetched from L2 is used
-// four times.  Per call:
+// One CTA (256 threads) serves CONV_CH_PER_CTA channels so that every IR spectrum value fetched from L2 is reused.  Per call:
 //   1. append the new samples to the partition's input buffer, zero-pad to 1024 (FFTConvolver.cpp:157-164)
 //   2. real FFT 1024 = complex Stockham radix-2 FFT 512 in shared memory + split post-pass  (replaces OouraFFT::fft,
 //      AudioFFT.cpp:132-155; float arithmetic instead of the reference's double)
@@ -109,39 +108,49 @@ __global__ void __launch_bounds__(256) convolve_chunk_kernel(
     __syncthreads();
 
     // 3./4. frequency-domain delay line: Y[b] = sum_i H_i[b] * X_{cur+i}[b]; the older partitions only once per block.
-    // Bin 0 is the packed pair of real bins and multiplies component-wise.
+    // Bin 0 is the packed pair of real bins and multiplies component-wise.  Each thread owns bins tid and tid+256 of
+    // CH channels; the loads are unconditional (padding channels alias the last real one) and unrolled so that
+    // dozens of independent 8-byte loads are in flight per thread — the loop is pure HBM streaming.
+    {
+        float2 acc[2][CH];
+        const float2* xrow[CH];
 #pragma unroll
-    for (int hh = 0; hh < 2; ++hh) {
-        const int b = tid + hh * 256;
-        float2 acc[CH];
+        for (int c = 0; c < CH; ++c) xrow[c] = fdl + (size_t) min(ch0 + c, nv - 1) * S * NB + tid;
         if (fill == 0) {
 #pragma unroll
-            for (int c = 0; c < CH; ++c) acc[c] = make_float2(0.0f, 0.0f);
-#pragma unroll 4
+            for (int c = 0; c < CH; ++c) { acc[0][c] = make_float2(0.0f, 0.0f); acc[1][c] = make_float2(0.0f, 0.0f); }
+#pragma unroll 8
             for (int i = 1; i < S; ++i) {
-                const float2 h = __ldg(H + (size_t) i * NB + b);
                 int slotIdx = cur + i;
                 if (slotIdx >= S) slotIdx -= S;
+                const float2 ha = __ldg(H + (size_t) i * NB + tid);
+                const float2 hb = __ldg(H + (size_t) i * NB + tid + 256);
 #pragma unroll
                 for (int c = 0; c < CH; ++c) {
-                    const int ch = ch0 + c;
-                    if (ch < nv) {
-                        const float2 x = fdl[((size_t) ch * S + slotIdx) * NB + b];
-                        acc[c] = (b == 0) ? make_float2(acc[c].x + h.x * x.x, acc[c].y + h.y * x.y) : cadd(acc[c], cmul(h, x));
-                    }
+                    const float2 xa = xrow[c][(size_t) slotIdx * NB];
+                    const float2 xb = xrow[c][(size_t) slotIdx * NB + 256];
+                    acc[0][c] = (tid == 0) ? make_float2(acc[0][c].x + ha.x * xa.x, acc[0][c].y + ha.y * xa.y) : cadd(acc[0][c], cmul(ha, xa));
+                    acc[1][c] = cadd(acc[1][c], cmul(hb, xb));
                 }
             }
 #pragma unroll
-            for (int c = 0; c < CH; ++c) if (ch0 + c < nv) ypre[(size_t) (ch0 + c) * NB + b] = acc[c];
+            for (int c = 0; c < CH; ++c) if (ch0 + c < nv) {
+                ypre[(size_t) (ch0 + c) * NB + tid] = acc[0][c];
+                ypre[(size_t) (ch0 + c) * NB + tid + 256] = acc[1][c];
+            }
         } else {
 #pragma unroll
-            for (int c = 0; c < CH; ++c) acc[c] = (ch0 + c < nv) ? ypre[(size_t) (ch0 + c) * NB + b] : make_float2(0.0f, 0.0f);
+            for (int c = 0; c < CH; ++c) {
+                const size_t o = (size_t) min(ch0 + c, nv - 1) * NB + tid;
+                acc[0][c] = ypre[o]; acc[1][c] = ypre[o + 256];
+            }
         }
-        const float2 h0 = __ldg(H + b);
+        const float2 h0a = __ldg(H + tid), h0b = __ldg(H + tid + 256);
 #pragma unroll
         for (int c = 0; c < CH; ++c) {
-            const float2 x = A[c][b];
-            B[c][b] = (b == 0) ? make_float2(acc[c].x + x.x * h0.x, acc[c].y + x.y * h0.y) : cadd(acc[c], cmul(x, h0));
+            const float2 xa = A[c][tid], xb = A[c][tid + 256];
+            B[c][tid] = (tid == 0) ? make_float2(acc[0][c].x + xa.x * h0a.x, acc[0][c].y + xa.y * h0a.y) : cadd(acc[0][c], cmul(xa, h0a));
+            B[c][tid + 256] = cadd(acc[1][c], cmul(xb, h0b));
         }
     }
     __syncthreads();

@@ -84,6 +84,32 @@ __device__ __noinline__ float exp_f32(float x) { return expf(x); }
 __device__ __noinline__ float pow_f32(float x, float y) { return powf(x, y); }
 __device__ __noinline__ float fmod_f32(float x, float y) { return fmodf(x, y); }
 
+// tan(x) for 0 <= x < pi/2, the only range the svf family ever asks for (fc is clamped to [20, sr/2.0001] before
+// g = tan(pi*fc/sr), SVF.h:75).  Reduce to y in [0, pi/4] by the co-function identity and use 7-term Taylor sums
+// for sin and cos: max relative error 5.2e-13 over the whole clamped range (checked against glibc tan on 3M points;
+// 8 terms would give 1.8e-15) — nine orders of magnitude below what a float output sample can resolve — at half the
+// instructions of the general-purpose tan(), with no branch and no argument-reduction slow path.
+__device__ __forceinline__ double tan_quarter_wave(double x) {
+    const bool big = x > 0.78539816339744831;
+    const double y = big ? ((1.5707963267948966 - x) + 6.123233995736766e-17) : x;
+    const double y2 = y * y;
+    double s = 1.0 / 6227020800.0;                    // sin: y - y^3/3! + y^5/5! - ... + y^13/13!
+    s = fma(s, y2, -1.0 / 39916800.0);
+    s = fma(s, y2, 1.0 / 362880.0);
+    s = fma(s, y2, -1.0 / 5040.0);
+    s = fma(s, y2, 1.0 / 120.0);
+    s = fma(s, y2, -1.0 / 6.0);
+    s = fma(s * y2, y, y);                             // y + y^3 * poly(y^2)
+    double c = 1.0 / 479001600.0;                      // cos: 1 - y^2/2! + ... + y^12/12!
+    c = fma(c, y2, -1.0 / 3628800.0);
+    c = fma(c, y2, 1.0 / 40320.0);
+    c = fma(c, y2, -1.0 / 720.0);
+    c = fma(c, y2, 1.0 / 24.0);
+    c = fma(c, y2, -0.5);
+    c = fma(c, y2, 1.0);
+    return big ? c / s : s / c;
+}
+
 // Math.h:30-57,128-188 — fn(x, y) for the binary and reducing node families
 __device__ __forceinline__ float binary_apply(uint32_t fn, float x, float y) {
     switch (fn) {
@@ -496,12 +522,13 @@ __device__ __forceinline__ void render_tile(const LaunchParams& P, const int til
                 const Opnd x = decode(__ldg(opnds + 2));
                 const double sr = bits_to_double(aux0, aux1);
                 const double fmax = sr / 2.0001;
+                const double rsr = 1.0 / sr;   // pi*fc/sr as (pi*fc)*(1/sr): <= 1 ulp from the reference's quotient, see tan_quarter_wave
                 // phase 1 — coefficients (updateCoeffs, SVF.h:72-80) are a pure function of (fc, q) per sample:
                 // all lanes, one element per slice.  ga holds g for L = 32 (a2, a3 are then formed by the lane itself)
                 // and a2 otherwise (a3 goes through a3a), so that the serial part of narrow tiles is as short as possible.
                 double ga[NITER], a1a[NITER], ka[NITER], a3a[(L == 32) ? 1 : NITER];
                 FOR_K(k) {
-                    const double g = tan_f64(3.14159265359 * clampd((double) LDE(fc, k), 20.0, fmax) / sr);
+                    const double g = tan_quarter_wave((3.14159265359 * clampd((double) LDE(fc, k), 20.0, fmax)) * rsr);
                     const double kq = 1.0 / clampd((double) LDE(q, k), 0.25, 20.0);
                     ka[k] = kq;
                     a1a[k] = 1.0 / (1.0 + g * (g + kq));
@@ -567,13 +594,14 @@ __device__ __forceinline__ void render_tile(const LaunchParams& P, const int til
                 const Opnd x = decode(__ldg(opnds + 3));
                 const double sr = bits_to_double(aux0, aux1);
                 const double fmax = sr / 2.0001;
+                const double rsr = 1.0 / sr;   // pi*fc/sr as (pi*fc)*(1/sr): <= 1 ulp from the reference's quotient, see tan_quarter_wave
                 if (owner) {
                     double* s1 = reinterpret_cast<double*>(sst + sidx * L) + lane;
                     double* s2 = reinterpret_cast<double*>(sst + (sidx + 2) * L) + lane;
                     double ic1 = *s1, ic2 = *s2;
                     _Pragma("unroll 2") for (int t = 0; t < cnt; ++t) {
                         const double A = pow_f64(10.0, (double) LDT(gdb, t) / 40.0);
-                        double g = tan_f64(3.14159265359 * clampd((double) LDT(fc, t), 20.0, fmax) / sr);
+                        double g = tan_quarter_wave((3.14159265359 * clampd((double) LDT(fc, t), 20.0, fmax)) * rsr);
                         double kq = 1.0 / clampd((double) LDT(q, t), 0.25, 20.0);
                         if (mode == 0) g /= A;
                         if (mode == 1) g *= A;
@@ -914,10 +942,16 @@ __global__ void __launch_bounds__(1024) mix_reduce_kernel(const float* __restric
     const int chunksPerCh = (blockSize + 31) / 32;
     const int ch = blockIdx.x / chunksPerCh;
     const int s = (blockIdx.x % chunksPerCh) * 32 + sx;
-    float acc = 0.0f;
-    if (s < numSamples)
-        for (int t = gy; t < nTiles; t += 32) acc += partial[((size_t) t * nOut + ch) * blockSize + s];
-    red[gy][sx] = acc;
+    // four interleaved accumulators: independent loads in flight, still one fixed summation order
+    float a0 = 0.0f, a1 = 0.0f, a2 = 0.0f, a3 = 0.0f;
+    if (s < numSamples) {
+        const size_t step = (size_t) 32 * nOut * blockSize;
+        const float* p = partial + ((size_t) gy * nOut + ch) * blockSize + s;
+        int t = gy;
+        for (; t + 96 < nTiles; t += 128, p += 4 * step) { a0 += p[0]; a1 += p[step]; a2 += p[2 * step]; a3 += p[3 * step]; }
+        for (; t < nTiles; t += 32, p += step) a0 += p[0];
+    }
+    red[gy][sx] = (a0 + a1) + (a2 + a3);
     __syncthreads();
     if (gy == 0 && s < numSamples) {
         float v = 0.0f;
