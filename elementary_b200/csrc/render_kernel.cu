@@ -968,13 +968,13 @@ __global__ void __launch_bounds__(1024) mix_reduce_kernel(const float* __restric
 // host-side launchers (called from graph_host.cpp)
 
 int render_niter_for(int tileWidth, int niterOverride) {
-    // E = L*T = 32*NITER elements per sample tile (measured choices, profiles/r01_i_tile_samples_ab.txt):
+    //   L >= 8 : E = 256 (T = 256/L);  L = 4 : T = 32;  L = 2 : T = 64 (fewer op dispatches per sample);  L = 1 : T = 32
     //   L >= 8 : E = 256 (T = 256/L);  L = 4 : T = 32;  L = 2, 1 : T = 64 (fewer op dispatches per sample)
     // L = 32 may also run with NITER = 4 (T = 4) for A/B runs.
     if (tileWidth == 32 && niterOverride == 4) return 4;
     if (tileWidth >= 8) return 8;
     if (tileWidth == 4) return 4;
-    return 2 * tileWidth;
+    return tileWidth == 2 ? 4 : 1;   // L = 1 keeps T = 32: with one voice per warp longer tiles push delay lines off their fast path (config 5)
 }
 
 size_t render_smem_bytes(int nSlots, int nOut, int nStateRows, int nParams, int warpsPerCta, int tileWidth, int niterOverride) {
@@ -1015,7 +1015,7 @@ cudaError_t launch_render_block(const LaunchParams& P, int warpsPerCta, int nite
         case 8:  return launch_impl<8, 3>(P, grid, threads, smem, stream);
         case 4:  return launch_impl<4, 2>(P, grid, threads, smem, stream);
         case 2:  return launch_impl<4, 1>(P, grid, threads, smem, stream);
-        default: return launch_impl<2, 0>(P, grid, threads, smem, stream);
+        default: return launch_impl<1, 0>(P, grid, threads, smem, stream);
     }
 }
 
@@ -1032,7 +1032,7 @@ cudaError_t launch_render_groups(const LaunchParams* descs, const int* tileStart
         case 8:  return launch_groups_impl<8, 3>(descs, tileStart, nGroups, totalTiles, grid, threads, smem, stream);
         case 4:  return launch_groups_impl<4, 2>(descs, tileStart, nGroups, totalTiles, grid, threads, smem, stream);
         case 2:  return launch_groups_impl<4, 1>(descs, tileStart, nGroups, totalTiles, grid, threads, smem, stream);
-        default: return launch_groups_impl<2, 0>(descs, tileStart, nGroups, totalTiles, grid, threads, smem, stream);
+        default: return launch_groups_impl<1, 0>(descs, tileStart, nGroups, totalTiles, grid, threads, smem, stream);
     }
 }
 
