@@ -41,6 +41,9 @@ struct ConvolverState {
 // Build the device state for `nv` channels sharing one impulse response. Returns false and fills `err` on failure.
 bool convolver_init(ConvolverState& st, const float* ir, size_t irLen, int nv, bool planOnly, cudaStream_t stream, std::string& err);
 
+// Copy of channels [c0, c0+n) of `src` (same IR, same position in the partition cycle) — used when a voice group is cut.
+bool convolver_clone_range(const ConvolverState& src, int c0, int n, ConvolverState& dst, cudaStream_t stream, std::string& err);
+
 // Convolve `n` more samples (n <= 512 - st.fill) of every channel: in/out are [channel][stride] device buffers, the
 // samples of this call start at `offset`.  Advances st.fill / st.cur.
 cudaError_t convolver_process_chunk(ConvolverState& st, const float* in, float* out, int stride, int offset, int n, cudaStream_t stream);

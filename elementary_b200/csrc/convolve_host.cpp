@@ -96,4 +96,26 @@ bool convolver_init(ConvolverState& st, const float* ir, size_t irLen, int nv, b
     return true;
 }
 
+bool convolver_clone_range(const ConvolverState& src, int c0, int n, ConvolverState& dst, cudaStream_t stream, std::string& err) {
+    dst.planOnly = src.planOnly;
+    dst.nv = n; dst.partitions = src.partitions; dst.cur = src.cur; dst.fill = src.fill;
+    if (src.partitions == 0) return true;
+    const size_t S = (size_t) src.partitions;
+    struct Part { void** d; const void* s; size_t bytes; };
+    const Part parts[] = {
+        {(void**) &dst.dH, src.dH, S * CONV_PACKED_BINS * sizeof(float2)},
+        {(void**) &dst.dTw, src.dTw, 512 * sizeof(float2)},
+        {(void**) &dst.dFdl, src.dFdl + (size_t) c0 * S * CONV_PACKED_BINS, (size_t) n * S * CONV_PACKED_BINS * sizeof(float2)},
+        {(void**) &dst.dYpre, src.dYpre + (size_t) c0 * CONV_PACKED_BINS, (size_t) n * CONV_PACKED_BINS * sizeof(float2)},
+        {(void**) &dst.dOverlap, src.dOverlap + (size_t) c0 * CONV_BLOCK, (size_t) n * CONV_BLOCK * sizeof(float)},
+        {(void**) &dst.dInBuf, src.dInBuf + (size_t) c0 * CONV_BLOCK, (size_t) n * CONV_BLOCK * sizeof(float)},
+    };
+    for (const Part& p : parts) {
+        if (!allocDev(p.d, p.bytes, src.planOnly, stream, err)) return false;
+        if (src.planOnly) std::memcpy(*p.d, p.s, p.bytes);
+        else if (cudaMemcpyAsync(*p.d, p.s, p.bytes, cudaMemcpyDeviceToDevice, stream) != cudaSuccess) { err = "convolver clone copy failed"; return false; }
+    }
+    return true;
+}
+
 } // namespace eb

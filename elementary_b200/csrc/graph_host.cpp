@@ -541,13 +541,87 @@ int Engine::splitGroupsAt(int v) {
     for (size_t i = 0; i < groups_.size(); ++i) {
         Group& g = *groups_[i];
         if (v <= g.v0 || v >= g.v0 + g.nv) continue;
-        // Only a group that owns no graph yet can be cut (its voices have no device state to migrate).
-        // Re-partitioning live voices is the "dynamic graph updates at voice scale" next-row.
-        if (!g.nodes.empty() || g.dRows) return fail(rc::InvariantViolation, "cannot split a voice group that already owns a graph; address whole groups or split before the first batch");
         auto ng = std::make_unique<Group>();
-        ng->v0 = v; ng->nv = g.v0 + g.nv - v; ng->Vpad = (ng->nv + 31) / 32 * 32;
-        g.nv = v - g.v0; g.Vpad = (g.nv + 31) / 32 * 32;
+        const int cut = v - g.v0;                       // first voice (group-relative) that moves to the new group
+        ng->v0 = v; ng->nv = g.nv - cut; ng->Vpad = (ng->nv + 31) / 32 * 32;
+        if (g.nodes.empty() && !g.dRows) {              // nothing to migrate
+            g.nv = cut; g.Vpad = (g.nv + 31) / 32 * 32;
+            groups_.insert(groups_.begin() + i + 1, std::move(ng));
+            return rc::Ok;
+        }
+        // ---- the group is live: the voices [cut, nv) leave with a copy of the graph and THEIR device state -------
+        // (dynamic graph updates at voice scale, SURVEY.md §8f N1: afterwards each half can be re-wired independently,
+        // every voice keeping its phases, filter memories, delay lines and taps, like a Runtime of its own would.)
+        const int L = g.tileWidth;
+        if (L > 0 && cut % L != 0)
+            return fail(rc::InvariantViolation, "voice groups can only be cut on a voice-tile boundary (multiple of the group's tile width)");
+        dsync();
+        ng->tileWidth = L;
+        ng->currentRoots = g.currentRoots;
+        // rows: column slice of every row; a double state is a row PAIR viewed as double[Vpad], sliced as doubles
+        ng->rowsCap = g.rowsCap; ng->rowsUsed = g.rowsUsed;
+        if (g.dRows && g.rowsCap > 0) {
+            if (!cuda(dmalloc((void**) &ng->dRows, sizeof(float) * (size_t) ng->rowsCap * ng->Vpad), "cudaMalloc rows (split)")) return rc::CudaError;
+            if (!cuda(dmemset(ng->dRows, 0, sizeof(float) * (size_t) ng->rowsCap * ng->Vpad), "memset rows (split)")) return rc::CudaError;
+            std::vector<char> isDoublePair((size_t) g.rowsUsed + 2, 0);
+            for (auto& kv : g.nodes) {
+                const Node& n = kv.second;
+                const auto& ti = typeTable().at(n.typeName);
+                if (ti.evenAlign && n.stateRow >= 0) for (int k = 0; k < ti.stateRows; k += 2) isDoublePair[(size_t) n.stateRow + k] = 1;
+            }
+            for (int r = 0; r < g.rowsUsed; ++r) {
+                if (isDoublePair[(size_t) r]) {
+                    const float* src = g.dRows + (size_t) r * g.Vpad + (size_t) 2 * cut;
+                    if (!cuda(dmemcpy(ng->dRows + (size_t) r * ng->Vpad, src, sizeof(double) * ng->nv, cudaMemcpyDeviceToDevice), "copy double row (split)")) return rc::CudaError;
+                    ++r;   // the pair's second row is part of the same double array
+                } else {
+                    if (!cuda(dmemcpy(ng->dRows + (size_t) r * ng->Vpad, g.dRows + (size_t) r * g.Vpad + cut, sizeof(float) * ng->nv, cudaMemcpyDeviceToDevice), "copy row (split)")) return rc::CudaError;
+                }
+            }
+        }
+        // tile-structured buffers [tile][pos][L]: the moving voices are a contiguous run of tiles
+        const size_t tile0 = L > 0 ? (size_t) cut / L : 0;
+        const size_t newTiles = L > 0 ? (size_t) (ng->nv + L - 1) / L : 0;
+        auto cloneTiles = [&](const float* src, size_t perTileFloats, float** dst) -> bool {
+            *dst = nullptr;
+            if (!src || newTiles == 0 || perTileFloats == 0) return true;
+            const size_t n = newTiles * perTileFloats;
+            if (!cuda(dmalloc((void**) dst, sizeof(float) * n), "cudaMalloc tile buffer (split)")) return false;
+            return cuda(dmemcpy(*dst, src + tile0 * perTileFloats, sizeof(float) * n, cudaMemcpyDeviceToDevice), "copy tile buffer (split)");
+        };
+        for (auto& kv : g.tapShared) {
+            float* d = nullptr;
+            if (!cloneTiles(kv.second, (size_t) blockSize_ * L, &d)) return rc::CudaError;
+            ng->tapShared[kv.first] = d;
+        }
+        for (auto& kv : g.nodes) {
+            Node n = kv.second;   // host-side copy: props, inlets, fades, resource handles, row indices (same layout)
+            n.ring = nullptr; n.tapPrivate = nullptr;
+            if (kv.second.ring) {
+                if (!cloneTiles(kv.second.ring, (size_t) kv.second.size * L, &n.ring)) return rc::CudaError;
+                n.ringFloats = newTiles * (size_t) kv.second.size * L;
+            }
+            if (kv.second.tapPrivate && !cloneTiles(kv.second.tapPrivate, (size_t) blockSize_ * L, &n.tapPrivate)) return rc::CudaError;
+            if (kv.second.conv) {
+                auto cs = std::make_shared<ConvolverState>();
+                std::string err;
+                if (!convolver_clone_range(*kv.second.conv, cut, ng->nv, *cs, stream_, err)) return fail(rc::CudaError, err);
+                n.conv = cs;
+                kv.second.conv->nv = cut;   // the old state keeps its (now partly unused) storage
+            }
+            ng->nodes.emplace(kv.first, std::move(n));
+        }
+        const bool hadActive = (bool) g.active, hadPending = (bool) g.pending;
+        const int nIn = g.active ? g.active->nIn : (g.pending ? g.pending->nIn : 0);
+        g.nv = cut;   // Vpad (the row stride) and the tile buffers of the old group stay as allocated
+        Group* ngp = ng.get();
         groups_.insert(groups_.begin() + i + 1, std::move(ng));
+        if (hadActive || hadPending) {   // the moved voices keep rendering the same sequence, now through their own program
+            std::shared_ptr<Program> p;
+            int rcode = compile(*ngp, nIn, p);
+            if (rcode != rc::Ok) return rcode;
+            if (hadActive && !hadPending) ngp->active = p; else ngp->pending = p;
+        }
         return rc::Ok;
     }
     return rc::Ok;

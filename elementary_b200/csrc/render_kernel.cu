@@ -968,8 +968,8 @@ __global__ void __launch_bounds__(1024) mix_reduce_kernel(const float* __restric
 // host-side launchers (called from graph_host.cpp)
 
 int render_niter_for(int tileWidth, int niterOverride) {
+    // E = L*T = 32*NITER elements per sample tile (measured choices, profiles/r01_i_tile_samples_ab.txt):
     //   L >= 8 : E = 256 (T = 256/L);  L = 4 : T = 32;  L = 2 : T = 64 (fewer op dispatches per sample);  L = 1 : T = 32
-    //   L >= 8 : E = 256 (T = 256/L);  L = 4 : T = 32;  L = 2, 1 : T = 64 (fewer op dispatches per sample)
     // L = 32 may also run with NITER = 4 (T = 4) for A/B runs.
     if (tileWidth == 32 && niterOverride == 4) return 4;
     if (tileWidth >= 8) return 8;

@@ -117,7 +117,9 @@ def test_value_only_batches_address_sub_ranges_but_structure_does_not_split_live
     assert rt.apply_instructions(graphs.subsynth32()) == 0
     assert rt.apply_instructions(graphs.subsynth32_voice_props(5), voices=(5, 6)) == 0
     assert len(rt.describe()["groups"]) == 1
-    assert rt.apply_instructions([[0, 99, "sin"]], voices=(5, 6)) == 7          # documented limitation (N1)
+    assert rt.apply_instructions([[0, 99, "sin"]], voices=(5, 6)) == 0          # structural batch: the live group is cut in 3
+    d = rt.describe()["groups"]
+    assert [(g["v0"], g["nv"]) for g in d] == [(0, 5), (5, 1), (6, 58)] and [g["nodes"] for g in d] == [32, 33, 32]
     ida, _ = graphs.subsynth32_param_ids()
     assert rt.set_property_per_voice(ida, "value", np.linspace(50, 500, 64)) == 0
     assert rt.set_property_per_voice(12345, "value", np.zeros(4)) == 2

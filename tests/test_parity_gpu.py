@@ -361,3 +361,53 @@ def test_process_mix_api_shared_inputs():
     ref = oracle_render(batch, 3, 1, SR, BS, x, voice_batches=vb)
     want = ref.astype(np.float64).sum(axis=0)
     assert np.abs(outs - want).max() <= 1e-5 * np.abs(want).max()
+
+
+@pytest.mark.parametrize("tile_width", [0, 4])
+def test_split_live_voice_group_keeps_every_voice_state(tile_width):
+    """a structural batch addressed to part of a running voice group cuts the group; the voices that
+    move keep their phases, filter memories and delay lines (nodes shared by the old and the new graph continue
+    seamlessly, exactly like they do inside one reference Runtime), the others are untouched."""
+    from helpers import oracle_cls
+    n_voices, bs = 8, BS
+    core = el.svf({"mode": "lowpass"}, el.add(900.0, el.mul(500.0, el.cycle(0.7))), 2.0, el.saw(el.const(110.0, key="f")))
+    g1 = el.add(core, el.mul(0.4, el.delay({"size": 3000}, 1234.5, 0.3, core)))
+    g2 = el.tanh(el.add(g1, el.mul(0.25, el.cycle(el.const(330.0, key="f2")))))
+    fid = el.const(0, key="f").id()
+    freqs = 55.0 * (1 + np.arange(n_voices))
+
+    opts = {"tile_width": tile_width} if tile_width else {}
+    rt = Runtime(SR, bs, n_voices, device=0, **opts)
+    rg = el.Renderer()
+    a = rg.render(g1)
+    b = rg.render(g2)                                  # incremental batch: only the new nodes + new root
+    assert rt.apply_instructions(a) == 0
+    assert rt.set_property_per_voice(fid, "value", freqs) == 0
+    oracles = []
+    for v in range(n_voices):
+        o = oracle_cls()(SR, bs)
+        assert o.apply(a) == 0 and o.apply([[3, fid, "value", float(freqs[v])]]) == 0
+        oracles.append(o)
+
+    got, ref = [], []
+    for blk in range(10):
+        if blk == 4:                                   # re-wire voices 4..7 only, while everything is running
+            assert rt.apply_instructions(b, voices=(4, 8)) == 0, rt.last_error()
+            for o in oracles[4:]:
+                assert o.apply(b) == 0
+            assert len(rt.describe()["groups"]) == 2
+        got.append(rt.process_voices(None, 1, bs)[0])
+        ref.append(np.stack([o.process(None, 1, bs) for o in oracles]))
+    g, r = np.concatenate(got, axis=2), np.concatenate(ref, axis=2)
+    ok, worst, ex = block_peak_tolerance_check(g, r, bs)
+    assert ok, f"worst err/tol {worst:.3g}, bit-exact {ex:.4f}"
+    # voices 0..3 never noticed anything
+    assert np.abs(g[:4, :, 4 * bs:]).max() > 0
+
+
+def test_split_must_respect_tile_boundaries():
+    rt = Runtime(SR, BS, 16, device=0, tile_width=4)
+    assert rt.apply_instructions(el.render(el.cycle(220.0))) == 0
+    rt.process_voices(None, 1, BS)
+    assert rt.apply_instructions([[0, 99, "sin"]], voices=(6, 16)) == 7        # 6 is not a multiple of the tile width
+    assert rt.apply_instructions([[0, 99, "sin"]], voices=(8, 16)) == 0
