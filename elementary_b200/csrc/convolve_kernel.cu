@@ -21,7 +21,39 @@ __device__ __forceinline__ float2 cadd(float2 a, float2 b) { return make_float2(
 __device__ __forceinline__ float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
 __device__ __forceinline__ float2 cconj(float2 a) { return make_float2(a.x, -a.y); }
 
+// ---- TMA (1-D bulk async copy) + mbarrier primitives: the frequency-domain delay line is streamed HBM -> shared memory
+// by cp.async.bulk (SASS: UBLKCP) through a multi-stage ring guarded by mbarriers, so the MAC loop never waits on a
+// per-thread global load and the first stages are already in flight while the forward FFT runs.
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t) __cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_load_1d(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred P1;\n"
+        "LAB_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+        "@P1 bra DONE;\n"
+        "bra LAB_WAIT;\n"
+        "DONE:\n"
+        "}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
 constexpr int CH = CONV_CH_PER_CTA;
+#ifndef EB_CONV_STAGES
+#define EB_CONV_STAGES 2   /* measured (profiles/r01_k_k3_tma_stages.txt): 2 stages keep 5 CTAs per SM = one wave for 512 CTAs */
+#endif
+constexpr int STAGES = EB_CONV_STAGES;                       // delay-line pipeline depth: STAGES x (CH + 1) rows of 4 KB in flight per CTA
+constexpr uint32_t ROW_BYTES = CONV_PACKED_BINS * sizeof(float2);
 constexpr int NB = CONV_PACKED_BINS;   // 512: bin 0 carries (Re X[0], Re X[512]) — both are purely real
 constexpr int N2 = 512;   // complex FFT length
 
@@ -55,15 +87,38 @@ __global__ void __launch_bounds__(256) convolve_chunk_kernel(
     const float* __restrict__ in, float* __restrict__ out, int stride, int offset, int n, int fill, int cur, int S, int nv,
     const float2* __restrict__ H, float2* __restrict__ fdl, float2* __restrict__ ypre,
     float* __restrict__ overlap, float* __restrict__ inbuf, const float2* __restrict__ twg) {
-    __shared__ float2 A[CH][N2];
-    __shared__ float2 B[CH][N2];
-    __shared__ float2 tw[N2];
+    extern __shared__ __align__(128) unsigned char smemRaw[];
+    float2 (*stX)[CH][N2] = reinterpret_cast<float2 (*)[CH][N2]>(smemRaw);                                   // [STAGES][CH][512]
+    float2 (*stH)[N2] = reinterpret_cast<float2 (*)[N2]>(smemRaw + (size_t) STAGES * CH * ROW_BYTES);        // [STAGES][512]
+    float2 (*A)[N2] = reinterpret_cast<float2 (*)[N2]>(smemRaw + (size_t) STAGES * (CH + 1) * ROW_BYTES);    // [CH][512]
+    float2 (*B)[N2] = A + CH;                                                                                 // [CH][512]
+    float2* tw = reinterpret_cast<float2*>(B + CH);                                                           // [512]
+    uint64_t* full = reinterpret_cast<uint64_t*>(tw + N2);                                                    // [STAGES]
 
     const int tid = threadIdx.x;
     const int ch0 = blockIdx.x * CH;
 
     tw[tid] = twg[tid];
     tw[tid + 256] = twg[tid + 256];
+
+    // Producer side of the delay-line pipeline: one thread arms the stage's mbarrier with the byte count and issues
+    // CH + 1 bulk copies (the CH channels' spectra of partition i and the IR spectrum H_i, 4 KB each).
+    auto issueStage = [&](int i) {
+        const int stg = (i - 1) % STAGES;
+        int slotIdx = cur + i;
+        if (slotIdx >= S) slotIdx -= S;
+        mbar_expect_tx(&full[stg], (CH + 1) * ROW_BYTES);
+#pragma unroll
+        for (int c = 0; c < CH; ++c)
+            tma_load_1d(&stX[stg][c][0], fdl + ((size_t) min(ch0 + c, nv - 1) * S + slotIdx) * NB, ROW_BYTES, &full[stg]);
+        tma_load_1d(&stH[stg][0], H + (size_t) i * NB, ROW_BYTES, &full[stg]);
+    };
+    if (fill == 0 && tid == 0) {
+        for (int sidx = 0; sidx < STAGES; ++sidx) mbar_init(&full[sidx], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        fence_proxy_async();
+        for (int i = 1; i < S && i <= STAGES; ++i) issueStage(i);   // in flight while the forward FFT runs
+    }
 
     // 1. append the chunk to the partition input buffer and load it as 512 complex points (even, odd), zero-padded
 #pragma unroll
@@ -113,25 +168,22 @@ __global__ void __launch_bounds__(256) convolve_chunk_kernel(
     // dozens of independent 8-byte loads are in flight per thread — the loop is pure HBM streaming.
     {
         float2 acc[2][CH];
-        const float2* xrow[CH];
-#pragma unroll
-        for (int c = 0; c < CH; ++c) xrow[c] = fdl + (size_t) min(ch0 + c, nv - 1) * S * NB + tid;
         if (fill == 0) {
 #pragma unroll
             for (int c = 0; c < CH; ++c) { acc[0][c] = make_float2(0.0f, 0.0f); acc[1][c] = make_float2(0.0f, 0.0f); }
-#pragma unroll 8
             for (int i = 1; i < S; ++i) {
-                int slotIdx = cur + i;
-                if (slotIdx >= S) slotIdx -= S;
-                const float2 ha = __ldg(H + (size_t) i * NB + tid);
-                const float2 hb = __ldg(H + (size_t) i * NB + tid + 256);
+                const int stg = (i - 1) % STAGES;
+                mbar_wait(&full[stg], ((i - 1) / STAGES) & 1);           // bytes of partition i have landed
+                const float2 ha = stH[stg][tid], hb = stH[stg][tid + 256];
 #pragma unroll
                 for (int c = 0; c < CH; ++c) {
-                    const float2 xa = xrow[c][(size_t) slotIdx * NB];
-                    const float2 xb = xrow[c][(size_t) slotIdx * NB + 256];
+                    const float2 xa = stX[stg][c][tid];
+                    const float2 xb = stX[stg][c][tid + 256];
                     acc[0][c] = (tid == 0) ? make_float2(acc[0][c].x + ha.x * xa.x, acc[0][c].y + ha.y * xa.y) : cadd(acc[0][c], cmul(ha, xa));
                     acc[1][c] = cadd(acc[1][c], cmul(hb, xb));
                 }
+                __syncthreads();                                           // everyone is done with this stage ...
+                if (tid == 0 && i + STAGES < S) { fence_proxy_async(); issueStage(i + STAGES); }   // ... refill it
             }
 #pragma unroll
             for (int c = 0; c < CH; ++c) if (ch0 + c < nv) {
@@ -208,7 +260,14 @@ cudaError_t convolver_process_chunk(ConvolverState& st, const float* in, float* 
         return cudaMemset2DAsync(out + offset, sizeof(float) * stride, 0, sizeof(float) * n, st.nv, stream);
     }
     const int grid = (st.nv + CONV_CH_PER_CTA - 1) / CONV_CH_PER_CTA;
-    convolve_chunk_kernel<<<grid, 256, 0, stream>>>(in, out, stride, offset, n, st.fill, st.cur, st.partitions, st.nv,
+    const size_t smem = (size_t) STAGES * (CH + 1) * ROW_BYTES + (size_t) 2 * CH * ROW_BYTES + ROW_BYTES + STAGES * sizeof(uint64_t);
+    static bool attrSet = false;
+    if (!attrSet) {
+        cudaError_t e = cudaFuncSetAttribute(convolve_chunk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
+        if (e != cudaSuccess) return e;
+        attrSet = true;
+    }
+    convolve_chunk_kernel<<<grid, 256, smem, stream>>>(in, out, stride, offset, n, st.fill, st.cur, st.partitions, st.nv,
                                                     st.dH, st.dFdl, st.dYpre, st.dOverlap, st.dInBuf, st.dTw);
     st.fill += n;
     if (st.fill == CONV_BLOCK) {
