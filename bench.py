@@ -238,11 +238,15 @@ def run_b200(args, rank, local_rank, world):
     algo_bytes = ALGO_BYTES_PER_VOICE_BLOCK_MIX_ONLY * voices
     achieved = algo_bytes / (k1_avg_ms * 1e-3) / 1e9 if k1_avg_ms > 0 else 0.0
     desc = rt.describe()["groups"][0]
-    traffic = None   # DRAM bytes of one K1 launch from the committed ncu --set full capture of this same configuration
+    traffic, ncu = None, None   # from the committed `ncu --set full` capture of this same configuration (profiles/)
     try:
         tj = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))["render_block_kernel"].get(str(voices))
         if tj:
             traffic = tj["dram_bytes_read"] + tj["dram_bytes_write"]
+            ncu = {k: tj[k] for k in ("warp_instructions", "issue_active_pct", "registers_per_thread", "fp64_pipe_pct",
+                                      "active_threads_per_warp_inst", "report") if k in tj}
+            if "warp_instructions" in tj:
+                ncu["warp_instructions_per_voice_sample"] = tj["warp_instructions"] / (voices * BS)
     except Exception:
         pass
 
@@ -273,7 +277,7 @@ def run_b200(args, rank, local_rank, world):
         "gpu_launches": int(launches),
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": traffic, "peak_kind": f"of {peak_kind}", "kernel": "render_block_kernel<NITER,LOGL> (K1)",
-                     "kernel_ms": k1_avg_ms, "kernel_launches_timed": k1_n,
+                     "kernel_ms": k1_avg_ms, "kernel_launches_timed": k1_n, "ncu": ncu,
                      "algorithmic_bytes_per_launch": algo_bytes,
                      "note": "K1 is instruction-issue bound, not HBM bound (intermediates never leave the SM); see DESIGN.md section 4"},
         "clocks": clocks,

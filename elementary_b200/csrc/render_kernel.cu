@@ -654,7 +654,9 @@ __device__ __forceinline__ void render_tile(const LaunchParams& P, const int til
                     if (T_OF(k) < cnt && !(offset <= kEps) &&
                         !(offset >= (float) (cnt + 1) && offset <= (float) (size - cnt - 1))) hazard = true;
                 }
-                if (!__any_sync(FULL, hazard)) {
+                const bool slow = __any_sync(FULL, hazard);
+                __syncwarp();   // every lane has read the write index before an owner lane may overwrite it
+                if (!slow) {
                     FOR_K(k) {
                         const int t = T_OF(k);
                         int w = w0 + t;
