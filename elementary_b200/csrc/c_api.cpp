@@ -64,9 +64,12 @@ int elem_b200_set_property_per_voice(elem_b200_runtime* rt, int32_t nodeId, cons
     GUARD(rt->engine->setPropertyPerVoice(nodeId, key, values, voiceBegin, count));
 }
 
-int elem_b200_process(elem_b200_runtime* rt, const float* const* in, size_t nIn, float* const* out, size_t nOut, size_t numSamples, void* /*userData*/) {
-    GUARD(rt->engine->process(in, nIn, out, nOut, numSamples));
+int elem_b200_process(elem_b200_runtime* rt, const float* const* in, size_t nIn, float* const* out, size_t nOut, size_t numSamples, void* userData) {
+    GUARD(rt->engine->process(in, nIn, out, nOut, numSamples, static_cast<const int64_t*>(userData)));
 }
+
+void elem_b200_set_current_time(elem_b200_runtime* rt, int64_t sampleTime) { if (rt) rt->engine->setCurrentTime(sampleTime); }
+int64_t elem_b200_current_time(elem_b200_runtime* rt) { return rt ? rt->engine->currentTime() : 0; }
 
 int elem_b200_process_voices(elem_b200_runtime* rt, const float* in, size_t nIn, float* outVoices, float* mix, size_t nOut, size_t numSamples) {
     GUARD(rt->engine->processVoices(in, nIn, outVoices, mix, nOut, numSamples));

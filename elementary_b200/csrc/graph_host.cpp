@@ -74,11 +74,13 @@ Program::~Program() {
     for (float* p : blockBuffers) rawFree(p, planOnly);
 }
 
+DeviceArray::~DeviceArray() { if (d) rawFree(d, planOnly); }
+
 struct TypeInfo { NodeKind kind; uint32_t fn; int stateRows; bool evenAlign; };
 
-// Registered builtin names: DefaultNodeTypes.h:53-143 (+ "convolve": wasm/Main.cpp:47).  Types that are out of
-// scope (seq*, sample*, mc.*, once, capture, fft, metro, time) are deliberately absent and yield
-// UnknownNodeType like any unregistered name (Runtime.h:304-305).
+// Registered builtin names: DefaultNodeTypes.h:53-143 (+ "convolve", "metro", "time": wasm/Main.cpp:47-61).  Types that
+// are out of scope (sample*, mc.*) are deliberately absent and yield UnknownNodeType like any
+// unregistered name (Runtime.h:304-305).
 static const std::unordered_map<std::string, TypeInfo>& typeTable() {
     static const std::unordered_map<std::string, TypeInfo> t = {
         {"in", {NodeKind::In, 0, 0, false}},
@@ -114,6 +116,10 @@ static const std::unordered_map<std::string, TypeInfo>& typeTable() {
         {"blepsaw", {NodeKind::Blep, 0, 2, false}}, {"blepsquare", {NodeKind::Blep, 1, 2, false}},
         {"bleptriangle", {NodeKind::Blep, 2, 2, false}},
         {"convolve", {NodeKind::Convolve, 0, 0, false}},
+        {"once", {NodeKind::Once, 0, 4, false}}, {"seq", {NodeKind::Seq, 0, 6, false}},
+        {"seq2", {NodeKind::Seq2, 0, 3, false}}, {"sparseq", {NodeKind::SparSeq, 0, 13, false}},
+        {"sparseq2", {NodeKind::SparSeq2, 0, 3, false}},
+        {"time", {NodeKind::Time, 0, 0, false}}, {"metro", {NodeKind::Metro, 0, 0, false}},
         {"meter", {NodeKind::PassThrough, 0, 0, false}}, {"scope", {NodeKind::PassThrough, 0, 0, false}},
     };
     return t;
@@ -257,6 +263,15 @@ int Engine::ensureResourceOnDevice(Resource& r) {
     return rc::Ok;
 }
 
+int Engine::uploadArray(std::shared_ptr<DeviceArray>& out, const void* data, size_t bytes, size_t count) {
+    auto a = std::make_shared<DeviceArray>();
+    a->planOnly = planOnly_; a->bytes = bytes; a->count = count;
+    if (!cuda(dmalloc(&a->d, std::max<size_t>(bytes, 16)), "cudaMalloc sequence data")) return rc::CudaError;
+    if (bytes && !cuda(dmemcpySync(a->d, data, bytes, cudaMemcpyHostToDevice), "upload sequence data")) return rc::CudaError;
+    out = a;   // programs compiled against the previous array keep it alive until they are released
+    return rc::Ok;
+}
+
 int Engine::addSharedResource(const char* name, const float* const* chans, size_t nCh, size_t nSamples) {
     // insert-only: SharedResource.h:44-46 (emplace fails on an existing key)
     if (resources_.count(name)) return 0;
@@ -323,6 +338,10 @@ int Engine::createNode(Group& g, const Value& a1, const Value& a2) {   // Runtim
         case NodeKind::Root: n.fade.init(sr_); n.channel = -1; break;          // Core.h:80-82
         case NodeKind::Delay: n.size = blockSize_; n.ringDirty = true; break;  // Delays.h:56
         case NodeKind::SDelay: n.length = blockSize_; n.size = bitceil(blockSize_ + blockSize_); n.ringDirty = true; break;   // Delays.h:183,197-198
+        case NodeKind::SparSeq: {   // SparSeq.h:353,342-345: edgeCount = -1, loopPoints = {-1, -1}
+            for (int k : {2, 5, 6}) { int r = fillRowBits(g, n.stateRow + k, 0, g.Vpad, 0xFFFFFFFFu); if (r != rc::Ok) return r; }
+        } break;
+        case NodeKind::Metro: n.intervalSamps = static_cast<int64_t>(std::max(2.0, 1000.0 * 0.001 * sr_)); break;   // Metro.h:14-18
         default: break;
     }
     g.nodes.emplace(id, std::move(n));
@@ -371,6 +390,7 @@ int Engine::nodeSetProperty(Group& g, Node& n, const std::string& key, const Val
             if (key == "channel") {
                 if (!val.isNumber()) return rc::InvalidPropertyType;
                 n.channel = static_cast<int>(val.asNumber());
+                g.codeDirty = true;
             }
             break;
         case NodeKind::Svf:         // filters/SVF.h:30-46
@@ -379,6 +399,7 @@ int Engine::nodeSetProperty(Group& g, Node& n, const std::string& key, const Val
                 const std::string& m = val.asString();
                 if (m == "lowpass") n.mode = 0; if (m == "bandpass") n.mode = 1; if (m == "highpass") n.mode = 2;
                 if (m == "notch") n.mode = 3; if (m == "allpass") n.mode = 4;
+                g.codeDirty = true;
             }
             break;
         case NodeKind::SvfShelf:    // filters/SVFShelf.h:30-44
@@ -386,6 +407,7 @@ int Engine::nodeSetProperty(Group& g, Node& n, const std::string& key, const Val
                 if (!val.isString()) return rc::InvalidPropertyType;
                 const std::string& m = val.asString();
                 if (m == "lowshelf") n.mode = 0; if (m == "highshelf") n.mode = 1; if (m == "bell" || m == "peak") n.mode = 2;
+                g.codeDirty = true;
             }
             break;
         case NodeKind::MM1p:        // filters/MultiMode1p.h:50-65
@@ -393,13 +415,14 @@ int Engine::nodeSetProperty(Group& g, Node& n, const std::string& key, const Val
                 if (!val.isString()) return rc::InvalidPropertyType;
                 const std::string& m = val.asString();
                 if (m == "lowpass") n.mode = 0; if (m == "highpass") n.mode = 2; if (m == "allpass") n.mode = 4;
+                g.codeDirty = true;
             }
             break;
         case NodeKind::Delay:       // Delays.h:59-76
             if (key == "size") {
                 if (!val.isNumber()) return rc::InvalidPropertyType;
                 n.size = std::max(0, static_cast<int>(val.asNumber()));
-                n.ringDirty = true;
+                n.ringDirty = true; g.codeDirty = true;
             }
             break;
         case NodeKind::SDelay:      // Delays.h:188-206
@@ -407,14 +430,14 @@ int Engine::nodeSetProperty(Group& g, Node& n, const std::string& key, const Val
                 if (!val.isNumber()) return rc::InvalidPropertyType;
                 n.length = std::max(0, static_cast<int>(val.asNumber()));
                 n.size = bitceil(n.length + blockSize_);
-                n.ringDirty = true;
+                n.ringDirty = true; g.codeDirty = true;
             }
             break;
         case NodeKind::MaxHold:     // Core.h:292-303
             if (key == "hold") {
                 if (!val.isNumber()) return rc::InvalidPropertyType;
                 const double h = sr_ * 0.001 * val.asNumber();
-                n.holdSamples = static_cast<uint32_t>(h);
+                n.holdSamples = static_cast<uint32_t>(h); g.codeDirty = true;
             }
             break;
         case NodeKind::Rand:        // Noise.h:13-23
@@ -428,7 +451,7 @@ int Engine::nodeSetProperty(Group& g, Node& n, const std::string& key, const Val
         case NodeKind::TapOut:      // Feedback.h:24-38,71-85
             if (key == "name") {
                 if (!val.isString()) return rc::InvalidPropertyType;
-                n.tapName = val.asString();
+                n.tapName = val.asString(); g.codeDirty = true;
             }
             break;
         case NodeKind::Table:       // Table.h:20-34
@@ -438,7 +461,103 @@ int Engine::nodeSetProperty(Group& g, Node& n, const std::string& key, const Val
                 auto it = resources_.find(val.asString());
                 if (it == resources_.end()) return rc::InvalidPropertyValue;
                 n.resource = it->second;
-                n.resourceDirty = true;
+                n.resourceDirty = true; g.codeDirty = true;
+            }
+            break;
+
+        case NodeKind::Once:        // Core.h:345-361: the prop can arm but never disarm
+            if (key == "arm") {
+                if (!val.isBool()) return rc::InvalidPropertyType;
+                if (val.asBool()) { int r = fillRow(g, n.stateRow, vb, ve, 1.0f); if (r != rc::Ok) return r; }
+            }
+            break;
+        case NodeKind::Seq:         // Core.h:411-466
+        case NodeKind::Seq2:        // Seq2.h:39-84
+            if (key == "hold") { if (!val.isBool()) return rc::InvalidPropertyType; n.seqHold = val.asBool(); g.codeDirty = true; }
+            if (key == "loop") { if (!val.isBool()) return rc::InvalidPropertyType; n.seqLoop = val.asBool(); g.codeDirty = true; }
+            if (key == "offset") {
+                if (!val.isNumber()) return rc::InvalidPropertyType;
+                if (val.asNumber() < 0.0) return rc::InvalidPropertyValue;
+                n.seqOffset = static_cast<uint64_t>(val.asNumber()); g.codeDirty = true;
+            }
+            if (key == "seq") {
+                if (!val.isArray()) return rc::InvalidPropertyType;
+                std::vector<float> data;
+                for (auto& e : val.asArray()) {
+                    if (!e.isNumber()) return rc::InvalidInstructionFormat;   // the reference throws bad_variant_access here
+                    data.push_back((float) e.asNumber());
+                }
+                int r = uploadArray(n.seqData, data.data(), data.size() * sizeof(float), data.size());
+                if (r != rc::Ok) return r;
+                ++n.seqGen; g.codeDirty = true;
+            }
+            break;
+        case NodeKind::SparSeq:     // SparSeq.h:40-124
+            if (key == "offset") {
+                if (!val.isNumber()) return rc::InvalidPropertyType;
+                if (val.asNumber() < 0.0) return rc::InvalidPropertyValue;
+                n.seqOffset = static_cast<uint64_t>(val.asNumber()); g.codeDirty = true;
+            }
+            if (key == "loop") {
+                if (val.isNull() || (val.isBool() && !val.asBool())) { n.loopStart = -1; n.loopEnd = -1; }
+                else {
+                    if (!val.isArray()) return rc::InvalidPropertyType;
+                    auto& pts = val.asArray();
+                    if (pts.size() < 2 || !pts[0].isNumber() || !pts[1].isNumber()) return rc::InvalidInstructionFormat;
+                    n.loopStart = static_cast<int32_t>(pts[0].asNumber()); n.loopEnd = static_cast<int32_t>(pts[1].asNumber());
+                }
+                ++n.loopGen; g.codeDirty = true;
+            }
+            if (key == "follow") { if (!val.isBool()) return rc::InvalidPropertyType; n.follow = val.asBool(); g.codeDirty = true; }
+            if (key == "interpolate") { if (!val.isNumber()) return rc::InvalidPropertyType; n.interpolate = static_cast<int32_t>(val.asNumber()); g.codeDirty = true; }
+            if (key == "tickInterval") {
+                if (!val.isNumber()) return rc::InvalidPropertyType;
+                if (val.asNumber() < 0.0) return rc::InvalidPropertyValue;
+                n.tickIntervalSamples = sr_ * val.asNumber(); g.codeDirty = true;
+            }
+            if (key == "seq") {   // std::map<int32_t, float>::insert keeps the FIRST value of a duplicated tick time (SparSeq.h:111)
+                if (!val.isArray()) return rc::InvalidPropertyType;
+                std::map<int32_t, float> m;
+                for (auto& e : val.asArray()) {
+                    if (!e.isObject()) return rc::InvalidInstructionFormat;
+                    auto& o = e.asObject();
+                    auto v = o.find("value"), t = o.find("tickTime");
+                    if (v == o.end() || t == o.end() || !v->second.isNumber() || !t->second.isNumber()) return rc::InvalidInstructionFormat;
+                    m.insert({static_cast<int32_t>(t->second.asNumber()), (float) v->second.asNumber()});
+                }
+                std::vector<char> blob(m.size() * 8);
+                size_t i = 0;
+                for (auto& kv : m) { std::memcpy(blob.data() + 4 * i, &kv.first, 4); std::memcpy(blob.data() + 4 * (m.size() + i), &kv.second, 4); ++i; }
+                int r = uploadArray(n.seqData, blob.data(), blob.size(), m.size());
+                if (r != rc::Ok) return r;
+                ++n.seqGen; g.codeDirty = true;
+            }
+            break;
+        case NodeKind::SparSeq2:    // SparSeq2.h:20-56
+            if (key == "seq") {
+                if (!val.isArray()) return rc::InvalidPropertyType;
+                std::map<double, float> m;
+                for (auto& e : val.asArray()) {
+                    if (!e.isObject()) return rc::InvalidInstructionFormat;
+                    auto& o = e.asObject();
+                    auto v = o.find("value"), t = o.find("time");
+                    if (v == o.end() || t == o.end() || !v->second.isNumber() || !t->second.isNumber()) return rc::InvalidInstructionFormat;
+                    m.insert({t->second.asNumber(), (float) v->second.asNumber()});
+                }
+                std::vector<char> blob(m.size() * 12);
+                size_t i = 0;
+                for (auto& kv : m) { std::memcpy(blob.data() + 8 * i, &kv.first, 8); std::memcpy(blob.data() + 8 * m.size() + 4 * i, &kv.second, 4); ++i; }
+                int r = uploadArray(n.seqData, blob.data(), blob.size(), m.size());
+                if (r != rc::Ok) return r;
+                ++n.seqGen; g.codeDirty = true;
+            }
+            if (key == "interpolate") { if (!val.isNumber()) return rc::InvalidPropertyType; n.interpolate = static_cast<int32_t>(val.asNumber()); g.codeDirty = true; }
+            break;
+        case NodeKind::Metro:       // wasm/Metro.h:20-37
+            if (key == "interval") {
+                if (!val.isNumber()) return rc::InvalidPropertyType;
+                if (0 >= val.asNumber()) return rc::InvalidPropertyValue;
+                n.intervalSamps = static_cast<int64_t>(std::max(2.0, val.asNumber() * 0.001 * sr_)); g.codeDirty = true;
             }
             break;
         default: break;
@@ -516,20 +635,21 @@ int Engine::applyToGroup(Group& g, const std::vector<Value>& batch, int vb, int 
 }
 
 bool Engine::isValueOnlyBatch(const std::vector<Value>& batch, int vb, int ve) {
-    // A batch made only of SET_PROPERTY on per-voice-capable props (const.value, rand.seed) never changes the
+    // A batch made only of SET_PROPERTY on per-voice-capable props (const.value, rand.seed, once.arm) never changes the
     // structure of a group, so it may address any sub-range of voices without splitting the group.
     for (auto& ins : batch) {
         if (!ins.isArray()) return false;
         auto& ar = ins.asArray();
         if (ar.size() < 4 || !ar[0].isNumber() || static_cast<int>(ar[0].asNumber()) != 3) return false;
         int32_t id;
-        if (!toInt32(ar[1], id) || !ar[2].isString() || !ar[3].isNumber()) return false;
+        if (!toInt32(ar[1], id) || !ar[2].isString() || !(ar[3].isNumber() || ar[3].isBool())) return false;
         for (auto& g : groups_) {
             if (g->v0 >= ve || g->v0 + g->nv <= vb) continue;
             auto it = g->nodes.find(id);
             if (it == g->nodes.end()) return false;
-            const bool ok = (it->second.kind == NodeKind::Const && ar[2].asString() == "value") ||
-                            (it->second.kind == NodeKind::Rand && ar[2].asString() == "seed");
+            const bool ok = (it->second.kind == NodeKind::Const && ar[2].asString() == "value" && ar[3].isNumber()) ||
+                            (it->second.kind == NodeKind::Rand && ar[2].asString() == "seed" && ar[3].isNumber()) ||
+                            (it->second.kind == NodeKind::Once && ar[2].asString() == "arm" && ar[3].isBool());
             if (!ok) return false;
         }
     }
@@ -752,6 +872,7 @@ struct Compiler {
         std::vector<std::pair<uint32_t, int32_t>> operands;   // (kind, node id | param row)
         struct Step { uint32_t fn; uint32_t kind; int32_t ref; };   // OP_CHAIN: acc = fn(acc, operand) / fn(acc)
         std::vector<Step> steps;
+        std::vector<uint32_t> imm;         // raw immediate words behind the operands (control nodes)
         int segment = 0;                   // root sub-sequence the op belongs to
         bool dead = false;                 // absorbed into a later chain
         bool isSeg = false;
@@ -786,13 +907,14 @@ int Compiler::emitNode(Node& n, int rootIndex) {
     if (n.kind == NodeKind::Const || n.kind == NodeKind::Sr) return rc::Ok;   // folded into PARAM operands
 
     const bool leaf = n.inlets.empty();
-    if (leaf && n.kind != NodeKind::Rand && n.kind != NodeKind::TapIn) prog.usesHostInputs = true;
+    const bool sourceNode = n.kind == NodeKind::Rand || n.kind == NodeKind::TapIn || n.kind == NodeKind::Time || n.kind == NodeKind::Metro;
+    if (leaf && !sourceNode) prog.usesHostInputs = true;
     // Inputs as the node's process() sees them: children, or — for a leaf — the host input channels
     // (GraphRenderSequence.h:126-135).
     std::vector<std::pair<uint32_t, int32_t>> inputs;
     if (!leaf) {
         for (auto& in : n.inlets) inputs.push_back(operandFor(in));
-    } else if (n.kind != NodeKind::In) {
+    } else if (n.kind != NodeKind::In && !sourceNode) {
         for (int ch = 0; ch < nIn; ++ch) {
             PendingOp ld;
             ld.opcode = OP_LOADIN; ld.aux0 = (uint32_t) ch; ld.outNode = newTemp();
@@ -860,6 +982,40 @@ int Compiler::emitNode(Node& n, int rootIndex) {
             op.opcode = OP_BLEP; op.mode = n.fn; op.aux0 = fbits((float) E.sr_); take(1);
             break;
         case NodeKind::PassThrough: if (numCh < 1) { zeros(); break; } op.opcode = OP_COPY; take(1); break;
+
+
+        // ---- sequencing / control nodes ----
+        case NodeKind::Once: if (numCh < 1) { zeros(); break; } op.opcode = OP_ONCE; take(1); break;
+        case NodeKind::Seq:
+        case NodeKind::Seq2: {   // Core.h:497-500, Seq2.h:100-103: zeros without a trigger input or a sequence
+            if (numCh < 1 || !n.seqData || n.seqData->count == 0) { zeros(); break; }
+            op.opcode = n.kind == NodeKind::Seq ? OP_SEQ : OP_SEQ2;
+            take(std::min(numCh, 2));
+            op.mode = (n.seqHold ? 1u : 0u) | (n.seqLoop ? 2u : 0u) | (numCh > 1 ? 4u : 0u);
+            op.aux0 = (uint32_t) n.seqData->count; op.ptr = (uint64_t) (uintptr_t) n.seqData->d;
+            op.imm = {(uint32_t) std::min<uint64_t>(n.seqOffset, 0xFFFFFFFFu), n.seqGen};
+            prog.pinned.push_back(n.seqData);
+        } break;
+        case NodeKind::SparSeq: {   // SparSeq.h:259-262: zeros without a trigger input; the loop-point logic still runs without a sequence
+            if (numCh < 1) { zeros(); break; }
+            op.opcode = OP_SPARSEQ;
+            take(std::min(numCh, 2));
+            op.mode = (numCh > 1 ? 4u : 0u);
+            if (n.seqData) { op.aux0 = (uint32_t) n.seqData->count; op.ptr = (uint64_t) (uintptr_t) n.seqData->d; prog.pinned.push_back(n.seqData); }
+            uint64_t tb; std::memcpy(&tb, &n.tickIntervalSamples, 8);
+            op.imm = {(uint32_t) n.seqOffset, n.follow ? 1u : 0u, (uint32_t) n.interpolate, n.seqGen, n.loopGen,
+                      (uint32_t) n.loopStart, (uint32_t) n.loopEnd, (uint32_t) tb, (uint32_t) (tb >> 32)};
+        } break;
+        case NodeKind::SparSeq2: {  // SparSeq2.h:90-91
+            if (numCh < 1 || !n.seqData || n.seqData->count == 0) { zeros(); break; }
+            op.opcode = OP_SPARSEQ2; take(1);
+            op.mode = (n.interpolate == 1) ? 1u : 0u;
+            op.aux0 = (uint32_t) n.seqData->count; op.ptr = (uint64_t) (uintptr_t) n.seqData->d;
+            op.imm = {n.seqGen};
+            prog.pinned.push_back(n.seqData);
+        } break;
+        case NodeKind::Time: op.opcode = OP_TIME; break;                                     // wasm/SampleTime.h:16-23
+        case NodeKind::Metro: op.opcode = OP_METRO; putDouble(op, (double) n.intervalSamps); break;   // wasm/Metro.h:39-55
 
         case NodeKind::Delay: {   // Delays.h:92-106
             const size_t tiles = (size_t) g.nTiles() * g.tileWidth;
@@ -953,6 +1109,7 @@ int Engine::compile(Group& g, int nIn, std::shared_ptr<Program>& out) {
     auto prog = std::make_shared<Program>();
     prog->planOnly = planOnly_;
     prog->nIn = nIn;
+    g.codeDirty = false;
     if (g.tileWidth == 0) g.tileWidth = chooseTileWidth(g.nv);
 
     // Root order: Runtime.h:544-559 — iterate currentRoots ascending; active roots are pushed to the FRONT,
@@ -1347,7 +1504,7 @@ int Engine::compile(Group& g, int nIn, std::shared_ptr<Program>& out) {
         };
         auto opWords = [&](const Compiler::PendingOp& op) -> size_t {
             if (op.isSeg) return OP_HEADER_WORDS;
-            size_t n = op.operands.size() + 2 * op.steps.size();
+            size_t n = op.operands.size() + 2 * op.steps.size() + op.imm.size();
             return OP_HEADER_WORDS + ((n + 3) & ~(size_t) 3);
         };
         std::vector<size_t> wordOffset(sops.size() + 1, 0);
@@ -1385,6 +1542,7 @@ int Engine::compile(Group& g, int nIn, std::shared_ptr<Program>& out) {
                 prog->code.push_back(chain_fn_is_unary(stp.fn) ? 0u : encodeOperand(stp.kind, stp.ref));
                 written += 2;
             }
+            for (uint32_t w : op.imm) { prog->code.push_back(w); ++written; }
             for (; written < nOperandWords; ++written) prog->code.push_back(0);
         }
         for (int k = 0; k < 8; ++k) prog->code.push_back(k == 0 ? make_w0(OP_END, 0, 0, 0) : 0u);
@@ -1483,6 +1641,15 @@ int Engine::enqueueBlock(size_t nIn, size_t nOut, size_t numSamples, bool perVoi
     for (auto& gp : groups_) {
         Group& g = *gp;
         if (g.pending) { g.active = g.pending; g.pending.reset(); g.superseded.clear(); }
+        if (g.active && g.codeDirty) {
+            // A property that is baked into the program (svf.mode, delay.size, seq data, ...) was set after the last
+            // COMMIT: the reference's nodes pick such changes up at the top of their next process() through atomics
+            // and SPSC queues (e.g. Delays.h:92-95, Core.h:470-495); here the sequence is recompiled.
+            std::shared_ptr<Program> p;
+            int r = compile(g, (int) nIn, p);
+            if (r != rc::Ok) return r;
+            g.active = p;
+        }
         if (g.active && g.active->nIn != (int) nIn) {
             if (g.active->usesHostInputs) {   // leaf nodes see the host channels: GraphRenderSequence.h:126-135
                 std::shared_ptr<Program> p;
@@ -1545,6 +1712,7 @@ int Engine::enqueueBlock(size_t nIn, size_t nOut, size_t numSamples, bool perVoi
             P.roots[ri] = RootDyn{rn.fade.current, rn.fade.step, rn.fade.target, rn.channel};
         }
         P.runMask = runMask;
+        P.sampleTime = sampleTime_;
 
         // launch geometry: spread warps over the SMs first, then stack them
         int wpc = opt_.warpsPerCta;
@@ -1656,6 +1824,7 @@ int Engine::enqueueBlock(size_t nIn, size_t nOut, size_t numSamples, bool perVoi
         }
     }
     curNOut_ = nOut;
+    sampleTime_ += (int64_t) numSamples;   // wasm/Main.cpp:217
     return rc::Ok;
 }
 
@@ -1685,9 +1854,10 @@ int Engine::synchronize() {
     return cuda(cudaStreamSynchronize(stream_), "stream synchronize") ? rc::Ok : rc::CudaError;
 }
 
-int Engine::process(const float* const* in, size_t nIn, float* const* out, size_t nOut, size_t numSamples) {
+int Engine::process(const float* const* in, size_t nIn, float* const* out, size_t nOut, size_t numSamples, const int64_t* sampleTime) {
     if (planOnly_) return fail(rc::CudaError, "plan-only runtime (no CUDA device): rendering is impossible, there is no CPU fallback");
     dsetdev();
+    if (sampleTime) sampleTime_ = *sampleTime;   // BlockContext::userData as the wasm host passes it (wasm/Main.cpp:206-215)
     if (numSamples > (size_t) blockSize_) return fail(rc::BadArgument, "numSamples > blockSize");
     const size_t need = (nIn + nOut) * blockSize_;
     if (need > pinnedFloats_) {

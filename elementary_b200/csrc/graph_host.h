@@ -27,7 +27,18 @@ constexpr int CudaError = -1, BadArgument = -2;
 enum class NodeKind : uint8_t {
     In, Unary, Binary, Reduce, Root, Const, Sr, Phasor, SPhasor, Counter, Accum, Latch, MaxHold, Rand,
     Delay, SDelay, Z, Pole, Env, Biquad, Prewarp, MM1p, Svf, SvfShelf, TapIn, TapOut, Table, Blep, Convolve,
-    PassThrough   // analysis nodes (meter/scope/snapshot): audio passes through, events are out of scope
+    PassThrough,  // analysis nodes whose events are not produced: audio passes through
+    Once, Seq, Seq2, SparSeq, SparSeq2, Time, Metro   // sequencing / control nodes
+};
+
+// A read-only device array owned jointly by the node that uploaded it and by every compiled program that points at it
+// (sequence data of seq/seq2/sparseq/sparseq2: the reference hands such data to the audio thread through a
+// RefCountedPool + SPSC queue, Core.h:447-466).
+struct DeviceArray {
+    void* d = nullptr;
+    size_t bytes = 0, count = 0;
+    bool planOnly = false;
+    ~DeviceArray();
 };
 
 struct Inlet { int32_t source; int32_t channel; };
@@ -78,6 +89,14 @@ struct Node {
     std::shared_ptr<Resource> resource;   // table / convolve
     bool resourceDirty = false;
     std::shared_ptr<ConvolverState> conv;
+    // seq / seq2 / sparseq / sparseq2 (Core.h:411-466, Seq2.h:39-84, SparSeq.h:40-124, SparSeq2.h:20-56)
+    std::shared_ptr<DeviceArray> seqData;
+    uint32_t seqGen = 0, loopGen = 0;
+    bool seqHold = false, seqLoop = true, follow = false;
+    uint64_t seqOffset = 0;
+    int32_t loopStart = -1, loopEnd = -1, interpolate = 0;
+    double tickIntervalSamples = 0.0;
+    int64_t intervalSamps = 0;       // metro (wasm/Metro.h:24-34)
 };
 
 struct Program {
@@ -100,6 +119,7 @@ struct Program {
     struct Stage { uint32_t codeOffset = 0; std::vector<Conv> convolves; };
     std::vector<Stage> stages;
     std::vector<float*> blockBuffers;     // [Vpad][blockSize] HBM buffers carrying values across stages
+    std::vector<std::shared_ptr<DeviceArray>> pinned;   // device arrays the code points at
     ~Program();
 };
 
@@ -112,6 +132,7 @@ struct Group {
     int rowsCap = 0, rowsUsed = 0;
     std::map<std::string, float*> tapShared;
     std::shared_ptr<Program> pending, active;
+    bool codeDirty = false;               // a property that is baked into the program changed: recompile at the next process()
     std::vector<std::shared_ptr<Program>> superseded;   // queued but never run (rseqQueue, Runtime.h:133,277-285): still pin their nodes for gc
     int nTiles() const { return tileWidth ? (nv + tileWidth - 1) / tileWidth : 0; }
 };
@@ -139,7 +160,7 @@ public:
     void reset();
 
     // Runtime::process shape: planar host buffers; inputs broadcast to every voice; out = mix bus.
-    int process(const float* const* in, size_t nIn, float* const* out, size_t nOut, size_t numSamples);
+    int process(const float* const* in, size_t nIn, float* const* out, size_t nOut, size_t numSamples, const int64_t* sampleTime = nullptr);
     // Voice-major host buffers: in[voice][nIn][n] (may be null), out[voice][nOut][n] (may be null), mix (may be null).
     int processVoices(const float* in, size_t nIn, float* outVoices, float* mix, size_t nOut, size_t numSamples);
     // Device-resident: no host I/O, no synchronisation; used for throughput timing and by processVoices/process.
@@ -156,6 +177,10 @@ public:
     int numVoices() const { return numVoices_; }
     int blockSize() const { return blockSize_; }
     uint64_t kernelLaunches() const { return launches_; }
+    // The int64 sample clock handed to nodes through BlockContext::userData (wasm/Main.cpp:206-217, Metro.h:44,
+    // SampleTime.h:19).  process() takes it from *userData when given; otherwise the engine counts samples itself.
+    void setCurrentTime(int64_t t) { sampleTime_ = t; }
+    int64_t currentTime() const { return sampleTime_; }
     // Sum of the device durations (ms) of the K1 render kernels launched since the last call, measured with
     // CUDA events recorded on the launching stream (option "time_kernels" = 1). Synchronises the stream.
     double takeKernelTimeMs(uint64_t* count);
@@ -173,6 +198,7 @@ private:
     std::map<std::string, std::shared_ptr<Resource>> resources_;
     std::string lastError_;
     uint64_t launches_ = 0;
+    int64_t sampleTime_ = 0;
     bool timeKernels_ = false;
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> timedEvents_, timedConvEvents_, eventPool_;
     double lastConvMs_ = 0.0; uint64_t lastConvCount_ = 0;
@@ -214,6 +240,7 @@ private:
     int fillRow(Group& g, int row, int vb, int ve, float value);
     int fillRowBits(Group& g, int row, int vb, int ve, uint32_t bits);
     int ensureResourceOnDevice(Resource& r);
+    int uploadArray(std::shared_ptr<DeviceArray>& out, const void* data, size_t bytes, size_t count);
 
     // compile (Runtime.h:521-577 + GraphRenderSequence.h:107-187)
     int compile(Group& g, int nIn, std::shared_ptr<Program>& out);

@@ -54,6 +54,18 @@ enum Opcode : uint32_t {
     OP_STOREBUF,   // stage boundary: in0 -> global per-voice block buffer (ptr), used around `convolve`
     OP_LOADBUF,    // stage boundary: global per-voice block buffer (ptr) -> out
     OP_PROMOTE,    // after the first OP_END: tap promotion record (w1 = root index, w2/w3 = src, w4/w5 = dst)
+    // ---- sequencing / control nodes ----
+    OP_ONCE,       // Core.h:341-404
+    OP_SEQ,        // Core.h:407-573  (ptr = float[aux0] sequence; imm: offset, generation; mode bit0 hold, bit1 loop, bit2 has reset input)
+    OP_SEQ2,       // Seq2.h:35-166   (same encoding, no generation)
+    OP_SPARSEQ,    // SparSeq.h:17-377 (ptr = int32 tickTime[aux0] then float value[aux0]; imm block see graph_host.cpp)
+    OP_SPARSEQ2,   // SparSeq2.h:17-141 (ptr = double time[aux0] then float value[aux0]; imm: generation; mode bit0 interpolate)
+    OP_TIME,       // wasm/SampleTime.h:12-24 (LaunchParams::sampleTime)
+    OP_METRO,      // wasm/Metro.h:10-71 ((aux0,aux1) = bits of double(intervalSamps))
+    // ---- analysis nodes: audio passes through, a per-voice record feeds processQueuedEvents ----
+    OP_METER,      // Analyzers.h:20-69   ptr = float2[voice] {min,max} + flag row
+    OP_SNAPSHOT,   // Analyzers.h:77-136
+    OP_SCOPE,      // Analyzers.h:146-255 / Capture
     OP_COUNT_
 };
 
@@ -82,6 +94,9 @@ constexpr int MAX_SLOTS = 255;
 inline uint32_t make_w0(uint32_t opcode, uint32_t nWords, uint32_t outSlot, uint32_t mode) {
     return (opcode & 0xFF) | ((nWords & 0xFF) << 8) | ((outSlot & 0xFF) << 16) | ((mode & 0xFF) << 24);
 }
+#ifdef __CUDACC__
+__host__ __device__
+#endif
 inline uint32_t make_operand(uint32_t kind, uint32_t index) { return (kind << 30) | (index & 0x3FFFFFFFu); }
 
 // Per-block dynamic root state (host mirrors GainFade, helpers/GainFade.h:56-72): the fade ramp of a block is a
@@ -119,6 +134,7 @@ struct LaunchParams {
     int outStride;
     int tileBase;                // index of this group's first tile in mixPartial
     uint32_t runMask;            // bit r: root r's sub-sequence runs this block; bit 16+r: root r promotes its taps
+    long long sampleTime;        // int64 sample clock of this block's first sample (*userData of Runtime::process: wasm/Main.cpp:206-217)
     RootDyn roots[MAX_ROOTS];
 };
 

@@ -135,6 +135,257 @@ __host__ __device__ constexpr int ilog2(int x) { return x <= 1 ? 0 : 1 + ilog2(x
 
 } // namespace
 
+
+// =========================================================================================================
+// Sequencing / control nodes.  They are rare in a render program and bulky, so each lives in
+// its own out-of-line function: the interpreter's hot loop keeps its instruction footprint.  All of them are true
+// recurrences (edge detectors + counters), run by the lane that owns the voice.
+struct CtlCtx {
+    float* sst;              // the warp's state area [row][L]
+    const float* spar;       // the warp's parameter area [row][L]
+    float* slots;            // the warp's slot area
+    float* outT;             // owner lane, sample t: outT[t * L]
+    const uint32_t* opnds;   // operand words, then immediates
+    uint64_t ptr;
+    long long sampleTime;    // of sample 0 of this tile
+    uint32_t sidx, aux0, aux1, mode, nopnd;
+    int cnt, s0, lane, vlane;
+};
+
+template <int L, int E>
+__device__ __forceinline__ Opnd ctl_decode(const CtlCtx& c, uint32_t w) {
+    Opnd o;
+    const uint32_t idx = w & 0x3FFFFFFFu;
+    if ((w >> 30) == K_SLOT) { o.p = c.slots + idx * E + c.lane; o.stride = 32; o.tstride = L; }
+    else { o.p = c.spar + idx * L + c.vlane; o.stride = 0; o.tstride = 0; }
+    return o;
+}
+
+#define ST(r) c.sst[(c.sidx + (r)) * L + c.lane]
+#define STU(r) __float_as_uint(ST(r))
+#define STI(r) __float_as_int(ST(r))
+
+// Core.h:341-404 — OnceNode.  state: armed, gain, change.lastIn, isArmed (armed as loaded at the top of process())
+template <int L, int E>
+__device__ __noinline__ void ctl_once(const CtlCtx& c) {
+    const Opnd x = ctl_decode<L, E>(c, __ldg(c.opnds));
+    float armed = ST(0), gain = ST(1), last = ST(2), isArmed = ST(3);
+    if (c.s0 == 0) isArmed = armed;                      // Core.h:370: one load per process() call
+    for (int t = 0; t < c.cnt; ++t) {
+        const float xin = LDT(x, t);
+        const float delta = change_tick(last, xin);
+        if (isArmed != 0.0f && delta > 0.5f) { gain = 1.0f; armed = 0.0f; }
+        if (delta < -0.5f) gain = 0.0f;
+        c.outT[t * L] = xin * gain;
+    }
+    ST(0) = armed; ST(1) = gain; ST(2) = last; ST(3) = isArmed;
+}
+
+// Core.h:407-573 — SequenceNode.  state: change.lastIn, resetChange.lastIn, holdValue, seqIndex, hasReceivedFirstPulse,
+// generation of the sequence data last seen.  imm: [offset, generation].  mode: 1 hold, 2 loop, 4 reset input present.
+template <int L, int E>
+__device__ __noinline__ void ctl_seq(const CtlCtx& c) {
+    const Opnd x = ctl_decode<L, E>(c, __ldg(c.opnds));
+    const bool hasReset = (c.mode & 4u) != 0, hold = (c.mode & 1u) != 0, loop = (c.mode & 2u) != 0;
+    const Opnd r = ctl_decode<L, E>(c, hasReset ? __ldg(c.opnds + 1) : make_operand(K_PARAM, 0));
+    const uint32_t offset = __ldg(c.opnds + c.nopnd), codeGen = __ldg(c.opnds + c.nopnd + 1);
+    const float* data = reinterpret_cast<const float*>(c.ptr);
+    const uint32_t n = c.aux0;
+    float last = ST(0), rlast = ST(1), holdv = ST(2);
+    uint32_t idx = STU(3), first = STU(4), gen = STU(5);
+    if (c.s0 == 0 && gen != codeGen) {                   // a new sequence was popped from the queue: Core.h:473-495
+        idx = idx % n;
+        if (first) holdv = __ldg(data + idx);
+        gen = codeGen;
+    }
+    for (int t = 0; t < c.cnt; ++t) {
+        const float in = LDT(x, t);
+        const float reset = hasReset ? LDT(r, t) : 0.0f;
+        if (change_tick(rlast, reset) > 0.5f) idx = offset;
+        if (change_tick(last, in) > 0.5f) {
+            holdv = __ldg(data + min(idx, n - 1));
+            first = 1;
+            if (++idx >= n && loop) idx = 0;
+        }
+        c.outT[t * L] = (idx < n) ? (hold ? holdv : holdv * in) : (hold ? holdv : 0.0f);
+    }
+    ST(0) = last; ST(1) = rlast; ST(2) = holdv;
+    ST(3) = __uint_as_float(idx); ST(4) = __uint_as_float(first); ST(5) = __uint_as_float(gen);
+}
+
+// Seq2.h:87-148 — Seq2Node.  state: change.lastIn, resetChange.lastIn, edgeCount.  imm: [offset].
+template <int L, int E>
+__device__ __noinline__ void ctl_seq2(const CtlCtx& c) {
+    const Opnd x = ctl_decode<L, E>(c, __ldg(c.opnds));
+    const bool hasReset = (c.mode & 4u) != 0, hold = (c.mode & 1u) != 0, loop = (c.mode & 2u) != 0;
+    const Opnd r = ctl_decode<L, E>(c, hasReset ? __ldg(c.opnds + 1) : make_operand(K_PARAM, 0));
+    const unsigned long long offset = __ldg(c.opnds + c.nopnd);
+    const float* data = reinterpret_cast<const float*>(c.ptr);
+    const unsigned long long n = c.aux0;
+    float last = ST(0), rlast = ST(1);
+    uint32_t edge = STU(2);
+    for (int t = 0; t < c.cnt; ++t) {
+        const float in = LDT(x, t);
+        const float reset = hasReset ? LDT(r, t) : 0.0f;
+        if (change_tick(last, in) > 0.5f) edge++;
+        if (change_tick(rlast, reset) > 0.5f) edge = 0;
+        const unsigned long long idx = offset + edge;
+        const float next = (idx < n) ? __ldg(data + idx)
+                         : (loop ? __ldg(data + idx % n) : (hold ? __ldg(data + (n - 1)) : 0.0f));
+        c.outT[t * L] = hold ? next : next * in;
+    }
+    ST(0) = last; ST(1) = rlast; ST(2) = __uint_as_float(edge);
+}
+
+// first index whose key is > t (std::map::upper_bound over the sorted key array)
+template <typename K>
+__device__ __forceinline__ int upper_bound_idx(const K* keys, int n, K t) {
+    int lo = 0, hi = n;
+    while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (t < keys[mid]) hi = mid; else lo = mid + 1;
+    }
+    return lo;
+}
+
+// SparSeq2.h:69-128 — SparSeq2Node.  ptr = double time[n] then float value[n].  state: prevEvent, nextEvent (indices, n =
+// end()), generation.  imm: [generation].  mode bit0 = interpolate.
+template <int L, int E>
+__device__ __noinline__ void ctl_sparseq2(const CtlCtx& c) {
+    const Opnd x = ctl_decode<L, E>(c, __ldg(c.opnds));
+    const int n = (int) c.aux0;
+    const double* times = reinterpret_cast<const double*>(c.ptr);
+    const float* values = reinterpret_cast<const float*>(times + n);
+    const bool interp = (c.mode & 1u) != 0;
+    const uint32_t codeGen = __ldg(c.opnds + c.nopnd);
+    int prev = STI(0), next = STI(1);
+    uint32_t gen = STU(2);
+    if (c.s0 == 0 && gen != codeGen) { prev = n; next = n; gen = codeGen; }   // SparSeq2.h:77-86
+    for (int i = 0; i < c.cnt; ++i) {
+        const double t = (double) LDT(x, i);
+        const bool update = (prev == n && next == n) || (prev != n && t <= (times[prev] + 1e-9)) || (next != n && t >= (times[next] - 1e-9));
+        if (update) {
+            next = upper_bound_idx<double>(times, n, t);
+            prev = (next == 0) ? n : next - 1;
+        }
+        float y;
+        if (prev == n) y = 0.0f;
+        else if (next == n) y = values[prev];
+        else {
+            const double alpha = interp ? ((t - times[prev]) / (times[next] - times[prev])) : 0.0;
+            y = values[prev] + (float) alpha * (values[next] - values[prev]);
+        }
+        c.outT[i * L] = y;
+    }
+    ST(0) = __int_as_float(prev); ST(1) = __int_as_float(next); ST(2) = __uint_as_float(gen);
+}
+
+// SparSeq.h:17-377 — SparSeqNode.  ptr = int32 tickTime[n] then float value[n] (0 = no sequence yet).
+// state rows: 0 change.lastIn, 1 resetChange.lastIn, 2 edgeCount, 3 samplesSinceClockEdge, 4 holdValue (index, n = end()),
+// 5/6 loopPoints, 7 pending flag, 8/9 pendingLoopPoints, 10 sequence generation seen, 11 loop-points generation seen,
+// 12 tickTime (a local of process(), carried between the sample tiles of one call).
+// imm: [offset, follow, interpolate, seqGen, loopGen, loopStart, loopEnd, tickInterval lo, hi].
+struct SparSeqState { int edge, ls, le, pend, ps, pe; };
+
+__device__ __forceinline__ int sparseq_tick_time(SparSeqState& s, int offset) {     // SparSeq.h:147-193
+    int tick = offset + s.edge;
+    const int ls = s.ls, le = s.le;
+    if (ls > -1 && le > -1 && tick >= le) {
+        const int dur = le - ls;
+        if (dur > 0) {
+            if (s.pend) {
+                s.ls = s.ps; s.le = s.pe; s.pend = 0;
+                const int nls = s.ls, nle = s.le;
+                if (nls == -1 && nle == -1) return tick;
+                if (nle - nls != 0) tick = nls + ((tick - le) % (nle - nls));
+            } else {
+                tick = ls + ((tick - le) % dur);
+            }
+            s.edge = tick - offset;
+        }
+    }
+    return tick;
+}
+
+__device__ __forceinline__ int sparseq_find(const int* times, int n, int tick) {      // SparSeq.h:126-145
+    if (n == 0) return 0;
+    const int it = upper_bound_idx<int>(times, n, tick);
+    if (it == 0) return (times[0] == 0) ? 0 : n;
+    return it - 1;
+}
+
+template <int L, int E>
+__device__ __noinline__ void ctl_sparseq(const CtlCtx& c) {
+    const Opnd x = ctl_decode<L, E>(c, __ldg(c.opnds));
+    const bool hasReset = (c.mode & 4u) != 0;
+    const Opnd r = ctl_decode<L, E>(c, hasReset ? __ldg(c.opnds + 1) : make_operand(K_PARAM, 0));
+    const uint32_t* imm = c.opnds + c.nopnd;
+    const int offset = (int) __ldg(imm), follow = (int) __ldg(imm + 1), ho = (int) __ldg(imm + 2);
+    const uint32_t seqGen = __ldg(imm + 3), loopGen = __ldg(imm + 4);
+    const double spc = bits_to_double(__ldg(imm + 7), __ldg(imm + 8));
+    const int n = (int) c.aux0;
+    const bool hasSeq = c.ptr != 0;
+    const int* times = reinterpret_cast<const int*>(c.ptr);
+    const float* values = reinterpret_cast<const float*>(times + n);
+
+    float last = ST(0), rlast = ST(1);
+    SparSeqState s{STI(2), STI(5), STI(6), STI(7), STI(8), STI(9)};
+    uint32_t since = STU(3);
+    int holdIdx = STI(4), tick = STI(12);
+    if (c.s0 == 0) {                                       // top of process(): SparSeq.h:209-257
+        tick = sparseq_tick_time(s, offset);
+        uint32_t sg = STU(10), lg = STU(11);
+        if (sg != seqGen || lg != loopGen) {
+            if (lg != loopGen) { s.pend = 1; s.ps = (int) __ldg(imm + 5); s.pe = (int) __ldg(imm + 6); }
+            ST(10) = __uint_as_float(seqGen); ST(11) = __uint_as_float(loopGen);
+            holdIdx = hasSeq ? sparseq_find(times, n, tick) : n;
+        }
+        if (s.pend) {
+            const bool takeImmediately = (s.ls == -1 && s.le == -1) || !follow;
+            if (takeImmediately) { s.ls = s.ps; s.le = s.pe; s.pend = 0; tick = sparseq_tick_time(s, offset); }
+        }
+    }
+    if (!hasSeq) {
+        for (int t = 0; t < c.cnt; ++t) c.outT[t * L] = 0.0f;
+    } else {
+        for (int i = 0; i < c.cnt; ++i) {
+            since++;
+            const float in = LDT(x, i);
+            const float reset = hasReset ? LDT(r, i) : 0.0f;
+            const bool trig = change_tick(last, in) > 0.5f;
+            const bool rst = change_tick(rlast, reset) > 0.5f;
+            if (rst) s.edge = 0;
+            if (trig) {
+                s.edge = rst ? 0 : s.edge + 1;
+                since = 0;
+                tick = sparseq_tick_time(s, offset);
+                holdIdx = sparseq_find(times, n, tick);
+            }
+            float y;
+            if (holdIdx == n) y = 0.0f;
+            else if (ho == 1) {
+                const int right = holdIdx + 1;
+                if (right == n) y = values[holdIdx];
+                else {
+                    const int tl = times[holdIdx], tr = times[right];
+                    const float lv = values[holdIdx], rv = values[right];
+                    double alpha = (double) max(0, tick - tl) / (double) (tr - tl);
+                    if (spc > 0.0) alpha += (fmin((double) since, spc) / spc) / (double) (tr - tl);
+                    y = (float) ((double) lv + alpha * (double) (rv - lv));
+                }
+            } else y = values[holdIdx];
+            c.outT[i * L] = y;
+        }
+    }
+    ST(0) = last; ST(1) = rlast;
+    ST(2) = __int_as_float(s.edge); ST(3) = __uint_as_float(since); ST(4) = __int_as_float(holdIdx);
+    ST(5) = __int_as_float(s.ls); ST(6) = __int_as_float(s.le); ST(7) = __int_as_float(s.pend);
+    ST(8) = __int_as_float(s.ps); ST(9) = __int_as_float(s.pe); ST(12) = __int_as_float(tick);
+}
+#undef ST
+#undef STU
+#undef STI
+
 // =========================================================================================================
 // The whole per-tile interpreter; instantiated by the two thin __global__ wrappers at the end of this section.
 template <int NITER, int LOGL>
@@ -830,6 +1081,35 @@ __device__ __forceinline__ void render_tile(const LaunchParams& P, const int til
                 if (rd.channel >= 0 && rd.channel < P.nOut) {   // GraphRenderSequence.h:227-231
                     float* acc = outacc + rd.channel * E + lane;
                     FOR_K(k) acc[k * 32] += out[k * 32];
+                }
+            } break;
+
+
+            // ---- sequencing / control nodes: out-of-line bodies above ----
+            case OP_ONCE: case OP_SEQ: case OP_SEQ2: case OP_SPARSEQ: case OP_SPARSEQ2: {
+                if (owner) {
+                    const CtlCtx c{sst, spar, slots, outT, opnds, ptrbits, P.sampleTime + s0, sidx, aux0, aux1, mode, count6, cnt, s0, lane, vlane};
+                    switch (opcode) {
+                        case OP_ONCE: ctl_once<L, E>(c); break;
+                        case OP_SEQ: ctl_seq<L, E>(c); break;
+                        case OP_SEQ2: ctl_seq2<L, E>(c); break;
+                        case OP_SPARSEQ: ctl_sparseq<L, E>(c); break;
+                        default: ctl_sparseq2<L, E>(c); break;
+                    }
+                }
+            } break;
+
+            case OP_TIME: {     // wasm/SampleTime.h:17-23: out[i] = double(sampleTime + i), rounded to float
+                const long long t0 = P.sampleTime + s0;
+                FOR_K(k) out[k * 32] = (float) (double) (t0 + T_OF(k));
+            } break;
+
+            case OP_METRO: {    // wasm/Metro.h:41-55; (aux0,aux1) = bits of double(intervalSamps)
+                const double is = bits_to_double(aux0, aux1);
+                const long long t0 = P.sampleTime + s0;
+                FOR_K(k) {
+                    const double tt = (double) (t0 + T_OF(k)) / is;
+                    out[k * 32] = ((tt - floor(tt)) < 0.5) ? 1.0f : 0.0f;
                 }
             } break;
 

@@ -261,6 +261,55 @@ def smooth(p: ElemNode, x: ElemNode) -> Node:
     return pole(p, mul(sub(1, p), x))
 
 
+# --- sequencing / control / analysis nodes (js/packages/core/lib/core.ts:17-66,103-153,304-355) ----------------
+def time() -> Node:
+    return Node("time", {})
+
+
+def once(props: Dict[str, Any], x: ElemNode) -> Node:
+    return create_node("once", props, [x])
+
+
+def metro(props: Optional[Dict[str, Any]] = None) -> Node:
+    return Node("metro", dict(props or {}))
+
+
+def seq(props: Dict[str, Any], trigger: ElemNode, reset: ElemNode = 0) -> Node:
+    return create_node("seq", props, [trigger, reset])
+
+
+def seq2(props: Dict[str, Any], trigger: ElemNode, reset: ElemNode = 0) -> Node:
+    return create_node("seq2", props, [trigger, reset])
+
+
+def sparseq(props: Dict[str, Any], trigger: ElemNode, reset: ElemNode = 0) -> Node:
+    return create_node("sparseq", props, [trigger, reset])
+
+
+def sparseq2(props: Dict[str, Any], t: ElemNode) -> Node:
+    return create_node("sparseq2", props, [t])
+
+
+def meter(props: Dict[str, Any], x: ElemNode) -> Node:
+    return create_node("meter", props, [x])
+
+
+def snapshot(props: Dict[str, Any], trigger: ElemNode, x: ElemNode) -> Node:
+    return create_node("snapshot", props, [trigger, x])
+
+
+def scope(props: Dict[str, Any], *args: ElemNode) -> Node:
+    return create_node("scope", props, list(args))
+
+
+def capture(props: Dict[str, Any], g: ElemNode, x: ElemNode) -> Node:
+    return create_node("capture", props, [g, x])
+
+
+def fft(props: Dict[str, Any], x: ElemNode) -> Node:
+    return create_node("fft", props, [x])
+
+
 def select(g: ElemNode, a: ElemNode, b: ElemNode) -> Node:
     # lib/signals.ts: add(mul(g, a), mul(sub(1, g), b))
     return add(mul(g, a), mul(sub(1, g), b))

@@ -55,6 +55,9 @@ def load_library() -> C.CDLL:
     lib.elem_b200_set_property_per_voice.argtypes = [C.c_void_p, C.c_int32, C.c_char_p, C.POINTER(C.c_double), C.c_int, C.c_int]
     lib.elem_b200_process.restype = C.c_int
     lib.elem_b200_process.argtypes = [C.c_void_p, _f32pp, C.c_size_t, _f32pp, C.c_size_t, C.c_size_t, C.c_void_p]
+    lib.elem_b200_set_current_time.argtypes = [C.c_void_p, C.c_int64]
+    lib.elem_b200_current_time.restype = C.c_int64
+    lib.elem_b200_current_time.argtypes = [C.c_void_p]
     lib.elem_b200_process_voices.restype = C.c_int
     lib.elem_b200_process_voices.argtypes = [C.c_void_p, _f32p, C.c_size_t, _f32p, _f32p, C.c_size_t, C.c_size_t]
     lib.elem_b200_enqueue_block.restype = C.c_int
@@ -155,7 +158,10 @@ class Runtime:
                                                           v.ctypes.data_as(C.POINTER(C.c_double)), int(voice_begin), v.size)
 
     # -- Runtime::process (Runtime.h:51-57,275-290): out = mix bus over all voices -------------------------------
-    def process(self, inputs: Optional[np.ndarray], num_outputs: int, num_samples: Optional[int] = None) -> np.ndarray:
+    def process(self, inputs: Optional[np.ndarray], num_outputs: int, num_samples: Optional[int] = None,
+                sample_time: Optional[int] = None) -> np.ndarray:
+        """``sample_time``: the int64 the reference's hosts pass as ``userData`` (wasm/Main.cpp:206-215); None lets the
+        engine keep the clock itself."""
         n = int(num_samples if num_samples is not None else self.block_size)
         if inputs is None or len(inputs) == 0:
             n_in, in_ptrs, keep = 0, None, None
@@ -166,7 +172,8 @@ class Runtime:
             in_ptrs = (_f32p * n_in)(*[keep[i].ctypes.data_as(_f32p) for i in range(n_in)])
         out = np.zeros((num_outputs, n), dtype=np.float32)
         out_ptrs = (_f32p * max(1, num_outputs))(*[out[i].ctypes.data_as(_f32p) for i in range(num_outputs)])
-        rc = self._lib.elem_b200_process(self._h, in_ptrs, n_in, out_ptrs, num_outputs, n, None)
+        user = None if sample_time is None else C.byref(C.c_int64(int(sample_time)))
+        rc = self._lib.elem_b200_process(self._h, in_ptrs, n_in, out_ptrs, num_outputs, n, user)
         self._check(rc, "process")
         return out
 
@@ -246,6 +253,13 @@ class Runtime:
 
     def reset(self) -> None:
         self._lib.elem_b200_reset(self._h)
+
+    # -- ElementaryAudioProcessor::setCurrentTime (wasm/Main.cpp:232-241) ---------------------------------------------
+    def set_current_time(self, sample_time: int) -> None:
+        self._lib.elem_b200_set_current_time(self._h, int(sample_time))
+
+    def current_time(self) -> int:
+        return int(self._lib.elem_b200_current_time(self._h))
 
     def process_queued_events(self, callback=None) -> None:
         self._lib.elem_b200_process_queued_events(self._h, None, None)

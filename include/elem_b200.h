@@ -49,9 +49,16 @@ int elem_b200_set_property_per_voice(elem_b200_runtime* rt, int32_t nodeId, cons
 
 /* Runtime::process(in, nIn, out, nOut, numSamples, userData) — Runtime.h:51-57,275-290.
  * `in` channels are broadcast to every voice; out[c] receives the MIX BUS: the sum over all voices of what
- * each voice's Runtime would have written to its out[c].  Host buffers; H2D/D2H copies are inside the call. */
+ * each voice's Runtime would have written to its out[c].  Host buffers; H2D/D2H copies are inside the call.
+ * userData: NULL, or — as every reference host passes it (wasm/Main.cpp:206-215) — a pointer to the int64 sample
+ * time of the block's first sample, read by the `time` and `metro` nodes (wasm/SampleTime.h:19, Metro.h:44).
+ * With NULL the engine keeps the clock itself (+= numSamples per call, like wasm/Main.cpp:217). */
 int elem_b200_process(elem_b200_runtime* rt, const float* const* in, size_t nIn,
                       float* const* out, size_t nOut, size_t numSamples, void* userData);
+
+/* ElementaryAudioProcessor::setCurrentTime — wasm/Main.cpp:232-241: (re)set the engine-kept sample clock. */
+void elem_b200_set_current_time(elem_b200_runtime* rt, int64_t sampleTime);
+int64_t elem_b200_current_time(elem_b200_runtime* rt);
 
 /* Voice-major variant for per-voice I/O and parity tests: in = [voice][nIn][numSamples] or NULL,
  * outVoices = [voice][nOut][numSamples] or NULL, mix = [nOut][numSamples] or NULL (all host memory). */

@@ -245,9 +245,11 @@ struct TwoStageConv {
 };
 
 struct PropValue {
-    char kind = 'N';   // N number, S string, B bool, J other json
+    char kind = 'N';   // N number, S string, B bool, A array of numbers, M array of {key: number} objects, U null, J other json
     double num = 0;
     std::string str;
+    std::vector<double> arr;
+    std::vector<std::map<std::string, double>> objs;
 };
 
 struct Resource { std::vector<float> data; };
@@ -277,6 +279,36 @@ struct Node {
     std::vector<float> tapPrivate;
     std::shared_ptr<Resource> res, pendingRes;
     std::shared_ptr<TwoStageConv> conv, pendingConv;   // convolve (wasm/Convolve.h)
+
+    // once (Core.h:341-404)
+    float armed = 0, gain = 0;
+    // seq / seq2 (Core.h:407-573, Seq2.h:35-166)
+    std::shared_ptr<std::vector<float>> seqActive, seqPending;
+    Change resetChange;
+    bool wantsHold = false, wantsLoop = true, firstPulse = false;
+    size_t seqOffset = 0, seqIndex = 0, edgeCount2 = 0;
+    float holdValue = 0;
+    // sparseq (SparSeq.h:17-377)
+    std::shared_ptr<std::map<int32_t, float>> spActive;
+    struct SpEvent { std::shared_ptr<std::map<int32_t, float>> seq; bool isLoop = false; int32_t ls = -1, le = -1; };
+    std::vector<SpEvent> spQueue;
+    int32_t loopStart = -1, loopEnd = -1, pendStart = -1, pendEnd = -1; bool hasPending = false;
+    bool follow = false; int32_t holdOrder = 0; double tickInterval = 0;
+    int32_t edgeCount = -1; size_t samplesSince = 0;
+    std::map<int32_t, float>::iterator spHold;
+    // sparseq2 (SparSeq2.h:17-141)
+    std::shared_ptr<std::map<double, float>> sp2Active, sp2Pending;
+    std::map<double, float>::iterator sp2Prev, sp2Next;
+    int32_t interpOrder = 0;
+    // metro (wasm/Metro.h)
+    int64_t intervalSamps = 0;
+    float lastOut = 0;
+    // analysis nodes (Analyzers.h): latest readout + flag, drained by processEvents
+    bool hasReadout = false; float roMin = 0, roMax = 0, roVal = 0;
+    bool metroFlag = false;
+
+    int32_t spTickTime(int32_t offset);
+    std::map<int32_t, float>::iterator spFind(int32_t tickTime);
 };
 
 struct RootSeq { int32_t root; std::vector<int32_t> order; std::vector<int32_t> tapOuts; };
@@ -290,6 +322,7 @@ struct Engine {
     std::map<std::string, std::shared_ptr<Resource>> resources;
     std::map<std::string, std::vector<float>> taps;
     std::shared_ptr<RenderSeq> queued, active;
+    int64_t sampleTime = 0;   // what the wasm host hands to nodes as userData (wasm/Main.cpp:206-217)
 
     Engine(double s, int b) : sr(s), bs(b) {}
 
@@ -299,7 +332,8 @@ struct Engine {
             "le", "leq", "ge", "geq", "pow", "eq", "and", "or", "add", "sub", "mul", "div", "mod", "min", "max",
             "root", "const", "phasor", "sphasor", "sr", "counter", "accum", "latch", "maxhold", "rand",
             "delay", "sdelay", "z", "pole", "env", "biquad", "prewarp", "mm1p", "svf", "svfshelf",
-            "tapIn", "tapOut", "table", "blepsaw", "blepsquare", "bleptriangle", "meter", "scope", "convolve"};
+            "tapIn", "tapOut", "table", "blepsaw", "blepsquare", "bleptriangle", "meter", "scope", "snapshot", "convolve",
+            "once", "seq", "seq2", "sparseq", "sparseq2", "time", "metro"};
         return k.count(t) > 0;
     }
 
@@ -315,6 +349,7 @@ struct Engine {
         if (type == "delay") { n.pendingRing.assign(bs, 0.0f); n.ringPending = true; }                       // Delays.h:56
         if (type == "sdelay") { n.pendingRing.assign(bitceil(bs + bs), 0.0f); n.ringPending = true; n.length = bs; }   // Delays.h:183
         if (type == "tapOut") n.tapPrivate.assign(bs, 0.0f);                                                  // Feedback.h:63-66
+        if (type == "metro") n.intervalSamps = (int64_t) std::max(2.0, 1000.0 * 0.001 * sr);                 // Metro.h:14-18,30-33
         nodes.emplace(id, std::move(n));
         return 0;
     }
@@ -372,6 +407,54 @@ struct Engine {
             if (!isStr) return 5;
             n.tapName = v.str;
             if (!taps.count(v.str)) taps[v.str].assign(bs, 0.0f);
+        }
+        if (t == "once" && key == "arm") {                                                                  // Core.h:345-361
+            if (!isBool) return 5;
+            if (n.armed == 0.0f) n.armed = (float) (v.num != 0);
+        }
+        if (t == "seq" || t == "seq2") {                                                                    // Core.h:411-466, Seq2.h:39-84
+            if (key == "hold") { if (!isBool) return 5; n.wantsHold = v.num != 0; }
+            if (key == "loop") { if (!isBool) return 5; n.wantsLoop = v.num != 0; }
+            if (key == "offset") { if (!isNum) return 5; if (v.num < 0.0) return 6; n.seqOffset = (size_t) v.num; }
+            if (key == "seq") {
+                if (v.kind != 'A') return 5;
+                auto d = std::make_shared<std::vector<float>>();
+                for (double x : v.arr) d->push_back((float) x);
+                n.seqPending = d;
+            }
+        }
+        if (t == "sparseq") {                                                                               // SparSeq.h:40-124
+            if (key == "offset") { if (!isNum) return 5; if (v.num < 0.0) return 6; n.seqOffset = (size_t) v.num; }
+            if (key == "loop") {
+                Node::SpEvent e; e.isLoop = true;
+                if (v.kind == 'U' || (isBool && v.num == 0)) { e.ls = -1; e.le = -1; }
+                else { if (v.kind != 'A') return 5; e.ls = (int32_t) v.arr.at(0); e.le = (int32_t) v.arr.at(1); }
+                n.spQueue.push_back(e);
+            }
+            if (key == "follow") { if (!isBool) return 5; n.follow = v.num != 0; }
+            if (key == "interpolate") { if (!isNum) return 5; n.holdOrder = (int32_t) v.num; }
+            if (key == "tickInterval") { if (!isNum) return 5; if (v.num < 0.0) return 6; n.tickInterval = sr * v.num; }
+            if (key == "seq") {
+                if (v.kind != 'M' && v.kind != 'A') return 5;
+                Node::SpEvent e;
+                e.seq = std::make_shared<std::map<int32_t, float>>();
+                for (auto& o : v.objs) e.seq->insert({(int32_t) o.at("tickTime"), (float) o.at("value")});
+                n.spQueue.push_back(e);
+            }
+        }
+        if (t == "sparseq2") {                                                                              // SparSeq2.h:20-56
+            if (key == "seq") {
+                if (v.kind != 'M' && v.kind != 'A') return 5;
+                auto d = std::make_shared<std::map<double, float>>();
+                for (auto& o : v.objs) d->insert({o.at("time"), (float) o.at("value")});
+                n.sp2Pending = d;
+            }
+            if (key == "interpolate") { if (!isNum) return 5; n.interpOrder = (int32_t) v.num; }
+        }
+        if (t == "metro" && key == "interval") {                                                            // Metro.h:20-37
+            if (!isNum) return 5;
+            if (0 >= v.num) return 6;
+            n.intervalSamps = (int64_t) std::max(2.0, v.num * 0.001 * sr);
         }
         if (t == "convolve" && key == "path") {                                                             // wasm/Convolve.h:35-56
             if (!isStr) return 5;
@@ -441,6 +524,36 @@ struct Engine {
     void process(const float* const* in, int nIn, float* const* out, int nOut, int ns);
 };
 
+
+// SparSeq.h:147-193
+int32_t Node::spTickTime(int32_t offset) {
+    int32_t tickTime = offset + edgeCount;
+    const int32_t ls = loopStart, le = loopEnd;
+    if ((ls > -1) && (le > -1) && (tickTime >= le)) {
+        const int32_t loopDuration = le - ls;
+        if (loopDuration > 0) {
+            if (hasPending) {
+                loopStart = pendStart; loopEnd = pendEnd; hasPending = false;
+                const int32_t nls = loopStart, nle = loopEnd;
+                if ((nls == -1) && (nle == -1)) return tickTime;
+                if (nle - nls != 0) tickTime = nls + ((tickTime - le) % (nle - nls));
+            } else {
+                tickTime = ls + ((tickTime - le) % loopDuration);
+            }
+            edgeCount = tickTime - offset;
+        }
+    }
+    return tickTime;
+}
+
+// SparSeq.h:126-145
+std::map<int32_t, float>::iterator Node::spFind(int32_t tickTime) {
+    if (spActive->empty()) return spActive->end();
+    auto it = spActive->upper_bound(tickTime);
+    if (it == spActive->begin()) return (it->first == 0) ? it : spActive->end();
+    return --it;
+}
+
 // ---- one node over one block: the builtins ---------------------------------------------------------------------
 void Engine::processNode(Node& n, const float* const* hostIn, int nHostIn, int ns) {
     // Inputs: child buffers, or for a leaf the host input channels (GraphRenderSequence.h:126-135,171-186)
@@ -504,6 +617,139 @@ void Engine::processNode(Node& n, const float* const* hostIn, int nHostIn, int n
     if (t == "meter" || t == "scope") {   // Analyzers.h: audio passes through (events out of scope)
         if (nch < 1) return zeros();
         std::copy_n(in[0], ns, out);
+        return;
+    }
+    if (t == "time") {   // wasm/SampleTime.h:16-23
+        for (int i = 0; i < ns; ++i) out[i] = (float) static_cast<double>(sampleTime + i);
+        return;
+    }
+    if (t == "metro") {  // wasm/Metro.h:39-55
+        const double is = (double) n.intervalSamps;
+        for (int i = 0; i < ns; ++i) {
+            const double tt = (double) (sampleTime + i) / is;
+            const float nextOut = (float) ((tt - std::floor(tt)) < 0.5);
+            if (n.lastOut < 0.5f && nextOut >= 0.5f) n.metroFlag = true;
+            out[i] = nextOut;
+            n.lastOut = nextOut;
+        }
+        return;
+    }
+    if (t == "once") {   // Core.h:363-396
+        if (nch < 1) return zeros();
+        const float isArmed = n.armed;
+        for (int i = 0; i < ns; ++i) {
+            const float delta = n.change(in[0][i]);
+            if (isArmed && delta > 0.5f) { n.gain = 1.0f; n.armed = 0.0f; }
+            if (delta < -0.5f) n.gain = 0.0f;
+            out[i] = in[0][i] * n.gain;
+        }
+        return;
+    }
+    if (t == "seq") {    // Core.h:468-555
+        if (n.seqPending) {
+            n.seqActive = n.seqPending; n.seqPending.reset();
+            n.seqIndex = n.seqIndex % n.seqActive->size();
+            if (n.firstPulse) n.holdValue = n.seqActive->at(n.seqIndex);
+        }
+        if (nch < 1 || !n.seqActive) return zeros();
+        const bool hasReset = nch > 1, hold = n.wantsHold, loop = n.wantsLoop;
+        for (int i = 0; i < ns; ++i) {
+            const float x = in[0][i];
+            const float reset = hasReset ? in[1][i] : 0.0f;
+            if (n.resetChange(reset) > 0.5f) n.seqIndex = n.seqOffset;
+            if (n.change(x) > 0.5f) {
+                n.holdValue = n.seqActive->at(std::min(n.seqIndex, n.seqActive->size() - 1));
+                n.firstPulse = true;
+                if ((++n.seqIndex >= n.seqActive->size()) && loop) n.seqIndex = 0;
+            }
+            if (n.seqIndex < n.seqActive->size()) out[i] = hold ? n.holdValue : n.holdValue * x;
+            else out[i] = hold ? n.holdValue : 0.0f;
+        }
+        return;
+    }
+    if (t == "seq2") {   // Seq2.h:87-148
+        if (n.seqPending) { n.seqActive = n.seqPending; n.seqPending.reset(); }
+        if (nch < 1 || !n.seqActive) return zeros();
+        const bool hasReset = nch > 1, hold = n.wantsHold, loop = n.wantsLoop;
+        const size_t offset = n.seqOffset;
+        for (int i = 0; i < ns; ++i) {
+            const float x = in[0][i];
+            const float reset = hasReset ? in[1][i] : 0.0f;
+            if (n.change(x) > 0.5f) n.edgeCount2++;
+            if (n.resetChange(reset) > 0.5f) n.edgeCount2 = 0;
+            const size_t size = n.seqActive->size();
+            const size_t idx = offset + n.edgeCount2;
+            const float nextOut = (idx < size) ? n.seqActive->at(idx)
+                                : (loop ? n.seqActive->at(idx % size) : (hold ? n.seqActive->at(size - 1) : 0.0f));
+            out[i] = hold ? nextOut : nextOut * x;
+        }
+        return;
+    }
+    if (t == "sparseq") {   // SparSeq.h:195-333
+        const bool hasReset = nch > 1;
+        const int32_t offset = (int32_t) n.seqOffset;
+        int32_t tickTime = n.spTickTime(offset);
+        if (!n.spQueue.empty()) {
+            for (auto& e : n.spQueue) {
+                if (e.isLoop) { n.hasPending = true; n.pendStart = e.ls; n.pendEnd = e.le; }
+                else n.spActive = e.seq;
+            }
+            n.spQueue.clear();
+            if (n.spActive) n.spHold = n.spFind(tickTime);
+        }
+        if (n.hasPending) {
+            const bool takeImmediately = (n.loopStart == -1 && n.loopEnd == -1) || !n.follow;
+            if (takeImmediately) { n.loopStart = n.pendStart; n.loopEnd = n.pendEnd; n.hasPending = false; tickTime = n.spTickTime(offset); }
+        }
+        if (nch < 1 || !n.spActive) return zeros();
+        for (int i = 0; i < ns; ++i) {
+            n.samplesSince++;
+            const float x = in[0][i];
+            const float reset = hasReset ? in[1][i] : 0.0f;
+            const bool trig = n.change(x) > 0.5f;
+            const bool rst = n.resetChange(reset) > 0.5f;
+            if (rst) n.edgeCount = 0;
+            if (trig) {
+                n.edgeCount = rst ? 0 : n.edgeCount + 1;
+                n.samplesSince = 0;
+                tickTime = n.spTickTime(offset);
+                n.spHold = n.spFind(tickTime);
+            }
+            if (n.spHold == n.spActive->end()) { out[i] = 0.0f; continue; }
+            if (n.holdOrder == 1) {
+                auto right = std::next(n.spHold);
+                if (right == n.spActive->end()) { out[i] = n.spHold->second; continue; }
+                const int32_t tl = n.spHold->first, tr = right->first;
+                const float lv = n.spHold->second, rv = right->second;
+                double alpha = (double) std::max(0, tickTime - tl) / (double) (tr - tl);
+                if (n.tickInterval > 0.0) alpha += (std::min((double) n.samplesSince, n.tickInterval) / n.tickInterval) / (double) (tr - tl);
+                out[i] = lv + alpha * (rv - lv);
+            } else out[i] = n.spHold->second;
+        }
+        return;
+    }
+    if (t == "sparseq2") {  // SparSeq2.h:69-128
+        if (n.sp2Pending) {
+            n.sp2Active = n.sp2Pending; n.sp2Pending.reset();
+            n.sp2Prev = n.sp2Active->end(); n.sp2Next = n.sp2Active->end();
+        }
+        if (nch < 1 || !n.sp2Active || n.sp2Active->empty()) return zeros();
+        const auto end = n.sp2Active->end();
+        const bool interp = n.interpOrder == 1;
+        for (int i = 0; i < ns; ++i) {
+            const double tt = (double) in[0][i];
+            const bool update = (n.sp2Prev == end && n.sp2Next == end)
+                || (n.sp2Prev != end && tt <= (n.sp2Prev->first + 1e-9))
+                || (n.sp2Next != end && tt >= (n.sp2Next->first - 1e-9));
+            if (update) {
+                n.sp2Next = n.sp2Active->upper_bound(tt);
+                n.sp2Prev = (n.sp2Next == n.sp2Active->begin()) ? end : std::prev(n.sp2Next);
+            }
+            if (n.sp2Prev == end) { out[i] = 0.0f; continue; }
+            if (n.sp2Next == end) { out[i] = n.sp2Prev->second; continue; }
+            const double alpha = interp ? ((tt - n.sp2Prev->first) / (n.sp2Next->first - n.sp2Prev->first)) : 0.0;
+            out[i] = n.sp2Prev->second + (float) alpha * (n.sp2Next->second - n.sp2Prev->second);
+        }
         return;
     }
     if (t == "const") { std::fill_n(out, ns, n.value); return; }          // Core.h:154-163
@@ -772,6 +1018,7 @@ void Engine::processNode(Node& n, const float* const* hostIn, int nHostIn, int n
 
 // ---- Runtime.h:275-290 + GraphRenderSequence.h:268-309,212-232 ----
 void Engine::process(const float* const* in, int nIn, float* const* out, int nOut, int ns) {
+    struct Tick { int64_t& t; int n; ~Tick() { t += n; } } tick{sampleTime, ns};   // wasm/Main.cpp:217
     if (queued) { active = queued; queued.reset(); }
     if (!active) return;
     for (int c = 0; c < nOut; ++c) std::fill_n(out[c], ns, 0.0f);
@@ -820,7 +1067,13 @@ int elem_oracle_apply_text(void* h, const char* text) {
             PropValue v; v.kind = kind;
             std::string rest; std::getline(ls, rest);
             if (!rest.empty() && rest[0] == ' ') rest.erase(0, 1);
-            if (kind == 'N' || kind == 'B') v.num = std::strtod(rest.c_str(), nullptr); else v.str = rest;
+            if (kind == 'N' || kind == 'B') v.num = std::strtod(rest.c_str(), nullptr);
+            else if (kind == 'A') { std::istringstream as(rest); size_t cnt; as >> cnt; double x; while (v.arr.size() < cnt && (as >> x)) v.arr.push_back(x); }
+            else if (kind == 'M') {
+                std::istringstream ms(rest); size_t cnt, nk; ms >> cnt >> nk;
+                for (size_t i = 0; i < cnt; ++i) { std::map<std::string, double> o; for (size_t k = 0; k < nk; ++k) { std::string kk; double x; ms >> kk >> x; o[kk] = x; } v.objs.push_back(o); }
+            }
+            else v.str = rest;
             res = e->setProperty((int32_t) id, key, v);
         } else if (op == 4) {
             std::vector<int32_t> ids; long long id;
@@ -841,6 +1094,8 @@ int elem_oracle_add_shared_resource(void* h, const char* name, const float* data
     e->resources[name] = r;
     return 1;
 }
+
+void elem_oracle_set_current_time(void* h, long long t) { static_cast<Engine*>(h)->sampleTime = t; }
 
 void elem_oracle_process_flat(void* h, const float* in, size_t nIn, float* out, size_t nOut, size_t ns) {
     auto* e = static_cast<Engine*>(h);

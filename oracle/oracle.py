@@ -49,6 +49,9 @@ def _load_ref():
         lib.elem_ref_add_shared_resource.restype = C.c_int
         lib.elem_ref_add_shared_resource.argtypes = [C.c_void_p, C.c_char_p, _f32p, C.c_size_t]
         lib.elem_ref_process_flat.argtypes = [C.c_void_p, _f32p, C.c_size_t, _f32p, C.c_size_t, C.c_size_t]
+        lib.elem_ref_set_current_time.argtypes = [C.c_void_p, C.c_int64]
+        lib.elem_ref_process_queued_events.restype = C.c_int
+        lib.elem_ref_process_queued_events.argtypes = [C.c_void_p, C.c_char_p, C.c_size_t]
         lib.elem_ref_gc.restype = C.c_int
         lib.elem_ref_gc.argtypes = [C.c_void_p, C.POINTER(C.c_int32), C.c_size_t]
         lib.elem_ref_bench.restype = C.c_double
@@ -71,6 +74,7 @@ def _load_port():
         lib.elem_oracle_add_shared_resource.restype = C.c_int
         lib.elem_oracle_add_shared_resource.argtypes = [C.c_void_p, C.c_char_p, _f32p, C.c_size_t]
         lib.elem_oracle_process_flat.argtypes = [C.c_void_p, _f32p, C.c_size_t, _f32p, C.c_size_t, C.c_size_t]
+        lib.elem_oracle_set_current_time.argtypes = [C.c_void_p, C.c_longlong]
         _port_lib = lib
     return _port_lib
 
@@ -98,6 +102,14 @@ def batch_to_text(batch: Sequence[list]) -> str:
                 lines.append(f"3 {int(ins[1])} {ins[2]} N {float(v)!r}")
             elif isinstance(v, str):
                 lines.append(f"3 {int(ins[1])} {ins[2]} S {v}")
+            elif v is None:
+                lines.append(f"3 {int(ins[1])} {ins[2]} U")
+            elif isinstance(v, (list, tuple)) and all(isinstance(x, (int, float)) and not isinstance(x, bool) for x in v):
+                lines.append(f"3 {int(ins[1])} {ins[2]} A {len(v)} " + " ".join(repr(float(x)) for x in v))
+            elif isinstance(v, (list, tuple)) and v and all(isinstance(x, dict) for x in v):
+                keys = sorted(v[0].keys())
+                lines.append(f"3 {int(ins[1])} {ins[2]} M {len(v)} {len(keys)} " +
+                             " ".join(f"{k} {float(x[k])!r}" for x in v for k in keys))
             else:
                 lines.append(f"3 {int(ins[1])} {ins[2]} J {json.dumps(v)}")
         elif op == 4:
@@ -159,6 +171,15 @@ class RefRuntime(_Base):
     def _process(self, inp, n_in, out, n_out, n):
         self.lib.elem_ref_process_flat(self.h, inp, n_in, out, n_out, n)
 
+    def set_current_time(self, t: int) -> None:
+        self.lib.elem_ref_set_current_time(self.h, int(t))
+
+    def process_queued_events(self) -> list:
+        """Runtime::processQueuedEvents relayed like wasm/Main.cpp:220-231: [{"type": ..., "event": {...}}, ...]."""
+        buf = C.create_string_buffer(1 << 20)
+        self.lib.elem_ref_process_queued_events(self.h, buf, len(buf))
+        return json.loads(buf.value.decode() or "[]")
+
 
 class PortRuntime(_Base):
     def __init__(self, sample_rate: float = 48000.0, block_size: int = 512):
@@ -182,6 +203,9 @@ class PortRuntime(_Base):
 
     def _process(self, inp, n_in, out, n_out, n):
         self.lib.elem_oracle_process_flat(self.h, inp, n_in, out, n_out, n)
+
+    def set_current_time(self, t: int) -> None:
+        self.lib.elem_oracle_set_current_time(self.h, int(t))
 
 
 def ref_bench(sample_rate: float, block_size: int, base_batch, voice_batches: Optional[Sequence], n_voices: int,

@@ -27,15 +27,28 @@
 #include <elem/JSON.h>
 #include <elem/AudioBufferResource.h>
 #include <Convolve.h>
+#include <FFT.h>
+#include <Metro.h>
+#include <SampleTime.h>
 
 namespace {
 
 struct RefRuntime {
     elem::Runtime<float> rt;
+    int64_t sampleTime = 0;   // the host-kept clock handed to nodes as userData (wasm/Main.cpp:206-217)
     RefRuntime(double sr, int bs) : rt(sr, bs) {
-        // Same registration the wasm host performs (wasm/Main.cpp:47-49).
+        // Same registrations the wasm host performs (wasm/Main.cpp:47-61).
         rt.registerNodeType("convolve", [](elem::NodeId const id, double fs, int const bs) {
             return std::make_shared<elem::ConvolutionNode<float>>(id, fs, bs);
+        });
+        rt.registerNodeType("fft", [](elem::NodeId const id, double fs, int const bs) {
+            return std::make_shared<elem::FFTNode<float>>(id, fs, bs);
+        });
+        rt.registerNodeType("metro", [](elem::NodeId const id, double fs, int const bs) {
+            return std::make_shared<elem::MetronomeNode<float>>(id, fs, bs);
+        });
+        rt.registerNodeType("time", [](elem::NodeId const id, double fs, int const bs) {
+            return std::make_shared<elem::SampleTimeNode<float>>(id, fs, bs);
         });
     }
 };
@@ -75,7 +88,27 @@ int elem_ref_add_shared_resource(void* h, const char* name, const float* data, s
 // Planar I/O exactly like Runtime::process (Runtime.h:51-57): in = nIn pointers, out = nOut pointers.
 void elem_ref_process(void* h, const float* const* in, size_t nIn, float* const* out, size_t nOut, size_t numSamples) {
     auto* r = static_cast<RefRuntime*>(h);
-    r->rt.process(const_cast<const float**>(in), nIn, const_cast<float**>(out), nOut, numSamples, nullptr);
+    r->rt.process(const_cast<const float**>(in), nIn, const_cast<float**>(out), nOut, numSamples, static_cast<void*>(&r->sampleTime));
+    r->sampleTime += static_cast<int64_t>(numSamples);   // wasm/Main.cpp:217
+}
+
+void elem_ref_set_current_time(void* h, int64_t t) { static_cast<RefRuntime*>(h)->sampleTime = t; }
+
+// Runtime::processQueuedEvents (Runtime.h:64,438-446) relayed the way wasm/Main.cpp:220-231 does: a JSON array of
+// {"type","event"} objects, serialised with the reference's own js::serialize.  Returns the bytes needed.
+int elem_ref_process_queued_events(void* h, char* buf, size_t cap) {
+    auto* r = static_cast<RefRuntime*>(h);
+    elem::js::Array batch;
+    r->rt.processQueuedEvents([&batch](std::string const& type, elem::js::Value evt) {
+        batch.push_back(elem::js::Object({{"type", type}, {"event", evt}}));
+    });
+    std::string s = elem::js::serialize(elem::js::Value(batch));
+    if (buf && cap) {
+        const size_t k = s.size() < cap - 1 ? s.size() : cap - 1;
+        std::memcpy(buf, s.data(), k);
+        buf[k] = 0;
+    }
+    return (int) s.size();
 }
 
 // Convenience for tests: contiguous buffers in[nIn][numSamples], out[nOut][numSamples].
@@ -139,7 +172,8 @@ double elem_ref_bench(double sampleRate, int blockSize, int numVoices, int threa
         double s = 0.0;
         for (int b = 0; b < nblocks; ++b) {
             for (int v = t; v < numVoices; v += threads) {
-                rts[v]->rt.process(ip.data(), nIn, op.data(), nOut, numSamples, nullptr);
+                rts[v]->rt.process(ip.data(), nIn, op.data(), nOut, numSamples, static_cast<void*>(&rts[v]->sampleTime));
+                rts[v]->sampleTime += static_cast<int64_t>(numSamples);
                 if (record && b == nblocks - 1)
                     for (float x : outBuf) s += x;
             }

@@ -73,6 +73,47 @@ for _k in ["blepsaw", "blepsquare", "bleptriangle"]:
 for _s in range(4):
     CASES.append(_c(f"random_graph_{_s}", None, 0, 6, None, 1, graphs.random_graph(_s, 32)))
 
+# ---- sequencing / control nodes: Core.h once/seq, Seq2.h, SparSeq.h, SparSeq2.h, wasm/Metro.h, SampleTime.h
+_trig = el.train(2000.0)          # 24-sample period @ 48 kHz
+_rst = el.train(170.0)
+_sq = [1.0, -2.0, 3.5, 0.25, 7.0]
+_sp = [{"value": 1.0, "tickTime": 0}, {"value": 4.0, "tickTime": 3}, {"value": -2.0, "tickTime": 4}, {"value": 9.0, "tickTime": 11}]
+_sp2 = [{"value": 0.5, "time": 0.002}, {"value": 2.0, "time": 0.004}, {"value": -1.0, "time": 0.011}, {"value": 3.0, "time": 0.02}]
+_secs = el.div(el.time(), el.sr())
+CASES += [
+    _c("time", el.time(), n_blocks=3),
+    _c("time_scaled", el.mul(el.time(), 1.0e-3), n_blocks=3),
+    _c("metro_default", el.metro({}), n_blocks=4),
+    _c("metro_5ms", el.metro({"interval": 5.0}), n_blocks=4),
+    _c("metro_tiny", el.metro({"interval": 0.001}), n_blocks=2),
+    _c("once_armed", el.once({"arm": True}, el.train(150.0)), n_blocks=4),
+    _c("once_unarmed", el.once({"arm": False}, el.train(150.0)), n_blocks=2),
+    _c("once_scaled_pulse", el.once({"arm": True}, el.mul(el.train(700.0), IN0)), 1, 3),
+    _c("seq_loop", el.seq({"seq": _sq}, _trig, _rst), n_blocks=4),
+    _c("seq_hold", el.seq({"seq": _sq, "hold": True}, _trig, _rst), n_blocks=4),
+    _c("seq_noloop", el.seq({"seq": _sq, "loop": False}, _trig, 0.0), n_blocks=2),
+    _c("seq_noloop_hold", el.seq({"seq": _sq, "loop": False, "hold": True, "offset": 2}, _trig, _rst), n_blocks=4),
+    _c("seq_offset", el.seq({"seq": _sq, "offset": 3}, _trig, _rst), n_blocks=4),
+    _c("seq_single_child", None, 0, 2, None, 1,
+       [[0, 1, "root"], [0, 2, "seq"], [0, 3, "le"], [0, 4, "phasor"], [0, 5, "const"], [0, 6, "const"],
+        [2, 4, 5, 0], [2, 3, 4, 0], [2, 3, 6, 0], [2, 2, 3, 0], [2, 1, 2, 0],
+        [3, 5, "value", 2000.0], [3, 6, "value", 0.5], [3, 2, "seq", [3.0, 1.0, 2.0]], [3, 1, "channel", 0], [4, [1]], [5]]),
+    _c("seq_no_data", el.seq({}, _trig, _rst), n_blocks=1),
+    _c("seq2_loop", el.seq2({"seq": _sq}, _trig, _rst), n_blocks=4),
+    _c("seq2_hold", el.seq2({"seq": _sq, "hold": True, "offset": 1}, _trig, _rst), n_blocks=4),
+    _c("seq2_noloop", el.seq2({"seq": _sq, "loop": False}, _trig, _rst), n_blocks=4),
+    _c("seq2_noloop_hold", el.seq2({"seq": _sq, "loop": False, "hold": True}, _trig, 0.0), n_blocks=2),
+    _c("sparseq_plain", el.sparseq({"seq": _sp}, _trig, _rst), n_blocks=4),
+    _c("sparseq_loop", el.sparseq({"seq": _sp, "loop": [1, 7]}, _trig, 0.0), n_blocks=4),
+    _c("sparseq_interp", el.sparseq({"seq": _sp, "interpolate": 1, "tickInterval": 0.0005}, _trig, _rst), n_blocks=4),
+    _c("sparseq_interp_loop_offset", el.sparseq({"seq": _sp, "interpolate": 1, "loop": [0, 12], "offset": 2}, _trig, _rst), n_blocks=6),
+    _c("sparseq2_hold", el.sparseq2({"seq": _sp2}, _secs), n_blocks=4),
+    _c("sparseq2_interp", el.sparseq2({"seq": _sp2, "interpolate": 1}, _secs), n_blocks=4),
+    _c("sparseq2_backwards", el.sparseq2({"seq": _sp2, "interpolate": 1}, el.mul(0.03, el.abs_(el.cycle(37.0)))), n_blocks=4),
+    _c("arp_voice", el.mul(el.seq({"seq": [0.2, 0.5, 1.0], "hold": True}, el.metro({"interval": 2.0})),
+                        el.cycle(el.seq({"seq": [220.0, 330.0, 440.0, 660.0], "hold": True}, el.metro({"interval": 2.0})))), n_blocks=6),
+]
+
 
 def lcg_noise(n, seed, lo=-1.0, hi=1.0):
     s = (seed * 2654435761 + 1) & 0xFFFFFFFF
