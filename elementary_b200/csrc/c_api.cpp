@@ -117,7 +117,22 @@ int elem_b200_gc(elem_b200_runtime* rt, int voice, int32_t* ids, size_t cap) {
 
 void elem_b200_reset(elem_b200_runtime* rt) { if (rt) rt->engine->reset(); }
 
-void elem_b200_process_queued_events(elem_b200_runtime*, elem_b200_event_cb, void*) {}
+namespace {
+struct EventTrampoline { elem_b200_event_cb cb; void* user; };
+void relayEvent(const char* type, const char* json, int /*voice*/, void* t) {
+    auto* tr = static_cast<EventTrampoline*>(t);
+    if (tr->cb) tr->cb(type, json, tr->user);
+}
+}
+
+int elem_b200_process_queued_events_range(elem_b200_runtime* rt, int voiceBegin, int voiceEnd, elem_b200_event_cb cb, void* user) {
+    EventTrampoline tr{cb, user};
+    GUARD(rt->engine->processQueuedEvents(voiceBegin, voiceEnd, relayEvent, &tr));
+}
+
+void elem_b200_process_queued_events(elem_b200_runtime* rt, elem_b200_event_cb cb, void* user) {
+    (void) elem_b200_process_queued_events_range(rt, 0, -1, cb, user);
+}
 
 int elem_b200_set_option(elem_b200_runtime* rt, const char* key, double value) {
     if (!key) return eb::rc::BadArgument;

@@ -120,7 +120,9 @@ static const std::unordered_map<std::string, TypeInfo>& typeTable() {
         {"seq2", {NodeKind::Seq2, 0, 3, false}}, {"sparseq", {NodeKind::SparSeq, 0, 13, false}},
         {"sparseq2", {NodeKind::SparSeq2, 0, 3, false}},
         {"time", {NodeKind::Time, 0, 0, false}}, {"metro", {NodeKind::Metro, 0, 0, false}},
-        {"meter", {NodeKind::PassThrough, 0, 0, false}}, {"scope", {NodeKind::PassThrough, 0, 0, false}},
+        {"meter", {NodeKind::Meter, 0, 3, false}}, {"snapshot", {NodeKind::Snapshot, 0, 3, false}},
+        {"scope", {NodeKind::Scope, 0, 0, false}}, {"capture", {NodeKind::Capture, 0, 5, false}},
+        {"fft", {NodeKind::PassThrough, 0, 0, false}},   // wasm/FFT.h: audio passes through; its spectrum events are not produced
     };
     return t;
 }
@@ -342,6 +344,10 @@ int Engine::createNode(Group& g, const Value& a1, const Value& a2) {   // Runtim
             for (int k : {2, 5, 6}) { int r = fillRowBits(g, n.stateRow + k, 0, g.Vpad, 0xFFFFFFFFu); if (r != rc::Ok) return r; }
         } break;
         case NodeKind::Metro: n.intervalSamps = static_cast<int64_t>(std::max(2.0, 1000.0 * 0.001 * sr_)); break;   // Metro.h:14-18
+        case NodeKind::Scope:   // Analyzers.h:147-153: the constructor sets both props
+            n.props["channels"] = Value::number(1); n.props["size"] = Value::number(512);
+            n.size = SCOPE_CHANNELS * SCOPE_RING; break;
+        case NodeKind::Capture: n.size = bitceil((int) (size_t) sr_) + CAPTURE_SCRATCH; break;   // Capture.h:17
         default: break;
     }
     g.nodes.emplace(id, std::move(n));
@@ -553,6 +559,17 @@ int Engine::nodeSetProperty(Group& g, Node& n, const std::string& key, const Val
             }
             if (key == "interpolate") { if (!val.isNumber()) return rc::InvalidPropertyType; n.interpolate = static_cast<int32_t>(val.asNumber()); g.codeDirty = true; }
             break;
+        case NodeKind::Scope:       // Analyzers.h:155-179
+            if (key == "size") {
+                if (!val.isNumber()) return rc::InvalidPropertyType;
+                if (val.asNumber() < 256 || val.asNumber() > 8192) return rc::InvalidPropertyValue;
+            }
+            if (key == "channels") {
+                if (!val.isNumber()) return rc::InvalidPropertyType;
+                if (val.asNumber() < 0 || val.asNumber() > 4) return rc::InvalidPropertyValue;
+            }
+            if (key == "name" && !val.isString()) return rc::InvalidPropertyType;
+            break;
         case NodeKind::Metro:       // wasm/Metro.h:20-37
             if (key == "interval") {
                 if (!val.isNumber()) return rc::InvalidPropertyType;
@@ -717,6 +734,10 @@ int Engine::splitGroupsAt(int v) {
         for (auto& kv : g.nodes) {
             Node n = kv.second;   // host-side copy: props, inlets, fades, resource handles, row indices (same layout)
             n.ring = nullptr; n.tapPrivate = nullptr;
+            if (!kv.second.relay.empty()) {   // capture relay buffers follow their voices
+                n.relay.assign(kv.second.relay.begin() + std::min<size_t>(cut, kv.second.relay.size()), kv.second.relay.end());
+                kv.second.relay.resize(std::min<size_t>(cut, kv.second.relay.size()));
+            }
             if (kv.second.ring) {
                 if (!cloneTiles(kv.second.ring, (size_t) kv.second.size * L, &n.ring)) return rc::CudaError;
                 n.ringFloats = newTiles * (size_t) kv.second.size * L;
@@ -925,6 +946,7 @@ int Compiler::emitNode(Node& n, int rootIndex) {
     }
     const int numCh = leaf ? nIn : (int) n.inlets.size();
 
+    bool evNode = n.kind == NodeKind::Metro;
     PendingOp op;
     op.outNode = n.id;
     op.state = (n.stateRow >= 0) ? (uint32_t) n.stateRow : NO_STATE;   // rewritten to a smem index later
@@ -1017,6 +1039,33 @@ int Compiler::emitNode(Node& n, int rootIndex) {
         case NodeKind::Time: op.opcode = OP_TIME; break;                                     // wasm/SampleTime.h:16-23
         case NodeKind::Metro: op.opcode = OP_METRO; putDouble(op, (double) n.intervalSamps); break;   // wasm/Metro.h:39-55
 
+
+        // ---- analysis nodes ----
+        case NodeKind::Meter: if (numCh < 1) { zeros(); break; } op.opcode = OP_METER; take(1); evNode = true; break;
+        case NodeKind::Snapshot: if (numCh < 2) { zeros(); break; } op.opcode = OP_SNAPSHOT; take(2); evNode = true; break;
+        case NodeKind::Scope:
+        case NodeKind::Capture: {
+            evNode = true;
+            const size_t floats = (size_t) g.nTiles() * g.tileWidth * (size_t) n.size;
+            if (!n.ring) {
+                if (!E.cuda(E.dmalloc((void**) &n.ring, sizeof(float) * floats), "cudaMalloc analysis ring")) return rc::CudaError;
+                if (!E.cuda(E.dmemset(n.ring, 0, sizeof(float) * floats), "memset analysis ring")) return rc::CudaError;
+                n.ringFloats = floats;
+            }
+            if (n.kind == NodeKind::Scope) {
+                if (numCh < 1) { zeros(); break; }
+                op.opcode = OP_SCOPE; take(std::min(numCh, (int) SCOPE_CHANNELS));
+                if (prog.dynNodes.size() >= (size_t) MAX_DYN) return E.fail(rc::InvariantViolation, "more than 16 scope nodes in one graph");
+                op.aux0 = (uint32_t) prog.dynNodes.size();
+                prog.dynNodes.push_back(n.id);
+            } else {
+                if (numCh < 2) { zeros(); break; }
+                op.opcode = OP_CAPTURE; take(2);
+                op.aux0 = (uint32_t) (n.size - CAPTURE_SCRATCH);
+            }
+            op.ptr = (uint64_t) (uintptr_t) n.ring;
+        } break;
+
         case NodeKind::Delay: {   // Delays.h:92-106
             const size_t tiles = (size_t) g.nTiles() * g.tileWidth;
             if (n.ringDirty) {
@@ -1101,6 +1150,7 @@ int Compiler::emitNode(Node& n, int rootIndex) {
 
         default: zeros(); break;
     }
+    if (evNode) prog.evNodes.push_back({n.id, rootIndex});
     ops.push_back(std::move(op));
     return rc::Ok;
 }
@@ -1713,6 +1763,30 @@ int Engine::enqueueBlock(size_t nIn, size_t nOut, size_t numSamples, bool perVoi
         }
         P.runMask = runMask;
         P.sampleTime = sampleTime_;
+        for (size_t di = 0; di < p.dynNodes.size(); ++di) {
+            auto it = g.nodes.find(p.dynNodes[di]);
+            if (it != g.nodes.end()) P.dyn[di] = it->second.scopeW;
+        }
+        for (auto& ev : p.evNodes) {       // host mirrors of what is identical for every voice of the group
+            if (!((runMask >> ev.root) & 1u)) continue;
+            auto it = g.nodes.find(ev.node);
+            if (it == g.nodes.end()) continue;
+            Node& en = it->second;
+            if (en.kind == NodeKind::Scope && (en.inlets.empty() ? nIn : en.inlets.size()) >= 1) {          // MultiChannelRingBuffer::write, :36-62
+                const uint32_t mask = SCOPE_RING - 1, w = en.scopeW, r = en.scopeR, n = (uint32_t) numSamples;
+                const uint32_t freeSlots = (r > w) ? (r - w) : ((uint32_t) SCOPE_RING - (w - r));
+                en.scopeW = (w + n) & mask;
+                if (n >= freeSlots) en.scopeR = (en.scopeW + 1) & mask;
+            } else if (en.kind == NodeKind::Metro) {                        // Metro.h:44-55
+                const double is = (double) en.intervalSamps;
+                for (size_t i = 0; i < numSamples; ++i) {
+                    const double t = (double) (sampleTime_ + (int64_t) i) / is;
+                    const float nextOut = (float) ((t - std::floor(t)) < 0.5);
+                    if (en.metroLastOut < 0.5f && nextOut >= 0.5f) en.metroFlag = true;
+                    en.metroLastOut = nextOut;
+                }
+            }
+        }
 
         // launch geometry: spread warps over the SMs first, then stack them
         int wpc = opt_.warpsPerCta;
@@ -1905,6 +1979,175 @@ int Engine::processVoices(const float* in, size_t nIn, float* outVoices, float* 
                                     nOut, cudaMemcpyDeviceToHost, stream_), "D2H mix")) return rc::CudaError;
     }
     return synchronize();
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Runtime::processQueuedEvents (Runtime.h:438-446) -> GraphRenderSequence::processQueuedEvents (:296-304) ->
+// RootRenderSequence::processQueuedEvents (:189-198): for every root sub-sequence whose root has active == true, every
+// node's processEvents() in render order.  Here the per-voice records the kernel left in HBM are read back and
+// turned into the same event objects, one per voice, as JSON text with the reference's keys plus "voice".
+static std::string jsonString(const std::string& s) {
+    std::string o = "\"";
+    for (unsigned char ch : s) {
+        if (ch == '"' || ch == '\\') { o += '\\'; o += (char) ch; }
+        else if (ch < 0x20) { char b[8]; std::snprintf(b, sizeof b, "\\u%04x", ch); o += b; }
+        else o += (char) ch;
+    }
+    return o + "\"";
+}
+static std::string jsonNumber(float f) {
+    if (!std::isfinite(f)) return "null";                 // nlohmann::json dumps non-finite numbers as null (JSON.h:175-179)
+    char b[40];
+    std::snprintf(b, sizeof b, "%.9g", (double) f);
+    return b;
+}
+static std::string sourceOf(const Node& n) {              // getPropertyWithDefault("name", js::Value()) — undefined serialises as null
+    auto it = n.props.find("name");
+    if (it == n.props.end() || !it->second.isString()) return "null";
+    return jsonString(it->second.asString());
+}
+static void appendFloatArray(std::string& o, const float* d, size_t n) {
+    o += '[';
+    for (size_t i = 0; i < n; ++i) { if (i) o += ", "; o += jsonNumber(d[i]); }
+    o += ']';
+}
+
+int Engine::processQueuedEvents(int vb, int ve, EventFn cb, void* user) {
+    if (planOnly_) return rc::Ok;
+    dsetdev();
+    if (vb < 0) vb = 0;
+    if (ve < 0 || ve > numVoices_) ve = numVoices_;
+    for (auto& gp : groups_) {
+        Group& g = *gp;
+        if (!g.active || g.active->evNodes.empty()) continue;      // `if (auto ptr = rtRenderSeq)`: the sequence process() last used
+        Program& p = *g.active;
+        const int b = std::max(vb, g.v0) - g.v0, e = std::min(ve, g.v0 + g.nv) - g.v0;   // group-relative voice range
+        const int L = g.tileWidth;
+        if (!cuda(cudaStreamSynchronize(stream_), "sync before events")) return rc::CudaError;
+        auto readRows = [&](int row, int count, std::vector<uint32_t>& out) -> bool {
+            out.resize((size_t) count * g.Vpad);
+            return cuda(cudaMemcpy(out.data(), g.dRows + (size_t) row * g.Vpad, sizeof(uint32_t) * out.size(), cudaMemcpyDeviceToHost), "read event rows");
+        };
+        auto asFloat = [](uint32_t u) { float f; std::memcpy(&f, &u, 4); return f; };
+        for (size_t ri = 0; ri < p.rootIds.size(); ++ri) {
+            auto rit = g.nodes.find(p.rootIds[ri]);
+            if (rit == g.nodes.end()) continue;
+            auto ap = rit->second.props.find("active");                                     // GraphRenderSequence.h:192
+            if (ap == rit->second.props.end() || !ap->second.isBool() || !ap->second.asBool()) continue;
+            for (auto& ev : p.evNodes) {
+                if (ev.root != (int) ri) continue;
+                auto nit = g.nodes.find(ev.node);
+                if (nit == g.nodes.end()) continue;
+                Node& n = nit->second;
+                const std::string src = sourceOf(n);
+                std::vector<uint32_t> rows;
+                switch (n.kind) {
+                case NodeKind::Meter: {        // Analyzers.h:42-60: the latest readout, if the queue shows any
+                    if (!readRows(n.stateRow, 3, rows)) return rc::CudaError;
+                    for (int v = 0; v < g.nv; ++v) {
+                        // SingleWriterSingleReaderQueue(32).size() == pushes mod 32 (:77-83,:86-98): a queue that was
+                        // pushed exactly 32 times since it was drained reads as empty
+                        if (rows[(size_t) 2 * g.Vpad + v] % 32u == 0 || v < b || v >= e || !cb) continue;
+                        std::string js = "{\"max\": " + jsonNumber(asFloat(rows[(size_t) g.Vpad + v])) + ", \"min\": " + jsonNumber(asFloat(rows[v])) +
+                                         ", \"source\": " + src + ", \"voice\": " + std::to_string(g.v0 + v) + "}";
+                        cb("meter", js.c_str(), g.v0 + v, user);
+                    }
+                    if (e > b && !cuda(cudaMemsetAsync(g.dRows + (size_t) (n.stateRow + 2) * g.Vpad + b, 0, sizeof(float) * (e - b), stream_), "reset meter queue")) return rc::CudaError;
+                } break;
+                case NodeKind::Snapshot: {     // Analyzers.h:108-127
+                    if (!readRows(n.stateRow, 3, rows)) return rc::CudaError;
+                    for (int v = b; v < e; ++v) {
+                        if (rows[(size_t) 2 * g.Vpad + v] % 32u == 0 || !cb) continue;
+                        std::string js = "{\"data\": " + jsonNumber(asFloat(rows[(size_t) g.Vpad + v])) + ", \"source\": " + src +
+                                         ", \"voice\": " + std::to_string(g.v0 + v) + "}";
+                        cb("snapshot", js.c_str(), g.v0 + v, user);
+                    }
+                    if (e > b && !cuda(cudaMemsetAsync(g.dRows + (size_t) (n.stateRow + 2) * g.Vpad + b, 0, sizeof(float) * (e - b), stream_), "reset snapshot queue")) return rc::CudaError;
+                } break;
+                case NodeKind::Scope: {        // Analyzers.h:203-251 (FloatType == float branch)
+                    auto num = [&](const char* k, double d) { auto it = n.props.find(k); return (it != n.props.end() && it->second.isNumber()) ? it->second.asNumber() : d; };
+                    const size_t size = (size_t) num("size", 512), channels = (size_t) num("channels", 1);
+                    const uint32_t mask = SCOPE_RING - 1, r = n.scopeR, w = n.scopeW;
+                    const size_t full = (w > r) ? (w - r) : (((uint32_t) SCOPE_RING - (r - w)) & mask);
+                    if (!(full > size) || !n.ring) break;
+                    if (full >= size) {        // ringBuffer.read(...) succeeds
+                        // one contiguous [pos][L] slab per (tile, channel), wrapped reads in two pieces; then de-interleave
+                        std::vector<float> slab((size_t) size * L);
+                        std::vector<std::vector<float>> chans(channels, std::vector<float>(size));
+                        const int t0 = b / L, t1 = (e + L - 1) / L;
+                        for (int tile = t0; tile < t1 && cb; ++tile) {
+                            std::vector<std::vector<float>> tileData(std::min(channels, (size_t) SCOPE_CHANNELS));
+                            for (size_t ch = 0; ch < tileData.size(); ++ch) {
+                                const float* base = n.ring + ((size_t) tile * SCOPE_CHANNELS + ch) * SCOPE_RING * L;
+                                const size_t first = std::min(size, (size_t) SCOPE_RING - r);
+                                if (!cuda(cudaMemcpy(slab.data(), base + (size_t) r * L, sizeof(float) * first * L, cudaMemcpyDeviceToHost), "read scope ring")) return rc::CudaError;
+                                if (first < size && !cuda(cudaMemcpy(slab.data() + first * L, base, sizeof(float) * (size - first) * L, cudaMemcpyDeviceToHost), "read scope ring (wrap)")) return rc::CudaError;
+                                tileData[ch] = slab;
+                            }
+                            for (int vl = 0; vl < L; ++vl) {
+                                const int v = tile * L + vl;
+                                if (v < b || v >= e) continue;
+                                std::string js = "{\"data\": [";
+                                for (size_t ch = 0; ch < channels; ++ch) {
+                                    if (ch) js += ", ";
+                                    std::vector<float> one(size, 0.0f);   // channels beyond the ring's 4 stay zero like a fresh Float32Array
+                                    if (ch < tileData.size()) for (size_t i = 0; i < size; ++i) one[i] = tileData[ch][i * L + vl];
+                                    appendFloatArray(js, one.data(), size);
+                                }
+                                js += "], \"source\": " + src + ", \"voice\": " + std::to_string(g.v0 + v) + "}";
+                                cb("scope", js.c_str(), g.v0 + v, user);
+                            }
+                        }
+                        n.scopeR = (r + (uint32_t) size) & mask;
+                    }
+                } break;
+                case NodeKind::Capture: {      // Capture.h:60-93
+                    if (!n.ring || !readRows(n.stateRow, 5, rows)) return rc::CudaError;
+                    const uint32_t cap = (uint32_t) (n.size - CAPTURE_SCRATCH), mask = cap - 1;
+                    if (n.relay.size() < (size_t) g.nv) n.relay.resize((size_t) g.nv);
+                    bool touched = false;
+                    std::vector<float> col;
+                    for (int v = b; v < e; ++v) {
+                        const uint32_t w = rows[(size_t) 2 * g.Vpad + v], r = rows[(size_t) 3 * g.Vpad + v];
+                        const uint32_t avail = (w > r) ? (w - r) : ((cap - (r - w)) & mask);
+                        if (avail > 0) {
+                            const float* base = n.ring + (size_t) (v / L) * (size_t) n.size * L + (v % L);
+                            col.resize(avail);
+                            const uint32_t first = std::min(avail, cap - r);
+                            if (!cuda(cudaMemcpy2D(col.data(), sizeof(float), base + (size_t) r * L, sizeof(float) * L, sizeof(float), first, cudaMemcpyDeviceToHost), "read capture ring")) return rc::CudaError;
+                            if (first < avail && !cuda(cudaMemcpy2D(col.data() + first, sizeof(float), base, sizeof(float) * L, sizeof(float), avail - first, cudaMemcpyDeviceToHost), "read capture ring (wrap)")) return rc::CudaError;
+                            n.relay[v].insert(n.relay[v].end(), col.begin(), col.end());
+                            rows[(size_t) 3 * g.Vpad + v] = (r + avail) & mask;
+                            touched = true;
+                        }
+                        if (rows[(size_t) 4 * g.Vpad + v]) {       // relayReady.exchange(false)
+                            rows[(size_t) 4 * g.Vpad + v] = 0;
+                            touched = true;
+                            if (cb) {
+                                std::string js = "{\"data\": ";
+                                appendFloatArray(js, n.relay[v].data(), n.relay[v].size());
+                                js += ", \"source\": " + src + ", \"voice\": " + std::to_string(g.v0 + v) + "}";
+                                cb("capture", js.c_str(), g.v0 + v, user);
+                            }
+                            n.relay[v].clear();
+                        }
+                    }
+                    if (touched && !cuda(cudaMemcpy(g.dRows + (size_t) (n.stateRow + 3) * g.Vpad, rows.data() + (size_t) 3 * g.Vpad, sizeof(uint32_t) * 2 * g.Vpad, cudaMemcpyHostToDevice), "write capture positions")) return rc::CudaError;
+                } break;
+                case NodeKind::Metro: {        // wasm/Metro.h:58-66
+                    if (!n.metroFlag) break;
+                    if (b == 0 && e == g.nv) n.metroFlag = false;      // the flag is one per group: cleared when every voice was served
+                    for (int v = b; v < e && cb; ++v) {
+                        std::string js = "{\"source\": " + src + ", \"voice\": " + std::to_string(g.v0 + v) + "}";
+                        cb("metro", js.c_str(), g.v0 + v, user);
+                    }
+                } break;
+                default: break;
+                }
+            }
+        }
+    }
+    return rc::Ok;
 }
 
 } // namespace eb

@@ -28,7 +28,8 @@ enum class NodeKind : uint8_t {
     In, Unary, Binary, Reduce, Root, Const, Sr, Phasor, SPhasor, Counter, Accum, Latch, MaxHold, Rand,
     Delay, SDelay, Z, Pole, Env, Biquad, Prewarp, MM1p, Svf, SvfShelf, TapIn, TapOut, Table, Blep, Convolve,
     PassThrough,  // analysis nodes whose events are not produced: audio passes through
-    Once, Seq, Seq2, SparSeq, SparSeq2, Time, Metro   // sequencing / control nodes
+    Once, Seq, Seq2, SparSeq, SparSeq2, Time, Metro,  // sequencing / control nodes
+    Meter, Snapshot, Scope, Capture                   // analysis nodes feeding processQueuedEvents
 };
 
 // A read-only device array owned jointly by the node that uploaded it and by every compiled program that points at it
@@ -97,6 +98,12 @@ struct Node {
     int32_t loopStart = -1, loopEnd = -1, interpolate = 0;
     double tickIntervalSamples = 0.0;
     int64_t intervalSamps = 0;       // metro (wasm/Metro.h:24-34)
+    // event side.  Ring positions that evolve identically for every voice of the group are mirrored
+    // on the host: scope's MultiChannelRingBuffer read/write positions (MultiChannelRingBuffer.h:36-96), metro's
+    // eventFlag/lastOut (Metro.h:47-52).  capture's relayBuffer (Capture.h:62-72) is a host vector per voice.
+    uint32_t scopeR = 0, scopeW = 0;
+    bool metroFlag = false; float metroLastOut = 0.0f;
+    std::vector<std::vector<float>> relay;
 };
 
 struct Program {
@@ -120,6 +127,9 @@ struct Program {
     std::vector<Stage> stages;
     std::vector<float*> blockBuffers;     // [Vpad][blockSize] HBM buffers carrying values across stages
     std::vector<std::shared_ptr<DeviceArray>> pinned;   // device arrays the code points at
+    struct EvNode { int32_t node; int root; };
+    std::vector<EvNode> evNodes;          // event-emitting nodes in render order (GraphRenderSequence.h:189-198 walks nodeList)
+    std::vector<int32_t> dynNodes;        // LaunchParams::dyn[i] belongs to node dynNodes[i]
     ~Program();
 };
 
@@ -179,6 +189,9 @@ public:
     uint64_t kernelLaunches() const { return launches_; }
     // The int64 sample clock handed to nodes through BlockContext::userData (wasm/Main.cpp:206-217, Metro.h:44,
     // SampleTime.h:19).  process() takes it from *userData when given; otherwise the engine counts samples itself.
+    // Runtime::processQueuedEvents (Runtime.h:64,438-446): events of the voices [vb, ve); cb(type, event JSON, voice).
+    typedef void (*EventFn)(const char* type, const char* json, int voice, void* user);
+    int processQueuedEvents(int vb, int ve, EventFn cb, void* user);
     void setCurrentTime(int64_t t) { sampleTime_ = t; }
     int64_t currentTime() const { return sampleTime_; }
     // Sum of the device durations (ms) of the K1 render kernels launched since the last call, measured with

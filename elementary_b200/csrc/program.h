@@ -63,9 +63,10 @@ enum Opcode : uint32_t {
     OP_TIME,       // wasm/SampleTime.h:12-24 (LaunchParams::sampleTime)
     OP_METRO,      // wasm/Metro.h:10-71 ((aux0,aux1) = bits of double(intervalSamps))
     // ---- analysis nodes: audio passes through, a per-voice record feeds processQueuedEvents ----
-    OP_METER,      // Analyzers.h:20-69   ptr = float2[voice] {min,max} + flag row
-    OP_SNAPSHOT,   // Analyzers.h:77-136
-    OP_SCOPE,      // Analyzers.h:146-255 / Capture
+    OP_METER,      // Analyzers.h:20-69    state: min, max, readouts pushed since the host last drained them
+    OP_SNAPSHOT,   // Analyzers.h:77-136   state: z, latest value, readouts pushed
+    OP_SCOPE,      // Analyzers.h:146-255  ptr = ring [tile][4][SCOPE_RING][L]; aux0 = index of the write position in LaunchParams::dyn
+    OP_CAPTURE,    // Capture.h:14-103     ptr = [tile][aux0 + CAPTURE_SCRATCH][L] (ring then scratch); state: lastIn, scratchSize, w, r, ready
     OP_COUNT_
 };
 
@@ -90,6 +91,10 @@ constexpr uint32_t STATE_PAD = 0x7FFFFFFFu;           // stateMap entry: one unu
 constexpr int MAX_ROOTS = 16;
 constexpr int MAX_OUT_CHANNELS = 8;
 constexpr int MAX_SLOTS = 255;
+constexpr int MAX_DYN = 16;                 // per-launch dynamic scalars (ring positions the host mirrors)
+constexpr int SCOPE_RING = 8192;            // MultiChannelRingBuffer default capacity (MultiChannelRingBuffer.h:17), 4 channels (Analyzers.h:149)
+constexpr int SCOPE_CHANNELS = 4;
+constexpr int CAPTURE_SCRATCH = 128;        // Capture.h:97
 
 inline uint32_t make_w0(uint32_t opcode, uint32_t nWords, uint32_t outSlot, uint32_t mode) {
     return (opcode & 0xFF) | ((nWords & 0xFF) << 8) | ((outSlot & 0xFF) << 16) | ((mode & 0xFF) << 24);
@@ -136,6 +141,7 @@ struct LaunchParams {
     uint32_t runMask;            // bit r: root r's sub-sequence runs this block; bit 16+r: root r promotes its taps
     long long sampleTime;        // int64 sample clock of this block's first sample (*userData of Runtime::process: wasm/Main.cpp:206-217)
     RootDyn roots[MAX_ROOTS];
+    uint32_t dyn[MAX_DYN];
 };
 
 } // namespace eb

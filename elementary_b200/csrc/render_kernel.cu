@@ -382,6 +382,37 @@ __device__ __noinline__ void ctl_sparseq(const CtlCtx& c) {
     ST(5) = __int_as_float(s.ls); ST(6) = __int_as_float(s.le); ST(7) = __int_as_float(s.pend);
     ST(8) = __int_as_float(s.ps); ST(9) = __int_as_float(s.pe); ST(12) = __int_as_float(tick);
 }
+
+// Capture.h:22-58 — CaptureNode.  state rows: 0 change.lastIn, 1 scratchSize, 2 ring writePos, 3 ring readPos, 4 relayReady.
+// ptr = this tile's [capacity + CAPTURE_SCRATCH][L] floats: ring, then the 128-sample scratch (Capture.h:96-98).
+// The ring follows MultiChannelRingBuffer::write (MultiChannelRingBuffer.h:36-62): a write that does not fit clobbers
+// and pushes the read pointer.
+template <int L, int E>
+__device__ __noinline__ void ctl_capture(const CtlCtx& c) {
+    const Opnd g = ctl_decode<L, E>(c, __ldg(c.opnds));
+    const Opnd x = ctl_decode<L, E>(c, __ldg(c.opnds + 1));
+    const uint32_t cap = c.aux0, mask = cap - 1;
+    float* ring = reinterpret_cast<float*>(c.ptr) + c.lane;      // position p: ring[p * L]
+    float* scratch = ring + (size_t) cap * L;
+    float last = ST(0);
+    uint32_t ssize = STU(1), w = STU(2), r = STU(3), ready = STU(4);
+    for (int i = 0; i < c.cnt; ++i) {
+        const float gv = LDT(g, i), xv = LDT(x, i);
+        const bool falling = change_tick(last, gv) < -0.5f;
+        if (falling || ssize >= (uint32_t) CAPTURE_SCRATCH) {
+            const uint32_t freeSlots = (r > w) ? (r - w) : (cap - (w - r));
+            const bool moveRead = ssize >= freeSlots;
+            for (uint32_t k = 0; k < ssize; ++k) ring[(size_t) ((w + k) & mask) * L] = scratch[(size_t) k * L];
+            w = (w + ssize) & mask;
+            if (moveRead) r = (w + 1) & mask;
+            ssize = 0;
+            if (falling) ready = 1;
+        }
+        if (gv != 0.0f) scratch[(size_t) (ssize++) * L] = xv;      // static_cast<bool>(float): anything but zero
+        c.outT[i * L] = xv;
+    }
+    ST(0) = last; ST(1) = __uint_as_float(ssize); ST(2) = __uint_as_float(w); ST(3) = __uint_as_float(r); ST(4) = __uint_as_float(ready);
+}
 #undef ST
 #undef STU
 #undef STI
@@ -1110,6 +1141,68 @@ __device__ __forceinline__ void render_tile(const LaunchParams& P, const int til
                 FOR_K(k) {
                     const double tt = (double) (t0 + T_OF(k)) / is;
                     out[k * 32] = ((tt - floor(tt)) < 0.5) ? 1.0f : 0.0f;
+                }
+            } break;
+
+
+            // ---- analysis nodes: audio passes through; a per-voice record feeds processQueuedEvents ----
+            case OP_METER: {    // Analyzers.h:23-40: min/max of the block -> readoutQueue; state: min, max, pushes
+                const Opnd x = decode(__ldg(opnds));
+                float mn = INFINITY, mx = -INFINITY;
+                FOR_K(k) {
+                    const float v = LDE(x, k);
+                    out[k * 32] = v;
+                    if (T_OF(k) < cnt) { mn = (v < mn) ? v : mn; mx = (mx < v) ? v : mx; }
+                }
+                _Pragma("unroll") for (int d = L; d < 32; d <<= 1) {
+                    const float omn = __shfl_xor_sync(FULL, mn, d), omx = __shfl_xor_sync(FULL, mx, d);
+                    mn = (omn < mn) ? omn : mn; mx = (mx < omx) ? omx : mx;
+                }
+                if (owner) {
+                    float smn = sst[sidx * L + lane], smx = sst[(sidx + 1) * L + lane];
+                    if (s0 == 0) {
+                        smn = mn; smx = mx;
+                        sst[(sidx + 2) * L + lane] = __uint_as_float(__float_as_uint(sst[(sidx + 2) * L + lane]) + 1u);
+                    } else { smn = (mn < smn) ? mn : smn; smx = (smx < mx) ? mx : smx; }
+                    sst[sidx * L + lane] = smn; sst[(sidx + 1) * L + lane] = smx;
+                }
+            } break;
+
+            case OP_SNAPSHOT: { // Analyzers.h:87-106: latch x on the rising edge of l; state: z, value, pushes
+                const Opnd l = decode(__ldg(opnds));
+                const Opnd x = decode(__ldg(opnds + 1));
+                if (owner) {
+                    float z = sst[sidx * L + lane], val = sst[(sidx + 1) * L + lane];
+                    uint32_t pushes = __float_as_uint(sst[(sidx + 2) * L + lane]);
+                    FOR_OWNER(t) {
+                        const float lv = LDT(l, t), xv = LDT(x, t);
+                        if (fabsf(z) <= kEps && lv > kEps) { val = xv; ++pushes; }
+                        z = lv;
+                        outT[t * L] = xv;
+                    }
+                    sst[sidx * L + lane] = z; sst[(sidx + 1) * L + lane] = val; sst[(sidx + 2) * L + lane] = __uint_as_float(pushes);
+                }
+            } break;
+
+            case OP_SCOPE: {    // Analyzers.h:184-201: copy in0 through, append every child (<= 4) to the ring
+                const int nch = min((int) count6, SCOPE_CHANNELS);
+                float* ring = reinterpret_cast<float*>(ptrbits) + (size_t) tile * SCOPE_CHANNELS * SCOPE_RING * L + vlane;
+                const uint32_t w = P.dyn[aux0] + (uint32_t) s0;
+                for (int ch = 0; ch < nch; ++ch) {
+                    const Opnd a = decode(__ldg(opnds + ch));
+                    FOR_K(k) {
+                        const float v = LDE(a, k);
+                        if (ch == 0) out[k * 32] = v;
+                        if (T_OF(k) < cnt) ring[((size_t) ch * SCOPE_RING + ((w + T_OF(k)) & (SCOPE_RING - 1))) * L] = v;
+                    }
+                }
+            } break;
+
+            case OP_CAPTURE: {  // Capture.h:22-58
+                if (owner) {
+                    const CtlCtx c{sst, spar, slots, outT, opnds, ptrbits + (uint64_t) tile * (aux0 + CAPTURE_SCRATCH) * L * sizeof(float),
+                                   P.sampleTime + s0, sidx, aux0, aux1, mode, count6, cnt, s0, lane, vlane};
+                    ctl_capture<L, E>(c);
                 }
             } break;
 

@@ -37,6 +37,9 @@ FLAG_VOICE_IN, FLAG_VOICE_OUT, FLAG_MIX = 1, 2, 4
 _lib = None
 
 
+EVENT_CB = C.CFUNCTYPE(None, C.c_char_p, C.c_char_p, C.c_void_p)
+
+
 def load_library() -> C.CDLL:
     """Load ``libelem_b200.so`` (built in-tree by ``__graft_entry__.build()``).  Fails loudly when missing."""
     global _lib
@@ -79,7 +82,9 @@ def load_library() -> C.CDLL:
     lib.elem_b200_gc.restype = C.c_int
     lib.elem_b200_gc.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_int32), C.c_size_t]
     lib.elem_b200_reset.argtypes = [C.c_void_p]
-    lib.elem_b200_process_queued_events.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.elem_b200_process_queued_events.argtypes = [C.c_void_p, EVENT_CB, C.c_void_p]
+    lib.elem_b200_process_queued_events_range.restype = C.c_int
+    lib.elem_b200_process_queued_events_range.argtypes = [C.c_void_p, C.c_int, C.c_int, EVENT_CB, C.c_void_p]
     lib.elem_b200_set_option.restype = C.c_int
     lib.elem_b200_set_option.argtypes = [C.c_void_p, C.c_char_p, C.c_double]
     lib.elem_b200_describe.restype = C.c_int
@@ -261,8 +266,23 @@ class Runtime:
     def current_time(self) -> int:
         return int(self._lib.elem_b200_current_time(self._h))
 
-    def process_queued_events(self, callback=None) -> None:
-        self._lib.elem_b200_process_queued_events(self._h, None, None)
+    def process_queued_events(self, callback=None, voices: Optional[Sequence[int]] = None) -> List[dict]:
+        """Runtime::processQueuedEvents (Runtime.h:64,438-446).  ``callback(type, event_dict)`` is called per event like
+        the reference's handler; the events are also returned as ``[{"type": ..., "event": {...}}, ...]`` — the batch
+        shape of wasm/Main.cpp:220-231.  Every event dict carries the reference's keys plus ``"voice"``."""
+        import json as _json
+        events: List[dict] = []
+
+        def _cb(type_, js, _user):
+            evt = _json.loads(js.decode())
+            events.append({"type": type_.decode(), "event": evt})
+            if callback is not None:
+                callback(type_.decode(), evt)
+
+        cb = EVENT_CB(_cb)
+        vb, ve = (0, -1) if voices is None else (int(voices[0]), int(voices[1]))
+        self._check(self._lib.elem_b200_process_queued_events_range(self._h, vb, ve, cb, None), "process_queued_events")
+        return events
 
     # -- introspection ------------------------------------------------------------------------------------------
     def set_option(self, key: str, value: float) -> None:

@@ -92,10 +92,17 @@ int elem_b200_list_shared_resources(elem_b200_runtime* rt, char* buf, size_t cap
 int elem_b200_gc(elem_b200_runtime* rt, int voice, int32_t* ids, size_t cap);
 /* Runtime::reset() — Runtime.h:70,449-458 */
 void elem_b200_reset(elem_b200_runtime* rt);
-/* Runtime::processQueuedEvents(cb) — Runtime.h:64,438-446.  No in-scope node emits events; the callback is
- * never invoked.  Present so callers keep their per-block sequence (offline-renderer/index.ts:104-132). */
+/* Runtime::processQueuedEvents(cb) — Runtime.h:64,438-446; relayed like wasm/Main.cpp:220-231.  For every root
+ * sub-sequence whose root is active, every event node in render order (GraphRenderSequence.h:189-198): `meter`
+ * {min,max,source}, `snapshot` {source,data}, `scope` {source,data:[[..],..]}, `capture` {source,data:[..]}
+ * (runtime/elem/builtins/Analyzers.h, Capture.h) and `metro` {source} (wasm/Metro.h:58-66).  One callback per voice
+ * that has something to report; jsonEvent is the reference's event object as JSON text plus a "voice" key.  Call it
+ * from the control thread between blocks (it synchronises the stream).  `fft` events are not produced. */
 typedef void (*elem_b200_event_cb)(const char* type, const char* jsonEvent, void* user);
 void elem_b200_process_queued_events(elem_b200_runtime* rt, elem_b200_event_cb cb, void* user);
+/* Same, restricted to the voices [voiceBegin, voiceEnd) (voiceEnd < 0 = all): at a million voices nobody wants a
+ * million meter callbacks per block; queues of the other voices keep their contents. */
+int elem_b200_process_queued_events_range(elem_b200_runtime* rt, int voiceBegin, int voiceEnd, elem_b200_event_cb cb, void* user);
 
 /* Tuning and introspection (no reference equivalent). Keys: "tile_width" (1..32, 0 =
  * auto), "warps_per_cta", "target_tiles", "time_kernels" (0|1). Must be set before the first COMMIT of a voice group. */

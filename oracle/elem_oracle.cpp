@@ -304,8 +304,32 @@ struct Node {
     int64_t intervalSamps = 0;
     float lastOut = 0;
     // analysis nodes (Analyzers.h): latest readout + flag, drained by processEvents
-    bool hasReadout = false; float roMin = 0, roMax = 0, roVal = 0;
+    // SingleWriterSingleReaderQueue(32) of readouts (meter / snapshot): positions + slots, with the reference's
+    // full-reads-as-empty arithmetic (SingleWriterSingleReaderQueue.h:31-45,63-83,86-111)
+    struct Readout { float a = 0, b = 0; };
+    Readout roQueue[32]; size_t roR = 0, roW = 0;
+    void roPush(Readout r) { roQueue[roW] = r; roW = (roW + 1) & 31; }       // numFreeSlots() is never 0: the push always lands
+    size_t roSize() const { return roW > roR ? roW - roR : ((32 - (roR - roW)) & 31); }
     bool metroFlag = false;
+    // scope: MultiChannelRingBuffer(4, 8192) (Analyzers.h:149); capture: (1, bitceil(sr)) + 128-sample scratch (Capture.h:17,96-98)
+    std::vector<std::vector<float>> mcRing; size_t mcR = 0, mcW = 0, mcCap = 0;
+    void mcInit(size_t ch, size_t cap) { mcRing.assign(ch, std::vector<float>(cap, 0.0f)); mcCap = cap; mcR = mcW = 0; }
+    size_t mcFull() const { return mcW > mcR ? mcW - mcR : ((mcCap - (mcR - mcW)) & (mcCap - 1)); }
+    size_t mcFree() const { return mcR > mcW ? mcR - mcW : mcCap - (mcW - mcR); }
+    void mcWrite(const float* const* data, size_t nch, size_t n) {             // MultiChannelRingBuffer.h:36-62
+        const bool move = n >= mcFree();
+        for (size_t c = 0; c < std::min(mcRing.size(), nch); ++c) for (size_t i = 0; i < n; ++i) mcRing[c][(mcW + i) & (mcCap - 1)] = data[c][i];
+        mcW = (mcW + n) & (mcCap - 1);
+        if (move) mcR = (mcW + 1) & (mcCap - 1);
+    }
+    bool mcRead(float* const* dst, size_t nch, size_t n) {                     // :64-88
+        if (mcFull() < n) return false;
+        for (size_t c = 0; c < std::min(mcRing.size(), nch); ++c) for (size_t i = 0; i < n; ++i) dst[c][i] = mcRing[c][(mcR + i) & (mcCap - 1)];
+        mcR = (mcR + n) & (mcCap - 1);
+        return true;
+    }
+    float scratch[128]; size_t scratchSize = 0; bool relayReady = false; std::vector<float> relayBuffer;
+    std::map<std::string, PropValue> props;   // GraphNode::props (GraphNode.h:60-63), what processEvents reads
 
     int32_t spTickTime(int32_t offset);
     std::map<int32_t, float>::iterator spFind(int32_t tickTime);
@@ -332,7 +356,7 @@ struct Engine {
             "le", "leq", "ge", "geq", "pow", "eq", "and", "or", "add", "sub", "mul", "div", "mod", "min", "max",
             "root", "const", "phasor", "sphasor", "sr", "counter", "accum", "latch", "maxhold", "rand",
             "delay", "sdelay", "z", "pole", "env", "biquad", "prewarp", "mm1p", "svf", "svfshelf",
-            "tapIn", "tapOut", "table", "blepsaw", "blepsquare", "bleptriangle", "meter", "scope", "snapshot", "convolve",
+            "tapIn", "tapOut", "table", "blepsaw", "blepsquare", "bleptriangle", "meter", "scope", "snapshot", "capture", "fft", "convolve",
             "once", "seq", "seq2", "sparseq", "sparseq2", "time", "metro"};
         return k.count(t) > 0;
     }
@@ -350,6 +374,8 @@ struct Engine {
         if (type == "sdelay") { n.pendingRing.assign(bitceil(bs + bs), 0.0f); n.ringPending = true; n.length = bs; }   // Delays.h:183
         if (type == "tapOut") n.tapPrivate.assign(bs, 0.0f);                                                  // Feedback.h:63-66
         if (type == "metro") n.intervalSamps = (int64_t) std::max(2.0, 1000.0 * 0.001 * sr);                 // Metro.h:14-18,30-33
+        if (type == "scope") { n.mcInit(4, 8192); PropValue c1; c1.num = 1; n.props["channels"] = c1; PropValue sz; sz.num = 512; n.props["size"] = sz; }   // Analyzers.h:147-153
+        if (type == "capture") n.mcInit(1, (size_t) bitceil((int) (size_t) sr));                              // Capture.h:15-19
         nodes.emplace(id, std::move(n));
         return 0;
     }
@@ -407,6 +433,11 @@ struct Engine {
             if (!isStr) return 5;
             n.tapName = v.str;
             if (!taps.count(v.str)) taps[v.str].assign(bs, 0.0f);
+        }
+        if (t == "scope") {                                                                                 // Analyzers.h:155-179
+            if (key == "size") { if (!isNum) return 5; if (v.num < 256 || v.num > 8192) return 6; }
+            if (key == "channels") { if (!isNum) return 5; if (v.num < 0 || v.num > 4) return 6; }
+            if (key == "name" && !isStr) return 5;
         }
         if (t == "once" && key == "arm") {                                                                  // Core.h:345-361
             if (!isBool) return 5;
@@ -470,6 +501,7 @@ struct Engine {
             if (r == resources.end()) return 6;
             n.pendingRes = r->second;
         }
+        n.props[key] = v;   // GraphNode.h:60-63
         return 0;
     }
 
@@ -614,7 +646,46 @@ void Engine::processNode(Node& n, const float* const* hostIn, int nHostIn, int n
         std::copy_n(in[ch], ns, out);
         return;
     }
-    if (t == "meter" || t == "scope") {   // Analyzers.h: audio passes through (events out of scope)
+    if (t == "meter") {   // Analyzers.h:23-40
+        if (nch < 1) return zeros();
+        std::copy_n(in[0], ns, out);
+        auto mm = std::minmax_element(in[0], in[0] + ns);
+        n.roPush({*mm.first, *mm.second});
+        return;
+    }
+    if (t == "snapshot") {   // Analyzers.h:80-106
+        if (nch < 2) return zeros();
+        for (int i = 0; i < ns; ++i) {
+            const float l = in[0][i], x = in[1][i];
+            if (std::abs(n.z) <= kEps && l > kEps) n.roPush({x, 0.0f});
+            n.z = l;
+            out[i] = x;
+        }
+        return;
+    }
+    if (t == "scope") {   // Analyzers.h:181-201
+        if (nch < 1) return zeros();
+        std::copy_n(in[0], ns, out);
+        n.mcWrite(in.data(), (size_t) nch, (size_t) ns);
+        return;
+    }
+    if (t == "capture") {   // Capture.h:22-58
+        if (nch < 2) return zeros();
+        std::copy_n(in[1], ns, out);
+        for (int i = 0; i < ns; ++i) {
+            const bool g = static_cast<bool>(in[0][i]);
+            const bool falling = n.change(in[0][i]) < -0.5f;
+            if (falling || n.scratchSize >= 128) {
+                const float* wd = n.scratch;
+                n.mcWrite(&wd, 1, n.scratchSize);
+                n.scratchSize = 0;
+                if (falling) n.relayReady = true;
+            }
+            if (g) n.scratch[n.scratchSize++] = in[1][i];
+        }
+        return;
+    }
+    if (t == "fft") {   // wasm/FFT.h: audio passes through (its analysis events are not restated)
         if (nch < 1) return zeros();
         std::copy_n(in[0], ns, out);
         return;
@@ -1040,9 +1111,73 @@ void Engine::process(const float* const* in, int nIn, float* const* out, int nOu
     }
 }
 
+// ---- Runtime.h:438-446 -> GraphRenderSequence.h:296-304,189-198: events of active roots, nodes in render order -----
+static std::string evNum(float f) { if (!std::isfinite(f)) return "null"; char b[40]; std::snprintf(b, sizeof b, "%.9g", (double) f); return b; }
+static std::string evSource(const Node& n) {
+    auto it = n.props.find("name");
+    if (it == n.props.end() || it->second.kind != 'S') return "null";
+    return "\"" + it->second.str + "\"";
+}
+static std::string evArray(const float* d, size_t n) { std::string o = "["; for (size_t i = 0; i < n; ++i) { if (i) o += ", "; o += evNum(d[i]); } return o + "]"; }
+
+std::string processQueuedEvents(Engine& e) {
+    std::string out = "[";
+    auto emit = [&](const char* type, const std::string& evt) {
+        if (out.size() > 1) out += ", ";
+        out += std::string("{\"event\": ") + evt + ", \"type\": \"" + type + "\"}";
+    };
+    if (!e.active) return "[]";
+    for (auto& sq : e.active->subseqs) {
+        if (!e.nodes.at(sq.root).activeProp) continue;
+        for (int32_t nid : sq.order) {
+            Node& n = e.nodes.at(nid);
+            if (n.type == "meter" || n.type == "snapshot") {          // Analyzers.h:42-60,108-127
+                if (n.roSize() == 0) continue;
+                Node::Readout ro;
+                while (n.roSize() > 0) { ro = n.roQueue[n.roR]; n.roR = (n.roR + 1) & 31; }
+                if (n.type == "meter") emit("meter", "{\"max\": " + evNum(ro.b) + ", \"min\": " + evNum(ro.a) + ", \"source\": " + evSource(n) + "}");
+                else emit("snapshot", "{\"data\": " + evNum(ro.a) + ", \"source\": " + evSource(n) + "}");
+            } else if (n.type == "scope") {                           // Analyzers.h:203-251
+                auto num = [&](const char* k, double d) { auto it = n.props.find(k); return (it != n.props.end() && it->second.kind == 'N') ? it->second.num : d; };
+                const size_t size = (size_t) num("size", 512), channels = (size_t) num("channels", 1);
+                if (!(n.mcFull() > size)) continue;
+                std::vector<std::vector<float>> data(channels, std::vector<float>(size, 0.0f));
+                std::vector<float*> ptrs(8, nullptr);
+                for (size_t c = 0; c < channels; ++c) ptrs[c] = data[c].data();
+                if (!n.mcRead(ptrs.data(), channels, size)) continue;
+                std::string arr = "[";
+                for (size_t c = 0; c < channels; ++c) { if (c) arr += ", "; arr += evArray(data[c].data(), size); }
+                emit("scope", "{\"data\": " + arr + "], \"source\": " + evSource(n) + "}");
+            } else if (n.type == "capture") {                         // Capture.h:60-93
+                const size_t avail = n.mcFull();
+                if (avail > 0) {
+                    const size_t cur = n.relayBuffer.size();
+                    n.relayBuffer.resize(cur + avail);
+                    float* dst = n.relayBuffer.data() + cur;
+                    if (!n.mcRead(&dst, 1, avail)) continue;
+                }
+                if (n.relayReady) {
+                    n.relayReady = false;
+                    emit("capture", "{\"data\": " + evArray(n.relayBuffer.data(), n.relayBuffer.size()) + ", \"source\": " + evSource(n) + "}");
+                    n.relayBuffer.clear();
+                }
+            } else if (n.type == "metro") {                           // wasm/Metro.h:58-66
+                if (n.metroFlag) { n.metroFlag = false; emit("metro", "{\"source\": " + evSource(n) + "}"); }
+            }
+        }
+    }
+    return out + "]";
+}
+
 } // namespace
 
 extern "C" {
+
+int elem_oracle_process_queued_events(void* h, char* buf, size_t cap) {
+    std::string s = processQueuedEvents(*static_cast<Engine*>(h));
+    if (buf && cap) { const size_t k = s.size() < cap - 1 ? s.size() : cap - 1; std::memcpy(buf, s.data(), k); buf[k] = 0; }
+    return (int) s.size();
+}
 
 void* elem_oracle_create(double sr, int bs) { return new Engine(sr, bs); }
 void elem_oracle_destroy(void* h) { delete static_cast<Engine*>(h); }

@@ -75,6 +75,8 @@ def _load_port():
         lib.elem_oracle_add_shared_resource.argtypes = [C.c_void_p, C.c_char_p, _f32p, C.c_size_t]
         lib.elem_oracle_process_flat.argtypes = [C.c_void_p, _f32p, C.c_size_t, _f32p, C.c_size_t, C.c_size_t]
         lib.elem_oracle_set_current_time.argtypes = [C.c_void_p, C.c_longlong]
+        lib.elem_oracle_process_queued_events.restype = C.c_int
+        lib.elem_oracle_process_queued_events.argtypes = [C.c_void_p, C.c_char_p, C.c_size_t]
         _port_lib = lib
     return _port_lib
 
@@ -176,7 +178,7 @@ class RefRuntime(_Base):
 
     def process_queued_events(self) -> list:
         """Runtime::processQueuedEvents relayed like wasm/Main.cpp:220-231: [{"type": ..., "event": {...}}, ...]."""
-        buf = C.create_string_buffer(1 << 20)
+        buf = C.create_string_buffer(1 << 22)
         self.lib.elem_ref_process_queued_events(self.h, buf, len(buf))
         return json.loads(buf.value.decode() or "[]")
 
@@ -206,6 +208,11 @@ class PortRuntime(_Base):
 
     def set_current_time(self, t: int) -> None:
         self.lib.elem_oracle_set_current_time(self.h, int(t))
+
+    def process_queued_events(self) -> list:
+        buf = C.create_string_buffer(1 << 22)
+        self.lib.elem_oracle_process_queued_events(self.h, buf, len(buf))
+        return json.loads(buf.value.decode() or "[]")
 
 
 def ref_bench(sample_rate: float, block_size: int, base_batch, voice_batches: Optional[Sequence], n_voices: int,

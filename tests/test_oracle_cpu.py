@@ -155,3 +155,24 @@ def test_convolve_varying_call_lengths_is_still_a_plain_convolution(cls):
     x, y = np.concatenate(xs), np.concatenate(ys)
     want = np.convolve(x.astype(np.float64), ir.astype(np.float64))[: len(x)]
     assert np.abs(y[1536:] - want[1536:]).max() <= 1e-6 * np.abs(want).max()
+
+
+# ---- events: the restatement's processQueuedEvents against the compiled reference ----------------
+@needs_ref
+def test_port_events_match_compiled_reference():
+    from events_common import scenarios, noise, canon
+    for sc in scenarios():
+        batch = el.render(*sc["graph"])
+        runs = []
+        for cls in (orc.PortRuntime, orc.RefRuntime):
+            r = cls(SR, BS)
+            assert r.apply(batch) == 0
+            log = []
+            for b in range(sc["blocks"]):
+                x = np.stack([noise(BS, 1000 * b + c) for c in range(sc["n_in"])]) if sc["n_in"] else None
+                r.process(x, len(sc["graph"]), BS)
+                if sc["poll"](b):
+                    log.append((b, canon(r.process_queued_events())))
+            runs.append(log)
+        assert runs[0] == runs[1], sc["name"]
+        assert any(ev for _, ev in runs[1]) != bool(sc.get("silent")), sc["name"] + ": unexpected (lack of) events"

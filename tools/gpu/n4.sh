@@ -1,0 +1,9 @@
+#!/bin/bash
+mkdir -p gpurun_out
+python -m pytest tests -m gpu -x -q 2>&1 | tail -25 | tee gpurun_out/n4_pytest.txt
+python bench.py --steps 200 --warmup 20 --no-cpu-baseline > gpurun_out/n4_bench.json 2> gpurun_out/n4_bench.err; tail -2 gpurun_out/n4_bench.err
+python - <<'PY'
+import json
+d = json.load(open("gpurun_out/n4_bench.json"))
+print("4096 voices: Msamples/s", round(d["value"]), "ms/step", round(d["ms_per_step"], 4), "k1 ms", round(d["roofline"]["kernel_ms"], 4), "e2e", round(d["e2e"]["value"]))
+PY
