@@ -151,6 +151,8 @@ def run_b200(args, rank, local_rank, world):
     import torch.distributed as dist
 
     torch.cuda.set_device(local_rank)
+    if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
+        os.environ["NCCL_DEBUG"] = "WARN"       # keep stdout to the one JSON line (the version banner goes to stdout)
     if world > 1 and not dist.is_initialized():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
@@ -165,12 +167,28 @@ def run_b200(args, rank, local_rank, world):
         mix = torch.as_tensor(rt.mix_device(1), device=f"cuda:{local_rank}")
         flush = torch.empty(256 << 20, dtype=torch.uint8, device=f"cuda:{local_rank}")
         host_mix = torch.empty((1, BS), dtype=torch.float32).pin_memory()
-        from elementary_b200.runtime import FLAG_MIX
+        from elementary_b200.runtime import FLAG_MIX, FLAG_ALLREDUCE
+        from elementary_b200.distributed import attach_peer_mix
+
+        # The single collective of the path: the sum of the [1][512] mix bus over the ranks.  Default: the engine's own
+        # kernel over NVLink/NVSwitch peer memory (K4, launched by enqueue_block in the same stream); --collective nccl
+        # (or a box without peer access) uses torch.distributed.all_reduce instead.
+        fused, fused_note = False, None
+        if world > 1 and args.collective == "fused":
+            try:
+                attach_peer_mix(rt)
+                fused = True
+            except Exception as e:      # reported in the JSON line, never silent
+                fused_note = f"peer attach failed ({e}); NCCL all_reduce used"
+            ok = torch.tensor([1 if fused else 0], device=f"cuda:{local_rank}")
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+            fused = bool(int(ok[0]))
+        step_flags = FLAG_MIX | (FLAG_ALLREDUCE if fused else 0)
 
         def step_device():
-            rt.enqueue_block(0, 1, BS, FLAG_MIX)
-            if world > 1:
-                dist.all_reduce(mix)          # the single collective of the path: the [1][512] mix bus
+            rt.enqueue_block(0, 1, BS, step_flags)
+            if world > 1 and not fused:
+                dist.all_reduce(mix)
 
         def barrier():
             if world > 1:
@@ -220,6 +238,7 @@ def run_b200(args, rank, local_rank, world):
             e2e_s += time.perf_counter() - t0
         barrier()
 
+        peer_fail = rt.peer_status() if fused else 0
         t = torch.tensor([dev_ms, e2e_s * 1e3], dtype=torch.float64, device=f"cuda:{local_rank}")
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -268,12 +287,16 @@ def run_b200(args, rank, local_rank, world):
                    "voices_total": world * voices, "block": BS, "sample_rate": SR,
                    "l2": "flushed between steps (256 MiB memset outside the timed events)",
                    "tile_width": desc["tile_width"], "slots": desc["slots"], "state_rows": desc["state_rows"],
-                   "collective": "none (1 GPU)" if world == 1 else "all_reduce(sum,f32) of the [1][512] mix bus per block"},
+                   "collective": "none (1 GPU)" if world == 1 else
+                                 ("K4 mix_exchange_kernel: all-reduce(sum,f32) of the [1][512] mix bus per block over NVLink peer memory, one launch in the render stream"
+                                  + ("" if not peer_fail else " — PEER TIMEOUT REPORTED") if fused else
+                                  "NCCL all_reduce(sum,f32) of the [1][512] mix bus per block" + (f" ({fused_note})" if fused_note else ""))},
         "voice_blocks_per_s": world * voices * args.steps / (dev_ms * 1e-3),
         "realtime_factor": value * 1e6 / (world * voices * SR),
         "wall_ms_per_step_incl_flush": t_wall / args.steps * 1e3,
         "e2e": {"value": e2e_value, "unit": "Msamples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 4 * BS,
-                "ms_per_step": e2e_ms / args.steps, "api": "elem_b200_process (host out buffers)" if world == 1 else "elem_b200_enqueue_block + NCCL all_reduce + D2H of the mix bus"},
+                "ms_per_step": e2e_ms / args.steps, "api": "elem_b200_process (host out buffers)" if world == 1 else
+                       ("elem_b200_enqueue_block (render + K4 cross-GPU mix) + D2H of the mix bus" if fused else "elem_b200_enqueue_block + NCCL all_reduce + D2H of the mix bus")},
         "gpu_launches": int(launches),
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": traffic, "peak_kind": f"of {peak_kind}", "kernel": "render_block_kernel<NITER,LOGL> (K1)",
@@ -294,6 +317,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--voices", type=int, default=VOICES_PER_GPU, help="voices per GPU (default: the BASELINE config)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--collective", default="fused", choices=["fused", "nccl"], help="N > 1: K4 peer-memory kernel (default) or NCCL all_reduce")
     ap.add_argument("--tile-width", type=int, default=0, help="override the voices-per-warp heuristic (exploration only)")
     ap.add_argument("--opt", action="append", default=[], help="extra runtime option key=value (exploration only)")
     args = ap.parse_args()

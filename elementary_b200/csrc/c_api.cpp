@@ -76,8 +76,18 @@ int elem_b200_process_voices(elem_b200_runtime* rt, const float* in, size_t nIn,
 }
 
 int elem_b200_enqueue_block(elem_b200_runtime* rt, size_t nIn, size_t nOut, size_t numSamples, int flags) {
-    GUARD(rt->engine->enqueueBlock(nIn, nOut, numSamples, (flags & 1) != 0, (flags & 2) != 0, (flags & 4) != 0));
+    GUARD(rt->engine->enqueueBlock(nIn, nOut, numSamples, (flags & 1) != 0, (flags & 2) != 0, (flags & 4) != 0, (flags & 8) != 0));
 }
+
+int elem_b200_peer_export(elem_b200_runtime* rt, void* handleOut64) {
+    if (!handleOut64) return eb::rc::BadArgument;
+    GUARD(rt->engine->peerExport(handleOut64));
+}
+int elem_b200_peer_attach(elem_b200_runtime* rt, int rank, int world, const void* handles) {
+    if (!handles) return eb::rc::BadArgument;
+    GUARD(rt->engine->peerAttach(rank, world, handles));
+}
+int elem_b200_peer_status(elem_b200_runtime* rt) { return rt ? rt->engine->peerStatus() : 0; }
 
 int elem_b200_synchronize(elem_b200_runtime* rt) { GUARD(rt->engine->synchronize()); }
 

@@ -165,6 +165,9 @@ Engine::~Engine() {
     for (auto& g : groups_) freeGroupStorage(*g, planOnly_);
     groups_.clear();
     for (auto& kv : resources_) if (kv.second->dChannel0) dfree(kv.second->dChannel0);
+    for (void* m : peerMapped_) cudaIpcCloseMemHandle(m);
+    if (dExchange_) cudaFree(dExchange_);
+    if (dPeerStatus_) cudaFree(dPeerStatus_);
     if (dMix_) dfree(dMix_);
     if (dPartial_) dfree(dPartial_);
     if (dOutVoice_) dfree(dOutVoice_);
@@ -1681,7 +1684,7 @@ float* Engine::sharedInDevicePtr(size_t nIn) {
     return dInShared_;
 }
 
-int Engine::enqueueBlock(size_t nIn, size_t nOut, size_t numSamples, bool perVoiceIn, bool materialise, bool mix) {
+int Engine::enqueueBlock(size_t nIn, size_t nOut, size_t numSamples, bool perVoiceIn, bool materialise, bool mix, bool allReduce) {
     if (planOnly_) return fail(rc::CudaError, "plan-only runtime (no CUDA device): rendering is impossible, there is no CPU fallback");
     dsetdev();
     if (numSamples > (size_t) blockSize_ || nOut > (size_t) MAX_OUT_CHANNELS) return fail(rc::BadArgument, "numSamples > blockSize or too many output channels");
@@ -1897,6 +1900,10 @@ int Engine::enqueueBlock(size_t nIn, size_t nOut, size_t numSamples, bool perVoi
             dmemset(dMix_, 0, sizeof(float) * nOut * blockSize_);
         }
     }
+    if (mix && allReduce && peerAttached_ && peer_.world > 1) {   // K4: the cross-GPU sum of the mix bus, in the same stream
+        if (!cuda(launch_mix_exchange(peer_, dMix_, (int) (nOut * blockSize_), ++peerEpoch_, dPeerStatus_, stream_), "mix exchange launch")) return rc::CudaError;
+        ++launches_;
+    }
     curNOut_ = nOut;
     sampleTime_ += (int64_t) numSamples;   // wasm/Main.cpp:217
     return rc::Ok;
@@ -1979,6 +1986,57 @@ int Engine::processVoices(const float* in, size_t nIn, float* outVoices, float* 
                                     nOut, cudaMemcpyDeviceToHost, stream_), "D2H mix")) return rc::CudaError;
     }
     return synchronize();
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// K4 plumbing: exchange buffers mapped across the ranks of one box with CUDA IPC (one process per GPU)
+int Engine::peerExport(void* handleOut64) {
+    if (planOnly_) return fail(rc::CudaError, "plan-only runtime has no device memory to export");
+    dsetdev();
+    if (!dExchange_) {
+        const size_t stride = (size_t) MAX_OUT_CHANNELS * blockSize_;
+        exchangeFlagOffset_ = sizeof(float) * 2 * MAX_PEERS * stride;
+        exchangeBytes_ = exchangeFlagOffset_ + sizeof(uint32_t) * 2 * MAX_PEERS;
+        if (!cuda(cudaMalloc(&dExchange_, exchangeBytes_), "cudaMalloc exchange buffer")) return rc::CudaError;
+        if (!cuda(cudaMemset(dExchange_, 0, exchangeBytes_), "memset exchange buffer")) return rc::CudaError;
+        if (!cuda(cudaMalloc((void**) &dPeerStatus_, sizeof(int)), "cudaMalloc peer status")) return rc::CudaError;
+        if (!cuda(cudaMemset(dPeerStatus_, 0, sizeof(int)), "memset peer status")) return rc::CudaError;
+    }
+    cudaIpcMemHandle_t h;
+    if (!cuda(cudaIpcGetMemHandle(&h, dExchange_), "cudaIpcGetMemHandle")) return rc::CudaError;
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "CUDA IPC handles are 64 bytes");
+    std::memcpy(handleOut64, &h, 64);
+    return rc::Ok;
+}
+
+int Engine::peerAttach(int rank, int world, const void* handles) {
+    if (planOnly_) return fail(rc::CudaError, "plan-only runtime cannot attach peers");
+    if (world < 1 || world > MAX_PEERS || rank < 0 || rank >= world || !dExchange_) return fail(rc::BadArgument, "peerAttach: bad rank/world, or peerExport was not called");
+    dsetdev();
+    peer_ = PeerMix{};
+    peer_.rank = rank; peer_.world = world; peer_.stride = MAX_OUT_CHANNELS * blockSize_;
+    for (int p = 0; p < world; ++p) {
+        void* base = dExchange_;
+        if (p != rank) {
+            cudaIpcMemHandle_t h;
+            std::memcpy(&h, static_cast<const char*>(handles) + (size_t) p * 64, 64);
+            if (!cuda(cudaIpcOpenMemHandle(&base, h, cudaIpcMemLazyEnablePeerAccess), "cudaIpcOpenMemHandle (is peer access available between the GPUs?)")) return rc::CudaError;
+            peerMapped_.push_back(base);
+        }
+        peer_.slot[p] = static_cast<float*>(base);
+        peer_.flag[p] = reinterpret_cast<uint32_t*>(static_cast<char*>(base) + exchangeFlagOffset_);
+    }
+    peerAttached_ = true;
+    peerEpoch_ = 0;
+    return rc::Ok;
+}
+
+int Engine::peerStatus() {
+    if (!dPeerStatus_) return 0;
+    int st = 0;
+    cudaStreamSynchronize(stream_);
+    cudaMemcpy(&st, dPeerStatus_, sizeof(int), cudaMemcpyDeviceToHost);
+    return st;
 }
 
 // ---------------------------------------------------------------------------------------------------------

@@ -12,6 +12,7 @@
 #include <unordered_map>
 #include <vector>
 
+#include "kernels.h"
 #include "program.h"
 #include "value.h"
 
@@ -174,9 +175,15 @@ public:
     // Voice-major host buffers: in[voice][nIn][n] (may be null), out[voice][nOut][n] (may be null), mix (may be null).
     int processVoices(const float* in, size_t nIn, float* outVoices, float* mix, size_t nOut, size_t numSamples);
     // Device-resident: no host I/O, no synchronisation; used for throughput timing and by processVoices/process.
-    int enqueueBlock(size_t nIn, size_t nOut, size_t numSamples, bool perVoiceIn, bool materialise, bool mix);
+    int enqueueBlock(size_t nIn, size_t nOut, size_t numSamples, bool perVoiceIn, bool materialise, bool mix, bool allReduce = false);
     int synchronize();
 
+    // Cross-GPU mix bus: peerExport() allocates this rank's exchange buffer and returns its CUDA IPC handle
+    // (64 bytes); peerAttach() maps the buffers of all ranks (handles = world x 64 bytes, in rank order).  Afterwards
+    // enqueueBlock(..., allReduce = true) leaves the sum over all ranks in the mix bus of every rank (K4, kernels.h).
+    int peerExport(void* handleOut64);
+    int peerAttach(int rank, int world, const void* handles);
+    int peerStatus();   // 0 = ok, 1 = a peer did not answer within the spin bound
     int setOption(const char* key, double value);
     void setStream(cudaStream_t s);
     float* mixDevicePtr() { return dMix_; }
@@ -226,6 +233,11 @@ private:
     size_t curNOut_ = 0;
     struct BatchBuffers { LaunchParams* dDescs = nullptr; int* dTileStart = nullptr; size_t capGroups = 0; std::vector<char> lastDescs; };
     std::map<int, BatchBuffers> batch_;   // per tile width
+
+    // K4 state
+    void* dExchange_ = nullptr; size_t exchangeBytes_ = 0; size_t exchangeFlagOffset_ = 0;
+    PeerMix peer_{}; bool peerAttached_ = false; uint32_t peerEpoch_ = 0; int* dPeerStatus_ = nullptr;
+    std::vector<void*> peerMapped_;
 
     bool planOnly_ = false;
     bool cuda(cudaError_t e, const char* what);

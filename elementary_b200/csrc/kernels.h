@@ -18,4 +18,15 @@ cudaError_t launch_render_groups(const LaunchParams* descs, const int* tileStart
 // K2: deterministic reduction of per-tile partial mixes into the [nOut][blockSize] mix bus.
 cudaError_t launch_mix_reduce(const float* partial, float* out, int nTiles, int nOut, int blockSize, int numSamples, cudaStream_t stream);
 
+// K4: the one collective of the path as our own kernel over NVLink/NVSwitch peer memory: every rank stores
+// its partial mix bus into a slot of every rank's exchange buffer, raises a flag there, waits for the flags of all sources in
+// its own buffer and sums the slots in rank order — one launch, deterministic, no NCCL call on the data path.
+constexpr int MAX_PEERS = 8;
+struct PeerMix {
+    float* slot[MAX_PEERS];       // slot[p]: rank p's exchange buffer [2][MAX_PEERS][stride] (peer-mapped for p != rank)
+    uint32_t* flag[MAX_PEERS];    // flag[p]: rank p's flags [2][MAX_PEERS]
+    int rank, world, stride;
+};
+cudaError_t launch_mix_exchange(const PeerMix& pm, float* mix, int count, uint32_t epoch, int* status, cudaStream_t stream);
+
 } // namespace eb

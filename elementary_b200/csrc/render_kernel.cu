@@ -1417,4 +1417,45 @@ cudaError_t launch_mix_reduce(const float* partial, float* out, int nTiles, int 
     return cudaGetLastError();
 }
 
+
+// ---- K4: cross-GPU all-reduce of the mix bus over peer memory (see kernels.h) -------------------------------------------
+__device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v) { asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
+__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) { uint32_t v; asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory"); return v; }
+__device__ __forceinline__ float ld_volatile_f32(const float* p) { float v; asm volatile("ld.volatile.global.f32 %0, [%1];" : "=f"(v) : "l"(p) : "memory"); return v; }
+
+__global__ void __launch_bounds__(512) mix_exchange_kernel(const PeerMix pm, float* __restrict__ mix, int count, uint32_t epoch, int* status) {
+    const int tid = threadIdx.x;
+    const int parity = (int) (epoch & 1u);
+    // 1. publish this rank's partial mix into slot [parity][rank] of every rank (NVLink stores for the peers)
+    for (int p = 0; p < pm.world; ++p) {
+        float* dst = pm.slot[p] + (size_t) (parity * MAX_PEERS + pm.rank) * pm.stride;
+        for (int i = tid; i < count; i += blockDim.x) dst[i] = mix[i];
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (tid < pm.world) st_release_sys(pm.flag[tid] + parity * MAX_PEERS + pm.rank, epoch);
+    // 2. wait until every source has published this epoch into OUR buffer (bounded spin: a dead peer must not hang the GPU)
+    if (tid < pm.world) {
+        const uint32_t* f = pm.flag[pm.rank] + parity * MAX_PEERS + tid;
+        const long long t0 = clock64();
+        while (ld_acquire_sys(f) != epoch) {
+            if (clock64() - t0 > 8000000000ll) { if (status) *status = 1; break; }
+            __nanosleep(64);
+        }
+    }
+    __syncthreads();
+    // 3. sum the slots in rank order: every rank computes the identical float sum
+    const float* mine = pm.slot[pm.rank] + (size_t) parity * MAX_PEERS * pm.stride;
+    for (int i = tid; i < count; i += blockDim.x) {
+        float s = 0.0f;
+        for (int src = 0; src < pm.world; ++src) s += ld_volatile_f32(mine + (size_t) src * pm.stride + i);
+        mix[i] = s;
+    }
+}
+
+cudaError_t launch_mix_exchange(const PeerMix& pm, float* mix, int count, uint32_t epoch, int* status, cudaStream_t stream) {
+    mix_exchange_kernel<<<1, 512, 0, stream>>>(pm, mix, count, epoch, status);
+    return cudaGetLastError();
+}
+
 } // namespace eb

@@ -3,8 +3,10 @@
 Voices / graph instances share no state, so rank ``r`` of ``W`` simply owns a contiguous voice range and renders it with its
 own :class:`elementary_b200.Runtime` on its own GPU; shared read-only resources (IRs, wavetables) are added on every rank.
 The only exchange is the element-wise sum of the per-rank partial mix buses ``[n_out][block]`` (4 KB per block for stereo
-at 512 samples — pure latency over NVLink/NVSwitch), done in place by ``torch.distributed.all_reduce`` (NCCL on GPUs, gloo
-in the CPU tests).
+at 512 samples — pure latency over NVLink/NVSwitch).  On GPUs it is done by the engine's own kernel over peer memory
+(K4: every rank stores its partial mix into every rank's exchange buffer over NVLink, flags, waits, sums in rank order —
+``attach_peer_mix`` + ``FLAG_ALLREDUCE``); ``reduce_mix`` is the plain ``torch.distributed.all_reduce`` form of the same
+sum (NCCL on GPUs, gloo in the CPU tests), kept as the cross-check and for setups without peer access.
 """
 from __future__ import annotations
 
@@ -32,3 +34,21 @@ def reduce_mix(mix, group=None, dst: int | None = None):
     else:
         dist.reduce(mix, dst=dst, op=dist.ReduceOp.SUM, group=group)
     return mix
+
+
+def attach_peer_mix(rt, group=None) -> int:
+    """Wire the runtimes of all ranks of one box together for the fused cross-GPU mix (K4): exchange the 64-byte CUDA IPC
+    handles of the per-rank exchange buffers with ``all_gather_object`` (host plumbing only) and map them.  Afterwards
+    ``rt.enqueue_block(..., flags=FLAG_MIX | FLAG_ALLREDUCE)`` leaves the whole-job mix in ``rt.mix_device()`` of every
+    rank.  Returns the world size."""
+    import torch.distributed as dist
+    if not dist.is_available() or not dist.is_initialized():
+        return 1
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    if world == 1:
+        return 1
+    handles = [None] * world
+    dist.all_gather_object(handles, rt.peer_export(), group=group)
+    rt.peer_attach(rank, handles)
+    dist.barrier(group=group)        # nobody publishes before every rank has mapped every buffer
+    return world

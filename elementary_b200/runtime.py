@@ -32,7 +32,7 @@ RETURN_CODES = {
     -1: "CudaError", -2: "BadArgument",
 }
 
-FLAG_VOICE_IN, FLAG_VOICE_OUT, FLAG_MIX = 1, 2, 4
+FLAG_VOICE_IN, FLAG_VOICE_OUT, FLAG_MIX, FLAG_ALLREDUCE = 1, 2, 4, 8
 
 _lib = None
 
@@ -65,6 +65,12 @@ def load_library() -> C.CDLL:
     lib.elem_b200_process_voices.argtypes = [C.c_void_p, _f32p, C.c_size_t, _f32p, _f32p, C.c_size_t, C.c_size_t]
     lib.elem_b200_enqueue_block.restype = C.c_int
     lib.elem_b200_enqueue_block.argtypes = [C.c_void_p, C.c_size_t, C.c_size_t, C.c_size_t, C.c_int]
+    lib.elem_b200_peer_export.restype = C.c_int
+    lib.elem_b200_peer_export.argtypes = [C.c_void_p, C.c_char_p]
+    lib.elem_b200_peer_attach.restype = C.c_int
+    lib.elem_b200_peer_attach.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_char_p]
+    lib.elem_b200_peer_status.restype = C.c_int
+    lib.elem_b200_peer_status.argtypes = [C.c_void_p]
     lib.elem_b200_synchronize.restype = C.c_int
     lib.elem_b200_synchronize.argtypes = [C.c_void_p]
     for name in ("elem_b200_mix_device", "elem_b200_voice_out_device"):
@@ -215,6 +221,20 @@ class Runtime:
     def enqueue_block(self, n_in: int = 0, n_out: int = 1, num_samples: Optional[int] = None, flags: int = FLAG_MIX) -> None:
         n = int(num_samples if num_samples is not None else self.block_size)
         self._check(self._lib.elem_b200_enqueue_block(self._h, n_in, n_out, n, flags), "enqueue_block")
+
+    # -- cross-GPU mix bus over peer memory (include/elem_b200.h: elem_b200_peer_*) ------------------------------------
+    def peer_export(self) -> bytes:
+        buf = C.create_string_buffer(64)
+        self._check(self._lib.elem_b200_peer_export(self._h, buf), "peer_export")
+        return buf.raw
+
+    def peer_attach(self, rank: int, handles: Sequence[bytes]) -> None:
+        blob = b"".join(handles)
+        assert len(blob) == 64 * len(handles)
+        self._check(self._lib.elem_b200_peer_attach(self._h, int(rank), len(handles), blob), "peer_attach")
+
+    def peer_status(self) -> int:
+        return int(self._lib.elem_b200_peer_status(self._h))
 
     def synchronize(self) -> None:
         self._check(self._lib.elem_b200_synchronize(self._h), "synchronize")

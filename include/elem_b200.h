@@ -67,7 +67,8 @@ int elem_b200_process_voices(elem_b200_runtime* rt, const float* in, size_t nIn,
 
 /* Device-resident stepping for throughput measurement and pipelines that keep audio in HBM: enqueue one block
  * on the engine's stream (no host copies, no synchronisation).  flags: 1 = read per-voice inputs from
- * elem_b200_voice_in_device(), 2 = materialise per-voice outputs, 4 = produce the mix bus. */
+ * elem_b200_voice_in_device(), 2 = materialise per-voice outputs, 4 = produce the mix bus, 8 = (with 4, after
+ * elem_b200_peer_attach) sum the mix bus over all ranks in place — every rank ends with the mix of the whole voice set. */
 int elem_b200_enqueue_block(elem_b200_runtime* rt, size_t nIn, size_t nOut, size_t numSamples, int flags);
 int elem_b200_synchronize(elem_b200_runtime* rt);
 float* elem_b200_mix_device(elem_b200_runtime* rt);                    /* device pointer [8][blockSize] */
@@ -75,6 +76,15 @@ float* elem_b200_voice_out_device(elem_b200_runtime* rt);              /* device
 float* elem_b200_voice_in_device(elem_b200_runtime* rt, size_t nIn);   /* device pointer [voice][nIn][blockSize] */
 float* elem_b200_shared_in_device(elem_b200_runtime* rt, size_t nIn);  /* device pointer [nIn][blockSize] */
 void elem_b200_set_stream(elem_b200_runtime* rt, void* cudaStream);    /* run on a caller-owned cudaStream_t */
+
+/* The one collective of the path (no reference equivalent: the reference has no voice axis): voices are
+ * sharded over one process per GPU, and the per-rank mix buses are summed by our own kernel over NVLink/NVSwitch peer
+ * memory.  elem_b200_peer_export writes this rank's 64-byte CUDA IPC handle; the caller gathers the handles of all ranks
+ * (any transport: torch.distributed.all_gather_object, MPI, a file) and passes them, in rank order, to
+ * elem_b200_peer_attach (world <= 8, one box).  elem_b200_peer_status: 0 = ok, 1 = a peer did not answer in time. */
+int elem_b200_peer_export(elem_b200_runtime* rt, void* handleOut64);
+int elem_b200_peer_attach(elem_b200_runtime* rt, int rank, int world, const void* handles);
+int elem_b200_peer_status(elem_b200_runtime* rt);
 
 /* Runtime::addSharedResource(name, unique_ptr<SharedResource>) — Runtime.h:83,462-465;
  * AudioBufferResource copies the samples (AudioBufferResource.h:13-24).  Returns 1 on success, 0 when the
