@@ -148,6 +148,12 @@ Engine::Engine(double sampleRate, int blockSize, int numVoices, int device)
     groups_.push_back(std::move(g));
     cuda(dmalloc((void**) &dMix_, sizeof(float) * MAX_OUT_CHANNELS * blockSize_), "cudaMalloc mix");
     if (dMix_) cuda(dmemset(dMix_, 0, sizeof(float) * MAX_OUT_CHANNELS * blockSize_), "memset mix");
+    if (!planOnly_) {
+        const size_t tick = (size_t) MAX_OUT_CHANNELS * ((blockSize_ + 31) / 32);
+        cuda(cudaMalloc((void**) &dMixScratch_, sizeof(float) * MIX_REDUCE_MAX_GROUPS * MAX_OUT_CHANNELS * blockSize_), "cudaMalloc mix scratch");
+        cuda(cudaMalloc((void**) &dMixTickets_, sizeof(unsigned int) * tick), "cudaMalloc mix tickets");
+        if (dMixTickets_) cuda(cudaMemsetAsync(dMixTickets_, 0, sizeof(unsigned int) * tick, stream_), "memset mix tickets");
+    }
 }
 
 static void freeGroupStorage(Group& g, bool plan) {
@@ -169,6 +175,8 @@ Engine::~Engine() {
     if (dExchange_) cudaFree(dExchange_);
     if (dPeerStatus_) cudaFree(dPeerStatus_);
     if (dMix_) dfree(dMix_);
+    if (dMixScratch_) cudaFree(dMixScratch_);
+    if (dMixTickets_) cudaFree(dMixTickets_);
     if (dPartial_) dfree(dPartial_);
     if (dOutVoice_) dfree(dOutVoice_);
     if (dInVoice_) dfree(dInVoice_);
@@ -1894,7 +1902,7 @@ int Engine::enqueueBlock(size_t nIn, size_t nOut, size_t numSamples, bool perVoi
     }
     if (mix) {
         if (tileBase > 0) {
-            if (!cuda(launch_mix_reduce(dPartial_, dMix_, tileBase, (int) nOut, blockSize_, (int) numSamples, stream_), "mix reduce launch")) return rc::CudaError;
+            if (!cuda(launch_mix_reduce(dPartial_, dMix_, dMixScratch_, dMixTickets_, tileBase, (int) nOut, blockSize_, (int) numSamples, stream_), "mix reduce launch")) return rc::CudaError;
             ++launches_;
         } else {
             dmemset(dMix_, 0, sizeof(float) * nOut * blockSize_);

@@ -225,6 +225,8 @@ private:
 
     // I/O staging
     float* dMix_ = nullptr;          // [MAX_OUT][blockSize]
+    float* dMixScratch_ = nullptr;   // K2 group sums [MIX_REDUCE_MAX_GROUPS][MAX_OUT][blockSize]
+    unsigned int* dMixTickets_ = nullptr;
     float* dPartial_ = nullptr; size_t partialFloats_ = 0;
     float* dOutVoice_ = nullptr; size_t outVoiceFloats_ = 0;
     float* dInVoice_ = nullptr; size_t inVoiceFloats_ = 0;

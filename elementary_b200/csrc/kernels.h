@@ -16,7 +16,11 @@ cudaError_t launch_render_groups(const LaunchParams* descs, const int* tileStart
                                  int maxSlots, int nOut, int maxStateRows, int maxParams, int warpsPerCta, cudaStream_t stream);
 
 // K2: deterministic reduction of per-tile partial mixes into the [nOut][blockSize] mix bus.
-cudaError_t launch_mix_reduce(const float* partial, float* out, int nTiles, int nOut, int blockSize, int numSamples, cudaStream_t stream);
+// scratch: [MIX_REDUCE_MAX_GROUPS][nOut][blockSize] floats, tickets: [nOut * ceil(blockSize/32)] zeroed counters (both may be null:
+// single-pass reduction).
+constexpr int MIX_REDUCE_MAX_GROUPS = 16;
+cudaError_t launch_mix_reduce(const float* partial, float* out, float* scratch, unsigned int* tickets, int nTiles, int nOut, int blockSize,
+                              int numSamples, cudaStream_t stream);
 
 // K4: the one collective of the path as our own kernel over NVLink/NVSwitch peer memory: every rank stores
 // its partial mix bus into a slot of every rank's exchange buffer, raises a flag there, waits for the flags of all sources in

@@ -1313,28 +1313,51 @@ __global__ void EB_BOUNDS render_groups_kernel(const LaunchParams* __restrict__ 
     render_tile<NITER, LOGL>(descs[lo], w - __ldg(tileStart + lo), perWarp);
 }
 
-// ---- deterministic reduction of the per-tile partial mixes: out[ch][s] = sum over tiles in fixed order ----
-__global__ void __launch_bounds__(1024) mix_reduce_kernel(const float* __restrict__ partial, float* __restrict__ out,
-                                                          int nTiles, int nOut, int blockSize, int numSamples) {
+// ---- K2: deterministic reduction of the per-tile partial mixes: out[ch][s] = sum over tiles in a fixed order ----
+// grid = (channel x 32-sample chunk, G tile groups).  Block (bx, g) sums the tiles of group g (32 tile lanes x 32 samples, four
+// interleaved accumulators per lane so that independent loads are in flight), leaves its result in scratch[g]; the block that
+// arrives last at the chunk's ticket counter adds the G group sums in group order.  The summation order is a function of
+// (nTiles, G) only — never of which block happens to be last — so the mix is reproducible run to run.
+__global__ void __launch_bounds__(1024) mix_reduce_kernel(const float* __restrict__ partial, float* __restrict__ out, float* __restrict__ scratch,
+                                                          unsigned int* __restrict__ tickets, int nTiles, int nOut, int blockSize, int numSamples) {
     __shared__ float red[32][33];
-    const int sx = threadIdx.x & 31, gy = threadIdx.x >> 5;       // 32 samples x 32 tile-groups
+    __shared__ bool last;
+    const int sx = threadIdx.x & 31, gy = threadIdx.x >> 5;       // 32 samples x 32 tile lanes
     const int chunksPerCh = (blockSize + 31) / 32;
     const int ch = blockIdx.x / chunksPerCh;
     const int s = (blockIdx.x % chunksPerCh) * 32 + sx;
-    // four interleaved accumulators: independent loads in flight, still one fixed summation order
+    const int G = gridDim.y, g = blockIdx.y;
+    const int perGroup = ((nTiles + G - 1) / G + 31) / 32 * 32;   // tiles per group, a multiple of the 32 lanes
+    const int tBegin = g * perGroup, tEnd = min(nTiles, tBegin + perGroup);
     float a0 = 0.0f, a1 = 0.0f, a2 = 0.0f, a3 = 0.0f;
     if (s < numSamples) {
         const size_t step = (size_t) 32 * nOut * blockSize;
-        const float* p = partial + ((size_t) gy * nOut + ch) * blockSize + s;
-        int t = gy;
-        for (; t + 96 < nTiles; t += 128, p += 4 * step) { a0 += p[0]; a1 += p[step]; a2 += p[2 * step]; a3 += p[3 * step]; }
-        for (; t < nTiles; t += 32, p += step) a0 += p[0];
+        int t = tBegin + gy;
+        const float* p = partial + ((size_t) t * nOut + ch) * blockSize + s;
+        for (; t + 96 < tEnd; t += 128, p += 4 * step) { a0 += p[0]; a1 += p[step]; a2 += p[2 * step]; a3 += p[3 * step]; }
+        for (; t < tEnd; t += 32, p += step) a0 += p[0];
     }
     red[gy][sx] = (a0 + a1) + (a2 + a3);
     __syncthreads();
-    if (gy == 0 && s < numSamples) {
+    if (gy == 0) {
         float v = 0.0f;
-        for (int g = 0; g < 32; ++g) v += red[g][sx];
+        for (int k = 0; k < 32; ++k) v += red[k][sx];
+        if (G == 1) { if (s < numSamples) out[(size_t) ch * blockSize + s] = v; }
+        else if (s < numSamples) scratch[((size_t) g * nOut + ch) * blockSize + s] = v;
+    }
+    if (G == 1) return;
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned int ticket = atomicAdd(&tickets[blockIdx.x], 1u);
+        last = (ticket == (unsigned int) G - 1);
+        if (last) tickets[blockIdx.x] = 0;                        // ready for the next block of audio
+    }
+    __syncthreads();
+    if (last && gy == 0 && s < numSamples) {
+        __threadfence();
+        float v = 0.0f;
+        for (int k = 0; k < G; ++k) v += __ldcg(scratch + ((size_t) k * nOut + ch) * blockSize + s);
         out[(size_t) ch * blockSize + s] = v;
     }
 }
@@ -1411,12 +1434,15 @@ cudaError_t launch_render_groups(const LaunchParams* descs, const int* tileStart
     }
 }
 
-cudaError_t launch_mix_reduce(const float* partial, float* out, int nTiles, int nOut, int blockSize, int numSamples, cudaStream_t stream) {
+cudaError_t launch_mix_reduce(const float* partial, float* out, float* scratch, unsigned int* tickets, int nTiles, int nOut, int blockSize,
+                              int numSamples, cudaStream_t stream) {
     const int chunksPerCh = (blockSize + 31) / 32;
-    mix_reduce_kernel<<<nOut * chunksPerCh, 1024, 0, stream>>>(partial, out, nTiles, nOut, blockSize, numSamples);
+    int G = (nTiles + 255) / 256;                 // ~8 tiles per lane per group; 4096 voices at L = 2 -> 8 groups x 16 chunks = 128 CTAs
+    if (G > MIX_REDUCE_MAX_GROUPS) G = MIX_REDUCE_MAX_GROUPS;
+    if (G < 1 || !scratch || !tickets) G = 1;
+    mix_reduce_kernel<<<dim3(nOut * chunksPerCh, G), 1024, 0, stream>>>(partial, out, scratch, tickets, nTiles, nOut, blockSize, numSamples);
     return cudaGetLastError();
 }
-
 
 // ---- K4: cross-GPU all-reduce of the mix bus over peer memory (see kernels.h) -------------------------------------------
 __device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v) { asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }

@@ -1,0 +1,12 @@
+#!/bin/bash
+mkdir -p gpurun_out
+python -m pytest tests -m gpu -x -q 2>&1 | tail -4
+for i in 1 2; do python bench.py --steps 200 --warmup 20 --no-cpu-baseline 2>/dev/null | python -c "
+import json,sys
+d=json.loads(sys.stdin.read()); print('4096: ms/step', round(d['ms_per_step'],4), 'k1', round(d['roofline']['kernel_ms'],4), 'e2e ms', round(d['e2e']['ms_per_step'],4), 'value', round(d['value']))"; done
+python bench.py --steps 30 --warmup 5 --voices 131072 --no-cpu-baseline 2>/dev/null | python -c "
+import json,sys
+d=json.loads(sys.stdin.read()); print('131072: ms/step', round(d['ms_per_step'],4), 'k1', round(d['roofline']['kernel_ms'],4))"
+timeout 300 python bench_configs.py 4 2>/dev/null | python -c "
+import json,sys
+d=json.loads(sys.stdin.readline()); print('config4 ms/block', round(d['ms_per_block'],4), 'k1', round(d['k1_ms'],4), 'k3', round(d['k3_ms'],4), 'frac', round(d['roofline']['frac'],3))"
