@@ -84,6 +84,25 @@ __device__ __noinline__ float exp_f32(float x) { return expf(x); }
 __device__ __noinline__ float pow_f32(float x, float y) { return powf(x, y); }
 __device__ __noinline__ float fmod_f32(float x, float y) { return fmodf(x, y); }
 
+// 1/b and a/b in double to ~1 ulp: MUFU.RCP64H seed (rcp.approx.ftz.f64, >= 20 good bits) + two Newton steps (+ one residual
+// correction for the quotient), 6-9 instructions instead of the ~30 of the IEEE-exact division sequence with its slow path.
+// Only used inside the svf coefficient math, whose results are rounded to float at the output: an ulp of double (1e-16) is nine
+// orders of magnitude below what a float sample resolves (same reasoning as the FMA contraction of the tick).  The profile
+// (profiles/r01_o_*) had the three divisions of SVF.h:72-80 at 10 % of all instructions of a SUBSYNTH32 voice.
+__device__ __forceinline__ double rcp_fast(double b) {
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(b));
+    double e = fma(-b, r, 1.0);
+    r = fma(r, e, r);
+    e = fma(-b, r, 1.0);
+    return fma(r, e, r);
+}
+__device__ __forceinline__ double div_fast(double a, double b) {
+    const double r = rcp_fast(b);
+    const double q = a * r;
+    return fma(fma(-b, q, a), r, q);
+}
+
 // tan(x) for 0 <= x < pi/2, the only range the svf family ever asks for (fc is clamped to [20, sr/2.0001] before
 // g = tan(pi*fc/sr), SVF.h:75).  Reduce to y in [0, pi/4] by the co-function identity and use 7-term Taylor sums
 // for sin and cos: max relative error 5.2e-13 over the whole clamped range (checked against glibc tan on 3M points;
@@ -107,7 +126,7 @@ __device__ __forceinline__ double tan_quarter_wave(double x) {
     c = fma(c, y2, 1.0 / 24.0);
     c = fma(c, y2, -0.5);
     c = fma(c, y2, 1.0);
-    return big ? c / s : s / c;
+    return big ? div_fast(c, s) : div_fast(s, c);
 }
 
 // Math.h:30-57,128-188 — fn(x, y) for the binary and reducing node families
@@ -809,11 +828,13 @@ __device__ __forceinline__ void render_tile(const LaunchParams& P, const int til
                 // all lanes, one element per slice.  ga holds g for L = 32 (a2, a3 are then formed by the lane itself)
                 // and a2 otherwise (a3 goes through a3a), so that the serial part of narrow tiles is as short as possible.
                 double ga[NITER], a1a[NITER], ka[NITER], a3a[(L == 32) ? 1 : NITER];
+                const bool qIsParam = (q.stride == 0);     // a per-voice constant: k = 1/clamp(q) once per tile, not per sample
+                const double kqParam = rcp_fast(clampd((double) LDE(q, 0), 0.25, 20.0));
                 FOR_K(k) {
                     const double g = tan_quarter_wave((3.14159265359 * clampd((double) LDE(fc, k), 20.0, fmax)) * rsr);
-                    const double kq = 1.0 / clampd((double) LDE(q, k), 0.25, 20.0);
+                    const double kq = qIsParam ? kqParam : rcp_fast(clampd((double) LDE(q, k), 0.25, 20.0));
                     ka[k] = kq;
-                    a1a[k] = 1.0 / fma(g, g + kq, 1.0);
+                    a1a[k] = rcp_fast(fma(g, g + kq, 1.0));
                     if (L == 32) ga[k] = g;
                     else { const double a2 = g * a1a[k]; ga[k] = a2; a3a[k] = g * a2; }
                 }
