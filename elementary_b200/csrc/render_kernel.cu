@@ -42,10 +42,22 @@ namespace {
 constexpr float kEps = FLT_EPSILON;
 constexpr unsigned FULL = 0xFFFFFFFFu;
 
+// Everything the interpreter touches per sample lives in the CTA's dynamic shared memory.  Addresses into it are kept as 32-bit
+// element indices (SP), not 64-bit generic pointers: half the registers per address, 32-bit address arithmetic, and LDS/STS
+// with immediate offsets — the kernel runs at a 64-register budget where every live pointer pair costs a spill or a
+// re-computation (profiles/r01_o_*: a fifth of all instructions were re-materialised address arithmetic).
+extern __shared__ __align__(16) float g_smem[];
+struct SP {
+    int i;
+    __device__ __forceinline__ float& operator[](int k) const { return g_smem[i + k]; }
+    __device__ __forceinline__ SP operator+(int d) const { return SP{i + d}; }
+    __device__ __forceinline__ float* ptr() const { return g_smem + i; }
+};
+
 // An operand is a shared-memory address plus strides: a slot advances 32 floats per element slice k and L floats
 // per sample; a parameter row (one float per voice) has stride 0 in both.
 struct Opnd {
-    const float* p;
+    SP p;
     int stride;    // per element slice k (stateless ops)
     int tstride;   // per sample t (owner-lane recurrences)
 };
@@ -175,8 +187,8 @@ template <int L, int E>
 __device__ __forceinline__ Opnd ctl_decode(const CtlCtx& c, uint32_t w) {
     Opnd o;
     const uint32_t idx = w & 0x3FFFFFFFu;
-    if ((w >> 30) == K_SLOT) { o.p = c.slots + idx * E + c.lane; o.stride = 32; o.tstride = L; }
-    else { o.p = c.spar + idx * L + c.vlane; o.stride = 0; o.tstride = 0; }
+    if ((w >> 30) == K_SLOT) { o.p = SP{(int) (c.slots - g_smem) + (int) idx * E + c.lane}; o.stride = 32; o.tstride = L; }
+    else { o.p = SP{(int) (c.spar - g_smem) + (int) idx * L + c.vlane}; o.stride = 0; o.tstride = 0; }
     return o;
 }
 
@@ -445,7 +457,6 @@ __device__ __forceinline__ void render_tile(const LaunchParams& P, const int til
     constexpr int T = E >> LOGL;          // samples per tile
     constexpr int LOGT = ilog2(T);
     constexpr int PER = 32 >> LOGL;       // samples of one voice inside one 32-element slice
-    extern __shared__ __align__(16) float smem[];
 
     const int warpInCta = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -456,16 +467,16 @@ __device__ __forceinline__ void render_tile(const LaunchParams& P, const int til
     const bool owner = lane < L;          // this lane runs the recurrences of `voice`
     const int tlane = lane >> LOGL;       // sample index of this lane's element inside slice 0
 
-    float* const slots = smem + (size_t) warpInCta * perWarp;
-    float* const outacc = slots + P.nSlots * E;
-    float* const sst = outacc + P.nOut * E;
-    float* const spar = sst + P.nStateRows * L;   // [nParams + 1][L], row 0 = zeros
+    const SP slots{warpInCta * perWarp};
+    const SP outacc = slots + P.nSlots * E;
+    const SP sst = outacc + P.nOut * E;
+    const SP spar = sst + P.nStateRows * L;   // [nParams + 1][L], row 0 = zeros
 
     auto decode = [&](uint32_t w) -> Opnd {
         Opnd o;
         const uint32_t idx = w & 0x3FFFFFFFu;
-        if ((w >> 30) == K_SLOT) { o.p = slots + idx * E + lane; o.stride = 32; o.tstride = L; }
-        else { o.p = spar + idx * L + vlane; o.stride = 0; o.tstride = 0; }
+        if ((w >> 30) == K_SLOT) { o.p = slots + ((int) idx * E + lane); o.stride = 32; o.tstride = L; }
+        else { o.p = spar + ((int) idx * L + vlane); o.stride = 0; o.tstride = 0; }
         return o;
     };
 
@@ -478,7 +489,7 @@ __device__ __forceinline__ void render_tile(const LaunchParams& P, const int til
             const size_t row = m & ~STATE_DOUBLE_FLAG;
             if (m & STATE_DOUBLE_FLAG) {
                 const double* g = reinterpret_cast<const double*>(P.rows + row * P.Vpad);
-                reinterpret_cast<double*>(sst + srow * L)[lane] = g[voice];
+                reinterpret_cast<double*>((sst + srow * L).ptr())[lane] = g[voice];
                 srow += 2;
             } else {
                 sst[srow * L + lane] = P.rows[row * P.Vpad + voice];
@@ -509,8 +520,8 @@ __device__ __forceinline__ void render_tile(const LaunchParams& P, const int til
             if (opcode == OP_END) break;
             const uint4 h1 = __ldg(reinterpret_cast<const uint4*>(pc + 4));
             const uint32_t nwords = (h0.x >> 8) & 0xFF, mode = h0.x >> 24;
-            float* const out = slots + ((h0.x >> 16) & 0xFF) * E + lane;    // element k of this lane: out[k * 32]
-            float* const outT = out;                                         // owner lane, sample t: outT[t * L]
+            const SP out = slots + ((int) ((h0.x >> 16) & 0xFF) * E + lane);    // element k of this lane: out[k * 32]
+            const SP outT = out;                                         // owner lane, sample t: outT[t * L]
             const uint32_t sidx = h0.y, aux0 = h0.z, aux1 = h0.w;
             const uint64_t ptrbits = (uint64_t) h1.x | ((uint64_t) h1.y << 32);
             const uint32_t count6 = h1.z;
@@ -607,7 +618,7 @@ __device__ __forceinline__ void render_tile(const LaunchParams& P, const int til
                     if (gi < (int) aux1) {
                         const uint32_t* mine = pc - OPW + gi * OPW;
                         const uint32_t mw0 = __ldg(mine), msidx = __ldg(mine + 1), mop = __ldg(mine + OP_HEADER_WORDS);
-                        float* const o = slots + ((mw0 >> 16) & 0xFF) * E + vlane;
+                        const SP o = slots + ((int) ((mw0 >> 16) & 0xFF) * E + vlane);
                         const float step = spar[(mop & 0x3FFFFFFFu) * L + vlane] * rsr;
                         float phase = sst[msidx * L + vlane];
                         FOR_OWNER(t) {
@@ -798,7 +809,7 @@ __device__ __forceinline__ void render_tile(const LaunchParams& P, const int til
                 const Opnd gi = decode(__ldg(opnds));
                 const Opnd x = decode(__ldg(opnds + 1));
                 if (owner) {
-                    double* zs = reinterpret_cast<double*>(sst + sidx * L) + lane;
+                    double* zs = reinterpret_cast<double*>((sst + sidx * L).ptr()) + lane;
                     double z = *zs;
                     FOR_OWNER(t) {
                         const double g = clampd((double) LDT(gi, t), 0.0, 0.9999);
@@ -843,8 +854,8 @@ __device__ __forceinline__ void render_tile(const LaunchParams& P, const int til
                 // lives in lane j*L + v of slice k)
                 double ic1 = 0.0, ic2 = 0.0;
                 if (owner) {
-                    ic1 = reinterpret_cast<const double*>(sst + sidx * L)[lane];
-                    ic2 = reinterpret_cast<const double*>(sst + (sidx + 2) * L)[lane];
+                    ic1 = reinterpret_cast<const double*>((sst + sidx * L).ptr())[lane];
+                    ic2 = reinterpret_cast<const double*>((sst + (sidx + 2) * L).ptr())[lane];
                 }
                 auto tickLoop = [&](auto lowpassTag) {
                     constexpr bool LOWPASS = decltype(lowpassTag)::value;
@@ -889,8 +900,8 @@ __device__ __forceinline__ void render_tile(const LaunchParams& P, const int til
                 };
                 if (mode == 0) tickLoop(std::true_type{}); else tickLoop(std::false_type{});
                 if (owner) {
-                    reinterpret_cast<double*>(sst + sidx * L)[lane] = ic1;
-                    reinterpret_cast<double*>(sst + (sidx + 2) * L)[lane] = ic2;
+                    reinterpret_cast<double*>((sst + sidx * L).ptr())[lane] = ic1;
+                    reinterpret_cast<double*>((sst + (sidx + 2) * L).ptr())[lane] = ic2;
                 }
             } break;
 
@@ -903,8 +914,8 @@ __device__ __forceinline__ void render_tile(const LaunchParams& P, const int til
                 const double fmax = sr / 2.0001;
                 const double rsr = 1.0 / sr;   // pi*fc/sr as (pi*fc)*(1/sr): <= 1 ulp from the reference's quotient, see tan_quarter_wave
                 if (owner) {
-                    double* s1 = reinterpret_cast<double*>(sst + sidx * L) + lane;
-                    double* s2 = reinterpret_cast<double*>(sst + (sidx + 2) * L) + lane;
+                    double* s1 = reinterpret_cast<double*>((sst + sidx * L).ptr()) + lane;
+                    double* s2 = reinterpret_cast<double*>((sst + (sidx + 2) * L).ptr()) + lane;
                     double ic1 = *s1, ic2 = *s2;
                     _Pragma("unroll 2") for (int t = 0; t < cnt; ++t) {
                         const double A = pow_f64(10.0, (double) LDT(gdb, t) / 40.0);
@@ -1094,20 +1105,21 @@ __device__ __forceinline__ void render_tile(const LaunchParams& P, const int til
 
             case OP_STOREBUF: { // stage boundary: ptr = [voice][blockSize] staging buffer (transposed element order)
                 const uint32_t w = __ldg(opnds);
-                const float* src = ((w >> 30) == K_SLOT) ? (slots + (w & 0x3FFFFFFFu) * E) : nullptr;
-                const float* par = spar + (w & 0x3FFFFFFFu) * L;
+                const bool fromSlot = (w >> 30) == K_SLOT;
+                const SP src = slots + (int) (w & 0x3FFFFFFFu) * E;
+                const SP par = spar + (int) (w & 0x3FFFFFFFu) * L;
                 float* base = reinterpret_cast<float*>(ptrbits);
                 FOR_K(k) {
                     const int qq = lane + 32 * k;
                     const int v = qq >> LOGT, t = qq & (T - 1);
                     const int vv = tile * L + v;
-                    if (t < cnt && vv < P.nv) base[(size_t) vv * P.blockSize + s0 + t] = src ? src[t * L + v] : par[v];
+                    if (t < cnt && vv < P.nv) base[(size_t) vv * P.blockSize + s0 + t] = fromSlot ? src[t * L + v] : par[v];
                 }
             } break;
 
             case OP_LOADBUF: {
                 const float* base = reinterpret_cast<const float*>(ptrbits);
-                float* dst = slots + ((h0.x >> 16) & 0xFF) * E;
+                const SP dst = slots + (int) ((h0.x >> 16) & 0xFF) * E;
                 FOR_K(k) {
                     const int qq = lane + 32 * k;
                     const int v = qq >> LOGT, t = qq & (T - 1);
@@ -1131,7 +1143,7 @@ __device__ __forceinline__ void render_tile(const LaunchParams& P, const int til
                     }
                 }
                 if (rd.channel >= 0 && rd.channel < P.nOut) {   // GraphRenderSequence.h:227-231
-                    float* acc = outacc + rd.channel * E + lane;
+                    const SP acc = outacc + (rd.channel * E + lane);
                     FOR_K(k) acc[k * 32] += out[k * 32];
                 }
             } break;
@@ -1140,7 +1152,7 @@ __device__ __forceinline__ void render_tile(const LaunchParams& P, const int til
             // ---- sequencing / control nodes: out-of-line bodies above ----
             case OP_ONCE: case OP_SEQ: case OP_SEQ2: case OP_SPARSEQ: case OP_SPARSEQ2: {
                 if (owner) {
-                    const CtlCtx c{sst, spar, slots, outT, opnds, ptrbits, P.sampleTime + s0, sidx, aux0, aux1, mode, count6, cnt, s0, lane, vlane};
+                    const CtlCtx c{sst.ptr(), spar.ptr(), slots.ptr(), outT.ptr(), opnds, ptrbits, P.sampleTime + s0, sidx, aux0, aux1, mode, count6, cnt, s0, lane, vlane};
                     switch (opcode) {
                         case OP_ONCE: ctl_once<L, E>(c); break;
                         case OP_SEQ: ctl_seq<L, E>(c); break;
@@ -1221,7 +1233,7 @@ __device__ __forceinline__ void render_tile(const LaunchParams& P, const int til
 
             case OP_CAPTURE: {  // Capture.h:22-58
                 if (owner) {
-                    const CtlCtx c{sst, spar, slots, outT, opnds, ptrbits + (uint64_t) tile * (aux0 + CAPTURE_SCRATCH) * L * sizeof(float),
+                    const CtlCtx c{sst.ptr(), spar.ptr(), slots.ptr(), outT.ptr(), opnds, ptrbits + (uint64_t) tile * (aux0 + CAPTURE_SCRATCH) * L * sizeof(float),
                                    P.sampleTime + s0, sidx, aux0, aux1, mode, count6, cnt, s0, lane, vlane};
                     ctl_capture<L, E>(c);
                 }
@@ -1234,7 +1246,7 @@ __device__ __forceinline__ void render_tile(const LaunchParams& P, const int til
         // ---- tile epilogue: per-voice output and per-tile partial mix ----
         if (P.outVoice) {
             for (int ch = 0; ch < P.nOut; ++ch) {
-                const float* a = outacc + ch * E;
+                const SP a = outacc + ch * E;
                 FOR_K(k) {
                     const int qq = lane + 32 * k;           // transposed: consecutive lanes = consecutive samples
                     const int v = qq >> LOGT, t = qq & (T - 1);
@@ -1247,7 +1259,7 @@ __device__ __forceinline__ void render_tile(const LaunchParams& P, const int til
         if (P.mixPartial) {
             // sum over the voices of the tile in a fixed order (xor butterfly over the voice bits of the lane id)
             for (int ch = 0; ch < P.nOut; ++ch) {
-                const float* a = outacc + ch * E + lane;
+                const SP a = outacc + (ch * E + lane);
                 float* gp = P.mixPartial + ((size_t) (P.tileBase + tile) * P.nOut + ch) * P.blockSize + s0;
                 FOR_K(k) {
                     const int t = T_OF(k);
@@ -1269,7 +1281,7 @@ __device__ __forceinline__ void render_tile(const LaunchParams& P, const int til
             const size_t row = m & ~STATE_DOUBLE_FLAG;
             if (m & STATE_DOUBLE_FLAG) {
                 double* g = reinterpret_cast<double*>(P.rows + row * P.Vpad);
-                g[voice] = reinterpret_cast<const double*>(sst + srow * L)[lane];
+                g[voice] = reinterpret_cast<const double*>((sst + srow * L).ptr())[lane];
                 srow += 2;
             } else {
                 P.rows[row * P.Vpad + voice] = sst[srow * L + lane];
