@@ -590,8 +590,9 @@ __device__ __forceinline__ void render_tile(const LaunchParams& P, const int til
                         const Opnd b = decode(__ldg(sp + 1));
                         const bool rev = (fw & CHAIN_REVERSED) != 0;
                         switch (fn) {   // hoisted so the element loops are branch-free
-                            case F_ADD: FOR_K(k) acc[k] = rev ? (LDE(b, k) + acc[k]) : (acc[k] + LDE(b, k)); break;
-                            case F_MUL: FOR_K(k) acc[k] = rev ? (LDE(b, k) * acc[k]) : (acc[k] * LDE(b, k)); break;
+                            // IEEE addition and multiplication are commutative bit for bit: no operand-order select needed
+                            case F_ADD: FOR_K(k) acc[k] = acc[k] + LDE(b, k); break;
+                            case F_MUL: FOR_K(k) acc[k] = acc[k] * LDE(b, k); break;
                             case F_SUB:
                                 if (rev) { FOR_K(k) acc[k] = LDE(b, k) - acc[k]; }
                                 else { FOR_K(k) acc[k] = acc[k] - LDE(b, k); }
@@ -962,11 +963,19 @@ __device__ __forceinline__ void render_tile(const LaunchParams& P, const int til
                 const int w0 = __float_as_int(sst[sidx * L + vlane]);
                 // Fast path: when no read head of this tile can land on a position written inside the tile (and
                 // no write of the tile can hit a position still to be read), samples are independent.
+                // delay time and feedback are usually per-voice constants (parameter rows, stride 0): clamp them once per tile
+                const bool lenParam = (len.stride == 0), fbParam = (fb.stride == 0);
+                const float offsetP = clampf(LDE(len, 0), 0.0f, fsize);
+                const float fbP = clampf(LDE(fb, 0), -1.0f, 1.0f);
                 bool hazard = false;
-                FOR_K(k) {
-                    const float offset = clampf(LDE(len, k), 0.0f, fsize);
-                    if (T_OF(k) < cnt && !(offset <= kEps) &&
-                        !(offset >= (float) (cnt + 1) && offset <= (float) (size - cnt - 1))) hazard = true;
+                if (lenParam) {
+                    hazard = !(offsetP <= kEps) && !(offsetP >= (float) (cnt + 1) && offsetP <= (float) (size - cnt - 1));
+                } else {
+                    FOR_K(k) {
+                        const float offset = clampf(LDE(len, k), 0.0f, fsize);
+                        if (T_OF(k) < cnt && !(offset <= kEps) &&
+                            !(offset >= (float) (cnt + 1) && offset <= (float) (size - cnt - 1))) hazard = true;
+                    }
                 }
                 const bool slow = __any_sync(FULL, hazard);
                 __syncwarp();   // every lane has read the write index before an owner lane may overwrite it
@@ -975,7 +984,7 @@ __device__ __forceinline__ void render_tile(const LaunchParams& P, const int til
                         const int t = T_OF(k);
                         int w = w0 + t;
                         while (w >= size) w -= size;
-                        const float offset = clampf(LDE(len, k), 0.0f, fsize);
+                        const float offset = lenParam ? offsetP : clampf(LDE(len, k), 0.0f, fsize);
                         float y, in;
                         if (offset <= kEps) { in = LDE(x, k); y = in; }
                         else {
@@ -989,7 +998,7 @@ __device__ __forceinline__ void render_tile(const LaunchParams& P, const int til
                             const float left = ring[(size_t) readLeft * L];
                             const float right = ring[(size_t) readRight * L];
                             y = left + frac * (right - left);
-                            in = LDE(x, k) + clampf(LDE(fb, k), -1.0f, 1.0f) * y;
+                            in = LDE(x, k) + (fbParam ? fbP : clampf(LDE(fb, k), -1.0f, 1.0f)) * y;
                         }
                         if (t < cnt) ring[(size_t) w * L] = in;
                         out[k * 32] = y;
@@ -1320,7 +1329,10 @@ __device__ __forceinline__ void render_tile(const LaunchParams& P, const int til
 // Occupancy target (measured, profiles/r01_d_occupancy_ab.txt): the full-width geometry (L = 32, every lane a voice)
 // is issue-latency bound and gains 20 % from 64-register / 8-CTA occupancy; the narrow geometries run few warps
 // anyway and prefer the 128-register budget.
-#define EB_BOUNDS __launch_bounds__(128, (LOGL == 5) ? 8 : 4)
+#ifndef EB_L32_MINBLOCKS
+#define EB_L32_MINBLOCKS 8
+#endif
+#define EB_BOUNDS __launch_bounds__(128, (LOGL == 5) ? EB_L32_MINBLOCKS : 4)
 
 // One voice group per launch: the descriptor travels in the constant bank.
 template <int NITER, int LOGL>
