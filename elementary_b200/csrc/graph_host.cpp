@@ -122,7 +122,7 @@ static const std::unordered_map<std::string, TypeInfo>& typeTable() {
         {"time", {NodeKind::Time, 0, 0, false}}, {"metro", {NodeKind::Metro, 0, 0, false}},
         {"meter", {NodeKind::Meter, 0, 3, false}}, {"snapshot", {NodeKind::Snapshot, 0, 3, false}},
         {"scope", {NodeKind::Scope, 0, 0, false}}, {"capture", {NodeKind::Capture, 0, 5, false}},
-        {"fft", {NodeKind::PassThrough, 0, 0, false}},   // wasm/FFT.h: audio passes through; its spectrum events are not produced
+        {"fft", {NodeKind::Fft, 0, 0, false}},
     };
     return t;
 }
@@ -271,7 +271,9 @@ int Engine::fillRow(Group& g, int row, int vb, int ve, float value) {
 
 int Engine::ensureResourceOnDevice(Resource& r) {
     if (r.dChannel0 || r.numSamples == 0) return rc::Ok;
-    if (!cuda(dmalloc((void**) &r.dChannel0, sizeof(float) * r.numSamples), "cudaMalloc resource")) return rc::CudaError;
+    const size_t padded = (r.numSamples + 3) / 4 * 4;
+    if (!cuda(dmalloc((void**) &r.dChannel0, sizeof(float) * padded), "cudaMalloc resource")) return rc::CudaError;
+    if (!cuda(dmemset(r.dChannel0, 0, sizeof(float) * padded), "memset resource")) return rc::CudaError;
     if (!cuda(dmemcpySync(r.dChannel0, r.channels[0].data(), sizeof(float) * r.numSamples, cudaMemcpyHostToDevice), "upload resource")) return rc::CudaError;
     return rc::Ok;
 }
@@ -359,6 +361,11 @@ int Engine::createNode(Group& g, const Value& a1, const Value& a2) {   // Runtim
             n.props["channels"] = Value::number(1); n.props["size"] = Value::number(512);
             n.size = SCOPE_CHANNELS * SCOPE_RING; break;
         case NodeKind::Capture: n.size = bitceil((int) (size_t) sr_) + CAPTURE_SCRATCH; break;   // Capture.h:17
+        case NodeKind::Fft: {   // wasm/FFT.h:18-26: ring of one channel, default size 1024 set through setProperty
+            n.size = SCOPE_RING;
+            Node& ref = g.nodes.emplace(id, std::move(n)).first->second;
+            return nodeSetProperty(g, ref, "size", Value::number(1024), 0, g.nv);
+        }
         default: break;
     }
     g.nodes.emplace(id, std::move(n));
@@ -578,6 +585,23 @@ int Engine::nodeSetProperty(Group& g, Node& n, const std::string& key, const Val
             if (key == "channels") {
                 if (!val.isNumber()) return rc::InvalidPropertyType;
                 if (val.asNumber() < 0 || val.asNumber() > 4) return rc::InvalidPropertyValue;
+            }
+            if (key == "name" && !val.isString()) return rc::InvalidPropertyType;
+            break;
+        case NodeKind::Fft:         // wasm/FFT.h:32-71
+            if (key == "size") {
+                if (!val.isNumber()) return rc::InvalidPropertyType;
+                const int size = static_cast<int>(val.asNumber());
+                if (!(size > 0 && (size & (size - 1)) == 0) || size < 256 || size > 8192) return rc::InvalidPropertyValue;
+                n.window.resize((size_t) size);
+                for (int i = 0; i < size; ++i) {   // Blackman-Harris in the reference's mixed float/double arithmetic (FFT.h:49-62)
+                    const float a0 = 0.35875f, a1 = 0.48829f, a2 = 0.14128f, a3 = 0.01168f;
+                    const float pi = 3.1415926535897932385f;
+                    const float t1 = (float) (a1 * std::cos(2.0 * pi * (i / (double) (size - 1))));
+                    const float t2 = (float) (a2 * std::cos(4.0 * pi * (i / (double) (size - 1))));
+                    const float t3 = (float) (a3 * std::cos(6.0 * pi * (i / (double) (size - 1))));
+                    n.window[(size_t) i] = a0 - t1 + t2 - t3;
+                }
             }
             if (key == "name" && !val.isString()) return rc::InvalidPropertyType;
             break;
@@ -1055,6 +1079,7 @@ int Compiler::emitNode(Node& n, int rootIndex) {
         case NodeKind::Meter: if (numCh < 1) { zeros(); break; } op.opcode = OP_METER; take(1); evNode = true; break;
         case NodeKind::Snapshot: if (numCh < 2) { zeros(); break; } op.opcode = OP_SNAPSHOT; take(2); evNode = true; break;
         case NodeKind::Scope:
+        case NodeKind::Fft:
         case NodeKind::Capture: {
             evNode = true;
             const size_t floats = (size_t) g.nTiles() * g.tileWidth * (size_t) n.size;
@@ -1063,9 +1088,10 @@ int Compiler::emitNode(Node& n, int rootIndex) {
                 if (!E.cuda(E.dmemset(n.ring, 0, sizeof(float) * floats), "memset analysis ring")) return rc::CudaError;
                 n.ringFloats = floats;
             }
-            if (n.kind == NodeKind::Scope) {
+            if (n.kind == NodeKind::Scope || n.kind == NodeKind::Fft) {
                 if (numCh < 1) { zeros(); break; }
-                op.opcode = OP_SCOPE; take(std::min(numCh, (int) SCOPE_CHANNELS));
+                const int ringCh = n.kind == NodeKind::Scope ? (int) SCOPE_CHANNELS : 1;
+                op.opcode = OP_SCOPE; take(std::min(numCh, ringCh)); op.aux1 = (uint32_t) ringCh;
                 if (prog.dynNodes.size() >= (size_t) MAX_DYN) return E.fail(rc::InvariantViolation, "more than 16 scope nodes in one graph");
                 op.aux0 = (uint32_t) prog.dynNodes.size();
                 prog.dynNodes.push_back(n.id);
@@ -1118,6 +1144,10 @@ int Compiler::emitNode(Node& n, int rootIndex) {
             int r = E.ensureResourceOnDevice(*n.resource);
             if (r != rc::Ok) return r;
             op.opcode = OP_TABLE; op.aux0 = (uint32_t) n.resource->numSamples; op.ptr = (uint64_t) (uintptr_t) n.resource->dChannel0; take(1);
+            if (!prog.stagedTable && n.resource->numSamples <= (size_t) TABLE_SMEM_MAX_FLOATS) {
+                prog.stagedTable = n.resource->dChannel0;
+                prog.stagedTableFloats = (int) ((n.resource->numSamples + 3) / 4 * 4);
+            }
         } break;
 
         case NodeKind::TapIn:
@@ -1774,6 +1804,7 @@ int Engine::enqueueBlock(size_t nIn, size_t nOut, size_t numSamples, bool perVoi
         }
         P.runMask = runMask;
         P.sampleTime = sampleTime_;
+        P.tableSrc = p.stagedTable; P.tableFloats = p.stagedTableFloats; P.tableSmem = -1;   // the launcher places it (single-group launches)
         for (size_t di = 0; di < p.dynNodes.size(); ++di) {
             auto it = g.nodes.find(p.dynNodes[di]);
             if (it != g.nodes.end()) P.dyn[di] = it->second.scopeW;
@@ -1783,7 +1814,7 @@ int Engine::enqueueBlock(size_t nIn, size_t nOut, size_t numSamples, bool perVoi
             auto it = g.nodes.find(ev.node);
             if (it == g.nodes.end()) continue;
             Node& en = it->second;
-            if (en.kind == NodeKind::Scope && (en.inlets.empty() ? nIn : en.inlets.size()) >= 1) {          // MultiChannelRingBuffer::write, :36-62
+            if ((en.kind == NodeKind::Scope || en.kind == NodeKind::Fft) && (en.inlets.empty() ? nIn : en.inlets.size()) >= 1) {          // MultiChannelRingBuffer::write, :36-62
                 const uint32_t mask = SCOPE_RING - 1, w = en.scopeW, r = en.scopeR, n = (uint32_t) numSamples;
                 const uint32_t freeSlots = (r > w) ? (r - w) : ((uint32_t) SCOPE_RING - (w - r));
                 en.scopeW = (w + n) & mask;
@@ -2078,6 +2109,33 @@ static void appendFloatArray(std::string& o, const float* d, size_t n) {
     o += ']';
 }
 
+// AudioFFT::fft semantics (wasm/FFTConvolver/AudioFFT.cpp:132-155): n real float samples -> n/2+1 bins, the transform itself in
+// double (the reference runs Ooura's rdft in double), Im of bins 0 and n/2 exactly zero.
+static void realFftFloatIO(const std::vector<float>& x, std::vector<float>& re, std::vector<float>& im) {
+    const size_t n = x.size();
+    std::vector<double> ar(x.begin(), x.end()), ai(n, 0.0);
+    for (size_t i = 1, j = 0; i < n; ++i) {
+        size_t bit = n >> 1;
+        for (; j & bit; bit >>= 1) j ^= bit;
+        j ^= bit;
+        if (i < j) { std::swap(ar[i], ar[j]); std::swap(ai[i], ai[j]); }
+    }
+    for (size_t len = 2; len <= n; len <<= 1) {
+        const double ang = -2.0 * M_PI / (double) len;
+        for (size_t k = 0; k < len / 2; ++k) {
+            const double wr = std::cos(ang * (double) k), wi = std::sin(ang * (double) k);
+            for (size_t i = k; i < n; i += len) {
+                const size_t j = i + len / 2;
+                const double xr = ar[j] * wr - ai[j] * wi, xi = ar[j] * wi + ai[j] * wr;
+                ar[j] = ar[i] - xr; ai[j] = ai[i] - xi;
+                ar[i] += xr; ai[i] += xi;
+            }
+        }
+    }
+    for (size_t k = 0; k <= n / 2; ++k) { re[k] = (float) ar[k]; im[k] = (float) ai[k]; }
+    im[0] = 0.0f; im[n / 2] = 0.0f;
+}
+
 int Engine::processQueuedEvents(int vb, int ve, EventFn cb, void* user) {
     if (planOnly_) return rc::Ok;
     dsetdev();
@@ -2166,6 +2224,33 @@ int Engine::processQueuedEvents(int vb, int ve, EventFn cb, void* user) {
                         }
                         n.scopeR = (r + (uint32_t) size) & mask;
                     }
+                } break;
+                case NodeKind::Fft: {          // wasm/FFT.h:90-131: one windowed real FFT per poll once `size` samples are waiting
+                    const size_t size = n.window.size();
+                    const uint32_t mask = SCOPE_RING - 1, r = n.scopeR, w = n.scopeW;
+                    const size_t full = (w > r) ? (w - r) : (((uint32_t) SCOPE_RING - (r - w)) & mask);
+                    if (size == 0 || full < size || !n.ring) break;
+                    std::vector<float> slab(size * (size_t) L), x(size), re(size / 2 + 1), im(size / 2 + 1);
+                    const int t0 = b / L, t1 = (e + L - 1) / L;
+                    for (int tile = t0; tile < t1 && cb; ++tile) {
+                        const float* base = n.ring + (size_t) tile * SCOPE_RING * L;
+                        const size_t first = std::min(size, (size_t) SCOPE_RING - r);
+                        if (!cuda(cudaMemcpy(slab.data(), base + (size_t) r * L, sizeof(float) * first * L, cudaMemcpyDeviceToHost), "read fft ring")) return rc::CudaError;
+                        if (first < size && !cuda(cudaMemcpy(slab.data() + first * L, base, sizeof(float) * (size - first) * L, cudaMemcpyDeviceToHost), "read fft ring (wrap)")) return rc::CudaError;
+                        for (int vl = 0; vl < L; ++vl) {
+                            const int v = tile * L + vl;
+                            if (v < b || v >= e) continue;
+                            for (size_t i = 0; i < size; ++i) x[i] = slab[i * L + vl] * n.window[i];
+                            realFftFloatIO(x, re, im);
+                            std::string js = "{\"data\": {\"imag\": ";
+                            appendFloatArray(js, im.data(), im.size());
+                            js += ", \"real\": ";
+                            appendFloatArray(js, re.data(), re.size());
+                            js += "}, \"source\": " + src + ", \"voice\": " + std::to_string(g.v0 + v) + "}";
+                            cb("fft", js.c_str(), g.v0 + v, user);
+                        }
+                    }
+                    n.scopeR = (r + (uint32_t) size) & mask;
                 } break;
                 case NodeKind::Capture: {      // Capture.h:60-93
                     if (!n.ring || !readRows(n.stateRow, 5, rows)) return rc::CudaError;

@@ -30,7 +30,7 @@ enum class NodeKind : uint8_t {
     Delay, SDelay, Z, Pole, Env, Biquad, Prewarp, MM1p, Svf, SvfShelf, TapIn, TapOut, Table, Blep, Convolve,
     PassThrough,  // analysis nodes whose events are not produced: audio passes through
     Once, Seq, Seq2, SparSeq, SparSeq2, Time, Metro,  // sequencing / control nodes
-    Meter, Snapshot, Scope, Capture                   // analysis nodes feeding processQueuedEvents
+    Meter, Snapshot, Scope, Capture, Fft              // analysis nodes feeding processQueuedEvents
 };
 
 // A read-only device array owned jointly by the node that uploaded it and by every compiled program that points at it
@@ -62,7 +62,7 @@ struct GainFade {
 struct Resource {
     std::string name;
     std::vector<std::vector<float>> channels;   // host copy (always float: AudioBufferResource.h:13-24)
-    float* dChannel0 = nullptr;                 // device copy of channel 0
+    float* dChannel0 = nullptr;                 // device copy of channel 0 (padded with zeros to a multiple of 16 bytes: TMA bulk copies)
     size_t numSamples = 0;
 };
 
@@ -105,6 +105,7 @@ struct Node {
     uint32_t scopeR = 0, scopeW = 0;
     bool metroFlag = false; float metroLastOut = 0.0f;
     std::vector<std::vector<float>> relay;
+    std::vector<float> window;       // fft: Blackman-Harris window of the current size (wasm/FFT.h:49-62)
 };
 
 struct Program {
@@ -131,6 +132,7 @@ struct Program {
     struct EvNode { int32_t node; int root; };
     std::vector<EvNode> evNodes;          // event-emitting nodes in render order (GraphRenderSequence.h:189-198 walks nodeList)
     std::vector<int32_t> dynNodes;        // LaunchParams::dyn[i] belongs to node dynNodes[i]
+    const float* stagedTable = nullptr; int stagedTableFloats = 0;   // the wavetable K1 stages into shared memory with TMA (first `table` node that fits)
     ~Program();
 };
 

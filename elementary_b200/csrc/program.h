@@ -65,7 +65,7 @@ enum Opcode : uint32_t {
     // ---- analysis nodes: audio passes through, a per-voice record feeds processQueuedEvents ----
     OP_METER,      // Analyzers.h:20-69    state: min, max, readouts pushed since the host last drained them
     OP_SNAPSHOT,   // Analyzers.h:77-136   state: z, latest value, readouts pushed
-    OP_SCOPE,      // Analyzers.h:146-255  ptr = ring [tile][4][SCOPE_RING][L]; aux0 = index of the write position in LaunchParams::dyn
+    OP_SCOPE,      // Analyzers.h:146-255, wasm/FFT.h:17-139  ptr = ring [tile][aux1][SCOPE_RING][L]; aux0 = index of the write position in LaunchParams::dyn
     OP_CAPTURE,    // Capture.h:14-103     ptr = [tile][aux0 + CAPTURE_SCRATCH][L] (ring then scratch); state: lastIn, scratchSize, w, r, ready
     OP_COUNT_
 };
@@ -142,6 +142,12 @@ struct LaunchParams {
     long long sampleTime;        // int64 sample clock of this block's first sample (*userData of Runtime::process: wasm/Main.cpp:206-217)
     RootDyn roots[MAX_ROOTS];
     uint32_t dyn[MAX_DYN];
+    // One wavetable of the program staged into shared memory by a TMA bulk copy at kernel start (single-group launches only):
+    // OP_TABLE ops whose table pointer equals tableSrc read shared memory at float index tableSmem instead of global memory.
+    const float* tableSrc;       // device copy of the resource (16-byte aligned, padded to a multiple of 16 bytes), or null
+    int tableFloats;             // padded length in floats
+    int tableSmem;               // float index of the staged copy in the CTA's dynamic shared memory, or -1
 };
+constexpr int TABLE_SMEM_MAX_FLOATS = 8192;   // tables up to 32 KB are staged
 
 } // namespace eb

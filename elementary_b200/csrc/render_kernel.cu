@@ -54,6 +54,30 @@ struct SP {
     __device__ __forceinline__ float* ptr() const { return g_smem + i; }
 };
 
+// ---- TMA (1-D bulk async copy) + mbarrier: stages a program's wavetable HBM -> shared memory once per CTA (SASS: UBLKCP)
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t) __cvta_generic_to_shared(p); }
+__device__ __forceinline__ void stage_table_tma(const float* src, int floats, float* dst, uint64_t* bar) {
+    if (threadIdx.x == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(bar)) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        const uint32_t bytes = (uint32_t) floats * 4u;
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                     ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+    }
+    __syncthreads();            // the barrier is initialised before anyone polls it
+    asm volatile(
+        "{\n"
+        ".reg .pred P1;\n"
+        "TBL_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], 0;\n"
+        "@P1 bra TBL_DONE;\n"
+        "bra TBL_WAIT;\n"
+        "TBL_DONE:\n"
+        "}" ::"r"(smem_u32(bar)) : "memory");
+}
+
 // An operand is a shared-memory address plus strides: a slot advances 32 floats per element slice k and L floats
 // per sample; a parameter row (one float per voice) has stride 0 in both.
 struct Opnd {
@@ -1056,6 +1080,8 @@ __device__ __forceinline__ void render_tile(const LaunchParams& P, const int til
                 const Opnd pos = decode(__ldg(opnds));
                 const int size = (int) aux0;
                 const float* tab = reinterpret_cast<const float*>(ptrbits);
+                const bool staged = (P.tableSmem >= 0) && (tab == P.tableSrc);   // the TMA-staged copy (warp-uniform)
+                const SP stab{P.tableSmem};
                 FOR_K(k) {
                     const float readPos = clampf(LDE(pos, k), 0.0f, 1.0f) * (float) (size - 1);
                     int readLeft = (int) readPos;                   // in [0, size-1]; NaN converts to 0
@@ -1063,8 +1089,8 @@ __device__ __forceinline__ void render_tile(const LaunchParams& P, const int til
                     const float frac = readPos - floorf(readPos);
                     if (readLeft >= size) readLeft -= size;
                     if (readRight >= size) readRight -= size;
-                    const float left = __ldg(tab + readLeft);
-                    const float right = __ldg(tab + readRight);
+                    const float left = staged ? stab[readLeft] : __ldg(tab + readLeft);
+                    const float right = staged ? stab[readRight] : __ldg(tab + readRight);
                     out[k * 32] = left + frac * (right - left);
                 }
             } break;
@@ -1227,8 +1253,9 @@ __device__ __forceinline__ void render_tile(const LaunchParams& P, const int til
             } break;
 
             case OP_SCOPE: {    // Analyzers.h:184-201: copy in0 through, append every child (<= 4) to the ring
-                const int nch = min((int) count6, SCOPE_CHANNELS);
-                float* ring = reinterpret_cast<float*>(ptrbits) + (size_t) tile * SCOPE_CHANNELS * SCOPE_RING * L + vlane;
+                const int ringCh = (int) aux1;     // channels of the ring: 4 for scope (Analyzers.h:149), 1 for fft (wasm/FFT.h:20)
+                const int nch = min((int) count6, ringCh);
+                float* ring = reinterpret_cast<float*>(ptrbits) + (size_t) tile * ringCh * SCOPE_RING * L + vlane;
                 const uint32_t w = P.dyn[aux0] + (uint32_t) s0;
                 for (int ch = 0; ch < nch; ++ch) {
                     const Opnd a = decode(__ldg(opnds + ch));
@@ -1337,6 +1364,8 @@ __device__ __forceinline__ void render_tile(const LaunchParams& P, const int til
 // One voice group per launch: the descriptor travels in the constant bank.
 template <int NITER, int LOGL>
 __global__ void EB_BOUNDS render_block_kernel(const __grid_constant__ LaunchParams P, const int perWarp) {
+    if (P.tableSmem >= 0)       // CTA-wide: one TMA bulk copy of the program's wavetable into shared memory, guarded by an mbarrier
+        stage_table_tma(P.tableSrc, P.tableFloats, g_smem + P.tableSmem, reinterpret_cast<uint64_t*>(g_smem + P.tableSmem + P.tableFloats));
     const int tile = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (tile >= ((P.nv + (1 << LOGL) - 1) >> LOGL)) return;   // whole warp leaves together
     render_tile<NITER, LOGL>(P, tile, perWarp);
@@ -1430,9 +1459,13 @@ template <int NITER, int LOGL>
 static cudaError_t launch_impl(const LaunchParams& P, int grid, int threads, size_t smem, cudaStream_t stream) {
     cudaError_t e = cudaFuncSetAttribute(render_block_kernel<NITER, LOGL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
     if (e != cudaSuccess) return e;
-    render_block_kernel<NITER, LOGL><<<grid, threads, smem, stream>>>(P, (int) (smem / sizeof(float) / (threads / 32)));
+    // per-warp area = everything in front of the (optional) staged table
+    const size_t warpArea = P.tableSmem >= 0 ? (size_t) P.tableSmem * sizeof(float) : smem;
+    render_block_kernel<NITER, LOGL><<<grid, threads, smem, stream>>>(P, (int) (warpArea / sizeof(float) / (threads / 32)));
     return cudaGetLastError();
 }
+
+static cudaError_t launch_render_block_geometry(const LaunchParams& P, int L, int grid, int threads, size_t smem, int perWarpFloats, int niterOverride, cudaStream_t stream);
 
 template <int NITER, int LOGL>
 static cudaError_t launch_groups_impl(const LaunchParams* descs, const int* tileStart, int nGroups, int totalTiles,
@@ -1450,7 +1483,18 @@ cudaError_t launch_render_block(const LaunchParams& P, int warpsPerCta, int nite
     if (nTiles <= 0) return cudaSuccess;
     const int grid = (nTiles + warpsPerCta - 1) / warpsPerCta;
     const int threads = warpsPerCta * 32;
-    const size_t smem = render_smem_bytes(P.nSlots, P.nOut, P.nStateRows, P.nParams, warpsPerCta, L, niterOverride);
+    size_t smem = render_smem_bytes(P.nSlots, P.nOut, P.nStateRows, P.nParams, warpsPerCta, L, niterOverride);
+    LaunchParams Q = P;
+    const int perWarpFloats = (int) (smem / sizeof(float) / warpsPerCta);
+    if (Q.tableSrc && Q.tableFloats > 0 && Q.tableFloats <= TABLE_SMEM_MAX_FLOATS &&
+        smem + (size_t) Q.tableFloats * 4 + 16 <= (size_t) 200 * 1024) {
+        Q.tableSmem = perWarpFloats * warpsPerCta;            // behind the per-warp areas; 16-byte aligned (perWarp is a multiple of 4 floats)
+        smem += (size_t) Q.tableFloats * 4 + 16;              // + the mbarrier
+    } else { Q.tableSmem = -1; Q.tableSrc = nullptr; }
+    return launch_render_block_geometry(Q, L, grid, threads, smem, perWarpFloats, niterOverride, stream);
+}
+
+static cudaError_t launch_render_block_geometry(const LaunchParams& P, int L, int grid, int threads, size_t smem, int perWarpFloats, int niterOverride, cudaStream_t stream) {
     switch (L) {
         case 32: return render_niter_for(32, niterOverride) == 4 ? launch_impl<4, 5>(P, grid, threads, smem, stream)
                                                                   : launch_impl<8, 5>(P, grid, threads, smem, stream);

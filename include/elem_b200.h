@@ -105,9 +105,10 @@ void elem_b200_reset(elem_b200_runtime* rt);
 /* Runtime::processQueuedEvents(cb) — Runtime.h:64,438-446; relayed like wasm/Main.cpp:220-231.  For every root
  * sub-sequence whose root is active, every event node in render order (GraphRenderSequence.h:189-198): `meter`
  * {min,max,source}, `snapshot` {source,data}, `scope` {source,data:[[..],..]}, `capture` {source,data:[..]}
- * (runtime/elem/builtins/Analyzers.h, Capture.h) and `metro` {source} (wasm/Metro.h:58-66).  One callback per voice
+ * (runtime/elem/builtins/Analyzers.h, Capture.h), `fft` {source,data:{real,imag}} (wasm/FFT.h:90-131) and `metro` {source}
+ * (wasm/Metro.h:58-66).  One callback per voice
  * that has something to report; jsonEvent is the reference's event object as JSON text plus a "voice" key.  Call it
- * from the control thread between blocks (it synchronises the stream).  `fft` events are not produced. */
+ * from the control thread between blocks (it synchronises the stream). */
 typedef void (*elem_b200_event_cb)(const char* type, const char* jsonEvent, void* user);
 void elem_b200_process_queued_events(elem_b200_runtime* rt, elem_b200_event_cb cb, void* user);
 /* Same, restricted to the voices [voiceBegin, voiceEnd) (voiceEnd < 0 = all): at a million voices nobody wants a

@@ -330,6 +330,7 @@ struct Node {
     }
     float scratch[128]; size_t scratchSize = 0; bool relayReady = false; std::vector<float> relayBuffer;
     std::map<std::string, PropValue> props;   // GraphNode::props (GraphNode.h:60-63), what processEvents reads
+    std::vector<float> window;                // fft (wasm/FFT.h:49-62)
 
     int32_t spTickTime(int32_t offset);
     std::map<int32_t, float>::iterator spFind(int32_t tickTime);
@@ -376,6 +377,7 @@ struct Engine {
         if (type == "metro") n.intervalSamps = (int64_t) std::max(2.0, 1000.0 * 0.001 * sr);                 // Metro.h:14-18,30-33
         if (type == "scope") { n.mcInit(4, 8192); PropValue c1; c1.num = 1; n.props["channels"] = c1; PropValue sz; sz.num = 512; n.props["size"] = sz; }   // Analyzers.h:147-153
         if (type == "capture") n.mcInit(1, (size_t) bitceil((int) (size_t) sr));                              // Capture.h:15-19
+        if (type == "fft") { n.mcInit(1, 8192); nodes.emplace(id, std::move(n)); PropValue sz; sz.num = 1024; return setProperty(id, "size", sz); }   // wasm/FFT.h:18-26
         nodes.emplace(id, std::move(n));
         return 0;
     }
@@ -437,6 +439,23 @@ struct Engine {
         if (t == "scope") {                                                                                 // Analyzers.h:155-179
             if (key == "size") { if (!isNum) return 5; if (v.num < 256 || v.num > 8192) return 6; }
             if (key == "channels") { if (!isNum) return 5; if (v.num < 0 || v.num > 4) return 6; }
+            if (key == "name" && !isStr) return 5;
+        }
+        if (t == "fft") {                                                                                   // wasm/FFT.h:32-71
+            if (key == "size") {
+                if (!isNum) return 5;
+                const int size = (int) v.num;
+                if (!(size > 0 && (size & (size - 1)) == 0) || size < 256 || size > 8192) return 6;
+                n.window.resize(size);
+                for (int i = 0; i < size; ++i) {
+                    float const a0 = 0.35875, a1 = 0.48829, a2 = 0.14128, a3 = 0.01168;
+                    float const pi = 3.1415926535897932385;
+                    float const t1 = a1 * std::cos(2.0 * pi * (i / (double) (size - 1)));
+                    float const t2 = a2 * std::cos(4.0 * pi * (i / (double) (size - 1)));
+                    float const t3 = a3 * std::cos(6.0 * pi * (i / (double) (size - 1)));
+                    n.window[i] = a0 - t1 + t2 - t3;
+                }
+            }
             if (key == "name" && !isStr) return 5;
         }
         if (t == "once" && key == "arm") {                                                                  // Core.h:345-361
@@ -685,9 +704,10 @@ void Engine::processNode(Node& n, const float* const* hostIn, int nHostIn, int n
         }
         return;
     }
-    if (t == "fft") {   // wasm/FFT.h: audio passes through (its analysis events are not restated)
+    if (t == "fft") {   // wasm/FFT.h:73-88
         if (nch < 1) return zeros();
         std::copy_n(in[0], ns, out);
+        n.mcWrite(in.data(), 1, (size_t) ns);
         return;
     }
     if (t == "time") {   // wasm/SampleTime.h:16-23
@@ -1161,6 +1181,17 @@ std::string processQueuedEvents(Engine& e) {
                     emit("capture", "{\"data\": " + evArray(n.relayBuffer.data(), n.relayBuffer.size()) + ", \"source\": " + evSource(n) + "}");
                     n.relayBuffer.clear();
                 }
+            } else if (n.type == "fft") {                             // wasm/FFT.h:90-131
+                const size_t size = n.window.size();
+                if (size == 0 || n.mcFull() < size) continue;
+                std::vector<float> x(size), re(size / 2 + 1), im(size / 2 + 1);
+                float* dst = x.data();
+                n.mcRead(&dst, 1, size);
+                for (size_t i = 0; i < size; ++i) x[i] *= n.window[i];
+                RealFFT f; f.init(size);
+                f.fft(x.data(), re.data(), im.data());
+                im[0] = 0.0f; im[size / 2] = 0.0f;
+                emit("fft", "{\"data\": {\"imag\": " + evArray(im.data(), im.size()) + ", \"real\": " + evArray(re.data(), re.size()) + "}, \"source\": " + evSource(n) + "}");
             } else if (n.type == "metro") {                           // wasm/Metro.h:58-66
                 if (n.metroFlag) { n.metroFlag = false; emit("metro", "{\"source\": " + evSource(n) + "}"); }
             }

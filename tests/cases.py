@@ -113,6 +113,7 @@ CASES += [
     _c("meter_passthrough", el.meter({"name": "m"}, el.mul(0.5, IN0)), 1, 2),
     _c("snapshot_passthrough", el.snapshot({"name": "s"}, el.train(500.0), IN0), 1, 2),
     _c("scope_passthrough", el.scope({"name": "sc", "channels": 2}, IN0, IN1), 2, 2),
+    _c("fft_passthrough", el.fft({"name": "f"}, IN0), 1, 2),
     _c("capture_passthrough", el.capture({"name": "c"}, el.train(40.0), IN0), 1, 2),
     _c("arp_voice", el.mul(el.seq({"seq": [0.2, 0.5, 1.0], "hold": True}, el.metro({"interval": 2.0})),
                         el.cycle(el.seq({"seq": [220.0, 330.0, 440.0, 660.0], "hold": True}, el.metro({"interval": 2.0})))), n_blocks=6),

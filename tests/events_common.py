@@ -25,6 +25,8 @@ def scenarios():
         dict(name="scope_big_window_clobbered", graph=(el.scope({"name": "big", "size": 2048}, IN0),), n_in=1, blocks=40, poll=lambda b: b in (3, 4, 5, 6, 30, 31, 39)),
         dict(name="capture", graph=(el.capture({"name": "cap"}, gate, IN0),), n_in=1, blocks=14, poll=lambda b: b % 2 == 1),
         dict(name="capture_polled_once", graph=(el.capture({}, gate, el.mul(2.0, IN0)),), n_in=1, blocks=12, poll=lambda b: b == 11),
+        dict(name="fft_default_1024", graph=(el.fft({"name": "spec"}, el.mul(0.5, IN0)),), n_in=1, blocks=7, poll=lambda b: True),
+        dict(name="fft_4096_polled_late", graph=(el.fft({"name": "big", "size": 4096}, el.add(el.cycle(1000.0), IN0)),), n_in=1, blocks=30, poll=lambda b: b in (6, 7, 8, 20, 29)),
         dict(name="metro", graph=(el.metro({"name": "tick", "interval": 25.0}),), n_in=0, blocks=12, poll=lambda b: True),
         dict(name="several_nodes_two_roots",
              graph=(el.meter({"name": "a"}, el.snapshot({"name": "b"}, el.train(97.0), IN0)), el.meter({"name": "c"}, el.cycle(440.0))),
@@ -40,6 +42,8 @@ def noise(n, seed):
 def canon(events):
     """Order-preserving, float32-rounded canonical form for comparison across implementations."""
     def f32(x):
+        if isinstance(x, dict):
+            return {k: f32(v) for k, v in x.items()}
         if isinstance(x, list):
             return [f32(y) for y in x]
         if isinstance(x, (int, float)):
@@ -50,3 +54,25 @@ def canon(events):
         evt = {k: f32(v) for k, v in e["event"].items() if k != "voice"}
         out.append((e["type"], evt))
     return out
+
+
+def same(got, want):
+    """Event lists (canonical form) equal: exactly, except `fft` spectra, whose double-precision transform may be evaluated by a
+    different (equally exact) FFT algorithm than Ooura's and is compared to 2e-6 of the spectrum's peak."""
+    if len(got) != len(want):
+        return False
+    for (tg, eg), (tw, ew) in zip(got, want):
+        if tg != tw:
+            return False
+        if tg != "fft":
+            if eg != ew:
+                return False
+            continue
+        if eg.get("source") != ew.get("source"):
+            return False
+        for part in ("real", "imag"):
+            a, b = np.asarray(eg["data"][part], dtype=np.float64), np.asarray(ew["data"][part], dtype=np.float64)
+            scale = max(1e-30, np.abs(np.asarray(ew["data"]["real"])).max(), np.abs(np.asarray(ew["data"]["imag"])).max())
+            if a.shape != b.shape or np.abs(a - b).max() > 2e-6 * scale:
+                return False
+    return True
