@@ -411,3 +411,18 @@ def test_split_must_respect_tile_boundaries():
     rt.process_voices(None, 1, BS)
     assert rt.apply_instructions([[0, 99, "sin"]], voices=(6, 16)) == 7        # 6 is not a multiple of the tile width
     assert rt.apply_instructions([[0, 99, "sin"]], voices=(8, 16)) == 0
+
+
+@pytest.mark.parametrize("seed", list(range(100, 116)))
+def test_random_graph_fuzz(seed):
+    """Differential fuzz: random 48-node DAGs over the builtin set (the generator of BASELINE config 5), every tile geometry
+    the host may pick, against the oracle from block 0."""
+    batch = graphs.random_graph(seed, 48)
+    tile_width = [0, 1, 4, 32][seed % 4]
+    opts = {"tile_width": tile_width} if tile_width else {}
+    n_voices = 33 if tile_width == 32 else 3
+    got, _, _ = run_gpu(batch, n_voices, 5, **opts)
+    ref = oracle_render(batch, 5, 1, SR, BS)
+    for v in range(n_voices):
+        ok, worst, ex = block_peak_tolerance_check(got[v], ref[0], BS)
+        assert ok, f"seed {seed} voice {v}: worst err/tol {worst:.3g}, bit-exact {ex:.4f}"
