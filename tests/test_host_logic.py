@@ -31,13 +31,41 @@ BAD_BATCHES = [
     ([["x", 1, "sin"]], 8),
     ([[0, "id", "sin"]], 8),
     ([[0, 8, "delay"], [3, 8, "size", "big"]], 5),
+    # sequencing / control / analysis nodes (Core.h:411-466, Seq2.h:39-84, SparSeq.h:40-124, SparSeq2.h:20-56, Core.h:345-361,
+    # wasm/Metro.h:20-37, Analyzers.h:155-179, wasm/FFT.h:32-71): property validation must return the reference's codes
+    ([[0, 9, "seq"], [3, 9, "hold", 1]], 5),
+    ([[0, 9, "seq"], [3, 9, "loop", "yes"]], 5),
+    ([[0, 9, "seq"], [3, 9, "offset", -1]], 6),
+    ([[0, 9, "seq"], [3, 9, "offset", "x"]], 5),
+    ([[0, 9, "seq"], [3, 9, "seq", 3]], 5),
+    ([[0, 9, "seq2"], [3, 9, "seq", "abc"]], 5),
+    ([[0, 9, "seq2"], [3, 9, "offset", -0.5]], 6),
+    ([[0, 9, "sparseq"], [3, 9, "loop", 4]], 5),
+    ([[0, 9, "sparseq"], [3, 9, "follow", 1]], 5),
+    ([[0, 9, "sparseq"], [3, 9, "interpolate", True]], 5),
+    ([[0, 9, "sparseq"], [3, 9, "tickInterval", -1]], 6),
+    ([[0, 9, "sparseq"], [3, 9, "seq", {}]], 5),
+    ([[0, 9, "sparseq2"], [3, 9, "seq", 1]], 5),
+    ([[0, 9, "sparseq2"], [3, 9, "interpolate", "1"]], 5),
+    ([[0, 9, "once"], [3, 9, "arm", 1]], 5),
+    ([[0, 9, "metro"], [3, 9, "interval", 0]], 6),
+    ([[0, 9, "metro"], [3, 9, "interval", "fast"]], 5),
+    ([[0, 9, "scope"], [3, 9, "size", 128]], 6),
+    ([[0, 9, "scope"], [3, 9, "channels", 5]], 6),
+    ([[0, 9, "scope"], [3, 9, "name", 7]], 5),
+    ([[0, 9, "fft"], [3, 9, "size", 300]], 6),
+    ([[0, 9, "fft"], [3, 9, "size", 16384]], 6),
+    ([[0, 9, "fft"], [3, 9, "size", "1k"]], 5),
+    ([[0, 9, "fft"], [3, 9, "name", 1]], 5),
+    ([[0, 9, "sampleseq"]], 1),         # sample playback stays out of scope: unknown type here (the reference knows it)
 ]
+OUT_OF_SCOPE_TYPES = {"sampleseq"}
 
 
 @pytest.mark.parametrize("batch,code", BAD_BATCHES)
 def test_error_codes_match_reference(batch, code):
     assert plan().apply_instructions(batch) == code
-    if orc.ref_available():
+    if orc.ref_available() and not any(len(i) > 2 and i[2] in OUT_OF_SCOPE_TYPES for i in batch if isinstance(i, list)):
         assert orc.RefRuntime(SR, BS).apply(batch) == code
 
 
