@@ -1,7 +1,8 @@
 #!/bin/bash
-# End-of-round measurement set on one B200 (run from the repo root under gpurun): smoke, headline bench + reference arm,
+# End-of-round measurement set on one B200 (run from the repo root under gpurun): GPU tests, smoke, headline bench + reference arm,
 # voice-count sweep, other configs.  Outputs land in gpurun_out/ and are copied into profiles/ by hand.
 mkdir -p gpurun_out
+python -m pytest tests -m gpu -x -q 2>&1 | tail -4 | tee gpurun_out/final_pytest.txt
 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -1
 python bench.py > gpurun_out/final_bench_n1.json 2> gpurun_out/final_bench_n1.err; tail -2 gpurun_out/final_bench_n1.err; cut -c1-400 gpurun_out/final_bench_n1.json
 python bench.py --impl reference --steps 100 --warmup 10 > gpurun_out/final_bench_ref.json 2>&1; cut -c1-300 gpurun_out/final_bench_ref.json
