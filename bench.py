@@ -151,8 +151,7 @@ def run_b200(args, rank, local_rank, world):
     import torch.distributed as dist
 
     torch.cuda.set_device(local_rank)
-    if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
-        os.environ["NCCL_DEBUG"] = "WARN"       # keep stdout to the one JSON line (the version banner goes to stdout)
+    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")   # NCCL's banner / warnings go to stderr: stdout carries the one JSON line
     if world > 1 and not dist.is_initialized():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
