@@ -44,9 +44,9 @@ bool convolver_init(ConvolverState& st, const float* ir, size_t irLen, int nv, b
 // Copy of channels [c0, c0+n) of `src` (same IR, same position in the partition cycle) — used when a voice group is cut.
 bool convolver_clone_range(const ConvolverState& src, int c0, int n, ConvolverState& dst, cudaStream_t stream, std::string& err);
 
-// Convolve `n` more samples (n <= 512 - st.fill) of every channel: in/out are [channel][stride] device buffers, the
-// samples of this call start at `offset`.  Advances st.fill / st.cur.
-cudaError_t convolver_process_chunk(ConvolverState& st, const float* in, float* out, int stride, int offset, int n, cudaStream_t stream);
+// Convolve `n` more samples (n <= 512 - st.fill) of every channel: in is [channel][inStride] (inStride 0 = one input shared by
+// all channels), out is [channel][outStride]; the samples of this call start at `offset`.  Advances st.fill / st.cur.
+cudaError_t convolver_process_chunk(ConvolverState& st, const float* in, int inStride, float* out, int outStride, int offset, int n, cudaStream_t stream);
 
 // Algorithmic HBM bytes of one full 512-sample block for one channel.
 inline size_t convolver_algorithmic_bytes_per_channel_block(int partitions) {

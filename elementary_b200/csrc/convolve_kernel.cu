@@ -114,7 +114,7 @@ __device__ __forceinline__ void fft512_t(float2 (*a)[N2], float2 (*b)[N2], const
 } // namespace
 
 __global__ void __launch_bounds__(TM_THREADS, TM_CTAS_PER_SM) convolve_chunk_tm_kernel(
-    const float* __restrict__ in, float* __restrict__ out, int stride, int offset, int n, int fill, int cur, int S, int nv,
+    const float* __restrict__ in, int inStride, float* __restrict__ out, int stride, int offset, int n, int fill, int cur, int S, int nv,
     const float2* __restrict__ H, float2* __restrict__ fdl, float2* __restrict__ ypre,
     float* __restrict__ overlap, float* __restrict__ inbuf, const float2* __restrict__ twg) {
     extern __shared__ __align__(128) unsigned char smemRaw[];
@@ -223,7 +223,7 @@ __global__ void __launch_bounds__(TM_THREADS, TM_CTAS_PER_SM) convolve_chunk_tm_
 
     // ---------------- T group: forward transform of pair n, inverse transform + output of pair n-1 ----------------
     const int t = tid;
-    const bool wholeBlock = (fill == 0) && (n == CONV_BLOCK) && (((stride | offset) & 1) == 0);
+    const bool wholeBlock = (fill == 0) && (n == CONV_BLOCK) && (((inStride | offset) & 1) == 0);
     const float scale = 1.0f / 512.0f;
 
     auto forward = [&](int u, int nloc) {
@@ -238,7 +238,7 @@ __global__ void __launch_bounds__(TM_THREADS, TM_CTAS_PER_SM) convolve_chunk_tm_
                 for (int h = 0; h < 2; ++h) {
                     const int k = t + h * TM_GROUP;
                     float2 z = make_float2(0.0f, 0.0f);
-                    if (ch < nv) z = __ldg(reinterpret_cast<const float2*>(in + (size_t) ch * stride + offset) + k);
+                    if (ch < nv) z = __ldg(reinterpret_cast<const float2*>(in + (size_t) ch * inStride + offset) + k);
                     Sc[c][k] = z;
                     Sc[c][k + 256] = make_float2(0.0f, 0.0f);
                 }
@@ -249,7 +249,7 @@ __global__ void __launch_bounds__(TM_THREADS, TM_CTAS_PER_SM) convolve_chunk_tm_
                 const int ch = ch0 + c;
                 if (ch < nv) {
                     float* ib = inbuf + (size_t) ch * CONV_BLOCK;
-                    for (int i = t; i < n; i += TM_GROUP) ib[fill + i] = in[(size_t) ch * stride + offset + i];
+                    for (int i = t; i < n; i += TM_GROUP) ib[fill + i] = in[(size_t) ch * inStride + offset + i];
                 }
             }
             tgroup_sync();
@@ -385,7 +385,7 @@ __global__ void __launch_bounds__(TM_THREADS, TM_CTAS_PER_SM) convolve_chunk_tm_
     if (prevU >= 0) inverse(prevU, nloc - 1);
 }
 
-cudaError_t convolver_process_chunk(ConvolverState& st, const float* in, float* out, int stride, int offset, int n, cudaStream_t stream) {
+cudaError_t convolver_process_chunk(ConvolverState& st, const float* in, int inStride, float* out, int stride, int offset, int n, cudaStream_t stream) {
     if (st.planOnly) return cudaErrorNotSupported;
     if (st.partitions == 0) {   // empty (fully trimmed) IR: silence (FFTConvolver.cpp:149-153)
         return cudaMemset2DAsync(out + offset, sizeof(float) * stride, 0, sizeof(float) * n, st.nv, stream);
@@ -403,7 +403,7 @@ cudaError_t convolver_process_chunk(ConvolverState& st, const float* in, float* 
     }
     const int persistent = smCount * TM_CTAS_PER_SM;                   // a multiple of the SM count: one resident wave
     const int grid = units < persistent ? units : persistent;
-    convolve_chunk_tm_kernel<<<grid, TM_THREADS, smem, stream>>>(in, out, stride, offset, n, st.fill, st.cur, st.partitions, st.nv,
+    convolve_chunk_tm_kernel<<<grid, TM_THREADS, smem, stream>>>(in, inStride, out, stride, offset, n, st.fill, st.cur, st.partitions, st.nv,
                                                                 st.dH, st.dFdl, st.dYpre, st.dOverlap, st.dInBuf, st.dTw);
     st.fill += n;
     if (st.fill == CONV_BLOCK) {

@@ -1445,11 +1445,34 @@ int Engine::compile(Group& g, int nIn, std::shared_ptr<Program>& out) {
             auto& op = ops[i];
             if (op.isSeg || op.opcode != OP_HOST_CONV) continue;
             Node& n = g.nodes.at(op.outNode);
-            float* inB = newBlockBuffer(); float* outB = newBlockBuffer();
-            if (!inB || !outB) return rc::CudaError;
-            prog->stages[stageOfOp[i]].convolves.push_back({n.id, inB, outB});
+            // A convolver fed straight by a host input channel (`convolve(in)`) reads that channel where it lies: no K1 staging
+            // copy, and — when nothing else lives in the stage — no K1 launch at all for it.
+            int inChannel = -1;
+            if (op.operands.size() == 1 && op.operands[0].first == K_SLOT) {
+                for (size_t j = 0; j < i; ++j)
+                    if (!ops[j].isSeg && ops[j].outNode == op.operands[0].second && ops[j].opcode == OP_LOADIN) inChannel = (int) ops[j].aux0;
+            }
+            float* inB = inChannel >= 0 ? nullptr : newBlockBuffer();
+            float* outB = newBlockBuffer();
+            if ((inChannel < 0 && !inB) || !outB) return rc::CudaError;
+            prog->stages[stageOfOp[i]].convolves.push_back({n.id, inB, outB, inChannel});
             spillOf[op.outNode] = outB;
             op.ptr = (uint64_t) (uintptr_t) inB;
+            if (inChannel >= 0) op.mode = 1;      // marks "no STOREBUF needed"
+        }
+        // LOADINs whose only consumers are bypassed convolvers are dead
+        {
+            std::unordered_map<int32_t, int> otherUses;
+            for (auto& op : ops) {
+                if (op.isSeg || (op.opcode == OP_HOST_CONV && op.mode == 1)) continue;
+                forEachSlotUse(op, [&](int32_t id) { ++otherUses[id]; });
+            }
+            for (auto& op : ops)
+                if (!op.isSeg && op.opcode == OP_LOADIN && !otherUses.count(op.outNode)) {
+                    bool feedsBypass = false;
+                    for (auto& c : ops) if (!c.isSeg && c.opcode == OP_HOST_CONV && c.mode == 1 && c.operands[0].second == op.outNode) feedsBypass = true;
+                    if (feedsBypass) op.dead = true;
+                }
         }
         // which values are read in a later stage than the one that produces them?
         std::unordered_map<int32_t, int> producedIn;
@@ -1474,7 +1497,7 @@ int Engine::compile(Group& g, int nIn, std::shared_ptr<Program>& out) {
                 out.push_back(ops[segBegin]);
                 std::unordered_map<int32_t, int32_t> loaded;   // value id -> temp id loaded in this stage+segment
                 for (size_t k = segBegin + 1; k < segEnd; ++k) {
-                    if (stageOfOp[k] != st) continue;
+                    if (stageOfOp[k] != st || ops[k].dead) continue;
                     Compiler::PendingOp op = ops[k];
                     // reload operands that were produced in an earlier stage (or by a convolver)
                     auto fix = [&](uint32_t& kind, int32_t& ref) {
@@ -1494,6 +1517,7 @@ int Engine::compile(Group& g, int nIn, std::shared_ptr<Program>& out) {
                     };
                     for (auto& o : op.operands) fix(o.first, o.second);
                     for (auto& stp : op.steps) if (!chain_fn_is_unary(stp.fn)) fix(stp.kind, stp.ref);
+                    if (op.opcode == OP_HOST_CONV && op.mode == 1) continue;   // reads the host input channel directly
                     if (op.opcode == OP_HOST_CONV) {          // stage the convolver input
                         op.opcode = OP_STOREBUF; op.state = NO_STATE; op.outNode = INT32_MIN + (++C.tempCounter);
                         out.push_back(op);
@@ -1512,6 +1536,9 @@ int Engine::compile(Group& g, int nIn, std::shared_ptr<Program>& out) {
                 out[headerAt].segEndOp = out.size();
                 i = segEnd;
             }
+            bool anyWork = false;
+            for (auto& op : out) if (!op.isSeg) anyWork = true;
+            prog->stages[st].empty = !anyWork;
         }
     }
 
@@ -1853,9 +1880,12 @@ int Engine::enqueueBlock(size_t nIn, size_t nOut, size_t numSamples, bool perVoi
                 else { cudaEventCreate(&ev.first); cudaEventCreate(&ev.second); }
                 cudaEventRecord(ev.first, stream_);
             }
-            if (!cuda(launch_render_block(P, wpc, opt_.niter, stream_), "render kernel launch")) return rc::CudaError;
+            const bool emptyStage = !p.stages.empty() && p.stages[stg].empty && !last;
+            if (!emptyStage) {
+                if (!cuda(launch_render_block(P, wpc, opt_.niter, stream_), "render kernel launch")) return rc::CudaError;
+                ++launches_;
+            }
             if (timeKernels_) { cudaEventRecord(ev.second, stream_); timedEvents_.push_back(ev); }
-            ++launches_;
             if (p.stages.empty()) continue;
             // K3: the convolvers fed by this stage (ConvolutionNode::process, wasm/Convolve.h:58-85); a call longer
             // than what is left of the current 512-sample partition is cut like FFTConvolver.cpp:155-203 does
@@ -1873,7 +1903,13 @@ int Engine::enqueueBlock(size_t nIn, size_t nOut, size_t numSamples, bool perVoi
                         else { cudaEventCreate(&ev3.first); cudaEventCreate(&ev3.second); }
                         cudaEventRecord(ev3.first, stream_);
                     }
-                    if (!cuda(convolver_process_chunk(cs, cv.in, cv.out, blockSize_, offset, n, stream_), "convolver launch")) return rc::CudaError;
+                    const float* cin = cv.in;
+                    int cinStride = blockSize_;
+                    if (cv.inChannel >= 0) {   // straight from the host input buffers: per-voice [voice][nIn][blockSize] or shared [nIn][blockSize]
+                        if (perVoiceIn) { cin = dInVoice_ + ((size_t) g.v0 * nIn + cv.inChannel) * blockSize_; cinStride = (int) nIn * blockSize_; }
+                        else { cin = dInShared_ + (size_t) cv.inChannel * blockSize_; cinStride = 0; }
+                    }
+                    if (!cuda(convolver_process_chunk(cs, cin, cinStride, cv.out, blockSize_, offset, n, stream_), "convolver launch")) return rc::CudaError;
                     if (timeKernels_) { cudaEventRecord(ev3.second, stream_); timedConvEvents_.push_back(ev3); }
                     ++launches_;
                     offset += n;

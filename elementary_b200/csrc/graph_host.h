@@ -124,8 +124,8 @@ struct Program {
     uint32_t* dParamMap = nullptr;
     bool planOnly = false;
     // K1 stages: stage k interprets code[stages[k].codeOffset ...]; after it the convolvers of that stage run (K3)
-    struct Conv { int32_t node; float* in; float* out; };
-    struct Stage { uint32_t codeOffset = 0; std::vector<Conv> convolves; };
+    struct Conv { int32_t node; float* in; float* out; int inChannel; };   // inChannel >= 0: K3 reads host input channel inChannel directly (no staging copy)
+    struct Stage { uint32_t codeOffset = 0; std::vector<Conv> convolves; bool empty = false; };   // empty: no K1 work in this stage
     std::vector<Stage> stages;
     std::vector<float*> blockBuffers;     // [Vpad][blockSize] HBM buffers carrying values across stages
     std::vector<std::shared_ptr<DeviceArray>> pinned;   // device arrays the code points at

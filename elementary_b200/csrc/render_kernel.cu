@@ -1554,7 +1554,7 @@ __global__ void __launch_bounds__(512) mix_exchange_kernel(const PeerMix pm, flo
         const uint32_t* f = pm.flag[pm.rank] + parity * MAX_PEERS + tid;
         const long long t0 = clock64();
         while (ld_acquire_sys(f) != epoch) {
-            if (clock64() - t0 > 8000000000ll) { if (status) *status = 1; break; }
+            if (clock64() - t0 > 2000000000ll) { if (status) *status = 1; break; }   // ~1 s
             __nanosleep(64);
         }
     }
