@@ -121,14 +121,14 @@ def cpu_reference_run(voices, threads, warmup_blocks, blocks, rank0_voice_offset
             "voice_blocks_per_s": voices * blocks / secs, "checksum": chk}
 
 
-def run_reference(args, rank, world):
+def run_reference(args, rank, world, emit=print):
     if rank != 0:
         return
     cores = os.cpu_count() or 1
     voices = VOICES_PER_GPU * world
     r = cpu_reference_run(voices, cores, args.warmup, args.steps)
     if r is None:
-        print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/libelem_ref.so missing (built only where /root/reference exists)"}))
+        emit(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/libelem_ref.so missing (built only where /root/reference exists)"}))
         return
     ms = r["seconds"] / args.steps * 1e3
     sample = f"all {voices} voices x {args.steps} blocks of 512 on {cores} host threads (whole workload, not a subset)"
@@ -142,16 +142,19 @@ def run_reference(args, rank, world):
         "cpu_baseline": {"value": r["msamples_per_s"], "unit": "Msamples/s", "cores": cores, "kind": "reference", "sample": sample},
         "e2e": {"value": r["msamples_per_s"], "unit": "Msamples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line))
+    emit(json.dumps(line))
 
 
-def run_b200(args, rank, local_rank, world):
+def run_b200(args, rank, local_rank, world, emit=print):
     import numpy as np
     import torch
     import torch.distributed as dist
 
     torch.cuda.set_device(local_rank)
-    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")   # NCCL's banner / warnings go to stderr: stdout carries the one JSON line
+    # NCCL prints its version banner to stdout when NCCL_DEBUG=VERSION (it honours NCCL_DEBUG_FILE only above that level)
+    if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+        os.environ["NCCL_DEBUG"] = "WARN"
+    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
     if world > 1 and not dist.is_initialized():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
@@ -305,7 +308,7 @@ def run_b200(args, rank, local_rank, world):
         "clocks": clocks,
         "cpu_baseline": cpu,
     }
-    print(json.dumps(line))
+    emit(json.dumps(line))
 
 
 def main():
@@ -323,10 +326,23 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
-    if args.impl == "reference":
-        run_reference(args, rank, world)
-    else:
-        run_b200(args, rank, local_rank, world)
+    # stdout carries exactly ONE JSON line: anything a native library writes to fd 1 meanwhile (NCCL's banner) goes to stderr
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+    lines = []
+    emit = lambda text: lines.append(text)
+    try:
+        if args.impl == "reference":
+            run_reference(args, rank, world, emit)
+        else:
+            run_b200(args, rank, local_rank, world, emit)
+    finally:
+        sys.stdout.flush()
+        os.dup2(real_stdout, 1)
+        os.close(real_stdout)
+    for text in lines:
+        print(text, flush=True)
 
 
 if __name__ == "__main__":
