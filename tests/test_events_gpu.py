@@ -85,3 +85,4 @@ def test_scope_property_validation_matches_reference():
                       ([[3, 5, "name", 3]], 5), ([[3, 5, "size", 1024], [3, 5, "channels", 4], [3, 5, "name", "ok"]], 0)]:
         assert rt.apply_instructions(ins) == code
         assert o.apply(ins) == code
+
