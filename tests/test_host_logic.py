@@ -169,3 +169,28 @@ def test_el_renderer_is_incremental():
     assert [i for i in b if i[0] == 0] == []             # nothing new is created ...
     assert [i[2:] for i in b if i[0] == 3] == [["value", 330.0]]   # ... only the keyed const changes
     assert b[-2][0] == 4 and b[-1] == [5]
+
+
+def test_live_group_split_with_sequencer_and_analysis_nodes_runs_the_migration_code():
+    """Plan-only runtimes keep "device" buffers in host memory, so cutting a compiled voice group executes the whole
+    migration path (row slicing, ring / scratch cloning of scope, capture and fft, sequence-data sharing, recompilation
+    of the moved half) on the CPU; the rendering side of the same scenario is covered on the GPU for the older node kinds."""
+    trig = el.train(1500.0)
+    seq = el.seq({"seq": [0.2, 0.4, 0.6], "hold": True, "key": "sq"}, trig, 0.0)
+    sp = el.sparseq({"seq": [{"value": 1, "tickTime": 0}, {"value": 2, "tickTime": 3}], "loop": [0, 4], "key": "sp"}, trig, 0.0)
+    core = el.mul(el.add(seq, sp), el.cycle(el.const(220.0, key="f")))
+    g1 = el.fft({"name": "ff"}, el.capture({"name": "cap"}, trig, el.scope({"name": "sc"}, el.meter({"name": "m"}, el.once({"arm": True}, core)))))
+    g2 = el.tanh(el.mul(2.0, g1))
+    rg = el.Renderer()
+    a, b = rg.render(g1), rg.render(g2)
+    rt = plan(16, tile_width=4)
+    assert rt.apply_instructions(a) == 0, rt.last_error()
+    d0 = rt.describe()
+    assert len(d0["groups"]) == 1 and d0["groups"][0]["nv"] == 16
+    assert rt.apply_instructions(b, voices=(6, 16)) == 7                 # not on a tile boundary (Types.h:58 InvariantViolation)
+    assert rt.apply_instructions(b, voices=(8, 16)) == 0, rt.last_error()
+    d1 = rt.describe()
+    assert [(g["v0"], g["nv"]) for g in d1["groups"]] == [(0, 8), (8, 8)]
+    assert d1["groups"][1]["ops"] > d1["groups"][0]["ops"]               # the moved half runs the extended graph
+    assert rt.apply_instructions([[3, seq.id(), "seq", [9.0, 8.0]]], voices=(8, 16)) == 0    # and can be re-programmed on its own
+    assert rt.gc(0) == [] and isinstance(rt.gc(8), list)
