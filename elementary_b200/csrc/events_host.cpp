@@ -131,6 +131,7 @@ int Engine::processQueuedEvents(int vb, int ve, EventFn cb, void* user) {
         if (!g.active || g.active->evNodes.empty()) continue;      // `if (auto ptr = rtRenderSeq)`: the sequence process() last used
         Program& p = *g.active;
         const int b = std::max(vb, g.v0) - g.v0, e = std::min(ve, g.v0 + g.nv) - g.v0;   // group-relative voice range
+        if (b >= e) continue;                                           // the poll does not touch this voice group at all
         const int L = g.tileWidth;
         if (!cuda(cudaStreamSynchronize(stream_), "sync before events")) return rc::CudaError;
         auto readRows = [&](int row, int count, std::vector<uint32_t>& out) -> bool {

@@ -112,7 +112,9 @@ void elem_b200_reset(elem_b200_runtime* rt);
 typedef void (*elem_b200_event_cb)(const char* type, const char* jsonEvent, void* user);
 void elem_b200_process_queued_events(elem_b200_runtime* rt, elem_b200_event_cb cb, void* user);
 /* Same, restricted to the voices [voiceBegin, voiceEnd) (voiceEnd < 0 = all): at a million voices nobody wants a
- * million meter callbacks per block; queues of the other voices keep their contents. */
+ * million meter callbacks per block.  Per-voice queues (meter, snapshot, capture) of the other voices keep their contents;
+ * the ring windows of scope / fft and the metro flag are shared by a voice group (their positions are identical for every
+ * voice), so a poll that reaches a group consumes that window for the whole group. */
 int elem_b200_process_queued_events_range(elem_b200_runtime* rt, int voiceBegin, int voiceEnd, elem_b200_event_cb cb, void* user);
 
 /* Tuning and introspection (no reference equivalent). Keys: "tile_width" (1..32, 0 =
