@@ -221,7 +221,6 @@ def run_b200(args, rank, local_rank, world, emit=print):
         dev_ms = sum(a.elapsed_time(b) for a, b in evs)
         k1_ms, k1_n = rt.take_kernel_time_ms()
         launches = rt.kernel_launches - launches0
-        clocks = sampler.stop() if rank == 0 else None
 
         # ---- e2e: the public call with host buffers (D2H + sync inside), no flush needed for honesty: flushed too ----
         barrier()
@@ -239,6 +238,7 @@ def run_b200(args, rank, local_rank, world, emit=print):
                 stream.synchronize()
             e2e_s += time.perf_counter() - t0
         barrier()
+        clocks = sampler.stop() if rank == 0 else None      # nvidia-smi samples cover both timed regions (value and e2e)
 
         peer_fail = rt.peer_status() if fused else 0
         t = torch.tensor([dev_ms, e2e_s * 1e3], dtype=torch.float64, device=f"cuda:{local_rank}")
