@@ -552,731 +552,20 @@ __device__ __forceinline__ void render_tile(const LaunchParams& P, const int til
             const uint32_t* opnds = pc + OP_HEADER_WORDS;
             pc += OP_HEADER_WORDS + nwords;
 
-            switch (opcode) {
-            case OP_SEG:
-                if (!((P.runMask >> aux0) & 1u)) pc += aux1;
-                break;
-
-            case OP_FILL0:
-                FOR_K(k) out[k * 32] = 0.0f;
-                break;
-
-            case OP_COPY: {
-                const Opnd a = decode(__ldg(opnds));
-                FOR_K(k) out[k * 32] = LDE(a, k);
-            } break;
-
-            case OP_LOADIN: {
-                if (P.inVoice) {
-                    // transposed element order so that the lanes of a warp read consecutive samples of a voice
-                    FOR_K(k) {
-                        const int q = lane + 32 * k;
-                        const int v = q >> LOGT, t = q & (T - 1);
-                        const int vv = tile * L + v;
-                        float x = 0.0f;
-                        if (t < cnt && vv < P.nv) x = P.inVoice[((size_t) (P.voice0 + vv) * P.nIn + aux0) * P.inStride + s0 + t];
-                        slots[((h0.x >> 16) & 0xFF) * E + t * L + v] = x;
-                    }
-                } else {
-                    const float* g = P.inShared + (size_t) aux0 * P.inStride + s0;
-                    FOR_K(k) out[k * 32] = (T_OF(k) < cnt) ? __ldg(g + T_OF(k)) : 0.0f;
-                }
-            } break;
-
-            case OP_CHAIN: {    // Math.h:9-89 — acc = operand0, then count6 steps acc = fn(acc[, operand])
-                float acc[NITER];
-                {
-                    const Opnd a = decode(__ldg(opnds));
-                    FOR_K(k) acc[k] = LDE(a, k);
-                }
-                const uint32_t* sp = opnds + 1;
-                for (uint32_t s = 0; s < count6; ++s, sp += 2) {
-                    const uint32_t fw = __ldg(sp);
-                    const uint32_t fn = fw & 0xFF;
-                    if (fn < 16) {
-                        switch (fn) {
-                            case F_SIN:   FOR_K(k) acc[k] = sinf(acc[k]); break;
-                            case F_COS:   FOR_K(k) acc[k] = cos_f32(acc[k]); break;
-                            case F_TAN:   FOR_K(k) acc[k] = tan_f32(acc[k]); break;
-                            case F_TANH:  FOR_K(k) acc[k] = tanhf(acc[k]); break;
-                            case F_ASINH: FOR_K(k) acc[k] = asinh_f32(acc[k]); break;
-                            case F_LN:    FOR_K(k) acc[k] = log_f32(acc[k]); break;
-                            case F_LOG10: FOR_K(k) acc[k] = log10_f32(acc[k]); break;
-                            case F_LOG2:  FOR_K(k) acc[k] = log2_f32(acc[k]); break;
-                            case F_CEIL:  FOR_K(k) acc[k] = ceilf(acc[k]); break;
-                            case F_FLOOR: FOR_K(k) acc[k] = floorf(acc[k]); break;
-                            case F_ROUND: FOR_K(k) acc[k] = roundf(acc[k]); break;
-                            case F_SQRT:  FOR_K(k) acc[k] = sqrtf(acc[k]); break;
-                            case F_EXP:   FOR_K(k) acc[k] = exp_f32(acc[k]); break;
-                            default:      FOR_K(k) acc[k] = fabsf(acc[k]); break;
-                        }
-                    } else {
-                        const Opnd b = decode(__ldg(sp + 1));
-                        const bool rev = (fw & CHAIN_REVERSED) != 0;
-                        switch (fn) {   // hoisted so the element loops are branch-free
-                            // IEEE addition and multiplication are commutative bit for bit: no operand-order select needed
-                            case F_ADD: FOR_K(k) acc[k] = acc[k] + LDE(b, k); break;
-                            case F_MUL: FOR_K(k) acc[k] = acc[k] * LDE(b, k); break;
-                            case F_SUB:
-                                if (rev) { FOR_K(k) acc[k] = LDE(b, k) - acc[k]; }
-                                else { FOR_K(k) acc[k] = acc[k] - LDE(b, k); }
-                                break;
-                            default:
-                                FOR_K(k) {
-                                    const float y = LDE(b, k);
-                                    acc[k] = rev ? binary_apply(fn, y, acc[k]) : binary_apply(fn, acc[k], y);
-                                }
-                                break;
-                        }
-                    }
-                }
-                FOR_K(k) out[k * 32] = acc[k];
-            } break;
-
-            case OP_PHASOR: {   // Core.h:89-97: step = f * (1/sr) in float; phase = next - floor(next)
-                const float rsr = __uint_as_float(aux0);
-                if (aux1 >= 1) {
-                    // A run of aux1 independent constant-frequency phasors (grouped by the host): lane group g = lane/L
-                    // runs phasor g of the run, so up to 32/L recurrences advance in one serial loop.
-                    constexpr int OPW = OP_HEADER_WORDS + 4;
-                    const int gi = lane >> LOGL;
-                    if (gi < (int) aux1) {
-                        const uint32_t* mine = pc - OPW + gi * OPW;
-                        const uint32_t mw0 = __ldg(mine), msidx = __ldg(mine + 1), mop = __ldg(mine + OP_HEADER_WORDS);
-                        const SP o = slots + ((int) ((mw0 >> 16) & 0xFF) * E + vlane);
-                        const float step = spar[(mop & 0x3FFFFFFFu) * L + vlane] * rsr;
-                        float phase = sst[msidx * L + vlane];
-                        FOR_OWNER(t) {
-                            o[t * L] = phase;
-                            const float next = phase + step;
-                            phase = next - floorf(next);
-                        }
-                        sst[msidx * L + vlane] = phase;
-                    }
-                    pc += (aux1 - 1) * OPW;
-                } else {
-                    const Opnd f = decode(__ldg(opnds));
-                    if (owner) {
-                        float phase = sst[sidx * L + lane];
-                        FOR_OWNER(t) {
-                            const float step = LDT(f, t) * rsr;
-                            outT[t * L] = phase;
-                            const float next = phase + step;
-                            phase = next - floorf(next);
-                        }
-                        sst[sidx * L + lane] = phase;
-                    }
-                }
-            } break;
-
-            case OP_SPHASOR: {  // Core.h:113-121; state: phase, change.lastIn
-                const Opnd f = decode(__ldg(opnds));
-                const Opnd r = decode(__ldg(opnds + 1));
-                const float rsr = __uint_as_float(aux0);
-                if (owner) {
-                    float phase = sst[sidx * L + lane];
-                    float last = sst[(sidx + 1) * L + lane];
-                    FOR_OWNER(t) {
-                        const float xn = LDT(f, t);
-                        if (change_tick(last, LDT(r, t)) > 0.5f) phase = 0.0f;
-                        const float step = xn * rsr;
-                        outT[t * L] = phase;
-                        const float next = phase + step;
-                        phase = next - floorf(next);
-                    }
-                    sst[sidx * L + lane] = phase;
-                    sst[(sidx + 1) * L + lane] = last;
-                }
-            } break;
-
-            case OP_COUNTER: {  // Core.h:198-211
-                const Opnd g = decode(__ldg(opnds));
-                if (owner) {
-                    float count = sst[sidx * L + lane];
-                    FOR_OWNER(t) {
-                        const float in = LDT(g, t);
-                        if ((1.0f - in) <= kEps) { outT[t * L] = count; count = count + 1.0f; }
-                        else { count = 0.0f; outT[t * L] = 0.0f; }
-                    }
-                    sst[sidx * L + lane] = count;
-                }
-            } break;
-
-            case OP_ACCUM: {    // Core.h:233-243; state: runningTotal, change.lastIn
-                const Opnd x = decode(__ldg(opnds));
-                const Opnd r = decode(__ldg(opnds + 1));
-                if (owner) {
-                    float total = sst[sidx * L + lane];
-                    float last = sst[(sidx + 1) * L + lane];
-                    FOR_OWNER(t) {
-                        if (change_tick(last, LDT(r, t)) > 0.5f) total = 0.0f;
-                        total += LDT(x, t);
-                        outT[t * L] = total;
-                    }
-                    sst[sidx * L + lane] = total;
-                    sst[(sidx + 1) * L + lane] = last;
-                }
-            } break;
-
-            case OP_LATCH: {    // Core.h:265-281; state: z, hold
-                const Opnd l = decode(__ldg(opnds));
-                const Opnd x = decode(__ldg(opnds + 1));
-                if (owner) {
-                    float z = sst[sidx * L + lane];
-                    float hold = sst[(sidx + 1) * L + lane];
-                    FOR_OWNER(t) {
-                        const float lv = LDT(l, t);
-                        if (fabsf(z) <= kEps && lv > kEps) hold = LDT(x, t);
-                        z = lv;
-                        outT[t * L] = hold;
-                    }
-                    sst[sidx * L + lane] = z;
-                    sst[(sidx + 1) * L + lane] = hold;
-                }
-            } break;
-
-            case OP_MAXHOLD: {  // Core.h:315-332; state: max, samplesAtCurrentMax(u32), change.lastIn; aux0 = holdTimeSamples
-                const Opnd x = decode(__ldg(opnds));
-                const Opnd r = decode(__ldg(opnds + 1));
-                if (owner) {
-                    float mx = sst[sidx * L + lane];
-                    uint32_t held = __float_as_uint(sst[(sidx + 1) * L + lane]);
-                    float last = sst[(sidx + 2) * L + lane];
-                    const uint32_t hts = aux0;
-                    FOR_OWNER(t) {
-                        const float in = LDT(x, t);
-                        bool reset = change_tick(last, LDT(r, t)) > 0.5f;
-                        if (!reset) reset = (++held >= hts);   // short-circuit || of the reference
-                        if (reset) { mx = in; held = 0; }
-                        else if (in > mx) { held = 0; mx = in; }
-                        outT[t * L] = mx;
-                    }
-                    sst[sidx * L + lane] = mx;
-                    sst[(sidx + 1) * L + lane] = __uint_as_float(held);
-                    sst[(sidx + 2) * L + lane] = last;
-                }
-            } break;
-
-            case OP_RAND: {     // Noise.h:25-38
-                if (owner) {
-                    uint32_t seed = __float_as_uint(sst[sidx * L + lane]);
-                    FOR_OWNER(t) {
-                        seed = 214013u * seed + 2531011u;
-                        const int r = (int) ((seed >> 16) & 0x7FFFu);
-                        outT[t * L] = (float) r / 32767.0f;
-                    }
-                    sst[sidx * L + lane] = __uint_as_float(seed);
-                }
-            } break;
-
-            case OP_POLE: {     // Filters.h:27-33
-                const Opnd pp = decode(__ldg(opnds));
-                const Opnd x = decode(__ldg(opnds + 1));
-                if (owner) {
-                    float z = sst[sidx * L + lane];
-                    FOR_OWNER(t) {
-                        z = LDT(x, t) + LDT(pp, t) * z;
-                        outT[t * L] = z;
-                    }
-                    sst[sidx * L + lane] = z;
-                }
-            } break;
-
-            case OP_ENV: {      // Filters.h:61-73
-                const Opnd ap = decode(__ldg(opnds));
-                const Opnd rp = decode(__ldg(opnds + 1));
-                const Opnd x = decode(__ldg(opnds + 2));
-                if (owner) {
-                    float z = sst[sidx * L + lane];
-                    FOR_OWNER(t) {
-                        const float vn = fabsf(LDT(x, t));
-                        const float pcoef = (vn > z) ? LDT(ap, t) : LDT(rp, t);
-                        z = pcoef * (z - vn) + vn;
-                        outT[t * L] = z;
-                    }
-                    sst[sidx * L + lane] = z;
-                }
-            } break;
-
-            case OP_BIQUAD: {   // Filters.h:102-114 (TDF-II, audio-rate coefficients)
-                const Opnd b0 = decode(__ldg(opnds));
-                const Opnd b1 = decode(__ldg(opnds + 1));
-                const Opnd b2 = decode(__ldg(opnds + 2));
-                const Opnd a1 = decode(__ldg(opnds + 3));
-                const Opnd a2 = decode(__ldg(opnds + 4));
-                const Opnd x = decode(__ldg(opnds + 5));
-                if (owner) {
-                    float z1 = sst[sidx * L + lane];
-                    float z2 = sst[(sidx + 1) * L + lane];
-                    FOR_OWNER(t) {
-                        const float xn = LDT(x, t);
-                        const float y = LDT(b0, t) * xn + z1;
-                        z1 = LDT(b1, t) * xn - LDT(a1, t) * y + z2;
-                        z2 = LDT(b2, t) * xn - LDT(a2, t) * y;
-                        outT[t * L] = y;
-                    }
-                    sst[sidx * L + lane] = z1;
-                    sst[(sidx + 1) * L + lane] = z2;
-                }
-            } break;
-
-            case OP_PREWARP: {  // filters/MultiMode1p.h:23-33; (aux0,aux1) = bits of T = 1.0/sr (double)
-                const Opnd fc = decode(__ldg(opnds));
-                const double Ts = bits_to_double(aux0, aux1);
-                FOR_K(k) {
-                    const double twoPi = 2.0 * 3.141592653589793238;
-                    const double wd = twoPi * (double) LDE(fc, k);
-                    out[k * 32] = (float) tan_f64(wd * Ts / 2.0);
-                }
-            } break;
-
-            case OP_MM1P: {     // filters/MultiMode1p.h:78-103; state: double z; mode 0 low / 2 high / 4 all
-                const Opnd gi = decode(__ldg(opnds));
-                const Opnd x = decode(__ldg(opnds + 1));
-                if (owner) {
-                    double* zs = reinterpret_cast<double*>((sst + sidx * L).ptr()) + lane;
-                    double z = *zs;
-                    FOR_OWNER(t) {
-                        const double g = clampd((double) LDT(gi, t), 0.0, 0.9999);
-                        const float xn = LDT(x, t);
-                        const double G = g / (1.0 + g);
-                        const double v = ((double) xn - z) * G;
-                        const double lp = v + z;
-                        z = lp + v;
-                        float y;
-                        if (mode == 0) y = (float) lp;
-                        else if (mode == 2) y = xn - (float) lp;
-                        else y = (float) (lp + lp - (double) xn);
-                        outT[t * L] = y;
-                    }
-                    *zs = z;
-                }
-            } break;
-
-            case OP_SVF: {      // filters/SVF.h:48-104; (aux0,aux1) = bits of sr (double); state: double ic1eq, ic2eq
-                const Opnd fc = decode(__ldg(opnds));
-                const Opnd q = decode(__ldg(opnds + 1));
-                const Opnd x = decode(__ldg(opnds + 2));
-                const double sr = bits_to_double(aux0, aux1);
-                const double fmax = sr / 2.0001;
-                const double rsr = 1.0 / sr;   // pi*fc/sr as (pi*fc)*(1/sr): <= 1 ulp from the reference's quotient, see tan_quarter_wave
-                // phase 1 — coefficients (updateCoeffs, SVF.h:72-80) are a pure function of (fc, q) per sample:
-                // all lanes, one element per slice.  ga holds g for L = 32 (a2, a3 are then formed by the lane itself)
-                // and a2 otherwise (a3 goes through a3a), so that the serial part of narrow tiles is as short as possible.
-                double ga[NITER], a1a[NITER], ka[NITER], a3a[(L == 32) ? 1 : NITER];
-                const bool qIsParam = (q.stride == 0);     // a per-voice constant: k = 1/clamp(q) once per tile, not per sample
-                const double kqParam = rcp_fast(clampd((double) LDE(q, 0), 0.25, 20.0));
-                FOR_K(k) {
-                    const double g = tan_quarter_wave((3.14159265359 * clampd((double) LDE(fc, k), 20.0, fmax)) * rsr);
-                    const double kq = qIsParam ? kqParam : rcp_fast(clampd((double) LDE(q, k), 0.25, 20.0));
-                    ka[k] = kq;
-                    a1a[k] = rcp_fast(fma(g, g + kq, 1.0));
-                    if (L == 32) ga[k] = g;
-                    else { const double a2 = g * a1a[k]; ga[k] = a2; a3a[k] = g * a2; }
-                }
-                // phase 2 — the tick recurrence (SVF.h:48-70), serial per voice; every lane walks the loop so the
-                // coefficients can be fetched from the lane that computed them (sample t = k*PER + j of voice v
-                // lives in lane j*L + v of slice k)
-                double ic1 = 0.0, ic2 = 0.0;
-                if (owner) {
-                    ic1 = reinterpret_cast<const double*>((sst + sidx * L).ptr())[lane];
-                    ic2 = reinterpret_cast<const double*>((sst + (sidx + 2) * L).ptr())[lane];
-                }
-                auto tickLoop = [&](auto lowpassTag) {
-                    constexpr bool LOWPASS = decltype(lowpassTag)::value;
-                    FOR_K(k) {
-                        _Pragma("unroll") for (int j = 0; j < PER; ++j) {
-                            const int t = k * PER + j;
-                            if (t < cnt) {     // warp-uniform
-                                const int src = j * L + vlane;
-                                double a1, a2, a3, kq = 0.0;
-                                if (L == 32) { a1 = a1a[k]; a2 = ga[k] * a1; a3 = ga[k] * a2; kq = ka[k]; }
-                                else {
-                                    a1 = __shfl_sync(FULL, a1a[k], src);
-                                    a2 = __shfl_sync(FULL, ga[k], src);
-                                    a3 = __shfl_sync(FULL, a3a[(L == 32) ? 0 : k], src);
-                                    if (!LOWPASS) kq = __shfl_sync(FULL, ka[k], src);
-                                }
-                                if (owner) {
-                                    const float v0 = LDT(x, t);
-                                    // The double-precision internals are contracted to FMAs: 7 FP64 instructions and a
-                                    // 4-deep dependency chain per sample instead of 12 and 5.  Each fused step differs from
-                                    // the reference's separately rounded one by <= 1 ulp(double) ~ 1e-16, nine orders below
-                                    // the float the output is rounded to (same reasoning as tan_quarter_wave).
-                                    const double v3 = (double) v0 - ic2;
-                                    const double v1 = fma(v3, a2, ic1 * a1);
-                                    const double v2 = fma(v3, a3, fma(ic1, a2, ic2));
-                                    ic1 = fma(v1, 2.0, -ic1);
-                                    ic2 = fma(v2, 2.0, -ic2);
-                                    float y;
-                                    if (LOWPASS) y = (float) v2;
-                                    else switch (mode) {
-                                        case 0: y = (float) v2; break;
-                                        case 1: y = (float) v1; break;
-                                        case 2: y = (float) ((double) v0 - kq * v1 - v2); break;
-                                        case 3: y = (float) ((double) v0 - kq * v1); break;
-                                        default: y = (float) ((double) v0 - 2.0 * kq * v1); break;
-                                    }
-                                    outT[t * L] = y;
-                                }
-                            }
-                        }
-                    }
-                };
-                if (mode == 0) tickLoop(std::true_type{}); else tickLoop(std::false_type{});
-                if (owner) {
-                    reinterpret_cast<double*>((sst + sidx * L).ptr())[lane] = ic1;
-                    reinterpret_cast<double*>((sst + (sidx + 2) * L).ptr())[lane] = ic2;
-                }
-            } break;
-
-            case OP_SVFSHELF: { // filters/SVFShelf.h:44-106; mode 0 lowshelf / 1 highshelf / 2 bell
-                const Opnd fc = decode(__ldg(opnds));
-                const Opnd q = decode(__ldg(opnds + 1));
-                const Opnd gdb = decode(__ldg(opnds + 2));
-                const Opnd x = decode(__ldg(opnds + 3));
-                const double sr = bits_to_double(aux0, aux1);
-                const double fmax = sr / 2.0001;
-                const double rsr = 1.0 / sr;   // pi*fc/sr as (pi*fc)*(1/sr): <= 1 ulp from the reference's quotient, see tan_quarter_wave
-                if (owner) {
-                    double* s1 = reinterpret_cast<double*>((sst + sidx * L).ptr()) + lane;
-                    double* s2 = reinterpret_cast<double*>((sst + (sidx + 2) * L).ptr()) + lane;
-                    double ic1 = *s1, ic2 = *s2;
-                    _Pragma("unroll 2") for (int t = 0; t < cnt; ++t) {
-                        const double A = pow_f64(10.0, (double) LDT(gdb, t) / 40.0);
-                        double g = tan_quarter_wave((3.14159265359 * clampd((double) LDT(fc, t), 20.0, fmax)) * rsr);
-                        double kq = 1.0 / clampd((double) LDT(q, t), 0.25, 20.0);
-                        if (mode == 0) g /= A;
-                        if (mode == 1) g *= A;
-                        if (mode == 2) kq /= A;
-                        const double a1 = 1.0 / (1.0 + g * (g + kq));
-                        const double a2 = g * a1;
-                        const double a3 = g * a2;
-                        const float v0 = LDT(x, t);
-                        const double v3 = (double) v0 - ic2;
-                        const double v1 = ic1 * a1 + v3 * a2;
-                        const double v2 = ic2 + ic1 * a2 + v3 * a3;
-                        ic1 = v1 * 2.0 - ic1;
-                        ic2 = v2 * 2.0 - ic2;
-                        float y;
-                        if (mode == 2) y = (float) ((double) v0 + kq * (A * A - 1.0) * v1);
-                        else if (mode == 0) y = (float) ((double) v0 + kq * (A - 1.0) * v1 + (A * A - 1.0) * v2);
-                        else y = (float) (A * A * (double) v0 + kq * (1.0 - A) * A * v1 + (1.0 - A * A) * v2);
-                        outT[t * L] = y;
-                    }
-                    *s1 = ic1; *s2 = ic2;
-                }
-            } break;
-
-            case OP_Z: {        // Delays.h:29-34 — out[t] = in[t-1]: no recurrence, only a carry between tiles
-                const Opnd x = decode(__ldg(opnds));
-                const float zprev = sst[sidx * L + vlane];
-                FOR_K(k) out[k * 32] = (T_OF(k) == 0) ? zprev : x.p[k * x.stride - x.tstride];
-                __syncwarp();
-                if (owner) sst[sidx * L + lane] = LDT(x, cnt - 1);
-            } break;
-
-            case OP_DELAY: {    // Delays.h:108-159; aux0 = size; ring [tile][pos][L]; state: writeIndex
-                const Opnd len = decode(__ldg(opnds));
-                const Opnd fb = decode(__ldg(opnds + 1));
-                const Opnd x = decode(__ldg(opnds + 2));
-                const int size = (int) aux0;
-                if (size == 0) { FOR_K(k) out[k * 32] = LDE(len, k); break; }   // Delays.h:105-106 copies inputData[0]
-                float* ring = reinterpret_cast<float*>(ptrbits) + (size_t) tile * size * L + vlane;
-                const float fsize = (float) size;
-                const int w0 = __float_as_int(sst[sidx * L + vlane]);
-                // Fast path: when no read head of this tile can land on a position written inside the tile (and
-                // no write of the tile can hit a position still to be read), samples are independent.
-                // delay time and feedback are usually per-voice constants (parameter rows, stride 0): clamp them once per tile
-                const bool lenParam = (len.stride == 0), fbParam = (fb.stride == 0);
-                const float offsetP = clampf(LDE(len, 0), 0.0f, fsize);
-                const float fbP = clampf(LDE(fb, 0), -1.0f, 1.0f);
-                bool hazard = false;
-                if (lenParam) {
-                    hazard = !(offsetP <= kEps) && !(offsetP >= (float) (cnt + 1) && offsetP <= (float) (size - cnt - 1));
-                } else {
-                    FOR_K(k) {
-                        const float offset = clampf(LDE(len, k), 0.0f, fsize);
-                        if (T_OF(k) < cnt && !(offset <= kEps) &&
-                            !(offset >= (float) (cnt + 1) && offset <= (float) (size - cnt - 1))) hazard = true;
-                    }
-                }
-                const bool slow = __any_sync(FULL, hazard);
-                __syncwarp();   // every lane has read the write index before an owner lane may overwrite it
-                if (!slow) {
-                    FOR_K(k) {
-                        const int t = T_OF(k);
-                        int w = w0 + t;
-                        while (w >= size) w -= size;
-                        const float offset = lenParam ? offsetP : clampf(LDE(len, k), 0.0f, fsize);
-                        float y, in;
-                        if (offset <= kEps) { in = LDE(x, k); y = in; }
-                        else {
-                            const float readFrac = (float) (size + w) - offset;
-                            int readLeft = (int) readFrac;
-                            const float frac = readFrac - floorf(readFrac);
-                            int readRight = readLeft + 1;                       // both in [0, 2*size]: % size by subtraction
-                            if (readLeft >= size) readLeft -= size;
-                            if (readRight >= size) readRight -= size;
-                            if (readRight >= size) readRight -= size;
-                            const float left = ring[(size_t) readLeft * L];
-                            const float right = ring[(size_t) readRight * L];
-                            y = left + frac * (right - left);
-                            in = LDE(x, k) + (fbParam ? fbP : clampf(LDE(fb, k), -1.0f, 1.0f)) * y;
-                        }
-                        if (t < cnt) ring[(size_t) w * L] = in;
-                        out[k * 32] = y;
-                    }
-                    __syncwarp();
-                    if (owner) {
-                        int w = w0 + cnt;
-                        while (w >= size) w -= size;
-                        sst[sidx * L + lane] = __int_as_float(w);
-                    }
-                } else if (owner) {
-                    int w = w0;
-                    FOR_OWNER(t) {
-                        const float offset = clampf(LDT(len, t), 0.0f, fsize);
-                        float y, in;
-                        if (offset <= kEps) { in = LDT(x, t); y = in; }
-                        else {
-                            const float readFrac = (float) (size + w) - offset;
-                            const int readLeft = (int) readFrac;
-                            const int readRight = readLeft + 1;
-                            const float frac = readFrac - floorf(readFrac);
-                            const float left = ring[(size_t) (readLeft % size) * L];
-                            const float right = ring[(size_t) (readRight % size) * L];
-                            y = left + frac * (right - left);
-                            in = LDT(x, t) + clampf(LDT(fb, t), -1.0f, 1.0f) * y;
-                        }
-                        ring[(size_t) w * L] = in;
-                        outT[t * L] = y;
-                        if (++w >= size) w -= size;
-                    }
-                    sst[sidx * L + lane] = __int_as_float(w);
-                }
-            } break;
-
-            case OP_SDELAY: {   // Delays.h:246-260; aux0 = ring size (pow2), aux1 = length; state: writeIndex
-                // out[t] = the sample written `len` samples ago: inside the tile it is still in the input slot,
-                // older ones are in the ring (size >= len + blockSize keeps reads and writes of a tile disjoint).
-                const Opnd x = decode(__ldg(opnds));
-                const int size = (int) aux0, mask = size - 1, len = (int) aux1;
-                float* ring = reinterpret_cast<float*>(ptrbits) + (size_t) tile * size * L + vlane;
-                const int w0 = __float_as_int(sst[sidx * L + vlane]);
-                FOR_K(k) {
-                    const int t = T_OF(k);
-                    float y;
-                    if (t >= len) y = x.p[k * x.stride - len * x.tstride];
-                    else y = ring[(size_t) ((w0 + t - len + size) & mask) * L];
-                    out[k * 32] = y;
-                }
-                FOR_K(k) { const int t = T_OF(k); if (t < cnt) ring[(size_t) ((w0 + t) & mask) * L] = LDE(x, k); }
-                __syncwarp();
-                if (owner) sst[sidx * L + lane] = __int_as_float((w0 + cnt) & mask);
-            } break;
-
-            case OP_TABLE: {    // Table.h:59-71; aux0 = table length; ptr = device copy of resource channel 0
-                const Opnd pos = decode(__ldg(opnds));
-                const int size = (int) aux0;
-                const float* tab = reinterpret_cast<const float*>(ptrbits);
-                const bool staged = (P.tableSmem >= 0) && (tab == P.tableSrc);   // the TMA-staged copy (warp-uniform)
-                const SP stab{P.tableSmem};
-                FOR_K(k) {
-                    const float readPos = clampf(LDE(pos, k), 0.0f, 1.0f) * (float) (size - 1);
-                    int readLeft = (int) readPos;                   // in [0, size-1]; NaN converts to 0
-                    int readRight = readLeft + 1;                   // in [1, size]
-                    const float frac = readPos - floorf(readPos);
-                    if (readLeft >= size) readLeft -= size;
-                    if (readRight >= size) readRight -= size;
-                    const float left = staged ? stab[readLeft] : __ldg(tab + readLeft);
-                    const float right = staged ? stab[readRight] : __ldg(tab + readRight);
-                    out[k * 32] = left + frac * (right - left);
-                }
-            } break;
-
-            case OP_BLEP: {     // Oscillators.h:23-89; state: phase, acc; aux0 = bits of float(sr)
-                const Opnd f = decode(__ldg(opnds));
-                const float sr = __uint_as_float(aux0);
-                auto blep = [](float ph, float inc) -> float {
-                    if (ph < inc) { const float p = ph / inc; return (2.0f - p) * p - 1.0f; }
-                    if (ph > (1.0f - inc)) { const float p = (ph - 1.0f) / inc; return (p + 2.0f) * p + 1.0f; }
-                    return 0.0f;
-                };
-                if (owner) {
-                    float phase = sst[sidx * L + lane];
-                    float acc = sst[(sidx + 1) * L + lane];
-                    FOR_OWNER(t) {
-                        const float inc = LDT(f, t) / sr;
-                        float y;
-                        if (mode == 0) {
-                            y = 2.0f * phase - 1.0f - blep(phase, inc);
-                        } else {
-                            const float naive = (phase < 0.5f) ? 1.0f : -1.0f;
-                            const float halfPhase = fmod_f32(phase + 0.5f, 1.0f);
-                            const float square = naive + blep(phase, inc) - blep(halfPhase, inc);
-                            if (mode == 1) y = square;
-                            else { acc += 4.0f * inc * square; y = acc; }
-                        }
-                        phase += inc;
-                        if (phase >= 1.0f) phase -= 1.0f;
-                        outT[t * L] = y;
-                    }
-                    sst[sidx * L + lane] = phase;
-                    sst[(sidx + 1) * L + lane] = acc;
-                }
-            } break;
-
-            case OP_TAPIN: {    // Feedback.h:42-52; ptr = shared tap buffer [tile][blockSize][L] (element order)
-                const float* tap = reinterpret_cast<const float*>(ptrbits) + ((size_t) tile * P.blockSize + s0) * L + lane;
-                FOR_K(k) out[k * 32] = (T_OF(k) < cnt) ? tap[k * 32] : 0.0f;
-            } break;
-
-            case OP_TAPOUT: {   // Feedback.h:109-121; ptr = this node's private delayBuffer [tile][blockSize][L]
-                const Opnd x = decode(__ldg(opnds));
-                float* buf = reinterpret_cast<float*>(ptrbits) + ((size_t) tile * P.blockSize + s0) * L + lane;
-                FOR_K(k) { const float v = LDE(x, k); if (T_OF(k) < cnt) buf[k * 32] = v; out[k * 32] = v; }
-            } break;
-
-            case OP_STOREBUF: { // stage boundary: ptr = [voice][blockSize] staging buffer (transposed element order)
-                const uint32_t w = __ldg(opnds);
-                const bool fromSlot = (w >> 30) == K_SLOT;
-                const SP src = slots + (int) (w & 0x3FFFFFFFu) * E;
-                const SP par = spar + (int) (w & 0x3FFFFFFFu) * L;
-                float* base = reinterpret_cast<float*>(ptrbits);
-                FOR_K(k) {
-                    const int qq = lane + 32 * k;
-                    const int v = qq >> LOGT, t = qq & (T - 1);
-                    const int vv = tile * L + v;
-                    if (t < cnt && vv < P.nv) base[(size_t) vv * P.blockSize + s0 + t] = fromSlot ? src[t * L + v] : par[v];
-                }
-            } break;
-
-            case OP_LOADBUF: {
-                const float* base = reinterpret_cast<const float*>(ptrbits);
-                const SP dst = slots + (int) ((h0.x >> 16) & 0xFF) * E;
-                FOR_K(k) {
-                    const int qq = lane + 32 * k;
-                    const int v = qq >> LOGT, t = qq & (T - 1);
-                    const int vv = tile * L + v;
-                    dst[t * L + v] = (t < cnt && vv < P.nv) ? base[(size_t) vv * P.blockSize + s0 + t] : 0.0f;
-                }
-            } break;
-
-            case OP_ROOT: {     // Core.h:66-78 + GainFade.h:56-72; aux0 = root index
-                const RootDyn rd = P.roots[aux0];
-                if (count6 < 1) { FOR_K(k) out[k * 32] = 0.0f; }
-                else {
-                    const Opnd x = decode(__ldg(opnds));
-                    if (rd.gain0 == rd.target) {
-                        FOR_K(k) out[k * 32] = LDE(x, k) * rd.target;
-                    } else {
-                        FOR_K(k) {
-                            const float g = clampf(rd.gain0 + rd.step * (float) (s0 + T_OF(k)), 0.0f, 1.0f);
-                            out[k * 32] = LDE(x, k) * g;
-                        }
-                    }
-                }
-                if (rd.channel >= 0 && rd.channel < P.nOut) {   // GraphRenderSequence.h:227-231
-                    const SP acc = outacc + (rd.channel * E + lane);
-                    FOR_K(k) acc[k * 32] += out[k * 32];
-                }
-            } break;
-
-
-            // ---- sequencing / control nodes: out-of-line bodies above ----
-            case OP_ONCE: case OP_SEQ: case OP_SEQ2: case OP_SPARSEQ: case OP_SPARSEQ2: {
-                if (owner) {
-                    const CtlCtx c{sst.ptr(), spar.ptr(), slots.ptr(), outT.ptr(), opnds, ptrbits, P.sampleTime + s0, sidx, aux0, aux1, mode, count6, cnt, s0, lane, vlane};
-                    switch (opcode) {
-                        case OP_ONCE: ctl_once<L, E>(c); break;
-                        case OP_SEQ: ctl_seq<L, E>(c); break;
-                        case OP_SEQ2: ctl_seq2<L, E>(c); break;
-                        case OP_SPARSEQ: ctl_sparseq<L, E>(c); break;
-                        default: ctl_sparseq2<L, E>(c); break;
-                    }
-                }
-            } break;
-
-            case OP_TIME: {     // wasm/SampleTime.h:17-23: out[i] = double(sampleTime + i), rounded to float
-                const long long t0 = P.sampleTime + s0;
-                FOR_K(k) out[k * 32] = (float) (double) (t0 + T_OF(k));
-            } break;
-
-            case OP_METRO: {    // wasm/Metro.h:41-55; (aux0,aux1) = bits of double(intervalSamps)
-                const double is = bits_to_double(aux0, aux1);
-                const long long t0 = P.sampleTime + s0;
-                FOR_K(k) {
-                    const double tt = (double) (t0 + T_OF(k)) / is;
-                    out[k * 32] = ((tt - floor(tt)) < 0.5) ? 1.0f : 0.0f;
-                }
-            } break;
-
-
-            // ---- analysis nodes: audio passes through; a per-voice record feeds processQueuedEvents ----
-            case OP_METER: {    // Analyzers.h:23-40: min/max of the block -> readoutQueue; state: min, max, pushes
-                const Opnd x = decode(__ldg(opnds));
-                float mn = INFINITY, mx = -INFINITY;
-                FOR_K(k) {
-                    const float v = LDE(x, k);
-                    out[k * 32] = v;
-                    if (T_OF(k) < cnt) { mn = (v < mn) ? v : mn; mx = (mx < v) ? v : mx; }
-                }
-                _Pragma("unroll") for (int d = L; d < 32; d <<= 1) {
-                    const float omn = __shfl_xor_sync(FULL, mn, d), omx = __shfl_xor_sync(FULL, mx, d);
-                    mn = (omn < mn) ? omn : mn; mx = (mx < omx) ? omx : mx;
-                }
-                if (owner) {
-                    float smn = sst[sidx * L + lane], smx = sst[(sidx + 1) * L + lane];
-                    if (s0 == 0) {
-                        smn = mn; smx = mx;
-                        sst[(sidx + 2) * L + lane] = __uint_as_float(__float_as_uint(sst[(sidx + 2) * L + lane]) + 1u);
-                    } else { smn = (mn < smn) ? mn : smn; smx = (smx < mx) ? mx : smx; }
-                    sst[sidx * L + lane] = smn; sst[(sidx + 1) * L + lane] = smx;
-                }
-            } break;
-
-            case OP_SNAPSHOT: { // Analyzers.h:87-106: latch x on the rising edge of l; state: z, value, pushes
-                const Opnd l = decode(__ldg(opnds));
-                const Opnd x = decode(__ldg(opnds + 1));
-                if (owner) {
-                    float z = sst[sidx * L + lane], val = sst[(sidx + 1) * L + lane];
-                    uint32_t pushes = __float_as_uint(sst[(sidx + 2) * L + lane]);
-                    FOR_OWNER(t) {
-                        const float lv = LDT(l, t), xv = LDT(x, t);
-                        if (fabsf(z) <= kEps && lv > kEps) { val = xv; ++pushes; }
-                        z = lv;
-                        outT[t * L] = xv;
-                    }
-                    sst[sidx * L + lane] = z; sst[(sidx + 1) * L + lane] = val; sst[(sidx + 2) * L + lane] = __uint_as_float(pushes);
-                }
-            } break;
-
-            case OP_SCOPE: {    // Analyzers.h:184-201: copy in0 through, append every child (<= 4) to the ring
-                const int ringCh = (int) aux1;     // channels of the ring: 4 for scope (Analyzers.h:149), 1 for fft (wasm/FFT.h:20)
-                const int nch = min((int) count6, ringCh);
-                float* ring = reinterpret_cast<float*>(ptrbits) + (size_t) tile * ringCh * SCOPE_RING * L + vlane;
-                const uint32_t w = P.dyn[aux0] + (uint32_t) s0;
-                for (int ch = 0; ch < nch; ++ch) {
-                    const Opnd a = decode(__ldg(opnds + ch));
-                    FOR_K(k) {
-                        const float v = LDE(a, k);
-                        if (ch == 0) out[k * 32] = v;
-                        if (T_OF(k) < cnt) ring[((size_t) ch * SCOPE_RING + ((w + T_OF(k)) & (SCOPE_RING - 1))) * L] = v;
-                    }
-                }
-            } break;
-
-            case OP_CAPTURE: {  // Capture.h:22-58
-                if (owner) {
-                    const CtlCtx c{sst.ptr(), spar.ptr(), slots.ptr(), outT.ptr(), opnds, ptrbits + (uint64_t) tile * (aux0 + CAPTURE_SCRATCH) * L * sizeof(float),
-                                   P.sampleTime + s0, sidx, aux0, aux1, mode, count6, cnt, s0, lane, vlane};
-                    ctl_capture<L, E>(c);
-                }
-            } break;
-
-            default: break;
-            }
+            // program-word access of the interpreter (render_ops.inc explains the contract)
+#define OPWORD(i) __ldg(opnds + (i))
+#define CHAIN_FOR_STEPS(s) const uint32_t* sp = opnds + 1; for (uint32_t s = 0; s < count6; ++s, sp += 2)
+#define CHAIN_FN_WORD(s) __ldg(sp)
+#define CHAIN_OPND_WORD(s) __ldg(sp + 1)
+#define PC_ADVANCE(n) pc += (n)
+#define PC_SKIP_SEGMENT_IF(cond, n) if (cond) pc += (n)
+#include "render_ops.inc"
+#undef OPWORD
+#undef CHAIN_FOR_STEPS
+#undef CHAIN_FN_WORD
+#undef CHAIN_OPND_WORD
+#undef PC_ADVANCE
+#undef PC_SKIP_SEGMENT_IF
         }
 
         // ---- tile epilogue: per-voice output and per-tile partial mix ----
