@@ -160,6 +160,15 @@ int elem_b200_describe(elem_b200_runtime* rt, char* buf, size_t cap) {
     return (int) s.size() + 1;
 }
 
+int elem_b200_program_words(elem_b200_runtime* rt, int voice, uint32_t* buf, size_t cap) {
+    if (!rt) return 0;
+    try {
+        auto w = rt->engine->programWords(voice);
+        if (buf) std::memcpy(buf, w.data(), sizeof(uint32_t) * (w.size() < cap ? w.size() : cap));
+        return (int) w.size();
+    } catch (...) { return 0; }
+}
+
 uint64_t elem_b200_kernel_launches(elem_b200_runtime* rt) { return rt ? rt->engine->kernelLaunches() : 0; }
 
 double elem_b200_take_kernel_time_ms(elem_b200_runtime* rt, uint64_t* count) {

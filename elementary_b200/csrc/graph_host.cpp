@@ -226,6 +226,15 @@ std::string Engine::describe() const {
     return os.str();
 }
 
+std::vector<uint32_t> Engine::programWords(int voice) const {
+    for (auto& g : groups_) {
+        if (voice < g->v0 || voice >= g->v0 + g->nv) continue;
+        auto& p = g->pending ? g->pending : g->active;
+        if (p) return p->code;
+    }
+    return {};
+}
+
 // ---------------------------------------------------------------------------------------------------------
 // storage
 int Engine::allocRows(Group& g, int count, bool evenAlign, int& row) {

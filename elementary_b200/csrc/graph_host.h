@@ -209,6 +209,9 @@ public:
     // K3 time/count gathered by the same takeKernelTimeMs() call
     double lastConvolveTimeMs(uint64_t* count) const { if (count) *count = lastConvCount_; return lastConvMs_; }
     std::string describe() const;
+    // The encoded render program (program.h) of the voice group containing `voice` — the newest compiled one.  Introspection:
+    // tests, and the input of per-program kernel specialisation.
+    std::vector<uint32_t> programWords(int voice) const;
 
 private:
     double sr_;

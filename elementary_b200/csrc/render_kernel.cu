@@ -536,6 +536,56 @@ __device__ __forceinline__ void render_tile(const LaunchParams& P, const int til
 
         for (int i = lane; i < P.nOut * E; i += 32) outacc[i] = 0.0f;
 
+#ifdef EB_SPEC_PROGRAM
+        // ---- per-program specialisation (compiled only when a generated header defines the program as the
+        // compile-time constant array eb::EB_SPEC_CODE, C++20): the same op bodies, but every header field and operand word
+        // is a constant expression, so each `switch (opcode)` folds to its one case, slot addresses become immediates and chain
+        // steps unroll — no dispatch, no decoding.  Device pointers (words 4/5 of a header) and the words that lanes index with
+        // their own id (phasor runs, out-of-line control ops) are still read from the copy of the program in memory.
+        {
+            const uint32_t* const codeMem = P.code;
+            auto run = [&]<int PC, int END>(auto&& self) -> void {
+                if constexpr (PC < END) {
+                    constexpr uint32_t opcode = EB_SPEC_CODE[PC] & 0xFF;
+                    if constexpr (opcode != OP_END) {
+                        constexpr struct { uint32_t x, y, z, w; } h0 = {EB_SPEC_CODE[PC], EB_SPEC_CODE[PC + 1], EB_SPEC_CODE[PC + 2], EB_SPEC_CODE[PC + 3]};
+                        constexpr uint32_t nwords = (h0.x >> 8) & 0xFF, mode = h0.x >> 24;
+                        constexpr uint32_t sidx = h0.y, aux0 = h0.z, aux1 = h0.w;
+                        constexpr uint32_t count6 = EB_SPEC_CODE[PC + 6];
+                        constexpr int NEXT0 = PC + (int) OP_HEADER_WORDS + (int) nwords;
+                        if constexpr (opcode == OP_SEG) {
+                            if ((P.runMask >> aux0) & 1u) self.template operator()<NEXT0, NEXT0 + (int) aux1>(self);
+                            self.template operator()<NEXT0 + (int) aux1, END>(self);
+                        } else {
+                            __syncwarp();   // slot / state traffic of the previous op is visible to every lane
+                            const SP out = slots + ((int) ((h0.x >> 16) & 0xFF) * E + lane);
+                            const SP outT = out;
+                            const uint64_t ptrbits = (uint64_t) __ldg(codeMem + PC + 4) | ((uint64_t) __ldg(codeMem + PC + 5) << 32);
+                            const uint32_t* opnds = codeMem + PC + OP_HEADER_WORDS;
+                            const uint32_t* pc = opnds + nwords;
+                            (void) outT; (void) ptrbits; (void) opnds; (void) pc; (void) mode; (void) sidx; (void) count6;
+#define OPWORD(i) (EB_SPEC_CODE[PC + (int) OP_HEADER_WORDS + (int) (i)])
+#define CHAIN_FOR_STEPS(s) _Pragma("unroll") for (uint32_t s = 0; s < count6; ++s)
+#define CHAIN_FN_WORD(s) (EB_SPEC_CODE[PC + (int) OP_HEADER_WORDS + 1 + 2 * (int) (s)])
+#define CHAIN_OPND_WORD(s) (EB_SPEC_CODE[PC + (int) OP_HEADER_WORDS + 2 + 2 * (int) (s)])
+#define PC_ADVANCE(n) ((void) 0)
+#define PC_SKIP_SEGMENT_IF(cond, n) ((void) 0)
+#include "render_ops.inc"
+#undef OPWORD
+#undef CHAIN_FOR_STEPS
+#undef CHAIN_FN_WORD
+#undef CHAIN_OPND_WORD
+#undef PC_ADVANCE
+#undef PC_SKIP_SEGMENT_IF
+                            constexpr int RUN_EXTRA = (opcode == OP_PHASOR && aux1 >= 1) ? (int) (aux1 - 1) * ((int) OP_HEADER_WORDS + 4) : 0;
+                            self.template operator()<NEXT0 + RUN_EXTRA, END>(self);
+                        }
+                    }
+                }
+            };
+            run.template operator()<0, EB_SPEC_CODE_LEN>(run);
+        }
+#else
         const uint32_t* pc = P.code;
         for (;;) {
             __syncwarp();   // slot / state traffic of the previous op is visible to every lane
@@ -567,6 +617,7 @@ __device__ __forceinline__ void render_tile(const LaunchParams& P, const int til
 #undef PC_ADVANCE
 #undef PC_SKIP_SEGMENT_IF
         }
+#endif   // EB_SPEC_PROGRAM
 
         // ---- tile epilogue: per-voice output and per-tile partial mix ----
         if (P.outVoice) {

@@ -95,6 +95,8 @@ def load_library() -> C.CDLL:
     lib.elem_b200_set_option.argtypes = [C.c_void_p, C.c_char_p, C.c_double]
     lib.elem_b200_describe.restype = C.c_int
     lib.elem_b200_describe.argtypes = [C.c_void_p, C.c_char_p, C.c_size_t]
+    lib.elem_b200_program_words.restype = C.c_int
+    lib.elem_b200_program_words.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_uint32), C.c_size_t]
     lib.elem_b200_kernel_launches.restype = C.c_uint64
     lib.elem_b200_kernel_launches.argtypes = [C.c_void_p]
     lib.elem_b200_take_kernel_time_ms.restype = C.c_double
@@ -313,6 +315,13 @@ class Runtime:
         buf = C.create_string_buffer(n + 16)
         self._lib.elem_b200_describe(self._h, buf, len(buf))
         return json.loads(buf.value.decode())
+
+    def program_words(self, voice: int = 0) -> np.ndarray:
+        """The encoded render program of the voice group containing ``voice`` (uint32 words, csrc/program.h)."""
+        n = self._lib.elem_b200_program_words(self._h, int(voice), None, 0)
+        buf = np.zeros(max(1, n), dtype=np.uint32)
+        self._lib.elem_b200_program_words(self._h, int(voice), buf.ctypes.data_as(C.POINTER(C.c_uint32)), n)
+        return buf[:n]
 
     @property
     def kernel_launches(self) -> int:

@@ -122,6 +122,9 @@ int elem_b200_process_queued_events_range(elem_b200_runtime* rt, int voiceBegin,
 int elem_b200_set_option(elem_b200_runtime* rt, const char* key, double value);
 /* JSON description of voice groups and compiled programs; returns bytes needed. */
 int elem_b200_describe(elem_b200_runtime* rt, char* buf, size_t cap);
+/* The encoded render program (32-bit words, elementary_b200/csrc/program.h) of the voice group containing `voice`; writes up to
+ * `cap` words, returns the program length.  Introspection only (tests; input of per-program kernel specialisation). */
+int elem_b200_program_words(elem_b200_runtime* rt, int voice, uint32_t* buf, size_t cap);
 /* Number of CUDA kernels this runtime has launched so far. */
 uint64_t elem_b200_kernel_launches(elem_b200_runtime* rt);
 /* With option "time_kernels" = 1 every K1 render-kernel launch is bracketed by CUDA events on the launching
