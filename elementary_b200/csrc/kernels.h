@@ -1,8 +1,8 @@
 // kernels.h — host-callable launchers of the device kernels (render_kernel.cu, convolve_kernel.cu).
 #pragma once
-#include <cuda_runtime.h>
-#include <cstddef>
 #include "program.h"
+#ifndef __CUDACC_RTC__   // host-callable launchers: not part of a run-time compiled specialisation of K1
+#include <cuda_runtime.h>
 
 namespace eb {
 
@@ -34,3 +34,4 @@ struct PeerMix {
 cudaError_t launch_mix_exchange(const PeerMix& pm, float* mix, int count, uint32_t epoch, int* status, cudaStream_t stream);
 
 } // namespace eb
+#endif   // __CUDACC_RTC__

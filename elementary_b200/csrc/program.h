@@ -18,7 +18,7 @@
 // Runs of stateless element-wise nodes (sin, mul, add, le, ...) whose intermediate has a single consumer are
 // fused by the host into one OP_CHAIN: the intermediate never leaves registers.
 #pragma once
-#include <cstdint>
+#include "rtc_compat.h"
 
 namespace eb {
 

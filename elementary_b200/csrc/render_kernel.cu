@@ -27,11 +27,10 @@
 // HBM layout (per voice group): rows[row][Vpad] f32 (params, scalar state; a double state is two rows viewed
 // as double[Vpad]); delay rings / tap buffers [tile][pos][L] so the lanes of a warp touch one contiguous line.
 
+#ifndef __CUDACC_RTC__
 #include <cuda_runtime.h>
-#include <cfloat>
-#include <cmath>
-#include <cstdint>
-#include <type_traits>
+#endif
+#include "rtc_compat.h"
 #include "program.h"
 #include "kernels.h"
 
@@ -727,6 +726,7 @@ __global__ void EB_BOUNDS render_groups_kernel(const LaunchParams* __restrict__ 
     render_tile<NITER, LOGL>(descs[lo], w - __ldg(tileStart + lo), perWarp);
 }
 
+#ifndef __CUDACC_RTC__   // K2, K4 and the host launchers are not needed by a run-time compiled specialisation of K1
 // ---- K2: deterministic reduction of the per-tile partial mixes: out[ch][s] = sum over tiles in a fixed order ----
 // grid = (channel x 32-sample chunk, G tile groups).  Block (bx, g) sums the tiles of group g (32 tile lanes x 32 samples, four
 // interleaved accumulators per lane so that independent loads are in flight), leaves its result in scratch[g]; the block that
@@ -912,5 +912,7 @@ cudaError_t launch_mix_exchange(const PeerMix& pm, float* mix, int count, uint32
     mix_exchange_kernel<<<1, 512, 0, stream>>>(pm, mix, count, epoch, status);
     return cudaGetLastError();
 }
+
+#endif   // __CUDACC_RTC__
 
 } // namespace eb
