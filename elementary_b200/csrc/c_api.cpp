@@ -169,6 +169,16 @@ int elem_b200_program_words(elem_b200_runtime* rt, int voice, uint32_t* buf, siz
     } catch (...) { return 0; }
 }
 
+long elem_b200_specialize_dry_run(elem_b200_runtime* rt, int voice, char* logBuf, size_t cap) {
+    if (!rt) return -1;
+    try {
+        std::string log;
+        const long n = rt->engine->specializeDryRun(voice, log);
+        if (logBuf && cap) { const size_t k = log.size() < cap - 1 ? log.size() : cap - 1; std::memcpy(logBuf, log.data(), k); logBuf[k] = 0; }
+        return n;
+    } catch (...) { return -1; }
+}
+
 uint64_t elem_b200_kernel_launches(elem_b200_runtime* rt) { return rt ? rt->engine->kernelLaunches() : 0; }
 
 double elem_b200_take_kernel_time_ms(elem_b200_runtime* rt, uint64_t* count) {

@@ -11,6 +11,7 @@
 
 #include "convolve.h"
 #include "kernels.h"
+#include "spec_host.h"
 
 namespace eb {
 
@@ -202,6 +203,8 @@ int Engine::setOption(const char* key, double value) {
     else if (k == "niter") { opt_.niter = (int) value; }
     else if (k == "batch_groups") { opt_.batchGroups = value != 0; }
     else if (k == "fuse_chains") { opt_.fuseChains = value != 0; }
+    else if (k == "specialize") { opt_.specialize = value != 0; }
+    else if (k == "specialize_max_words") { opt_.specializeMaxWords = (int) value; }
     else if (k == "time_kernels") { timeKernels_ = value != 0 && !planOnly_; }
     else return rc::BadArgument;
     return rc::Ok;
@@ -224,6 +227,20 @@ std::string Engine::describe() const {
     }
     os << "]}";
     return os.str();
+}
+
+long Engine::specializeDryRun(int voice, std::string& log) {
+    for (auto& g : groups_) {
+        if (voice < g->v0 || voice >= g->v0 + g->nv) continue;
+        auto& p = g->pending ? g->pending : g->active;
+        if (!p) { log = "no compiled program for this voice"; return -1; }
+        if (p->stages.size() > 1) { log = "multi-stage programs (convolve) are not specialised"; return -1; }
+        SpecKernel k;
+        if (!specialise_compile(p->code, g->tileWidth, opt_.niter, /*load=*/false, k, log)) return -1;
+        return (long) k.cubin.size();
+    }
+    log = "voice out of range";
+    return -1;
 }
 
 std::vector<uint32_t> Engine::programWords(int voice) const {
@@ -1701,6 +1718,12 @@ int Engine::compile(Group& g, int nIn, std::shared_ptr<Program>& out) {
         if (!cuda(dmalloc((void**) &prog->dParamMap, sizeof(uint32_t) * prog->paramMap.size()), "cudaMalloc paramMap")) return rc::CudaError;
         if (!cuda(dmemcpySync(prog->dParamMap, prog->paramMap.data(), sizeof(uint32_t) * prog->paramMap.size(), cudaMemcpyHostToDevice), "upload paramMap")) return rc::CudaError;
     }
+    if (opt_.specialize && !planOnly_ && prog->stages.size() <= 1 && (int) prog->code.size() <= opt_.specializeMaxWords) {
+        auto k = std::make_shared<SpecKernel>();
+        std::string log;
+        if (specialise_compile(prog->code, g.tileWidth, opt_.niter, /*load=*/true, *k, log)) prog->spec = k;
+        else lastError_ = "specialisation skipped, interpreter in use: " + log.substr(0, 400);   // never fatal
+    }
     out = prog;
     return rc::Ok;
 }
@@ -1891,7 +1914,7 @@ int Engine::enqueueBlock(size_t nIn, size_t nOut, size_t numSamples, bool perVoi
             }
             const bool emptyStage = !p.stages.empty() && p.stages[stg].empty && !last;
             if (!emptyStage) {
-                if (!cuda(launch_render_block(P, wpc, opt_.niter, stream_), "render kernel launch")) return rc::CudaError;
+                if (!cuda(launch_render_block(P, wpc, opt_.niter, stream_, p.spec.get()), "render kernel launch")) return rc::CudaError;
                 ++launches_;
             }
             if (timeKernels_) { cudaEventRecord(ev.second, stream_); timedEvents_.push_back(ev); }

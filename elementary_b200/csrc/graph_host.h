@@ -67,6 +67,7 @@ struct Resource {
 };
 
 struct ConvolverState;   // convolve.h
+struct SpecKernel;       // spec_host.h
 
 struct Node {
     int32_t id = 0;
@@ -132,6 +133,7 @@ struct Program {
     struct EvNode { int32_t node; int root; };
     std::vector<EvNode> evNodes;          // event-emitting nodes in render order (GraphRenderSequence.h:189-198 walks nodeList)
     std::vector<int32_t> dynNodes;        // LaunchParams::dyn[i] belongs to node dynNodes[i]
+    std::shared_ptr<SpecKernel> spec;     // K1 specialised for this program (option "specialize"), else null: the interpreter runs
     const float* stagedTable = nullptr; int stagedTableFloats = 0;   // the wavetable K1 stages into shared memory with TMA (first `table` node that fits)
     ~Program();
 };
@@ -157,6 +159,8 @@ struct EngineOptions {
     int niter = 0;                // 0 = default elements-per-lane per tile; 4 selects the T = 4 variant for L = 32
     bool batchGroups = true;      // launch all single-stage voice groups of one tile geometry together
     bool fuseChains = true;       // fold runs of element-wise nodes into one OP_CHAIN
+    bool specialize = false;      // EXPERIMENTAL: NVRTC-compile K1 against each (small, single-stage) program — spec_host.h
+    int specializeMaxWords = 512; // programs longer than this keep the interpreter (compile time grows with the unrolled program)
 };
 
 class Engine {
@@ -212,6 +216,9 @@ public:
     // The encoded render program (program.h) of the voice group containing `voice` — the newest compiled one.  Introspection:
     // tests, and the input of per-program kernel specialisation.
     std::vector<uint32_t> programWords(int voice) const;
+    // Compile (not load, not run) the specialised K1 of the voice group containing `voice`: returns the cubin size or -1, the
+    // NVRTC log in `log`.  Works without a GPU (NVRTC is a pure compiler): the CPU test-suite uses it.
+    long specializeDryRun(int voice, std::string& log);
 
 private:
     double sr_;

@@ -9,7 +9,8 @@ namespace eb {
 // K1: fused render-sequence kernel, one launch per voice group per block.
 int render_niter_for(int tileWidth, int niterOverride);   // elements per lane per sample tile (E = 32*NITER = L*T)
 size_t render_smem_bytes(int nSlots, int nOut, int nStateRows, int nParams, int warpsPerCta, int tileWidth, int niterOverride);
-cudaError_t launch_render_block(const LaunchParams& P, int warpsPerCta, int niterOverride, cudaStream_t stream);
+struct SpecKernel;   // spec_host.h: K1 compiled at run time against one program (nullptr = the built-in interpreter)
+cudaError_t launch_render_block(const LaunchParams& P, int warpsPerCta, int niterOverride, cudaStream_t stream, const SpecKernel* spec = nullptr);
 
 // K1 for many voice groups of one tile geometry in one launch (descs / tileStart are device pointers).
 cudaError_t launch_render_groups(const LaunchParams* descs, const int* tileStart, int nGroups, int totalTiles, int tileWidth,

@@ -727,6 +727,9 @@ __global__ void EB_BOUNDS render_groups_kernel(const LaunchParams* __restrict__ 
 }
 
 #ifndef __CUDACC_RTC__   // K2, K4 and the host launchers are not needed by a run-time compiled specialisation of K1
+} // namespace eb
+#include "spec_host.h"
+namespace eb {
 // ---- K2: deterministic reduction of the per-tile partial mixes: out[ch][s] = sum over tiles in a fixed order ----
 // grid = (channel x 32-sample chunk, G tile groups).  Block (bx, g) sums the tiles of group g (32 tile lanes x 32 samples, four
 // interleaved accumulators per lane so that independent loads are in flight), leaves its result in scratch[g]; the block that
@@ -817,7 +820,7 @@ static cudaError_t launch_groups_impl(const LaunchParams* descs, const int* tile
     return cudaGetLastError();
 }
 
-cudaError_t launch_render_block(const LaunchParams& P, int warpsPerCta, int niterOverride, cudaStream_t stream) {
+cudaError_t launch_render_block(const LaunchParams& P, int warpsPerCta, int niterOverride, cudaStream_t stream, const SpecKernel* spec) {
     const int L = P.tileWidth;
     const int nTiles = (P.nv + L - 1) / L;
     if (nTiles <= 0) return cudaSuccess;
@@ -831,6 +834,7 @@ cudaError_t launch_render_block(const LaunchParams& P, int warpsPerCta, int nite
         Q.tableSmem = perWarpFloats * warpsPerCta;            // behind the per-warp areas; 16-byte aligned (perWarp is a multiple of 4 floats)
         smem += (size_t) Q.tableFloats * 4 + 16;              // + the mbarrier
     } else { Q.tableSmem = -1; Q.tableSrc = nullptr; }
+    if (spec && spec->function) return specialise_launch(*spec, Q, grid, threads, smem, perWarpFloats, stream);
     return launch_render_block_geometry(Q, L, grid, threads, smem, perWarpFloats, niterOverride, stream);
 }
 

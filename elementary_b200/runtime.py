@@ -97,6 +97,8 @@ def load_library() -> C.CDLL:
     lib.elem_b200_describe.argtypes = [C.c_void_p, C.c_char_p, C.c_size_t]
     lib.elem_b200_program_words.restype = C.c_int
     lib.elem_b200_program_words.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_uint32), C.c_size_t]
+    lib.elem_b200_specialize_dry_run.restype = C.c_long
+    lib.elem_b200_specialize_dry_run.argtypes = [C.c_void_p, C.c_int, C.c_char_p, C.c_size_t]
     lib.elem_b200_kernel_launches.restype = C.c_uint64
     lib.elem_b200_kernel_launches.argtypes = [C.c_void_p]
     lib.elem_b200_take_kernel_time_ms.restype = C.c_double
@@ -322,6 +324,13 @@ class Runtime:
         buf = np.zeros(max(1, n), dtype=np.uint32)
         self._lib.elem_b200_program_words(self._h, int(voice), buf.ctypes.data_as(C.POINTER(C.c_uint32)), n)
         return buf[:n]
+
+    def specialize_dry_run(self, voice: int = 0):
+        """EXPERIMENTAL: NVRTC-compile (only) the specialised K1 of the voice group containing ``voice``.  Returns
+        (cubin_bytes | -1, compiler_log)."""
+        buf = C.create_string_buffer(1 << 16)
+        n = self._lib.elem_b200_specialize_dry_run(self._h, int(voice), buf, len(buf))
+        return int(n), buf.value.decode(errors="replace")
 
     @property
     def kernel_launches(self) -> int:

@@ -118,13 +118,17 @@ void elem_b200_process_queued_events(elem_b200_runtime* rt, elem_b200_event_cb c
 int elem_b200_process_queued_events_range(elem_b200_runtime* rt, int voiceBegin, int voiceEnd, elem_b200_event_cb cb, void* user);
 
 /* Tuning and introspection (no reference equivalent). Keys: "tile_width" (1..32, 0 =
- * auto), "warps_per_cta", "target_tiles", "time_kernels" (0|1). Must be set before the first COMMIT of a voice group. */
+ * auto), "warps_per_cta", "target_tiles", "time_kernels" (0|1), "specialize" (0|1, experimental). Must be set before the first COMMIT of a voice group. */
 int elem_b200_set_option(elem_b200_runtime* rt, const char* key, double value);
 /* JSON description of voice groups and compiled programs; returns bytes needed. */
 int elem_b200_describe(elem_b200_runtime* rt, char* buf, size_t cap);
 /* The encoded render program (32-bit words, elementary_b200/csrc/program.h) of the voice group containing `voice`; writes up to
  * `cap` words, returns the program length.  Introspection only (tests; input of per-program kernel specialisation). */
 int elem_b200_program_words(elem_b200_runtime* rt, int voice, uint32_t* buf, size_t cap);
+/* EXPERIMENTAL (option "specialize" = 1, off by default): K1 compiled at run time by NVRTC against the render
+ * program of a voice group as a compile-time constant.  This entry point only COMPILES the specialised kernel of the group
+ * containing `voice` (no GPU needed) and returns the cubin size, or -1 with the compiler log in logBuf. */
+long elem_b200_specialize_dry_run(elem_b200_runtime* rt, int voice, char* logBuf, size_t cap);
 /* Number of CUDA kernels this runtime has launched so far. */
 uint64_t elem_b200_kernel_launches(elem_b200_runtime* rt);
 /* With option "time_kernels" = 1 every K1 render-kernel launch is bracketed by CUDA events on the launching

@@ -194,3 +194,20 @@ def test_live_group_split_with_sequencer_and_analysis_nodes_runs_the_migration_c
     assert d1["groups"][1]["ops"] > d1["groups"][0]["ops"]               # the moved half runs the extended graph
     assert rt.apply_instructions([[3, seq.id(), "seq", [9.0, 8.0]]], voices=(8, 16)) == 0    # and can be re-programmed on its own
     assert rt.gc(0) == [] and isinstance(rt.gc(8), list)
+
+
+def test_per_program_specialisation_compiles_without_a_gpu():
+    """EXPERIMENTAL path (option "specialize", off by default): NVRTC compiles K1 against the render program of a
+    voice group as a compile-time constant.  NVRTC is a pure compiler, so the compile step is checked here; launching the result
+    is left to the first GPU session that has minutes for it."""
+    rt = plan(4096)
+    assert rt.apply_instructions(graphs.subsynth32()) == 0
+    words = rt.program_words(0)
+    assert len(words) == rt.describe()["groups"][0]["code_words"] and words[0] & 0xFF == 1      # OP_SEG opens the program
+    n, log = rt.specialize_dry_run(0)
+    assert n > 50_000, log
+    rt2 = plan(2)
+    assert rt2.add_shared_resource("ir", np.ones(700, dtype=np.float32))
+    assert rt2.apply_instructions(graphs.convolve_channel("ir")) == 0
+    n2, log2 = rt2.specialize_dry_run(0)
+    assert n2 == -1 and "multi-stage" in log2
