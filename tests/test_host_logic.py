@@ -211,3 +211,17 @@ def test_per_program_specialisation_compiles_without_a_gpu():
     assert rt2.apply_instructions(graphs.convolve_channel("ir")) == 0
     n2, log2 = rt2.specialize_dry_run(0)
     assert n2 == -1 and "multi-stage" in log2
+
+
+@pytest.mark.parametrize("name", ["delay_mod", "table", "taps", "two_roots", "sparseq_interp_loop_offset", "seq_hold",
+                                  "scope_passthrough", "capture_passthrough", "bleptriangle", "random_graph_1"])
+def test_specialised_kernel_compiles_for_every_kind_of_op(name):
+    """The specialised path reuses the interpreter's per-op text (render_ops.inc); this keeps every family of op bodies
+    compilable with compile-time operands (all 113 cases x 2 tile widths were swept offline: profiles/r01_r_*)."""
+    case = next(c for c in CASES if c["name"] == name)
+    rt = plan(64, tile_width=32 if len(name) % 2 else 2)
+    for k, v in (case["resources"] or {}).items():
+        assert rt.add_shared_resource(k, v)
+    assert rt.apply_instructions(case["batch"]) == 0
+    n, log = rt.specialize_dry_run(0)
+    assert n > 0, log
