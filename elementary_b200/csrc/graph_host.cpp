@@ -8,6 +8,7 @@
 #include <functional>
 #include <list>
 #include <sstream>
+#include <thread>
 
 #include "convolve.h"
 #include "kernels.h"
@@ -203,7 +204,7 @@ int Engine::setOption(const char* key, double value) {
     else if (k == "niter") { opt_.niter = (int) value; }
     else if (k == "batch_groups") { opt_.batchGroups = value != 0; }
     else if (k == "fuse_chains") { opt_.fuseChains = value != 0; }
-    else if (k == "specialize") { opt_.specialize = value != 0; }
+    else if (k == "specialize") { opt_.specialize = (int) value; }
     else if (k == "specialize_max_words") { opt_.specializeMaxWords = (int) value; }
     else if (k == "time_kernels") { timeKernels_ = value != 0 && !planOnly_; }
     else return rc::BadArgument;
@@ -222,6 +223,7 @@ std::string Engine::describe() const {
             auto& p = g->pending ? g->pending : g->active;
             os << ",\"slots\":" << p->nSlots << ",\"state_rows\":" << p->nStateRows << ",\"params\":" << p->paramMap.size() << ",\"ops\":" << p->nOps << ",\"code_words\":" << p->code.size()
                << ",\"roots\":" << p->rootIds.size();
+            if (p->specJob) os << ",\"spec_state\":" << p->specJob->state.load() << ",\"spec_cubin_bytes\":" << (p->specJob->state.load() > 0 ? p->specJob->kernel.cubin.size() : 0);
         }
         os << "}";
     }
@@ -236,7 +238,7 @@ long Engine::specializeDryRun(int voice, std::string& log) {
         if (!p) { log = "no compiled program for this voice"; return -1; }
         if (p->stages.size() > 1) { log = "multi-stage programs (convolve) are not specialised"; return -1; }
         SpecKernel k;
-        if (!specialise_compile(p->code, g->tileWidth, opt_.niter, /*load=*/false, k, log)) return -1;
+        if (!specialise_compile(p->code, g->tileWidth, opt_.niter, k, log)) return -1;
         return (long) k.cubin.size();
     }
     log = "voice out of range";
@@ -1718,11 +1720,10 @@ int Engine::compile(Group& g, int nIn, std::shared_ptr<Program>& out) {
         if (!cuda(dmalloc((void**) &prog->dParamMap, sizeof(uint32_t) * prog->paramMap.size()), "cudaMalloc paramMap")) return rc::CudaError;
         if (!cuda(dmemcpySync(prog->dParamMap, prog->paramMap.data(), sizeof(uint32_t) * prog->paramMap.size(), cudaMemcpyHostToDevice), "upload paramMap")) return rc::CudaError;
     }
-    if (opt_.specialize && !planOnly_ && prog->stages.size() <= 1 && (int) prog->code.size() <= opt_.specializeMaxWords) {
-        auto k = std::make_shared<SpecKernel>();
-        std::string log;
-        if (specialise_compile(prog->code, g.tileWidth, opt_.niter, /*load=*/true, *k, log)) prog->spec = k;
-        else lastError_ = "specialisation skipped, interpreter in use: " + log.substr(0, 400);   // never fatal
+    if (opt_.specialize && prog->stages.size() <= 1 && (int) prog->code.size() <= opt_.specializeMaxWords) {
+        prog->specJob = specialise_async(prog->code, g.tileWidth, opt_.niter);     // NVRTC on its own thread
+        if (opt_.specialize >= 2)                                                   // synchronous mode: wait for the compiler here
+            while (prog->specJob->state.load(std::memory_order_acquire) == 0) std::this_thread::yield();
     }
     out = prog;
     return rc::Ok;
@@ -1914,7 +1915,16 @@ int Engine::enqueueBlock(size_t nIn, size_t nOut, size_t numSamples, bool perVoi
             }
             const bool emptyStage = !p.stages.empty() && p.stages[stg].empty && !last;
             if (!emptyStage) {
-                if (!cuda(launch_render_block(P, wpc, opt_.niter, stream_, p.spec.get()), "render kernel launch")) return rc::CudaError;
+                const SpecKernel* spec = nullptr;
+                if (p.specJob) {
+                    const int st = p.specJob->state.load(std::memory_order_acquire);
+                    if (st == 1) {   // the cubin arrived: load it on this thread (its CUDA context is current), a matter of milliseconds
+                        std::string log;
+                        p.specJob->state.store(specialise_load(p.specJob->kernel, log) ? 2 : -1, std::memory_order_release);
+                    }
+                    if (p.specJob->state.load(std::memory_order_acquire) == 2) spec = &p.specJob->kernel;
+                }
+                if (!cuda(launch_render_block(P, wpc, opt_.niter, stream_, spec), "render kernel launch")) return rc::CudaError;
                 ++launches_;
             }
             if (timeKernels_) { cudaEventRecord(ev.second, stream_); timedEvents_.push_back(ev); }

@@ -68,6 +68,7 @@ struct Resource {
 
 struct ConvolverState;   // convolve.h
 struct SpecKernel;       // spec_host.h
+struct SpecJob;
 
 struct Node {
     int32_t id = 0;
@@ -133,7 +134,7 @@ struct Program {
     struct EvNode { int32_t node; int root; };
     std::vector<EvNode> evNodes;          // event-emitting nodes in render order (GraphRenderSequence.h:189-198 walks nodeList)
     std::vector<int32_t> dynNodes;        // LaunchParams::dyn[i] belongs to node dynNodes[i]
-    std::shared_ptr<SpecKernel> spec;     // K1 specialised for this program (option "specialize"), else null: the interpreter runs
+    std::shared_ptr<SpecJob> specJob;     // K1 being / having been specialised for this program (option "specialize"); the interpreter runs until it is loaded
     const float* stagedTable = nullptr; int stagedTableFloats = 0;   // the wavetable K1 stages into shared memory with TMA (first `table` node that fits)
     ~Program();
 };
@@ -159,7 +160,8 @@ struct EngineOptions {
     int niter = 0;                // 0 = default elements-per-lane per tile; 4 selects the T = 4 variant for L = 32
     bool batchGroups = true;      // launch all single-stage voice groups of one tile geometry together
     bool fuseChains = true;       // fold runs of element-wise nodes into one OP_CHAIN
-    bool specialize = false;      // EXPERIMENTAL: NVRTC-compile K1 against each (small, single-stage) program — spec_host.h
+    int specialize = 0;           // EXPERIMENTAL (spec_host.h): NVRTC-compile K1 against each small single-stage program; 1 = on a background
+                                  // thread (the interpreter serves meanwhile), 2 = wait for the compiler at COMMIT (benchmarks, parity runs)
     int specializeMaxWords = 512; // programs longer than this keep the interpreter (compile time grows with the unrolled program)
 };
 

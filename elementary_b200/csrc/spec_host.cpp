@@ -92,7 +92,7 @@ SpecKernel::~SpecKernel() {
     if (module && api().moduleUnload) api().moduleUnload(static_cast<CUmodule>(module));
 }
 
-bool specialise_compile(const std::vector<uint32_t>& code, int tileWidth, int niterOverride, bool load, SpecKernel& out, std::string& log) {
+bool specialise_compile(const std::vector<uint32_t>& code, int tileWidth, int niterOverride, SpecKernel& out, std::string& log) {
     if (!loadNvrtc(log)) return false;
     Api& a = api();
     const std::string dir = sourceDir();
@@ -134,16 +134,32 @@ bool specialise_compile(const std::vector<uint32_t>& code, int tileWidth, int ni
     }
     a.destroyProgram(&prog);
     if (!ok) { if (log.empty()) log = "NVRTC compilation failed"; return false; }
-    if (!load) return true;
+    out.loweredName = lowered;
+    return true;
+}
 
+bool specialise_load(SpecKernel& k, std::string& log) {
+    if (k.function) return true;
+    if (k.cubin.empty() || k.loweredName.empty()) { log = "nothing compiled"; return false; }
     if (!loadDriver(log)) return false;
+    Api& a = api();
     CUmodule mod = nullptr;
     CUfunction fn = nullptr;
-    if (a.moduleLoadData(&mod, out.cubin.data()) != CUDA_SUCCESS) { log = "cuModuleLoadData failed"; return false; }
-    if (a.moduleGetFunction(&fn, mod, lowered.c_str()) != CUDA_SUCCESS) { a.moduleUnload(mod); log = "cuModuleGetFunction failed for " + lowered; return false; }
-    out.module = mod;
-    out.function = fn;
+    if (a.moduleLoadData(&mod, k.cubin.data()) != CUDA_SUCCESS) { log = "cuModuleLoadData failed"; return false; }
+    if (a.moduleGetFunction(&fn, mod, k.loweredName.c_str()) != CUDA_SUCCESS) { a.moduleUnload(mod); log = "cuModuleGetFunction failed for " + k.loweredName; return false; }
+    k.module = mod;
+    k.function = fn;
     return true;
+}
+
+std::shared_ptr<SpecJob> specialise_async(std::vector<uint32_t> code, int tileWidth, int niterOverride) {
+    auto job = std::make_shared<SpecJob>();
+    SpecJob* j = job.get();   // the job outlives its worker: ~SpecJob joins
+    job->worker = std::thread([j, code = std::move(code), tileWidth, niterOverride]() {
+        const bool ok = specialise_compile(code, tileWidth, niterOverride, j->kernel, j->log);
+        j->state.store(ok ? 1 : -1, std::memory_order_release);
+    });
+    return job;
 }
 
 cudaError_t specialise_launch(const SpecKernel& k, const LaunchParams& P, int grid, int threads, size_t smem, int perWarpFloats, cudaStream_t stream) {

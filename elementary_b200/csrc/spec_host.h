@@ -6,8 +6,11 @@
 // decoding fold away.  libnvrtc and libcuda are opened with dlopen, so the library has no load-time dependency on either.
 #pragma once
 #include <cuda_runtime.h>
+#include <atomic>
 #include <cstdint>
+#include <memory>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "program.h"
@@ -18,12 +21,26 @@ struct SpecKernel {
     void* module = nullptr;      // CUmodule
     void* function = nullptr;    // CUfunction of render_block_kernel<NITER, LOGL> specialised for one program
     std::vector<char> cubin;
+    std::string loweredName;     // mangled name of the kernel inside the cubin
     ~SpecKernel();
 };
 
-// Compile K1 for (tileWidth, niterOverride) against `code` (one single-stage program).  Fills out.cubin; when `load` is set also
-// loads the module into the current CUDA context and resolves the kernel.  Returns false and a message in `log` on failure.
-bool specialise_compile(const std::vector<uint32_t>& code, int tileWidth, int niterOverride, bool load, SpecKernel& out, std::string& log);
+// Step 1 — pure compilation (NVRTC only; thread safe, needs no CUDA context, works without a GPU): K1 for (tileWidth,
+// niterOverride) against `code` (one single-stage program).  Fills out.cubin / out.loweredName.
+bool specialise_compile(const std::vector<uint32_t>& code, int tileWidth, int niterOverride, SpecKernel& out, std::string& log);
+// Step 2 — on a thread whose CUDA context is current: load the cubin and resolve the kernel (milliseconds).
+bool specialise_load(SpecKernel& k, std::string& log);
+
+// A compilation running on its own thread: the interpreter serves the voice group until the cubin is there, so a live graph edit
+// never waits for the compiler.  state: 0 compiling, 1 compiled (cubin ready, not loaded), 2 loaded, -1 failed.
+struct SpecJob {
+    std::atomic<int> state{0};
+    SpecKernel kernel;
+    std::string log;
+    std::thread worker;
+    ~SpecJob() { if (worker.joinable()) worker.join(); }
+};
+std::shared_ptr<SpecJob> specialise_async(std::vector<uint32_t> code, int tileWidth, int niterOverride);
 
 // cuLaunchKernel of a specialised kernel with the same launch geometry the built-in instantiation would get.
 cudaError_t specialise_launch(const SpecKernel& k, const LaunchParams& P, int grid, int threads, size_t smem, int perWarpFloats, cudaStream_t stream);

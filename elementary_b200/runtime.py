@@ -146,7 +146,7 @@ class Runtime:
             raise RuntimeError("elem_b200_create failed: " + self._lib.elem_b200_last_error(None).decode())
         self._h = C.c_void_p(h)
         if os.environ.get("ELEM_B200_SPECIALIZE") == "1":      # run anything (the GPU parity suite) on the experimental per-program kernels
-            options.setdefault("specialize", 1)
+            options.setdefault("specialize", 2)                 # 2 = wait for the compiler at COMMIT: no interpreter blocks in between
         for k, v in options.items():
             self.set_option(k, v)
 

@@ -225,3 +225,24 @@ def test_specialised_kernel_compiles_for_every_kind_of_op(name):
     assert rt.apply_instructions(case["batch"]) == 0
     n, log = rt.specialize_dry_run(0)
     assert n > 0, log
+
+
+def test_specialisation_runs_in_the_background_or_on_demand():
+    """option "specialize": 2 waits for NVRTC at COMMIT, 1 compiles on a worker thread while the interpreter would keep
+    serving; describe() shows the state (0 compiling, 1 cubin ready, 2 loaded on a GPU, -1 failed)."""
+    import time
+    rt = plan(256, specialize=2)
+    assert rt.apply_instructions(graphs.subsynth32()) == 0
+    g = rt.describe()["groups"][0]
+    assert g["spec_state"] == 1 and g["spec_cubin_bytes"] > 50_000
+    rt = plan(256, specialize=1)
+    assert rt.apply_instructions(graphs.subsynth32()) == 0      # returns at once
+    for _ in range(600):
+        g = rt.describe()["groups"][0]
+        if g["spec_state"] != 0:
+            break
+        time.sleep(0.05)
+    assert g["spec_state"] == 1 and g["spec_cubin_bytes"] > 50_000
+    rt = plan(64, specialize=2, specialize_max_words=100)        # too long for the limit: the interpreter stays
+    assert rt.apply_instructions(graphs.subsynth32()) == 0
+    assert "spec_state" not in rt.describe()["groups"][0]
