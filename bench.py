@@ -289,6 +289,7 @@ def run_b200(args, rank, local_rank, world, emit=print):
                    "voices_total": world * voices, "block": BS, "sample_rate": SR,
                    "l2": "flushed between steps (256 MiB memset outside the timed events)",
                    "tile_width": desc["tile_width"], "slots": desc["slots"], "state_rows": desc["state_rows"],
+                   "spec": {k: desc[k] for k in ("spec_state", "spec_regs", "spec_local_bytes", "spec_cubin_bytes", "spec_log") if k in desc},
                    "collective": "none (1 GPU)" if world == 1 else
                                  ("K4 mix_exchange_kernel: all-reduce(sum,f32) of the [1][512] mix bus per block over NVLink peer memory, one launch in the render stream"
                                   + ("" if not peer_fail else " — PEER TIMEOUT REPORTED") if fused else

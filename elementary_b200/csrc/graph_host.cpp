@@ -206,6 +206,7 @@ int Engine::setOption(const char* key, double value) {
     else if (k == "fuse_chains") { opt_.fuseChains = value != 0; }
     else if (k == "specialize") { opt_.specialize = (int) value; }
     else if (k == "specialize_max_words") { opt_.specializeMaxWords = (int) value; }
+    else if (k == "specialize_strict") { opt_.specializeStrict = value != 0; }
     else if (k == "time_kernels") { timeKernels_ = value != 0 && !planOnly_; }
     else return rc::BadArgument;
     return rc::Ok;
@@ -223,7 +224,20 @@ std::string Engine::describe() const {
             auto& p = g->pending ? g->pending : g->active;
             os << ",\"slots\":" << p->nSlots << ",\"state_rows\":" << p->nStateRows << ",\"params\":" << p->paramMap.size() << ",\"ops\":" << p->nOps << ",\"code_words\":" << p->code.size()
                << ",\"roots\":" << p->rootIds.size();
-            if (p->specJob) os << ",\"spec_state\":" << p->specJob->state.load() << ",\"spec_cubin_bytes\":" << (p->specJob->state.load() > 0 ? p->specJob->kernel.cubin.size() : 0);
+            if (p->specJob) {
+                const int st = p->specJob->state.load(std::memory_order_acquire);
+                os << ",\"spec_state\":" << st << ",\"spec_cubin_bytes\":" << (st > 0 ? p->specJob->kernel.cubin.size() : 0);
+                if (st == 2) os << ",\"spec_regs\":" << p->specJob->kernel.numRegs << ",\"spec_local_bytes\":" << p->specJob->kernel.localBytes;
+                if (st < 0) {   // the compiler / loader log, JSON-escaped
+                    os << ",\"spec_log\":\"";
+                    for (char c : p->specJob->log) {
+                        if (c == '"' || c == '\\') os << '\\' << c;
+                        else if (c == '\n') os << "\\n";
+                        else if ((unsigned char) c >= 0x20) os << c;
+                    }
+                    os << "\"";
+                }
+            }
         }
         os << "}";
     }
@@ -1720,10 +1734,16 @@ int Engine::compile(Group& g, int nIn, std::shared_ptr<Program>& out) {
         if (!cuda(dmalloc((void**) &prog->dParamMap, sizeof(uint32_t) * prog->paramMap.size()), "cudaMalloc paramMap")) return rc::CudaError;
         if (!cuda(dmemcpySync(prog->dParamMap, prog->paramMap.data(), sizeof(uint32_t) * prog->paramMap.size(), cudaMemcpyHostToDevice), "upload paramMap")) return rc::CudaError;
     }
-    if (opt_.specialize && prog->stages.size() <= 1 && (int) prog->code.size() <= opt_.specializeMaxWords) {
-        prog->specJob = specialise_async(prog->code, g.tileWidth, opt_.niter);     // NVRTC on its own thread
-        if (opt_.specialize >= 2)                                                   // synchronous mode: wait for the compiler here
-            while (prog->specJob->state.load(std::memory_order_acquire) == 0) std::this_thread::yield();
+    // Per-program specialisation of K1 (spec_host.h).  Not for groups that render through the batched many-groups launch (that
+    // kernel is the interpreter by construction: one launch serves different programs), not for multi-stage programs.
+    const bool batched = groups_.size() > 1 && opt_.batchGroups;
+    if (opt_.specialize && !batched && prog->stages.size() <= 1 && (int) prog->code.size() <= opt_.specializeMaxWords) {
+        prog->specJob = specialise_request(prog->code, g.tileWidth, opt_.niter, device_);   // NVRTC on the compile-queue thread
+        if (opt_.specialize >= 2) {                                                          // synchronous mode: wait for the compiler here
+            specialise_wait(*prog->specJob);
+            if (prog->specJob->state.load(std::memory_order_acquire) < 0 && opt_.specializeStrict)
+                return fail(rc::InvariantViolation, "K1 specialisation failed: " + prog->specJob->log);
+        }
     }
     out = prog;
     return rc::Ok;
@@ -1916,13 +1936,10 @@ int Engine::enqueueBlock(size_t nIn, size_t nOut, size_t numSamples, bool perVoi
             const bool emptyStage = !p.stages.empty() && p.stages[stg].empty && !last;
             if (!emptyStage) {
                 const SpecKernel* spec = nullptr;
-                if (p.specJob) {
-                    const int st = p.specJob->state.load(std::memory_order_acquire);
-                    if (st == 1) {   // the cubin arrived: load it on this thread (its CUDA context is current), a matter of milliseconds
-                        std::string log;
-                        p.specJob->state.store(specialise_load(p.specJob->kernel, log) ? 2 : -1, std::memory_order_release);
-                    }
-                    if (p.specJob->state.load(std::memory_order_acquire) == 2) spec = &p.specJob->kernel;
+                if (p.specJob) {   // the cubin arrived: load it on this thread (its CUDA context is current), a matter of milliseconds
+                    const int st = specialise_ensure_loaded(*p.specJob);
+                    if (st == 2) spec = &p.specJob->kernel;
+                    else if (st < 0 && opt_.specializeStrict) return fail(rc::CudaError, "K1 specialisation failed: " + p.specJob->log);
                 }
                 if (!cuda(launch_render_block(P, wpc, opt_.niter, stream_, spec), "render kernel launch")) return rc::CudaError;
                 ++launches_;

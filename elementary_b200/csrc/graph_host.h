@@ -160,9 +160,10 @@ struct EngineOptions {
     int niter = 0;                // 0 = default elements-per-lane per tile; 4 selects the T = 4 variant for L = 32
     bool batchGroups = true;      // launch all single-stage voice groups of one tile geometry together
     bool fuseChains = true;       // fold runs of element-wise nodes into one OP_CHAIN
-    int specialize = 0;           // EXPERIMENTAL (spec_host.h): NVRTC-compile K1 against each small single-stage program; 1 = on a background
-                                  // thread (the interpreter serves meanwhile), 2 = wait for the compiler at COMMIT (benchmarks, parity runs)
+    int specialize = 0;           // spec_host.h: NVRTC-compile K1 against each small single-stage program; 1 = on the compile-queue thread
+                                  // (the interpreter serves meanwhile), 2 = wait for the compiler at COMMIT (benchmarks, parity runs)
     int specializeMaxWords = 512; // programs longer than this keep the interpreter (compile time grows with the unrolled program)
+    bool specializeStrict = false; // a failed specialisation is an error (COMMIT returns 7 / process -1) instead of a silent stay on the interpreter
 };
 
 class Engine {

@@ -147,6 +147,7 @@ class Runtime:
         self._h = C.c_void_p(h)
         if os.environ.get("ELEM_B200_SPECIALIZE") == "1":      # run anything (the GPU parity suite) on the experimental per-program kernels
             options.setdefault("specialize", 2)                 # 2 = wait for the compiler at COMMIT: no interpreter blocks in between
+            options.setdefault("specialize_strict", 1)          # a specialisation that fails to compile or load is an error, never a silent fallback
         for k, v in options.items():
             self.set_option(k, v)
 

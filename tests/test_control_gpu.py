@@ -53,10 +53,10 @@ def test_live_updates_match_oracle(sc):
     assert np.abs(g).max() > 0
 
 
-@pytest.mark.parametrize("tile_width", [1, 8, 32])
+@pytest.mark.parametrize("tile_width", [1, 2, 8, 16, 32])
 def test_seq_live_updates_in_every_tile_geometry(tile_width):
     sc = SCEN[0]
-    g = lockstep(sc["batch"], sc["script"], sc["n_blocks"], n_voices=5 if tile_width != 32 else 40, tile_width=tile_width)
+    g = lockstep(sc["batch"], sc["script"], sc["n_blocks"], n_voices=5 if tile_width < 16 else 40, tile_width=tile_width)
     assert np.abs(g).max() >= 30.0
 
 

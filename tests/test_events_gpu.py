@@ -15,9 +15,9 @@ SCEN = scenarios()
 
 
 @pytest.mark.parametrize("sc", SCEN, ids=[s["name"] for s in SCEN])
-@pytest.mark.parametrize("tile_width", [0, 32])
+@pytest.mark.parametrize("tile_width", [0, 2, 16, 32])
 def test_events_match_oracle_per_voice(sc, tile_width):
-    n_voices = 3 if tile_width == 0 else 35
+    n_voices = 3 if tile_width in (0, 2) else 35
     batch = el.render(*sc["graph"])
     opts = {"tile_width": tile_width} if tile_width else {}
     rt = Runtime(SR, BS, n_voices, device=0, **opts)
