@@ -2,30 +2,38 @@
 """bench.py — headline measurement of the hot path (BASELINE.json configs[1]).
 
 Workload: 4096 SUBSYNTH32 voices (32-node subtractive-synth graph, per-voice f0 = 55*(1 + v mod 40) Hz) per GPU,
-512-sample blocks @ 48 kHz.  One "step" = one block of all voices through the fused render kernel (+ the
-mix-bus reduction, + the cross-GPU all-reduce of the [1][512] mix bus when N > 1).  Weak scaling: every rank
-owns its own 4096 voices; the only data-path collective is the mix-bus reduce.
+512-sample blocks @ 48 kHz.  One "step" = one block of all voices through the fused render kernel K1 (+ K2, the
+mix-bus reduction, + K4, the cross-GPU sum of the [1][512] mix bus when N > 1).  Weak scaling: every rank
+owns its own 4096 voices; the only data-path collective is the mix-bus sum.
 
   value  : Msamples/s, device-resident (state, delay rings and parameters in HBM; no host I/O in the step),
-           CUDA events per step, L2 flushed (256 MiB memset) between steps outside the timed events.
+           CUDA events per step on the launching stream, L2 flushed (256 MiB memset) between steps outside the events;
+           at N > 1 a device-side cross-GPU barrier sits between the flush and the first event, so the skew of the
+           per-rank flushes is not charged to the step.
   e2e    : same metric through the public API call a user makes (elem_b200_process: host output buffers,
            D2H of the mix bus and the synchronisation inside the timed region; the graph has no audio inputs,
            so h2d_bytes_per_step is 0).
-  roofline: K1 render kernel only — algorithmic bytes per launch / mean launch duration measured
-           with CUDA events around every K1 launch on its own stream, against MEASURED_PEAKS.json hbm_gbs.
+  roofline: K1 only — algorithmic bytes per launch / mean launch duration measured with CUDA events
+           around every K1 launch on its own stream, against MEASURED_PEAKS.json hbm_gbs; beside it the issue-slot
+           roofline (K1's real bound): warp instructions per launch (ncu capture of the SAME K1 sources, else null)
+           / duration against SMs x 4 schedulers x the SM clock sampled during the run.
+  parity : after the timed loops the SAME runtime renders one more block with per-voice outputs; every voice and the
+           mix bus are compared with the reference engine advanced by exactly as many blocks (parity_checked,
+           worst_err_over_tol).  A bench line whose kernel computed something else says so.
   cpu_baseline / --impl reference: the UNMODIFIED reference engine (oracle/_ref/libelem_ref.so, built from
-           /root/reference in place) on the box's host cores.
+           /root/reference in place) on the box's host cores: T = all threads (value) and T = 1, pinned threads created
+           and warmed up outside the timed region, >= 2 s timed (oracle/ref_driver.cpp:elem_ref_bench_stable).
 """
 from __future__ import annotations
 
 import argparse
+import hashlib
 import json
 import os
 import statistics
 import subprocess
 import sys
 import tempfile
-import threading
 import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
@@ -33,8 +41,10 @@ sys.path.insert(0, ROOT)
 
 SR, BS = 48000.0, 512
 VOICES_PER_GPU = 4096
+T1_VOICES_PER_GPU = 131072                      # 8 x 131072 = the 1 M-voice target of BASELINE.json's north_star
 ALGO_BYTES_PER_VOICE_BLOCK_MIX_ONLY = 4236      # SURVEY.md §8d / DESIGN.md §4: 88 state + 52 params + 4096 delay ring
 METRIC = "Msamples/s (voices x 512-sample blocks / s), 4096-voice SUBSYNTH32 per GPU @ 48 kHz"
+K1_SOURCES = ("render_kernel.cu", "render_ops.inc", "program.h")
 
 
 def measured_hbm_peak():
@@ -43,6 +53,13 @@ def measured_hbm_peak():
         return float(json.load(open(p))["hbm_gbs"]), "measured"
     except Exception:
         return 6650.0, "fallback"
+
+
+def k1_source_sha16():
+    h = hashlib.sha256()
+    for f in K1_SOURCES:
+        h.update(open(os.path.join(ROOT, "elementary_b200", "csrc", f), "rb").read())
+    return h.hexdigest()[:16]
 
 
 class ClockSampler:
@@ -107,46 +124,226 @@ def build_runtime(voices, device, rank, stream_handle=None, **opts):
     return rt
 
 
-def cpu_reference_run(voices, threads, warmup_blocks, blocks, rank0_voice_offset=0):
-    """Time the unmodified reference (or, if oracle/_ref did not travel, nothing) on `threads` host threads."""
+# ---- the reference engine on the host cores ---------------------------------------------------------------------------------
+def cpu_reference_run(voices, threads, warmup_blocks, blocks, min_seconds, voice_offset=0):
+    """Time the unmodified reference (or, if oracle/_ref did not travel, nothing) on `threads` pinned host threads."""
     from elementary_b200 import graphs
     from oracle import oracle as orc
     if not orc.ref_available():
         return None
-    vb = [graphs.subsynth32_voice_props(rank0_voice_offset + v) for v in range(voices)]
-    secs, chk = orc.ref_bench(SR, BS, graphs.subsynth32(), vb, voices, threads, 0, 1, warmup_blocks, blocks)
+    vb = [graphs.subsynth32_voice_props(voice_offset + v) for v in range(voices)]
+    secs, chk, rep = orc.ref_bench(SR, BS, graphs.subsynth32(), vb, voices, threads, 0, 1, warmup_blocks, blocks, min_seconds=min_seconds)
     if secs <= 0:
         return None
-    return {"seconds": secs, "msamples_per_s": voices * BS * blocks / secs / 1e6,
-            "voice_blocks_per_s": voices * blocks / secs, "checksum": chk}
+    nb = blocks * rep
+    return {"seconds": secs, "blocks": nb, "repeats": rep, "msamples_per_s": voices * BS * nb / secs / 1e6,
+            "voice_blocks_per_s": voices * nb / secs, "checksum": chk}
+
+
+def host_description():
+    from oracle import oracle as orc
+    try:
+        model = orc.ref_cpu_model()
+    except Exception:
+        model = "unknown"
+    try:
+        usable = len(os.sched_getaffinity(0))
+    except Exception:
+        usable = os.cpu_count() or 1
+    return {"nproc": os.cpu_count() or 1, "usable_cpus": usable, "cpu_model": model}
 
 
 def run_reference(args, rank, world, emit=print):
     if rank != 0:
         return
-    cores = os.cpu_count() or 1
+    host = host_description()
+    cores = host["usable_cpus"]
     voices = VOICES_PER_GPU * world
-    r = cpu_reference_run(voices, cores, args.warmup, args.steps)
-    if r is None:
+    rall = cpu_reference_run(voices, cores, max(1, args.warmup), args.steps, 2.5)
+    if rall is None:
         emit(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/libelem_ref.so missing (built only where /root/reference exists)"}))
         return
-    ms = r["seconds"] / args.steps * 1e3
-    sample = f"all {voices} voices x {args.steps} blocks of 512 on {cores} host threads (whole workload, not a subset)"
+    r1 = cpu_reference_run(32, 1, 5, 20, 2.0)
+    ms = rall["seconds"] / rall["blocks"] * 1e3
+    sample = (f"all {voices} voices x {args.steps} blocks of 512, rendered {rall['repeats']}x back to back = {rall['seconds']:.2f} s timed, "
+              f"{cores} pinned threads created and warmed up outside the timed region (whole workload, not a subset)")
     line = {
-        "impl": "reference", "metric": METRIC, "value": r["msamples_per_s"], "unit": "Msamples/s", "n_gpus": world,
+        "impl": "reference", "metric": METRIC, "value": rall["msamples_per_s"], "unit": "Msamples/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": f"{VOICES_PER_GPU} SUBSYNTH32 voices per GPU x {world} (BASELINE.json configs[1]), 512-sample blocks, 48 kHz",
                    "engine": "elem::Runtime<float> (unmodified reference, oracle/_ref), one instance per voice, round-robin per thread"},
-        "voice_blocks_per_s": r["voice_blocks_per_s"],
-        "cpu_baseline": {"value": r["msamples_per_s"], "unit": "Msamples/s", "cores": cores, "kind": "reference", "sample": sample},
-        "e2e": {"value": r["msamples_per_s"], "unit": "Msamples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "voice_blocks_per_s": rall["voice_blocks_per_s"],
+        "cpu_baseline": {"value": rall["msamples_per_s"], "unit": "Msamples/s", "cores": cores, "kind": "reference", "sample": sample,
+                         "t1": None if r1 is None else {"value": r1["msamples_per_s"], "unit": "Msamples/s", "cores": 1,
+                                                        "sample": f"32 voices x {r1['blocks']} blocks on one pinned thread, {r1['seconds']:.2f} s"},
+                         "host": host},
+        "e2e": {"value": rall["msamples_per_s"], "unit": "Msamples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     emit(json.dumps(line))
 
 
-def run_b200(args, rank, local_rank, world, emit=print):
+# ---- the CUDA path ----------------------------------------------------------------------------------------------------------
+def class_references(n_blocks):
+    """SUBSYNTH32 has 40 distinct voices (f0 = 55 * (1 + v mod 40)).  Advance one reference engine per class by n_blocks blocks and
+    return the LAST block of each: [40, BS] float32.  Compiled reference if it travelled, else the bit-exact CPU restatement."""
     import numpy as np
+    from elementary_b200 import graphs
+    from oracle import oracle as orc
+    cls = orc.RefRuntime if orc.ref_available() else orc.PortRuntime
+    out = np.zeros((40, BS), dtype=np.float32)
+    for c in range(40):
+        o = cls(SR, BS)
+        assert o.apply(graphs.subsynth32()) == 0 and o.apply(graphs.subsynth32_voice_props(c)) == 0
+        last = None
+        for _ in range(n_blocks):
+            last = o.process(None, 1, BS)
+        out[c] = last[0]
+    return out, cls.__name__
+
+
+def measure(args, voices, steps, warmup, rank, local_rank, world, stream, flush, with_clocks, check_parity):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from elementary_b200.runtime import FLAG_MIX, FLAG_ALLREDUCE, FLAG_VOICE_OUT
+    from elementary_b200.distributed import attach_peer_mix
+
+    extra = {"tile_width": args.tile_width} if args.tile_width else {}
+    extra["specialize"] = args.specialize
+    for kv in args.opt:
+        k, v = kv.split("=")
+        extra[k] = float(v)
+    rt = build_runtime(voices, local_rank, rank, stream.cuda_stream, time_kernels=1, **extra)
+    mix = torch.as_tensor(rt.mix_device(1), device=f"cuda:{local_rank}")
+    host_mix = torch.empty((1, BS), dtype=torch.float32).pin_memory()
+
+    # The single collective of the path: the sum of the [1][512] mix bus over the ranks.  Default: the engine's own
+    # kernel over NVLink/NVSwitch peer memory (K4, launched by enqueue_block in the same stream); --collective nccl
+    # (or a box without peer access) uses torch.distributed.all_reduce instead.
+    fused, fused_note = False, None
+    if world > 1 and args.collective == "fused":
+        try:
+            attach_peer_mix(rt)
+            fused = True
+        except Exception as e:      # reported in the JSON line, never silent
+            fused_note = f"peer attach failed ({e}); NCCL all_reduce used"
+        ok = torch.tensor([1 if fused else 0], device=f"cuda:{local_rank}")
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        fused = bool(int(ok[0]))
+    step_flags = FLAG_MIX | (FLAG_ALLREDUCE if fused else 0)
+    blocks_done = 0
+
+    def step_device(flags=step_flags):
+        nonlocal blocks_done
+        rt.enqueue_block(0, 1, BS, flags)
+        blocks_done += 1
+        if world > 1 and not fused:
+            dist.all_reduce(mix)
+
+    def line_up():
+        """all ranks' streams meet here (device side), so a timed region starts on every GPU together"""
+        if world > 1:
+            if fused:
+                rt.peer_barrier()
+            else:
+                dist.barrier()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- warm-up (also carries every voice past the 20 ms root fade) ----
+    for _ in range(max(3, warmup)):
+        step_device()
+    barrier()
+    rt.take_kernel_time_ms()
+
+    # ---- value: device-resident, per-step CUDA events, L2 flushed between steps ----
+    sampler = ClockSampler(local_rank) if with_clocks and rank == 0 else None
+    if sampler:
+        sampler.start()
+    launches0 = rt.kernel_launches
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+    barrier()
+    t_wall0 = time.perf_counter()
+    for a, b in evs:
+        flush.zero_()
+        line_up()
+        a.record(stream)
+        step_device()
+        b.record(stream)
+    barrier()
+    t_wall = time.perf_counter() - t_wall0
+    dev_ms = sum(a.elapsed_time(b) for a, b in evs)
+    k1_ms, k1_n = rt.take_kernel_time_ms()
+    kinds = rt.last_kernel_times()
+    launches = rt.kernel_launches - launches0      # K1 + K2 (+ K4) per step; the line-up barriers are not counted by the engine
+
+    # ---- e2e: the public call with host buffers (D2H + sync inside) ----
+    barrier()
+    e2e_s = 0.0
+    for _ in range(steps):
+        flush.zero_()
+        line_up()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        if world == 1:
+            rt.process(None, 1, BS)
+            blocks_done += 1
+        else:
+            step_device()
+            if rank == 0:
+                host_mix.copy_(mix[:1], non_blocking=True)
+            stream.synchronize()
+        e2e_s += time.perf_counter() - t0
+    barrier()
+    clocks = sampler.stop() if sampler else None      # nvidia-smi samples cover both timed regions (value and e2e)
+    rt.take_kernel_time_ms()
+
+    # ---- parity of what was just timed: one more block, every voice + the (all-reduced) mix against the reference ----
+    parity = {"parity_checked": False}
+    if check_parity:
+        step_device(step_flags | FLAG_VOICE_OUT)
+        barrier()
+        got = torch.as_tensor(rt.voice_out_device(1), device=f"cuda:{local_rank}")[:, 0].cpu().numpy()
+        got_mix = mix[0].cpu().numpy().astype(np.float64)
+        refs, oracle_name = class_references(blocks_done)
+        tol40 = 1e-5 * np.abs(refs.astype(np.float64)).max(axis=1, keepdims=True) + 1e-7
+        worst, exact = 0.0, 0
+        for v0 in range(0, voices, 8192):                    # chunked: 131072 voices x 512 samples in float64 would be 0.5 GB per temporary
+            cls_of = (rank * voices + np.arange(v0, min(voices, v0 + 8192))) % 40
+            g = got[v0:v0 + 8192]
+            worst = max(worst, float((np.abs(g.astype(np.float64) - refs[cls_of]) / tol40[cls_of]).max()))
+            exact += int((g == refs[cls_of]).sum())
+        counts = np.bincount((np.arange(world * voices)) % 40, minlength=40).astype(np.float64)    # the mix bus is the sum over ALL ranks
+        want_mix = (refs.astype(np.float64) * counts[:, None]).sum(axis=0)
+        mix_tol = 1e-5 * np.abs(want_mix).max() + 1e-7
+        worst_mix = float((np.abs(got_mix - want_mix) / mix_tol).max())
+        w = torch.tensor([worst, worst_mix], dtype=torch.float64, device=f"cuda:{local_rank}")
+        if world > 1:
+            dist.all_reduce(w, op=dist.ReduceOp.MAX)
+        parity = {"parity_checked": True, "worst_err_over_tol": float(w[0]), "mix_worst_err_over_tol": float(w[1]),
+                  "parity_ok": bool(float(w[0]) <= 1.0 and float(w[1]) <= 1.0),
+                  "parity_detail": f"block {blocks_done} of the timed runtime: all {voices} voices per rank vs {oracle_name} (40 f0 classes), "
+                                   f"mix bus vs the float64 sum of the references over all {world * voices} voices; tolerance 1e-5 x block peak",
+                  "bit_exact_rate": exact / float(voices * BS)}
+
+    peer_fail = rt.peer_status() if fused else 0
+    t = torch.tensor([dev_ms, e2e_s * 1e3, kinds["K1"][0], kinds["K2"][0], kinds["K4"][0]], dtype=torch.float64, device=f"cuda:{local_rank}")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    desc = rt.describe()["groups"][0]
+    res = {"voices": voices, "steps": steps, "dev_ms": float(t[0]), "e2e_ms": float(t[1]), "k1_ms": float(t[2]), "k1_n": k1_n,
+           "k2_ms": float(t[3]), "k2_n": kinds["K2"][1], "k4_ms": float(t[4]), "k4_n": kinds["K4"][1],
+           "launches": int(launches), "t_wall": t_wall, "clocks": clocks, "desc": desc, "fused": fused, "fused_note": fused_note,
+           "peer_fail": peer_fail, "parity": parity}
+    rt.close()
+    return res
+
+
+def run_b200(args, rank, local_rank, world, emit=print):
     import torch
     import torch.distributed as dist
 
@@ -161,154 +358,109 @@ def run_b200(args, rank, local_rank, world, emit=print):
     voices = args.voices
     stream = torch.cuda.Stream()
     with torch.cuda.stream(stream):
-        extra = {"tile_width": args.tile_width} if args.tile_width else {}
-        for kv in args.opt:
-            k, v = kv.split("=")
-            extra[k] = float(v)
-        rt = build_runtime(voices, local_rank, rank, stream.cuda_stream, time_kernels=1, **extra)
-        mix = torch.as_tensor(rt.mix_device(1), device=f"cuda:{local_rank}")
         flush = torch.empty(256 << 20, dtype=torch.uint8, device=f"cuda:{local_rank}")
-        host_mix = torch.empty((1, BS), dtype=torch.float32).pin_memory()
-        from elementary_b200.runtime import FLAG_MIX, FLAG_ALLREDUCE
-        from elementary_b200.distributed import attach_peer_mix
-
-        # The single collective of the path: the sum of the [1][512] mix bus over the ranks.  Default: the engine's own
-        # kernel over NVLink/NVSwitch peer memory (K4, launched by enqueue_block in the same stream); --collective nccl
-        # (or a box without peer access) uses torch.distributed.all_reduce instead.
-        fused, fused_note = False, None
-        if world > 1 and args.collective == "fused":
-            try:
-                attach_peer_mix(rt)
-                fused = True
-            except Exception as e:      # reported in the JSON line, never silent
-                fused_note = f"peer attach failed ({e}); NCCL all_reduce used"
-            ok = torch.tensor([1 if fused else 0], device=f"cuda:{local_rank}")
-            dist.all_reduce(ok, op=dist.ReduceOp.MIN)
-            fused = bool(int(ok[0]))
-        step_flags = FLAG_MIX | (FLAG_ALLREDUCE if fused else 0)
-
-        def step_device():
-            rt.enqueue_block(0, 1, BS, step_flags)
-            if world > 1 and not fused:
-                dist.all_reduce(mix)
-
-        def barrier():
-            if world > 1:
-                dist.barrier()
-            torch.cuda.synchronize()
-
-        # ---- warm-up (also carries every voice past the 20 ms root fade) ----
-        for _ in range(max(3, args.warmup)):
-            step_device()
-        barrier()
-        rt.take_kernel_time_ms()
-
-        # ---- value: device-resident, per-step CUDA events, L2 flushed between steps ----
-        sampler = ClockSampler(local_rank)
-        if rank == 0:
-            sampler.start()
-        launches0 = rt.kernel_launches
-        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-        barrier()
-        t_wall0 = time.perf_counter()
-        for a, b in evs:
-            flush.zero_()
-            a.record(stream)
-            step_device()
-            b.record(stream)
-        barrier()
-        t_wall = time.perf_counter() - t_wall0
-        dev_ms = sum(a.elapsed_time(b) for a, b in evs)
-        k1_ms, k1_n = rt.take_kernel_time_ms()
-        launches = rt.kernel_launches - launches0
-
-        # ---- e2e: the public call with host buffers (D2H + sync inside), no flush needed for honesty: flushed too ----
-        barrier()
-        e2e_s = 0.0
-        for _ in range(args.steps):
-            flush.zero_()
-            torch.cuda.synchronize()
-            t0 = time.perf_counter()
-            if world == 1:
-                out = rt.process(None, 1, BS)
-            else:
-                step_device()
-                if rank == 0:
-                    host_mix.copy_(mix[:1], non_blocking=True)
-                stream.synchronize()
-            e2e_s += time.perf_counter() - t0
-        barrier()
-        clocks = sampler.stop() if rank == 0 else None      # nvidia-smi samples cover both timed regions (value and e2e)
-
-        peer_fail = rt.peer_status() if fused else 0
-        t = torch.tensor([dev_ms, e2e_s * 1e3], dtype=torch.float64, device=f"cuda:{local_rank}")
-        if world > 1:
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        dev_ms, e2e_ms = float(t[0]), float(t[1])
+        m = measure(args, voices, args.steps, args.warmup, rank, local_rank, world, stream, flush, True, not args.no_parity)
+        t1 = None
+        if not args.no_t1 and voices != T1_VOICES_PER_GPU:      # row T1: the 1 M-voice target = 131072 voices on each of 8 GPUs
+            t1 = measure(args, T1_VOICES_PER_GPU, min(args.steps, 30), 5, rank, local_rank, world, stream, flush, False, not args.no_parity)
         if world > 1:
             dist.barrier()
             dist.destroy_process_group()
-
     if rank != 0:
         return
-    total_samples = world * voices * BS * args.steps
+
+    steps = args.steps
+    dev_ms, e2e_ms = m["dev_ms"], m["e2e_ms"]
+    total_samples = world * voices * BS * steps
     value = total_samples / (dev_ms * 1e-3) / 1e6
     e2e_value = total_samples / (e2e_ms * 1e-3) / 1e6
     peak, peak_kind = measured_hbm_peak()
-    k1_avg_ms = k1_ms / max(1, k1_n)
+    k1_avg_ms = m["k1_ms"] / max(1, m["k1_n"])
     algo_bytes = ALGO_BYTES_PER_VOICE_BLOCK_MIX_ONLY * voices
     achieved = algo_bytes / (k1_avg_ms * 1e-3) / 1e9 if k1_avg_ms > 0 else 0.0
-    desc = rt.describe()["groups"][0]
-    traffic, ncu = None, None   # from the committed `ncu --set full` capture of this same configuration (profiles/)
+    desc, clocks = m["desc"], m["clocks"]
+    specialised = desc.get("spec_state") == 2
+
+    # ncu numbers (DRAM traffic, instruction count) are only quoted when the capture was made from the K1 sources of THIS build
+    traffic, ncu, issue = None, None, None
+    sha = k1_source_sha16()
     try:
-        tj = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))["render_block_kernel"].get(str(voices))
-        if tj:
+        tj_all = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
+        key = "render_block_kernel_spec" if specialised else "render_block_kernel"
+        tj = tj_all.get(key, {}).get(str(voices))
+        if tj and tj_all.get("k1_source_sha16") == sha:
             traffic = tj["dram_bytes_read"] + tj["dram_bytes_write"]
             ncu = {k: tj[k] for k in ("warp_instructions", "issue_active_pct", "registers_per_thread", "fp64_pipe_pct",
-                                      "active_threads_per_warp_inst", "report") if k in tj}
+                                      "active_threads_per_warp_inst", "report", "local_load_sectors", "local_store_sectors") if k in tj}
             if "warp_instructions" in tj:
                 ncu["warp_instructions_per_voice_sample"] = tj["warp_instructions"] / (voices * BS)
+                clk_hz = ((clocks or {}).get("sm_mhz") or 1965.0) * 1e6
+                slots = 148 * 4 * clk_hz
+                rate = tj["warp_instructions"] / (k1_avg_ms * 1e-3) if k1_avg_ms > 0 else 0.0
+                issue = {"bound": "issue", "achieved": rate / 1e9, "peak": slots / 1e9, "unit": "G warp-instr/s", "frac": rate / slots,
+                         "note": "warp instructions per launch (ncu) / K1 duration (CUDA events) against 148 SMs x 4 schedulers x the SM clock sampled during the run"}
+        elif tj:
+            ncu = {"stale": True, "note": f"profiles/ncu_traffic.json was captured from other K1 sources ({tj_all.get('k1_source_sha16')} != {sha}): not quoted"}
     except Exception:
         pass
 
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
-        cores = os.cpu_count() or 1
-        cv = 16 * cores
-        blocks = 1500
-        r = cpu_reference_run(cv, cores, 20, blocks)
-        if r is not None:
-            cpu = {"value": r["msamples_per_s"], "unit": "Msamples/s", "cores": cores, "kind": "reference",
-                   "sample": f"{cv} voices (16 per thread) x {blocks} blocks of 512, {r['seconds']:.1f} s on {cores} threads, unmodified reference via oracle/_ref"}
+        host = host_description()
+        cores = host["usable_cpus"]
+        rall = cpu_reference_run(16 * cores, cores, 10, 50, 8.0)
+        r1 = cpu_reference_run(16, 1, 5, 20, 3.0)
+        if rall is not None:
+            cpu = {"value": rall["msamples_per_s"], "unit": "Msamples/s", "cores": cores, "kind": "reference",
+                   "sample": f"{16 * cores} voices (16 per thread) x {rall['blocks']} blocks of 512, {rall['seconds']:.1f} s timed on {cores} pinned threads, unmodified reference via oracle/_ref",
+                   "t1": None if r1 is None else {"value": r1["msamples_per_s"], "unit": "Msamples/s", "cores": 1,
+                                                  "sample": f"16 voices x {r1['blocks']} blocks on one pinned thread, {r1['seconds']:.1f} s"},
+                   "host": host}
 
+    fused, fused_note, peer_fail = m["fused"], m["fused_note"], m["peer_fail"]
     line = {
-        "metric": METRIC, "value": value, "unit": "Msamples/s", "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
-        "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "metric": METRIC, "value": value, "unit": "Msamples/s", "n_gpus": world, "steps": steps, "warmup": max(3, args.warmup),
+        "ms_per_step": dev_ms / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
         "config": {"workload": f"{voices} SUBSYNTH32 voices per GPU (BASELINE.json configs[1]: 32-node subtractive synth), 512-sample blocks, 48 kHz",
                    "voices_total": world * voices, "block": BS, "sample_rate": SR,
                    "l2": "flushed between steps (256 MiB memset outside the timed events)",
                    "tile_width": desc["tile_width"], "slots": desc["slots"], "state_rows": desc["state_rows"],
+                   "k1": ("specialised per program (NVRTC, option specialize=%d)" % args.specialize) if specialised else "interpreter",
                    "spec": {k: desc[k] for k in ("spec_state", "spec_regs", "spec_local_bytes", "spec_cubin_bytes", "spec_log") if k in desc},
                    "collective": "none (1 GPU)" if world == 1 else
                                  ("K4 mix_exchange_kernel: all-reduce(sum,f32) of the [1][512] mix bus per block over NVLink peer memory, one launch in the render stream"
                                   + ("" if not peer_fail else " — PEER TIMEOUT REPORTED") if fused else
                                   "NCCL all_reduce(sum,f32) of the [1][512] mix bus per block" + (f" ({fused_note})" if fused_note else ""))},
-        "voice_blocks_per_s": world * voices * args.steps / (dev_ms * 1e-3),
+        "voice_blocks_per_s": world * voices * steps / (dev_ms * 1e-3),
         "realtime_factor": value * 1e6 / (world * voices * SR),
-        "wall_ms_per_step_incl_flush": t_wall / args.steps * 1e3,
+        "wall_ms_per_step_incl_flush": m["t_wall"] / steps * 1e3,
         "e2e": {"value": e2e_value, "unit": "Msamples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 4 * BS,
-                "ms_per_step": e2e_ms / args.steps, "api": "elem_b200_process (host out buffers)" if world == 1 else
+                "ms_per_step": e2e_ms / steps, "api": "elem_b200_process (host out buffers)" if world == 1 else
                        ("elem_b200_enqueue_block (render + K4 cross-GPU mix) + D2H of the mix bus" if fused else "elem_b200_enqueue_block + NCCL all_reduce + D2H of the mix bus")},
-        "gpu_launches": int(launches),
+        "gpu_launches": m["launches"],
+        "kernel_ms": {"K1_render": k1_avg_ms, "K2_mix_reduce": m["k2_ms"] / max(1, m["k2_n"]),
+                      "K4_mix_exchange": (m["k4_ms"] / m["k4_n"]) if m["k4_n"] else None,
+                      "note": "mean device time per launch, CUDA events around each launch on the render stream, max over ranks"},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": traffic, "peak_kind": f"of {peak_kind}", "kernel": "render_block_kernel<NITER,LOGL> (K1)",
-                     "kernel_ms": k1_avg_ms, "kernel_launches_timed": k1_n, "ncu": ncu,
-                     "algorithmic_bytes_per_launch": algo_bytes,
+                     "traffic": traffic, "peak_kind": f"of {peak_kind}", "kernel": "render_block_kernel<NITER,LOGL> (K1)" + (" specialised" if specialised else ""),
+                     "kernel_ms": k1_avg_ms, "kernel_launches_timed": m["k1_n"], "ncu": ncu, "k1_source_sha16": sha,
+                     "algorithmic_bytes_per_launch": algo_bytes, "issue_slots": issue,
                      "note": "K1 is instruction-issue bound, not HBM bound (intermediates never leave the SM); see DESIGN.md section 4"},
         "clocks": clocks,
         "cpu_baseline": cpu,
     }
+    line.update(m["parity"])
+    if t1 is not None:
+        ms = t1["dev_ms"] / t1["steps"]
+        line["t1_million_voices"] = {
+            "voices_per_gpu": T1_VOICES_PER_GPU, "voices_total": world * T1_VOICES_PER_GPU, "ms_per_block": ms,
+            "block_budget_ms": BS / SR * 1e3, "realtime_factor": (BS / SR * 1e3) / ms,
+            "value": world * T1_VOICES_PER_GPU * BS / (ms * 1e-3) / 1e6, "unit": "Msamples/s",
+            "k1_ms": t1["k1_ms"] / max(1, t1["k1_n"]), "tile_width": t1["desc"]["tile_width"],
+            "k1": "specialised" if t1["desc"].get("spec_state") == 2 else "interpreter",
+            "hbm_frac": (ALGO_BYTES_PER_VOICE_BLOCK_MIX_ONLY * T1_VOICES_PER_GPU / (t1["k1_ms"] / max(1, t1["k1_n"]) * 1e-3) / 1e9) / peak,
+            "steps": t1["steps"], **t1["parity"]}
     emit(json.dumps(line))
 
 
@@ -320,6 +472,9 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--voices", type=int, default=VOICES_PER_GPU, help="voices per GPU (default: the BASELINE config)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-parity", action="store_true", help="skip the parity check of the timed runtime (exploration only)")
+    ap.add_argument("--no-t1", action="store_true", help="skip the extra 131072-voices-per-GPU measurement")
+    ap.add_argument("--specialize", type=int, default=2, help="K1 per-program specialisation: 0 interpreter, 2 NVRTC at COMMIT (default)")
     ap.add_argument("--collective", default="fused", choices=["fused", "nccl"], help="N > 1: K4 peer-memory kernel (default) or NCCL all_reduce")
     ap.add_argument("--tile-width", type=int, default=0, help="override the voices-per-warp heuristic (exploration only)")
     ap.add_argument("--opt", action="append", default=[], help="extra runtime option key=value (exploration only)")

@@ -88,6 +88,7 @@ int elem_b200_peer_attach(elem_b200_runtime* rt, int rank, int world, const void
     GUARD(rt->engine->peerAttach(rank, world, handles));
 }
 int elem_b200_peer_status(elem_b200_runtime* rt) { return rt ? rt->engine->peerStatus() : 0; }
+int elem_b200_peer_barrier(elem_b200_runtime* rt) { GUARD(rt->engine->peerBarrier()); }
 
 int elem_b200_synchronize(elem_b200_runtime* rt) { GUARD(rt->engine->synchronize()); }
 
@@ -189,6 +190,13 @@ double elem_b200_take_kernel_time_ms(elem_b200_runtime* rt, uint64_t* count) {
 double elem_b200_last_convolve_time_ms(elem_b200_runtime* rt, uint64_t* count) {
     if (!rt) { if (count) *count = 0; return 0.0; }
     return rt->engine->lastConvolveTimeMs(count);
+}
+
+void elem_b200_last_kernel_times(elem_b200_runtime* rt, double* ms4, uint64_t* counts4) {
+    double ms[4] = {0, 0, 0, 0};
+    uint64_t n[4] = {0, 0, 0, 0};
+    if (rt) rt->engine->lastKernelTimes(ms, n);
+    for (int i = 0; i < 4; ++i) { if (ms4) ms4[i] = ms[i]; if (counts4) counts4[i] = n[i]; }
 }
 
 const char* elem_b200_last_error(elem_b200_runtime* rt) {

@@ -185,7 +185,8 @@ Engine::~Engine() {
     if (dInShared_) dfree(dInShared_);
     if (hPinned_ && !planOnly_) cudaFreeHost(hPinned_);
     for (auto& kv : batch_) { if (kv.second.dDescs) dfree(kv.second.dDescs); if (kv.second.dTileStart) dfree(kv.second.dTileStart); }
-    for (auto& ev : timedEvents_) { cudaEventDestroy(ev.first); cudaEventDestroy(ev.second); }
+    for (auto* l : {&timedEvents_, &timedMixEvents_, &timedConvEvents_, &timedXchgEvents_})
+        for (auto& ev : *l) { cudaEventDestroy(ev.first); cudaEventDestroy(ev.second); }
     for (auto& ev : eventPool_) { cudaEventDestroy(ev.first); cudaEventDestroy(ev.second); }
     if (ownStream_ && stream_) cudaStreamDestroy(stream_);
 }
@@ -2026,16 +2027,28 @@ int Engine::enqueueBlock(size_t nIn, size_t nOut, size_t numSamples, bool perVoi
         if (timeKernels_) { cudaEventRecord(ev.second, stream_); timedEvents_.push_back(ev); }
         ++launches_;
     }
+    // With the cross-GPU sum behind it, K2 leaves this rank's partial mix directly in its own slot of the exchange buffer (K4 pushes
+    // it to the peers from there and writes the total to the mix bus): no staging copy, no in-place hazard between K4's CTAs.
+    const bool exchange = mix && allReduce && peerAttached_ && peer_.world > 1;
+    float* mixOut = dMix_;
+    if (exchange) {
+        ++peerEpoch_;
+        mixOut = peer_.slot[peer_.rank] + (size_t) ((peerEpoch_ & 1u) * MAX_PEERS + peer_.rank) * peer_.stride;
+    }
     if (mix) {
         if (tileBase > 0) {
-            if (!cuda(launch_mix_reduce(dPartial_, dMix_, dMixScratch_, dMixTickets_, tileBase, (int) nOut, blockSize_, (int) numSamples, stream_), "mix reduce launch")) return rc::CudaError;
+            auto ev = timedBegin();
+            if (!cuda(launch_mix_reduce(dPartial_, mixOut, dMixScratch_, dMixTickets_, tileBase, (int) nOut, blockSize_, (int) numSamples, stream_), "mix reduce launch")) return rc::CudaError;
+            if (timeKernels_) { cudaEventRecord(ev.second, stream_); timedMixEvents_.push_back(ev); }
             ++launches_;
         } else {
-            dmemset(dMix_, 0, sizeof(float) * nOut * blockSize_);
+            dmemset(mixOut, 0, sizeof(float) * nOut * blockSize_);
         }
     }
-    if (mix && allReduce && peerAttached_ && peer_.world > 1) {   // K4: the cross-GPU sum of the mix bus, in the same stream
-        if (!cuda(launch_mix_exchange(peer_, dMix_, (int) (nOut * blockSize_), ++peerEpoch_, dPeerStatus_, stream_), "mix exchange launch")) return rc::CudaError;
+    if (exchange) {   // K4: the cross-GPU sum of the mix bus, in the same stream
+        auto ev = timedBegin();
+        if (!cuda(launch_mix_exchange(peer_, dMix_, (int) (nOut * blockSize_), peerEpoch_, dPeerStatus_, stream_), "mix exchange launch")) return rc::CudaError;
+        if (timeKernels_) { cudaEventRecord(ev.second, stream_); timedXchgEvents_.push_back(ev); }
         ++launches_;
     }
     curNOut_ = nOut;
@@ -2043,25 +2056,38 @@ int Engine::enqueueBlock(size_t nIn, size_t nOut, size_t numSamples, bool perVoi
     return rc::Ok;
 }
 
+std::pair<cudaEvent_t, cudaEvent_t> Engine::timedBegin() {
+    std::pair<cudaEvent_t, cudaEvent_t> ev{nullptr, nullptr};
+    if (!timeKernels_) return ev;
+    if (!eventPool_.empty()) { ev = eventPool_.back(); eventPool_.pop_back(); }
+    else { cudaEventCreate(&ev.first); cudaEventCreate(&ev.second); }
+    cudaEventRecord(ev.first, stream_);
+    return ev;
+}
+
+int Engine::peerBarrier() {
+    if (planOnly_ || !peerAttached_ || peer_.world <= 1) return rc::Ok;
+    dsetdev();
+    if (!cuda(launch_mix_exchange(peer_, dMix_, 0, ++peerEpoch_, dPeerStatus_, stream_), "peer barrier launch")) return rc::CudaError;
+    return rc::Ok;
+}
+
 double Engine::takeKernelTimeMs(uint64_t* count) {
     if (planOnly_) { if (count) *count = 0; return 0.0; }
     cudaStreamSynchronize(stream_);
-    double total = 0.0;
-    for (auto& ev : timedEvents_) {
-        float ms = 0.0f;
-        if (cudaEventElapsedTime(&ms, ev.first, ev.second) == cudaSuccess) total += ms;
-        eventPool_.push_back(ev);
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>>* lists[4] = {&timedEvents_, &timedMixEvents_, &timedConvEvents_, &timedXchgEvents_};
+    for (int k = 0; k < 4; ++k) {
+        lastKindMs_[k] = 0.0; lastKindCount_[k] = lists[k]->size();
+        for (auto& ev : *lists[k]) {
+            float ms = 0.0f;
+            if (cudaEventElapsedTime(&ms, ev.first, ev.second) == cudaSuccess) lastKindMs_[k] += ms;
+            eventPool_.push_back(ev);
+        }
+        lists[k]->clear();
     }
-    if (count) *count = timedEvents_.size();
-    timedEvents_.clear();
-    lastConvMs_ = 0.0; lastConvCount_ = timedConvEvents_.size();
-    for (auto& ev : timedConvEvents_) {
-        float ms = 0.0f;
-        if (cudaEventElapsedTime(&ms, ev.first, ev.second) == cudaSuccess) lastConvMs_ += ms;
-        eventPool_.push_back(ev);
-    }
-    timedConvEvents_.clear();
-    return total;
+    lastConvMs_ = lastKindMs_[2]; lastConvCount_ = lastKindCount_[2];
+    if (count) *count = lastKindCount_[0];
+    return lastKindMs_[0];
 }
 
 int Engine::synchronize() {

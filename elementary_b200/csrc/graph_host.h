@@ -215,6 +215,10 @@ public:
     double takeKernelTimeMs(uint64_t* count);
     // K3 time/count gathered by the same takeKernelTimeMs() call
     double lastConvolveTimeMs(uint64_t* count) const { if (count) *count = lastConvCount_; return lastConvMs_; }
+    // per kernel kind (0 = K1 render, 1 = K2 mix reduce, 2 = K3 convolve, 3 = K4 mix exchange): summed ms and launch counts of the same call
+    void lastKernelTimes(double ms[4], uint64_t counts[4]) const { for (int i = 0; i < 4; ++i) { ms[i] = lastKindMs_[i]; counts[i] = lastKindCount_[i]; } }
+    // A cross-GPU barrier on the render stream (K4 with an empty payload): returns once every rank's stream has reached it.
+    int peerBarrier();
     std::string describe() const;
     // The encoded render program (program.h) of the voice group containing `voice` — the newest compiled one.  Introspection:
     // tests, and the input of per-program kernel specialisation.
@@ -235,8 +239,10 @@ private:
     uint64_t launches_ = 0;
     int64_t sampleTime_ = 0;
     bool timeKernels_ = false;
-    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> timedEvents_, timedConvEvents_, eventPool_;
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> timedEvents_, timedConvEvents_, timedMixEvents_, timedXchgEvents_, eventPool_;
     double lastConvMs_ = 0.0; uint64_t lastConvCount_ = 0;
+    double lastKindMs_[4] = {0, 0, 0, 0}; uint64_t lastKindCount_[4] = {0, 0, 0, 0};   // K1, K2, K3, K4 of the latest takeKernelTimeMs()
+    std::pair<cudaEvent_t, cudaEvent_t> timedBegin();
 
     // I/O staging
     float* dMix_ = nullptr;          // [MAX_OUT][blockSize]

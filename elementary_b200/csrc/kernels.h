@@ -23,9 +23,10 @@ constexpr int MIX_REDUCE_MAX_GROUPS = 16;
 cudaError_t launch_mix_reduce(const float* partial, float* out, float* scratch, unsigned int* tickets, int nTiles, int nOut, int blockSize,
                               int numSamples, cudaStream_t stream);
 
-// K4: the one collective of the path as our own kernel over NVLink/NVSwitch peer memory: every rank stores
-// its partial mix bus into a slot of every rank's exchange buffer, raises a flag there, waits for the flags of all sources in
-// its own buffer and sums the slots in rank order — one launch, deterministic, no NCCL call on the data path.
+// K4: the one collective of the path as our own kernel over NVLink/NVSwitch peer memory: K2 leaves this rank's
+// partial mix bus in the rank's own slot of its exchange buffer; world-1 CTAs each push it into one peer's buffer, raise a flag there,
+// wait for the flags of all sources in their own buffer and sum a share of the samples over the slots in rank order — one launch,
+// deterministic, no NCCL call on the data path.  count = 0 makes it a cross-GPU stream barrier.
 constexpr int MAX_PEERS = 8;
 struct PeerMix {
     float* slot[MAX_PEERS];       // slot[p]: rank p's exchange buffer [2][MAX_PEERS][stride] (peer-mapped for p != rank)

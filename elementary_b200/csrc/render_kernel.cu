@@ -882,38 +882,53 @@ __device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v) { asm vo
 __device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) { uint32_t v; asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory"); return v; }
 __device__ __forceinline__ float ld_volatile_f32(const float* p) { float v; asm volatile("ld.volatile.global.f32 %0, [%1];" : "=f"(v) : "l"(p) : "memory"); return v; }
 
-__global__ void __launch_bounds__(512) mix_exchange_kernel(const PeerMix pm, float* __restrict__ mix, int count, uint32_t epoch, int* status) {
-    const int tid = threadIdx.x;
+// grid = world - 1 CTAs.  CTA b PUSHES this rank's partial mix (left in the rank's own slot [parity][rank] of its exchange buffer by
+// K2) into the same slot of ONE peer — peer (rank + 1 + b) mod world, so at any moment every link carries one stream — fences and
+// raises flag[parity][rank] there; then every CTA waits (bounded) until the flags of all remote sources show this epoch in its OWN
+// buffer (local polling: the peers' stores come to us, we never read over the link) and sums its 1/(world-1) share of the samples
+// over the slots in rank order — every rank computes the bit-identical float sum — into the mix bus.  Two parities: a rank can be
+// one epoch ahead of a slow peer, never two (it needs the peer's flag of epoch e+1, which the peer raises after finishing e).
+// count = 0 is a pure barrier.
+__global__ void __launch_bounds__(256) mix_exchange_kernel(const PeerMix pm, float* __restrict__ mix, int count, uint32_t epoch, int* status) {
+    const int tid = threadIdx.x, b = blockIdx.x, nb = gridDim.x;
     const int parity = (int) (epoch & 1u);
-    // 1. publish this rank's partial mix into slot [parity][rank] of every rank (NVLink stores for the peers)
-    for (int p = 0; p < pm.world; ++p) {
+    const float* own = pm.slot[pm.rank] + (size_t) parity * MAX_PEERS * pm.stride;             // [src rank][stride] in OUR buffer
+    {   // 1. push
+        const int p = (pm.rank + 1 + b) % pm.world;
+        const float* src = own + (size_t) pm.rank * pm.stride;
         float* dst = pm.slot[p] + (size_t) (parity * MAX_PEERS + pm.rank) * pm.stride;
-        for (int i = tid; i < count; i += blockDim.x) dst[i] = mix[i];
+        if ((count & 3) == 0) {
+            for (int i = tid; i < (count >> 2); i += blockDim.x) reinterpret_cast<float4*>(dst)[i] = reinterpret_cast<const float4*>(src)[i];
+        } else {
+            for (int i = tid; i < count; i += blockDim.x) dst[i] = src[i];
+        }
+        __threadfence_system();
+        __syncthreads();
+        if (tid == 0) st_release_sys(pm.flag[p] + parity * MAX_PEERS + pm.rank, epoch);
     }
-    __threadfence_system();
-    __syncthreads();
-    if (tid < pm.world) st_release_sys(pm.flag[tid] + parity * MAX_PEERS + pm.rank, epoch);
-    // 2. wait until every source has published this epoch into OUR buffer (bounded spin: a dead peer must not hang the GPU)
-    if (tid < pm.world) {
+    // 2. wait until every remote source has published this epoch into OUR buffer (bounded spin: a dead peer must not hang the GPU)
+    if (tid < pm.world && tid != pm.rank) {
         const uint32_t* f = pm.flag[pm.rank] + parity * MAX_PEERS + tid;
         const long long t0 = clock64();
         while (ld_acquire_sys(f) != epoch) {
             if (clock64() - t0 > 2000000000ll) { if (status) *status = 1; break; }   // ~1 s
-            __nanosleep(64);
+            __nanosleep(32);
         }
     }
     __syncthreads();
-    // 3. sum the slots in rank order: every rank computes the identical float sum
-    const float* mine = pm.slot[pm.rank] + (size_t) parity * MAX_PEERS * pm.stride;
-    for (int i = tid; i < count; i += blockDim.x) {
+    // 3. sum this CTA's share of the samples over the slots in rank order
+    const int per = (count + nb - 1) / nb;
+    const int i1 = min(count, (b + 1) * per);
+    for (int i = b * per + tid; i < i1; i += blockDim.x) {
         float s = 0.0f;
-        for (int src = 0; src < pm.world; ++src) s += ld_volatile_f32(mine + (size_t) src * pm.stride + i);
+        for (int src = 0; src < pm.world; ++src) s += ld_volatile_f32(own + (size_t) src * pm.stride + i);
         mix[i] = s;
     }
 }
 
 cudaError_t launch_mix_exchange(const PeerMix& pm, float* mix, int count, uint32_t epoch, int* status, cudaStream_t stream) {
-    mix_exchange_kernel<<<1, 512, 0, stream>>>(pm, mix, count, epoch, status);
+    if (pm.world < 2) return cudaSuccess;
+    mix_exchange_kernel<<<pm.world - 1, 256, 0, stream>>>(pm, mix, count, epoch, status);
     return cudaGetLastError();
 }
 

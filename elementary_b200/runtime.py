@@ -71,6 +71,9 @@ def load_library() -> C.CDLL:
     lib.elem_b200_peer_attach.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_char_p]
     lib.elem_b200_peer_status.restype = C.c_int
     lib.elem_b200_peer_status.argtypes = [C.c_void_p]
+    lib.elem_b200_peer_barrier.restype = C.c_int
+    lib.elem_b200_peer_barrier.argtypes = [C.c_void_p]
+    lib.elem_b200_last_kernel_times.argtypes = [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_uint64)]
     lib.elem_b200_synchronize.restype = C.c_int
     lib.elem_b200_synchronize.argtypes = [C.c_void_p]
     for name in ("elem_b200_mix_device", "elem_b200_voice_out_device"):
@@ -243,6 +246,10 @@ class Runtime:
     def peer_status(self) -> int:
         return int(self._lib.elem_b200_peer_status(self._h))
 
+    def peer_barrier(self) -> None:
+        """Enqueue a cross-GPU barrier on the render stream (no-op without attached peers)."""
+        self._check(self._lib.elem_b200_peer_barrier(self._h), "peer_barrier")
+
     def synchronize(self) -> None:
         self._check(self._lib.elem_b200_synchronize(self._h), "synchronize")
 
@@ -344,6 +351,13 @@ class Runtime:
         n = C.c_uint64(0)
         ms = self._lib.elem_b200_take_kernel_time_ms(self._h, C.byref(n))
         return float(ms), int(n.value)
+
+    def last_kernel_times(self) -> dict:
+        """{"K1": (ms, n), "K2": ..., "K3": ..., "K4": ...} gathered by the latest take_kernel_time_ms()."""
+        ms = (C.c_double * 4)()
+        n = (C.c_uint64 * 4)()
+        self._lib.elem_b200_last_kernel_times(self._h, ms, n)
+        return {k: (float(ms[i]), int(n[i])) for i, k in enumerate(("K1", "K2", "K3", "K4"))}
 
     def last_convolve_time_ms(self):
         """(summed device ms of the K3 launches, count) gathered by the latest take_kernel_time_ms()."""

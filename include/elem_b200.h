@@ -85,6 +85,10 @@ void elem_b200_set_stream(elem_b200_runtime* rt, void* cudaStream);    /* run on
 int elem_b200_peer_export(elem_b200_runtime* rt, void* handleOut64);
 int elem_b200_peer_attach(elem_b200_runtime* rt, int rank, int world, const void* handles);
 int elem_b200_peer_status(elem_b200_runtime* rt);
+/* A cross-GPU barrier enqueued on the render stream (the exchange kernel with an empty payload): the stream passes it once the
+ * streams of all attached ranks have reached theirs.  Lets a host line the GPUs up before a timed region without a host-side
+ * collective.  No-op (0) without attached peers. */
+int elem_b200_peer_barrier(elem_b200_runtime* rt);
 
 /* Runtime::addSharedResource(name, unique_ptr<SharedResource>) — Runtime.h:83,462-465;
  * AudioBufferResource copies the samples (AudioBufferResource.h:13-24).  Returns 1 on success, 0 when the
@@ -137,6 +141,9 @@ uint64_t elem_b200_kernel_launches(elem_b200_runtime* rt);
 double elem_b200_take_kernel_time_ms(elem_b200_runtime* rt, uint64_t* count);
 /* Same for the K3 convolver launches, as gathered by the most recent elem_b200_take_kernel_time_ms() call. */
 double elem_b200_last_convolve_time_ms(elem_b200_runtime* rt, uint64_t* count);
+/* Per kernel kind, as gathered by the most recent elem_b200_take_kernel_time_ms() call: ms[4] / counts[4] = summed device ms and
+ * launch counts of K1 (render), K2 (mix reduce), K3 (convolver), K4 (cross-GPU mix exchange). */
+void elem_b200_last_kernel_times(elem_b200_runtime* rt, double* ms4, uint64_t* counts4);
 const char* elem_b200_last_error(elem_b200_runtime* rt);
 /* ReturnCode::describe — runtime/elem/Types.h:62-85 */
 const char* elem_b200_describe_return_code(int code);
