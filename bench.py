@@ -132,11 +132,10 @@ def cpu_reference_run(voices, threads, warmup_blocks, blocks, min_seconds, voice
     if not orc.ref_available():
         return None
     vb = [graphs.subsynth32_voice_props(voice_offset + v) for v in range(voices)]
-    secs, chk, rep = orc.ref_bench(SR, BS, graphs.subsynth32(), vb, voices, threads, 0, 1, warmup_blocks, blocks, min_seconds=min_seconds)
+    secs, chk, nb = orc.ref_bench(SR, BS, graphs.subsynth32(), vb, voices, threads, 0, 1, warmup_blocks, blocks, min_seconds=min_seconds)
     if secs <= 0:
         return None
-    nb = blocks * rep
-    return {"seconds": secs, "blocks": nb, "repeats": rep, "msamples_per_s": voices * BS * nb / secs / 1e6,
+    return {"seconds": secs, "blocks": nb, "msamples_per_s": voices * BS * nb / secs / 1e6,
             "voice_blocks_per_s": voices * nb / secs, "checksum": chk}
 
 
@@ -150,7 +149,23 @@ def host_description():
         usable = len(os.sched_getaffinity(0))
     except Exception:
         usable = os.cpu_count() or 1
-    return {"nproc": os.cpu_count() or 1, "usable_cpus": usable, "cpu_model": model}
+    quota = None                       # a container CPU quota (cgroup v2 cpu.max / v1 cfs_quota) bounds the cores the threads really get
+    try:
+        q, per = open("/sys/fs/cgroup/cpu.max").read().split()[:2]
+        if q != "max":
+            quota = float(q) / float(per)
+    except Exception:
+        try:
+            q = float(open("/sys/fs/cgroup/cpu/cpu.cfs_quota_us").read()); per = float(open("/sys/fs/cgroup/cpu/cpu.cfs_period_us").read())
+            if q > 0:
+                quota = q / per
+        except Exception:
+            pass
+    try:
+        load1 = float(open("/proc/loadavg").read().split()[0])
+    except Exception:
+        load1 = None
+    return {"nproc": os.cpu_count() or 1, "usable_cpus": usable, "cgroup_cpu_quota": quota, "loadavg_1m_before": load1, "cpu_model": model}
 
 
 def run_reference(args, rank, world, emit=print):
@@ -165,7 +180,7 @@ def run_reference(args, rank, world, emit=print):
         return
     r1 = cpu_reference_run(32, 1, 5, 20, 2.0)
     ms = rall["seconds"] / rall["blocks"] * 1e3
-    sample = (f"all {voices} voices x {args.steps} blocks of 512, rendered {rall['repeats']}x back to back = {rall['seconds']:.2f} s timed, "
+    sample = (f"all {voices} voices, {rall['blocks']:.1f} blocks of 512 each in {rall['seconds']:.2f} s (time-bounded, >= {args.steps} blocks), "
               f"{cores} pinned threads created and warmed up outside the timed region (whole workload, not a subset)")
     line = {
         "impl": "reference", "metric": METRIC, "value": rall["msamples_per_s"], "unit": "Msamples/s", "n_gpus": world,
@@ -176,7 +191,7 @@ def run_reference(args, rank, world, emit=print):
         "voice_blocks_per_s": rall["voice_blocks_per_s"],
         "cpu_baseline": {"value": rall["msamples_per_s"], "unit": "Msamples/s", "cores": cores, "kind": "reference", "sample": sample,
                          "t1": None if r1 is None else {"value": r1["msamples_per_s"], "unit": "Msamples/s", "cores": 1,
-                                                        "sample": f"32 voices x {r1['blocks']} blocks on one pinned thread, {r1['seconds']:.2f} s"},
+                                                        "sample": f"32 voices x {r1['blocks']:.0f} blocks on one pinned thread, {r1['seconds']:.2f} s"},
                          "host": host},
         "e2e": {"value": rall["msamples_per_s"], "unit": "Msamples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
@@ -408,13 +423,13 @@ def run_b200(args, rank, local_rank, world, emit=print):
     if world == 1 and not args.no_cpu_baseline:
         host = host_description()
         cores = host["usable_cpus"]
-        rall = cpu_reference_run(16 * cores, cores, 10, 50, 8.0)
+        rall = cpu_reference_run(16 * cores, cores, 10, 50, 10.0)
         r1 = cpu_reference_run(16, 1, 5, 20, 3.0)
         if rall is not None:
             cpu = {"value": rall["msamples_per_s"], "unit": "Msamples/s", "cores": cores, "kind": "reference",
-                   "sample": f"{16 * cores} voices (16 per thread) x {rall['blocks']} blocks of 512, {rall['seconds']:.1f} s timed on {cores} pinned threads, unmodified reference via oracle/_ref",
+                   "sample": f"{16 * cores} voices (16 per thread) x {rall['blocks']:.0f} blocks of 512, {rall['seconds']:.1f} s timed on {cores} pinned threads, unmodified reference via oracle/_ref",
                    "t1": None if r1 is None else {"value": r1["msamples_per_s"], "unit": "Msamples/s", "cores": 1,
-                                                  "sample": f"16 voices x {r1['blocks']} blocks on one pinned thread, {r1['seconds']:.1f} s"},
+                                                  "sample": f"16 voices x {r1['blocks']:.0f} blocks on one pinned thread, {r1['seconds']:.1f} s"},
                    "host": host}
 
     fused, fused_note, peer_fail = m["fused"], m["fused_note"], m["peer_fail"]

@@ -15,6 +15,7 @@ namespace eb {
 // ---------------------------------------------------------------------------------------------------------
 // K4 plumbing: exchange buffers mapped across the ranks of one box with CUDA IPC (one process per GPU)
 int Engine::peerExport(void* handleOut64) {
+    Lock lk(mu_);
     if (planOnly_) return fail(rc::CudaError, "plan-only runtime has no device memory to export");
     dsetdev();
     if (!dExchange_) {
@@ -34,6 +35,7 @@ int Engine::peerExport(void* handleOut64) {
 }
 
 int Engine::peerAttach(int rank, int world, const void* handles) {
+    Lock lk(mu_);
     if (planOnly_) return fail(rc::CudaError, "plan-only runtime cannot attach peers");
     if (world < 1 || world > MAX_PEERS || rank < 0 || rank >= world || !dExchange_) return fail(rc::BadArgument, "peerAttach: bad rank/world, or peerExport was not called");
     dsetdev();
@@ -56,6 +58,7 @@ int Engine::peerAttach(int rank, int world, const void* handles) {
 }
 
 int Engine::peerStatus() {
+    Lock lk(mu_);
     if (!dPeerStatus_) return 0;
     int st = 0;
     cudaStreamSynchronize(stream_);
@@ -122,6 +125,7 @@ static void realFftFloatIO(const std::vector<float>& x, std::vector<float>& re, 
 }
 
 int Engine::processQueuedEvents(int vb, int ve, EventFn cb, void* user) {
+    Lock lk(mu_);
     if (planOnly_) return rc::Ok;
     dsetdev();
     if (vb < 0) vb = 0;

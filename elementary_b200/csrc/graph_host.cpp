@@ -63,6 +63,7 @@ cudaError_t Engine::dmemcpySync(void* dst, const void* src, size_t bytes, cudaMe
 void Engine::dsync() { if (!planOnly_ && stream_) cudaStreamSynchronize(stream_); }
 void Engine::dsetdev() { if (!planOnly_) cudaSetDevice(device_); }
 void Engine::setStream(cudaStream_t s) {
+    Lock lk(mu_);
     if (planOnly_) return;
     if (ownStream_ && stream_) { cudaStreamSynchronize(stream_); cudaStreamDestroy(stream_); }
     stream_ = s; ownStream_ = false;
@@ -198,6 +199,7 @@ bool Engine::cuda(cudaError_t e, const char* what) {
 }
 
 int Engine::setOption(const char* key, double value) {
+    Lock lk(mu_);
     const std::string k(key);
     if (k == "tile_width") { opt_.tileWidth = (int) value; }
     else if (k == "warps_per_cta") { opt_.warpsPerCta = (int) value; }
@@ -209,11 +211,13 @@ int Engine::setOption(const char* key, double value) {
     else if (k == "specialize_max_words") { opt_.specializeMaxWords = (int) value; }
     else if (k == "specialize_strict") { opt_.specializeStrict = value != 0; }
     else if (k == "time_kernels") { timeKernels_ = value != 0 && !planOnly_; }
+    else if (k == "plan_dry_run") { planDryRun_ = value != 0 && planOnly_; }
     else return rc::BadArgument;
     return rc::Ok;
 }
 
 std::string Engine::describe() const {
+    Lock lk(mu_);
     std::ostringstream os;
     os << "{\"voices\":" << numVoices_ << ",\"groups\":[";
     bool first = true;
@@ -247,6 +251,7 @@ std::string Engine::describe() const {
 }
 
 long Engine::specializeDryRun(int voice, std::string& log) {
+    Lock lk(mu_);
     for (auto& g : groups_) {
         if (voice < g->v0 || voice >= g->v0 + g->nv) continue;
         auto& p = g->pending ? g->pending : g->active;
@@ -261,6 +266,7 @@ long Engine::specializeDryRun(int voice, std::string& log) {
 }
 
 std::vector<uint32_t> Engine::programWords(int voice) const {
+    Lock lk(mu_);
     for (auto& g : groups_) {
         if (voice < g->v0 || voice >= g->v0 + g->nv) continue;
         auto& p = g->pending ? g->pending : g->active;
@@ -331,6 +337,7 @@ int Engine::uploadArray(std::shared_ptr<DeviceArray>& out, const void* data, siz
 }
 
 int Engine::addSharedResource(const char* name, const float* const* chans, size_t nCh, size_t nSamples) {
+    Lock lk(mu_);
     // insert-only: SharedResource.h:44-46 (emplace fails on an existing key)
     if (resources_.count(name)) return 0;
     auto r = std::make_shared<Resource>();
@@ -342,7 +349,8 @@ int Engine::addSharedResource(const char* name, const float* const* chans, size_
     return 1;
 }
 
-void Engine::pruneSharedResources() {   // SharedResource.h:93-101: drop entries nobody else references
+void Engine::pruneSharedResources() {
+    Lock lk(mu_);   // SharedResource.h:93-101: drop entries nobody else references
     dsync();
     for (auto it = resources_.begin(); it != resources_.end();) {
         if (it->second.use_count() == 1) {
@@ -353,6 +361,7 @@ void Engine::pruneSharedResources() {   // SharedResource.h:93-101: drop entries
 }
 
 std::vector<std::string> Engine::listSharedResources() const {
+    Lock lk(mu_);
     std::vector<std::string> out;
     for (auto& kv : resources_) out.push_back(kv.first);
     return out;
@@ -847,16 +856,20 @@ int Engine::splitGroupsAt(int v) {
 }
 
 int Engine::applyInstructions(int vb, int ve, const char* json, size_t len) {
+    Value doc;
+    bool parsed = true;
+    std::string parseError;
+    try {
+        doc = parseJson(json, len);           // outside the lock: the render thread never waits for a JSON parse
+    } catch (const std::exception& e) {   // the reference throws here (JSON.h:146-154); the C ABI maps it to a code
+        parsed = false; parseError = e.what();
+    }
+    Lock lk(mu_);
     dsetdev();
     if (vb < 0) vb = 0;
     if (ve < 0 || ve > numVoices_) ve = numVoices_;
     if (vb >= ve) return fail(rc::BadArgument, "empty voice range");
-    Value doc;
-    try {
-        doc = parseJson(json, len);
-    } catch (const std::exception& e) {   // the reference throws here (JSON.h:146-154); the C ABI maps it to a code
-        return fail(rc::InvalidInstructionFormat, e.what());
-    }
+    if (!parsed) return fail(rc::InvalidInstructionFormat, parseError);
     if (!doc.isArray()) return fail(rc::InvalidInstructionFormat, "batch is not an array");
     auto& batch = doc.asArray();
 
@@ -875,6 +888,7 @@ int Engine::applyInstructions(int vb, int ve, const char* json, size_t len) {
 }
 
 int Engine::setPropertyPerVoice(int32_t nodeId, const char* key, const double* values, int vb, int count) {
+    Lock lk(mu_);
     // Vectorised SET_PROPERTY: values[i] goes to voice vb+i. Same semantics as `count`
     // single-voice [3,id,key,value] batches, without `count` JSON parses.
     dsetdev();
@@ -903,7 +917,8 @@ int Engine::setPropertyPerVoice(int32_t nodeId, const char* key, const double* v
     return rc::Ok;
 }
 
-int Engine::gc(int voice, std::vector<int32_t>& pruned) {   // Runtime.h:221-272
+int Engine::gc(int voice, std::vector<int32_t>& pruned) {
+    Lock lk(mu_);   // Runtime.h:221-272
     pruned.clear();
     for (auto& gp : groups_) {
         Group& g = *gp;
@@ -927,6 +942,7 @@ int Engine::gc(int voice, std::vector<int32_t>& pruned) {   // Runtime.h:221-272
 }
 
 void Engine::reset() {
+    Lock lk(mu_);
     // Runtime.h:449-458: only SampleNode does anything on reset() in the reference; no in-scope node does.
 }
 
@@ -1778,6 +1794,7 @@ int Engine::ensureBuffers(size_t nIn, size_t nOut, bool perVoiceIn, bool materia
 }
 
 float* Engine::voiceInDevicePtr(size_t nIn) {
+    Lock lk(mu_);
     const size_t f = (size_t) numVoices_ * nIn * blockSize_;
     if (f > inVoiceFloats_) {
         dsync();
@@ -1791,6 +1808,7 @@ float* Engine::voiceInDevicePtr(size_t nIn) {
 }
 
 float* Engine::sharedInDevicePtr(size_t nIn) {
+    Lock lk(mu_);
     const size_t f = nIn * blockSize_;
     if (f > inSharedFloats_) {
         dsync();
@@ -1804,7 +1822,11 @@ float* Engine::sharedInDevicePtr(size_t nIn) {
 }
 
 int Engine::enqueueBlock(size_t nIn, size_t nOut, size_t numSamples, bool perVoiceIn, bool materialise, bool mix, bool allReduce) {
-    if (planOnly_) return fail(rc::CudaError, "plan-only runtime (no CUDA device): rendering is impossible, there is no CPU fallback");
+    Lock lk(mu_);
+    // A plan-only engine cannot render.  With option "plan_dry_run" it still walks the whole host side of a block — program swap,
+    // recompiles, descriptors, fades, event mirrors — and skips exactly the CUDA calls: the thread-safety tests (TSAN, no GPU) use it.
+    if (planOnly_ && !planDryRun_) return fail(rc::CudaError, "plan-only runtime (no CUDA device): rendering is impossible, there is no CPU fallback");
+    const bool dry = planOnly_;
     dsetdev();
     if (numSamples > (size_t) blockSize_ || nOut > (size_t) MAX_OUT_CHANNELS) return fail(rc::BadArgument, "numSamples > blockSize or too many output channels");
 
@@ -1942,7 +1964,7 @@ int Engine::enqueueBlock(size_t nIn, size_t nOut, size_t numSamples, bool perVoi
                     if (st == 2) spec = &p.specJob->kernel;
                     else if (st < 0 && opt_.specializeStrict) return fail(rc::CudaError, "K1 specialisation failed: " + p.specJob->log);
                 }
-                if (!cuda(launch_render_block(P, wpc, opt_.niter, stream_, spec), "render kernel launch")) return rc::CudaError;
+                if (!dry && !cuda(launch_render_block(P, wpc, opt_.niter, stream_, spec), "render kernel launch")) return rc::CudaError;
                 ++launches_;
             }
             if (timeKernels_) { cudaEventRecord(ev.second, stream_); timedEvents_.push_back(ev); }
@@ -1969,7 +1991,8 @@ int Engine::enqueueBlock(size_t nIn, size_t nOut, size_t numSamples, bool perVoi
                         if (perVoiceIn) { cin = dInVoice_ + ((size_t) g.v0 * nIn + cv.inChannel) * blockSize_; cinStride = (int) nIn * blockSize_; }
                         else { cin = dInShared_ + (size_t) cv.inChannel * blockSize_; cinStride = 0; }
                     }
-                    if (!cuda(convolver_process_chunk(cs, cin, cinStride, cv.out, blockSize_, offset, n, stream_), "convolver launch")) return rc::CudaError;
+                    if (!dry && !cuda(convolver_process_chunk(cs, cin, cinStride, cv.out, blockSize_, offset, n, stream_), "convolver launch")) return rc::CudaError;
+                    if (dry) { offset += n; continue; }
                     if (timeKernels_) { cudaEventRecord(ev3.second, stream_); timedConvEvents_.push_back(ev3); }
                     ++launches_;
                     offset += n;
@@ -2008,7 +2031,7 @@ int Engine::enqueueBlock(size_t nIn, size_t nOut, size_t numSamples, bool perVoi
             if (!cuda(dmalloc((void**) &bb.dTileStart, bb.capGroups * sizeof(int)), "cudaMalloc tile table")) return rc::CudaError;
             bb.lastDescs.clear();
         }
-        if (bb.lastDescs.size() != dbytes || std::memcmp(bb.lastDescs.data(), descs.data(), dbytes) != 0) {
+        if (!dry && (bb.lastDescs.size() != dbytes || std::memcmp(bb.lastDescs.data(), descs.data(), dbytes) != 0)) {
             if (!cuda(cudaMemcpyAsync(bb.dDescs, descs.data(), dbytes, cudaMemcpyHostToDevice, stream_), "upload group descriptors")) return rc::CudaError;
             if (!cuda(cudaMemcpyAsync(bb.dTileStart, tileStart.data(), tbytes, cudaMemcpyHostToDevice, stream_), "upload tile table")) return rc::CudaError;
             bb.lastDescs.assign(reinterpret_cast<const char*>(descs.data()), reinterpret_cast<const char*>(descs.data()) + dbytes);
@@ -2022,7 +2045,7 @@ int Engine::enqueueBlock(size_t nIn, size_t nOut, size_t numSamples, bool perVoi
             else { cudaEventCreate(&ev.first); cudaEventCreate(&ev.second); }
             cudaEventRecord(ev.first, stream_);
         }
-        if (!cuda(launch_render_groups(bb.dDescs, bb.dTileStart, (int) descs.size(), total, L, maxSlots, (int) nOut, maxState, maxParams, wpc, stream_),
+        if (!dry && !cuda(launch_render_groups(bb.dDescs, bb.dTileStart, (int) descs.size(), total, L, maxSlots, (int) nOut, maxState, maxParams, wpc, stream_),
                   "render groups kernel launch")) return rc::CudaError;
         if (timeKernels_) { cudaEventRecord(ev.second, stream_); timedEvents_.push_back(ev); }
         ++launches_;
@@ -2038,7 +2061,7 @@ int Engine::enqueueBlock(size_t nIn, size_t nOut, size_t numSamples, bool perVoi
     if (mix) {
         if (tileBase > 0) {
             auto ev = timedBegin();
-            if (!cuda(launch_mix_reduce(dPartial_, mixOut, dMixScratch_, dMixTickets_, tileBase, (int) nOut, blockSize_, (int) numSamples, stream_), "mix reduce launch")) return rc::CudaError;
+            if (!dry && !cuda(launch_mix_reduce(dPartial_, mixOut, dMixScratch_, dMixTickets_, tileBase, (int) nOut, blockSize_, (int) numSamples, stream_), "mix reduce launch")) return rc::CudaError;
             if (timeKernels_) { cudaEventRecord(ev.second, stream_); timedMixEvents_.push_back(ev); }
             ++launches_;
         } else {
@@ -2066,6 +2089,7 @@ std::pair<cudaEvent_t, cudaEvent_t> Engine::timedBegin() {
 }
 
 int Engine::peerBarrier() {
+    Lock lk(mu_);
     if (planOnly_ || !peerAttached_ || peer_.world <= 1) return rc::Ok;
     dsetdev();
     if (!cuda(launch_mix_exchange(peer_, dMix_, 0, ++peerEpoch_, dPeerStatus_, stream_), "peer barrier launch")) return rc::CudaError;
@@ -2073,6 +2097,7 @@ int Engine::peerBarrier() {
 }
 
 double Engine::takeKernelTimeMs(uint64_t* count) {
+    Lock lk(mu_);
     if (planOnly_) { if (count) *count = 0; return 0.0; }
     cudaStreamSynchronize(stream_);
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>>* lists[4] = {&timedEvents_, &timedMixEvents_, &timedConvEvents_, &timedXchgEvents_};
@@ -2092,58 +2117,71 @@ double Engine::takeKernelTimeMs(uint64_t* count) {
 
 int Engine::synchronize() {
     if (planOnly_) return rc::Ok;
-    return cuda(cudaStreamSynchronize(stream_), "stream synchronize") ? rc::Ok : rc::CudaError;
+    const cudaError_t e = cudaStreamSynchronize(stream_);     // no lock while waiting for the GPU
+    if (e == cudaSuccess) return rc::Ok;
+    Lock lk(mu_);
+    cuda(e, "stream synchronize");
+    return rc::CudaError;
 }
 
 int Engine::process(const float* const* in, size_t nIn, float* const* out, size_t nOut, size_t numSamples, const int64_t* sampleTime) {
-    if (planOnly_) return fail(rc::CudaError, "plan-only runtime (no CUDA device): rendering is impossible, there is no CPU fallback");
-    dsetdev();
-    if (sampleTime) sampleTime_ = *sampleTime;   // BlockContext::userData as the wasm host passes it (wasm/Main.cpp:206-215)
-    if (numSamples > (size_t) blockSize_) return fail(rc::BadArgument, "numSamples > blockSize");
-    const size_t need = (nIn + nOut) * blockSize_;
-    if (need > pinnedFloats_) {
-        if (hPinned_) cudaFreeHost(hPinned_);
-        if (!cuda(cudaMallocHost(&hPinned_, sizeof(float) * need), "cudaMallocHost")) return rc::CudaError;
-        pinnedFloats_ = need;
+    float* hOut = nullptr;
+    {
+        Lock lk(mu_);   // held while the block is ENQUEUED; the wait for the GPU below runs without it (the control thread may work meanwhile)
+        if (planOnly_) return fail(rc::CudaError, "plan-only runtime (no CUDA device): rendering is impossible, there is no CPU fallback");
+        dsetdev();
+        if (sampleTime) sampleTime_ = *sampleTime;   // BlockContext::userData as the wasm host passes it (wasm/Main.cpp:206-215)
+        if (numSamples > (size_t) blockSize_) return fail(rc::BadArgument, "numSamples > blockSize");
+        const size_t need = (nIn + nOut) * blockSize_;
+        if (need > pinnedFloats_) {
+            if (hPinned_) { dsync(); cudaFreeHost(hPinned_); }
+            if (!cuda(cudaMallocHost(&hPinned_, sizeof(float) * need), "cudaMallocHost")) return rc::CudaError;
+            pinnedFloats_ = need;
+        }
+        if (nIn) {
+            float* d = sharedInDevicePtr(nIn);
+            if (!d) return rc::CudaError;
+            for (size_t c = 0; c < nIn; ++c) std::memcpy(hPinned_ + c * blockSize_, in[c], sizeof(float) * numSamples);
+            if (!cuda(dmemcpy(d, hPinned_, sizeof(float) * nIn * blockSize_, cudaMemcpyHostToDevice), "H2D inputs")) return rc::CudaError;
+        }
+        int r = enqueueBlock(nIn, nOut, numSamples, false, false, true);
+        if (r != rc::Ok) return r;
+        hOut = hPinned_ + nIn * blockSize_;
+        if (nOut) {
+            if (!cuda(dmemcpy(hOut, dMix_, sizeof(float) * nOut * blockSize_, cudaMemcpyDeviceToHost), "D2H mix")) return rc::CudaError;
+        }
     }
-    if (nIn) {
-        float* d = sharedInDevicePtr(nIn);
-        if (!d) return rc::CudaError;
-        for (size_t c = 0; c < nIn; ++c) std::memcpy(hPinned_ + c * blockSize_, in[c], sizeof(float) * numSamples);
-        if (!cuda(dmemcpy(d, hPinned_, sizeof(float) * nIn * blockSize_, cudaMemcpyHostToDevice), "H2D inputs")) return rc::CudaError;
-    }
-    int r = enqueueBlock(nIn, nOut, numSamples, false, false, true);
+    int r = synchronize();
     if (r != rc::Ok) return r;
-    float* hOut = hPinned_ + nIn * blockSize_;
-    if (nOut) {
-        if (!cuda(dmemcpy(hOut, dMix_, sizeof(float) * nOut * blockSize_, cudaMemcpyDeviceToHost), "D2H mix")) return rc::CudaError;
-    }
-    if ((r = synchronize()) != rc::Ok) return r;
+    // hPinned_ belongs to the render thread: only process() (re)allocates it
     for (size_t c = 0; c < nOut; ++c) std::memcpy(out[c], hOut + c * blockSize_, sizeof(float) * numSamples);
     return rc::Ok;
 }
 
 int Engine::processVoices(const float* in, size_t nIn, float* outVoices, float* mix, size_t nOut, size_t numSamples) {
-    if (planOnly_) return fail(rc::CudaError, "plan-only runtime (no CUDA device): rendering is impossible, there is no CPU fallback");
-    dsetdev();
-    if (numSamples > (size_t) blockSize_) return fail(rc::BadArgument, "numSamples > blockSize");
-    const bool perVoiceIn = in != nullptr && nIn > 0;
-    if (perVoiceIn) {
-        float* d = voiceInDevicePtr(nIn);
-        if (!d) return rc::CudaError;
-        // host layout [voice][nIn][numSamples] -> device [voice][nIn][blockSize]
-        if (!cuda(cudaMemcpy2DAsync(d, sizeof(float) * blockSize_, in, sizeof(float) * numSamples, sizeof(float) * numSamples,
-                                    (size_t) numVoices_ * nIn, cudaMemcpyHostToDevice, stream_), "H2D voice inputs")) return rc::CudaError;
-    }
-    int r = enqueueBlock(nIn, nOut, numSamples, perVoiceIn, outVoices != nullptr, mix != nullptr);
-    if (r != rc::Ok) return r;
-    if (outVoices) {
-        if (!cuda(cudaMemcpy2DAsync(outVoices, sizeof(float) * numSamples, dOutVoice_, sizeof(float) * blockSize_, sizeof(float) * numSamples,
-                                    (size_t) numVoices_ * nOut, cudaMemcpyDeviceToHost, stream_), "D2H voice outputs")) return rc::CudaError;
-    }
-    if (mix) {
-        if (!cuda(cudaMemcpy2DAsync(mix, sizeof(float) * numSamples, dMix_, sizeof(float) * blockSize_, sizeof(float) * numSamples,
-                                    nOut, cudaMemcpyDeviceToHost, stream_), "D2H mix")) return rc::CudaError;
+    {
+        Lock lk(mu_);
+        if (planOnly_) return fail(rc::CudaError, "plan-only runtime (no CUDA device): rendering is impossible, there is no CPU fallback");
+        dsetdev();
+        if (numSamples > (size_t) blockSize_) return fail(rc::BadArgument, "numSamples > blockSize");
+        const bool perVoiceIn = in != nullptr && nIn > 0;
+        if (perVoiceIn) {
+            float* d = voiceInDevicePtr(nIn);
+            if (!d) return rc::CudaError;
+            // host layout [voice][nIn][numSamples] -> device [voice][nIn][blockSize]
+            if (!cuda(cudaMemcpy2DAsync(d, sizeof(float) * blockSize_, in, sizeof(float) * numSamples, sizeof(float) * numSamples,
+                                        (size_t) numVoices_ * nIn, cudaMemcpyHostToDevice, stream_), "H2D voice inputs")) return rc::CudaError;
+        }
+        int r = enqueueBlock(nIn, nOut, numSamples, perVoiceIn, outVoices != nullptr, mix != nullptr);
+        if (r != rc::Ok) return r;
+        if (outVoices) {
+            if (!cuda(cudaMemcpy2DAsync(outVoices, sizeof(float) * numSamples, dOutVoice_, sizeof(float) * blockSize_, sizeof(float) * numSamples,
+                                        (size_t) numVoices_ * nOut, cudaMemcpyDeviceToHost, stream_), "D2H voice outputs")) return rc::CudaError;
+        }
+        if (mix) {
+            if (!cuda(cudaMemcpy2DAsync(mix, sizeof(float) * numSamples, dMix_, sizeof(float) * blockSize_, sizeof(float) * numSamples,
+                                        nOut, cudaMemcpyDeviceToHost, stream_), "D2H mix")) return rc::CudaError;
+        }
     }
     return synchronize();
 }

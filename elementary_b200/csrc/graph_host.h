@@ -7,6 +7,7 @@
 #include <cstdint>
 #include <map>
 #include <memory>
+#include <mutex>
 #include <set>
 #include <string>
 #include <unordered_map>
@@ -199,24 +200,24 @@ public:
     float* voiceOutDevicePtr() { return dOutVoice_; }
     float* voiceInDevicePtr(size_t nIn);
     float* sharedInDevicePtr(size_t nIn);
-    const std::string& lastError() const { return lastError_; }
+    std::string lastError() const { Lock lk(mu_); return lastError_; }
     int numVoices() const { return numVoices_; }
     int blockSize() const { return blockSize_; }
-    uint64_t kernelLaunches() const { return launches_; }
+    uint64_t kernelLaunches() const { Lock lk(mu_); return launches_; }
     // The int64 sample clock handed to nodes through BlockContext::userData (wasm/Main.cpp:206-217, Metro.h:44,
     // SampleTime.h:19).  process() takes it from *userData when given; otherwise the engine counts samples itself.
     // Runtime::processQueuedEvents (Runtime.h:64,438-446): events of the voices [vb, ve); cb(type, event JSON, voice).
     typedef void (*EventFn)(const char* type, const char* json, int voice, void* user);
     int processQueuedEvents(int vb, int ve, EventFn cb, void* user);
-    void setCurrentTime(int64_t t) { sampleTime_ = t; }
-    int64_t currentTime() const { return sampleTime_; }
+    void setCurrentTime(int64_t t) { Lock lk(mu_); sampleTime_ = t; }
+    int64_t currentTime() const { Lock lk(mu_); return sampleTime_; }
     // Sum of the device durations (ms) of the K1 render kernels launched since the last call, measured with
     // CUDA events recorded on the launching stream (option "time_kernels" = 1). Synchronises the stream.
     double takeKernelTimeMs(uint64_t* count);
     // K3 time/count gathered by the same takeKernelTimeMs() call
-    double lastConvolveTimeMs(uint64_t* count) const { if (count) *count = lastConvCount_; return lastConvMs_; }
+    double lastConvolveTimeMs(uint64_t* count) const { Lock lk(mu_); if (count) *count = lastConvCount_; return lastConvMs_; }
     // per kernel kind (0 = K1 render, 1 = K2 mix reduce, 2 = K3 convolve, 3 = K4 mix exchange): summed ms and launch counts of the same call
-    void lastKernelTimes(double ms[4], uint64_t counts[4]) const { for (int i = 0; i < 4; ++i) { ms[i] = lastKindMs_[i]; counts[i] = lastKindCount_[i]; } }
+    void lastKernelTimes(double ms[4], uint64_t counts[4]) const { Lock lk(mu_); for (int i = 0; i < 4; ++i) { ms[i] = lastKindMs_[i]; counts[i] = lastKindCount_[i]; } }
     // A cross-GPU barrier on the render stream (K4 with an empty payload): returns once every rank's stream has reached it.
     int peerBarrier();
     std::string describe() const;
@@ -228,6 +229,14 @@ public:
     long specializeDryRun(int voice, std::string& log);
 
 private:
+    // Threading contract of the boundary (Runtime.h:133,204,277-285: one control thread + one render thread, concurrently): every
+    // public entry point takes this lock for its host-side work.  process()/processVoices() hold it only while they ENQUEUE the block
+    // (tens of microseconds) and wait for the GPU without it, so the control thread works while a block renders; a control call
+    // holds it while it mutates the node table / compiles (NVRTC never runs under it in "specialize" = 1 mode).  Recursive because
+    // public methods call each other.
+    mutable std::recursive_mutex mu_;
+    typedef std::lock_guard<std::recursive_mutex> Lock;
+    bool planDryRun_ = false;     // plan-only engines: enqueueBlock runs ALL its host logic and skips only the CUDA calls (thread-safety tests)
     double sr_;
     int blockSize_, numVoices_, device_;
     cudaStream_t stream_ = nullptr;

@@ -39,6 +39,9 @@ namespace eb {
 namespace {
 
 constexpr float kEps = FLT_EPSILON;
+#ifndef EB_SVF_SCAN_MAX_L
+#define EB_SVF_SCAN_MAX_L 4      // tiles of up to this many voices run the svf tick as a warp scan (render_ops.inc, OP_SVF)
+#endif
 constexpr unsigned FULL = 0xFFFFFFFFu;
 
 // Everything the interpreter touches per sample lives in the CTA's dynamic shared memory.  Addresses into it are kept as 32-bit

@@ -61,7 +61,7 @@ def _load_ref():
         lib.elem_ref_bench_stable.restype = C.c_double
         lib.elem_ref_bench_stable.argtypes = [C.c_double, C.c_int, C.c_int, C.c_int, C.c_char_p, C.POINTER(C.c_char_p),
                                               C.c_char_p, _f32p, C.c_size_t, _f32p, C.c_size_t, C.c_size_t, C.c_size_t,
-                                              C.c_int, C.c_int, C.c_double, C.POINTER(C.c_int), C.POINTER(C.c_double)]
+                                              C.c_int, C.c_int, C.c_double, C.POINTER(C.c_double), C.POINTER(C.c_double)]
         lib.elem_ref_cpu_model.restype = C.c_int
         lib.elem_ref_cpu_model.argtypes = [C.c_char_p, C.c_size_t]
         _ref_lib = lib
@@ -224,7 +224,7 @@ class PortRuntime(_Base):
 def ref_bench(sample_rate: float, block_size: int, base_batch, voice_batches: Optional[Sequence], n_voices: int,
               threads: int, n_in: int, n_out: int, warmup_blocks: int, blocks: int,
               resource: Optional[tuple] = None, inputs: Optional[np.ndarray] = None, min_seconds: float = 0.0):
-    """Time the reference's own CPU path: returns (seconds, checksum[, repeats when min_seconds > 0]).  Threads are pinned, created
+    """Time the reference's own CPU path: returns (seconds, checksum[, steps = blocks of all voices rendered, when min_seconds > 0]).  Threads are pinned, created
     and warmed up outside the timed region, rounds are barrier-bracketed: oracle/ref_driver.cpp:elem_ref_bench_stable."""
     lib = _load_ref()
     base = json.dumps(base_batch).encode()
@@ -243,11 +243,11 @@ def ref_bench(sample_rate: float, block_size: int, base_batch, voice_batches: Op
     else:
         iptr = None
     chk = C.c_double(0.0)
-    rep = C.c_int(1)
+    rep = C.c_double(0.0)
     secs = lib.elem_ref_bench_stable(sample_rate, block_size, n_voices, threads, base, arr, rname, rptr, rlen,
                                      iptr, n_in, n_out, block_size, warmup_blocks, blocks, float(min_seconds), C.byref(rep), C.byref(chk))
     if min_seconds > 0:
-        return secs, chk.value, rep.value      # the timed round rendered `blocks` blocks rep.value times
+        return secs, chk.value, rep.value      # the timed round amounts to rep.value blocks of all voices
     return secs, chk.value
 
 

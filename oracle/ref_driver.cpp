@@ -150,10 +150,10 @@ void elem_ref_reset(void* h) { static_cast<RefRuntime*>(h)->rt.reset(); }
 //   * every round (warm-up, timed) starts and ends at a barrier; each worker stamps steady_clock right after the start barrier and
 //     right after its last block, elapsed = latest end - earliest start, so neither thread creation nor a straggler's start-up
 //     is inside — and the slowest thread is;
-//   * the timed round renders `blocks` blocks `repeats` times, `repeats` chosen from a calibration round so that the timed region
-//     lasts at least `minSeconds`.
-// Returns the seconds of the timed round; *repeatsOut tells how many times `blocks` was rendered in it; *checksum receives the
-// sum of all output samples of the last block so the work cannot be elided.
+//   * the timed round renders at least `blocks` blocks and keeps going until `minSeconds` have passed (every thread stops at a
+//     block boundary of its own voices).
+// Returns the seconds of the timed round; *stepsOut = voice-blocks rendered / numVoices (how many blocks of ALL voices it amounts
+// to); *checksum receives the sum of all output samples of the last block so the work cannot be elided.
 namespace {
 struct Barrier {
     std::mutex m; std::condition_variable cv; int count, waiting = 0; unsigned gen = 0;
@@ -171,7 +171,7 @@ double elem_ref_bench_stable(double sampleRate, int blockSize, int numVoices, in
                              const char* baseJson, const char* const* voiceJson,
                              const char* resName, const float* resData, size_t resLen,
                              const float* in, size_t nIn, size_t nOut, size_t numSamples,
-                             int warmupBlocks, int blocks, double minSeconds, int* repeatsOut, double* checksum) {
+                             int warmupBlocks, int blocks, double minSeconds, double* stepsOut, double* checksum) {
     if (threads < 1) threads = 1;
     if (threads > numVoices) threads = numVoices;
     std::vector<std::unique_ptr<RefRuntime>> rts(numVoices);
@@ -180,6 +180,8 @@ double elem_ref_bench_stable(double sampleRate, int blockSize, int numVoices, in
     std::vector<double> sums(threads, 0.0);
     std::atomic<int> failed{0};
     std::atomic<int> roundBlocks{0};
+    std::atomic<double> roundSeconds{0.0};
+    std::vector<long> voiceBlocks(threads, 0);
     std::atomic<bool> quit{false};
     Barrier bar(threads + 1);
     std::vector<std::chrono::steady_clock::time_point> tStart(threads), tEnd(threads);
@@ -217,14 +219,20 @@ double elem_ref_bench_stable(double sampleRate, int blockSize, int numVoices, in
             if (quit.load()) return;
             tStart[t] = std::chrono::steady_clock::now();
             const int nb = roundBlocks.load();
+            const double limit = roundSeconds.load();     // > 0: keep rendering whole blocks of this thread's voices until the time is up
             double s = 0.0;
-            for (int b = 0; b < nb; ++b)
+            long done = 0;
+            for (int b = 0; limit > 0.0 || b < nb; ++b) {
                 for (int v = t; v < numVoices; v += threads) {
                     rts[v]->rt.process(ip.data(), nIn, op.data(), nOut, numSamples, static_cast<void*>(&rts[v]->sampleTime));
                     rts[v]->sampleTime += static_cast<int64_t>(numSamples);
-                    if (b == nb - 1) for (float x : outBuf) s += x;
+                    ++done;
                 }
+                if (limit > 0.0 && b + 1 >= nb && std::chrono::duration<double>(std::chrono::steady_clock::now() - tStart[t]).count() >= limit) break;
+            }
+            for (float x : outBuf) s += x;
             sums[t] = s;
+            voiceBlocks[t] = done;
             tEnd[t] = std::chrono::steady_clock::now();
             bar.wait();                                   // round end
         }
@@ -243,13 +251,14 @@ double elem_ref_bench_stable(double sampleRate, int blockSize, int numVoices, in
         return std::chrono::duration<double>(t1 - t0).count();
     };
     round(std::max(1, warmupBlocks));                     // includes construction: never timed
-    int repeats = 1;
-    if (minSeconds > 0.0) {
-        const int calib = std::max(1, std::min(blocks, 8));
-        const double per = round(calib) / calib;          // seconds per block, all voices
-        if (per > 0.0) repeats = std::max(1, (int) std::ceil(minSeconds / (per * blocks)));
-    }
-    const double secs = round(blocks * repeats);
+    // Timed round: at least `blocks` blocks and — when minSeconds > 0 — at least that long.  Time-bounded rather than a block count
+    // from a calibration: on a box whose container has a CPU quota the first milliseconds run unthrottled and a calibration
+    // underestimates the steady state by the throttling factor (seen: 7x).
+    roundSeconds = minSeconds;
+    const double secs = round(blocks);
+    long totalVoiceBlocks = 0;
+    for (long n : voiceBlocks) totalVoiceBlocks += n;
+    const double steps = (double) totalVoiceBlocks / (double) numVoices;      // blocks of ALL voices the timed round amounts to
     quit = true;
     bar.wait();
     for (auto& x : th) x.join();
@@ -257,7 +266,7 @@ double elem_ref_bench_stable(double sampleRate, int blockSize, int numVoices, in
     double total = 0.0;
     for (double s : sums) total += s;
     if (checksum) *checksum = total;
-    if (repeatsOut) *repeatsOut = repeats;
+    if (stepsOut) *stepsOut = steps;
     return failed.load() ? -1.0 : secs;
 }
 

@@ -524,3 +524,19 @@ def test_soak_60_seconds_no_drift():
         pass
     assert worst_by_block.max() <= 1.0, summary
     assert worst_by_block[-100:].max() <= 4 * max(worst_by_block[:100].max(), 0.01), f"error grows: {summary}"
+
+
+def test_control_thread_edits_while_render_thread_processes(tmp_path):
+    """The two-thread contract on the real render path: tests/native/thread_stress.cpp (control thread: re-renders with cross-fades,
+    a live voice-group cut, gc, events; render thread: elem_b200_process in a loop) against the GPU for two seconds."""
+    import json, os, subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    p = subprocess.run(["make", "stress"], cwd=os.path.join(root, "elementary_b200", "csrc"), capture_output=True, text=True)
+    assert p.returncode == 0, p.stdout[-2000:] + p.stderr[-2000:]
+    a, b = tmp_path / "a.json", tmp_path / "b.json"
+    a.write_text(json.dumps(graphs.subsynth32()))
+    b.write_text(json.dumps(el.render(el.tanh(el.add(graphs.subsynth32_graph(220.0), el.mul(0.2, el.cycle(330.0)))))))
+    r = subprocess.run([os.path.join(root, "build", "thread_stress"), "0", "2.0", str(a), str(b)], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, (r.stdout[-500:], r.stderr[-2000:])
+    stats = json.loads(r.stdout.strip().splitlines()[-1])
+    assert stats["blocks"] > 100 and stats["edits"] > 10 and stats["failures"] == 0, stats
