@@ -165,14 +165,19 @@ def host_description():
         load1 = float(open("/proc/loadavg").read().split()[0])
     except Exception:
         load1 = None
-    return {"nproc": os.cpu_count() or 1, "usable_cpus": usable, "cgroup_cpu_quota": quota, "loadavg_1m_before": load1, "cpu_model": model}
+    # threads the reference arm uses: one per CPU the container may really use (a CFS quota of 16 on a 128-CPU host means 16 —
+    # 128 pinned threads there are throttled 8:1 and measure the throttling, not the engine)
+    import math
+    threads = usable if quota is None else max(1, min(usable, int(math.ceil(quota))))
+    return {"nproc": os.cpu_count() or 1, "usable_cpus": usable, "cgroup_cpu_quota": quota, "threads_used": threads,
+            "loadavg_1m_before": load1, "cpu_model": model}
 
 
 def run_reference(args, rank, world, emit=print):
     if rank != 0:
         return
     host = host_description()
-    cores = host["usable_cpus"]
+    cores = host["threads_used"]
     voices = VOICES_PER_GPU * world
     rall = cpu_reference_run(voices, cores, max(1, args.warmup), args.steps, 2.5)
     if rall is None:
@@ -422,7 +427,7 @@ def run_b200(args, rank, local_rank, world, emit=print):
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
         host = host_description()
-        cores = host["usable_cpus"]
+        cores = host["threads_used"]
         rall = cpu_reference_run(16 * cores, cores, 10, 50, 10.0)
         r1 = cpu_reference_run(16, 1, 5, 20, 3.0)
         if rall is not None:

@@ -1,13 +1,14 @@
 #!/usr/bin/env python
 """Secondary measurements for the other BASELINE.json configs (not the driver's headline; bench.py is).
 
+  config 1: the reference's own elembench (cli/Benchmark.cpp, unmodified) on the plumbing graph, against both engines
   config 3: additive synth, 64 el.cycle partials per voice (387 nodes)          — K1, many recurrences per voice
   config 4: el.convolve reverb, 16384-tap IR, one channel per voice             — K3 (partitioned FFT convolver)
   config 5: independent random 64-node graphs, one voice group each             — K1, one launch per graph
 
 Each prints one JSON line: device-resident ms/block (CUDA events), Msamples/s, x real time, the kernel time measured
 with events around the K1/K3 launches, the algorithmic-bytes roofline fraction and a CPU reference sample
-(unmodified reference via oracle/_ref on all host threads).  Usage: python bench_configs.py [3] [4] [5] [--quick]
+(unmodified reference via oracle/_ref on all host threads).  Usage: python bench_configs.py [1] [3] [4] [5] [--quick]
 """
 from __future__ import annotations
 
@@ -56,9 +57,35 @@ def cpu_ref(batch, voice_batches, voices, blocks, n_in=0, resource=None, inputs=
     from oracle import oracle as orc
     if not orc.ref_available():
         return None
-    cores = os.cpu_count() or 1
-    secs, _ = orc.ref_bench(SR, BS, batch, voice_batches, voices, cores, n_in, 1, 3, blocks, resource=resource, inputs=inputs)
-    return {"msamples_per_s": voices * BS * blocks / secs / 1e6, "cores": cores, "sample": f"{voices} voices x {blocks} blocks, {secs:.1f} s"}
+    from bench import host_description
+    cores = host_description()["threads_used"]
+    secs, _, nb = orc.ref_bench(SR, BS, batch, voice_batches, voices, cores, n_in, 1, 3, blocks, resource=resource, inputs=inputs, min_seconds=3.0)
+    return {"msamples_per_s": voices * BS * nb / secs / 1e6, "cores": cores, "sample": f"{voices} voices x {nb:.0f} blocks, {secs:.1f} s, pinned threads"}
+
+
+def config1(quick):
+    """BASELINE config 1: the reference's own benchmark program (cli/Benchmark.cpp + cli/BenchmarkMain.cpp, compiled unmodified by
+    oracle/Makefile) on the plumbing graph — once against the reference runtime (host CPU), once against the source-compatible
+    elem::Runtime of include/elem_b200_compat over libelem_b200.so (one voice on the GPU: pure plumbing / launch latency)."""
+    import re, subprocess
+    js = os.path.join(ROOT, "oracle", "config1_plumbing.js")
+    out = {"config": "1: cli/Benchmark (elembench) on the saw->svf->mul plumbing graph, 44.1 kHz, 512-sample blocks, 10000 iterations, float then double"}
+    for name, exe, env in (("reference", "elembench_ref", {}),
+                           ("b200_1_voice", "elembench_b200", {"ELEM_B200_VOICES": "1", "ELEM_B200_SPECIALIZE": "2"}),
+                           ("b200_4096_voices", "elembench_b200", {"ELEM_B200_VOICES": "4096", "ELEM_B200_SPECIALIZE": "2"})):
+        path = os.path.join(ROOT, "oracle", "_ref", exe)
+        if not os.path.exists(path):
+            out[name] = {"unavailable": f"{path} missing (built only where /root/reference exists)"}
+            continue
+        p = subprocess.run([path, js], capture_output=True, text=True, env=dict(os.environ, **env), timeout=600)
+        avg = [float(x) for x in re.findall(r"Average iteration time: ([0-9.eE+-]+)us", p.stdout)]
+        if p.returncode != 0 or len(avg) < 2:
+            out[name] = {"failed": p.returncode, "stderr": p.stderr[-500:], "stdout": p.stdout[-300:]}
+            continue
+        voices = int(env.get("ELEM_B200_VOICES", "1"))
+        out[name] = {"float_us_per_block": avg[0], "double_us_per_block": avg[1], "voices": voices,
+                     "msamples_per_s_float": voices * 512 / avg[0], "note": "the program's own report: mean of 10000 per-iteration times truncated to integer microseconds (Benchmark.cpp:99)"}
+    return out
 
 
 def config3(quick):
@@ -135,9 +162,9 @@ def config5(quick):
 
 def main():
     quick = "--quick" in sys.argv
-    which = [a for a in sys.argv[1:] if a in ("3", "4", "5")] or ["3", "4", "5"]
+    which = [a for a in sys.argv[1:] if a in ("1", "3", "4", "5")] or ["1", "3", "4", "5"]
     for w in which:
-        r = {"3": config3, "4": config4, "5": config5}[w](quick)
+        r = {"1": config1, "3": config3, "4": config4, "5": config5}[w](quick)
         print(json.dumps(r))
         sys.stdout.flush()
 

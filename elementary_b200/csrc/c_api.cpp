@@ -161,6 +161,21 @@ int elem_b200_describe(elem_b200_runtime* rt, char* buf, size_t cap) {
     return (int) s.size() + 1;
 }
 
+int elem_b200_register_node_type(elem_b200_runtime* rt, const char* type, int numInputs, int numStateFloats, const char* cudaBody) {
+    if (!type || !cudaBody) return eb::rc::BadArgument;
+    GUARD(rt->engine->registerNodeType(type, numInputs, numStateFloats, cudaBody));
+}
+int elem_b200_has_node_type(elem_b200_runtime* rt, const char* type) { return (rt && type && rt->engine->hasNodeType(type)) ? 1 : 0; }
+
+int elem_b200_snapshot(elem_b200_runtime* rt, int voice, char* buf, size_t cap) {
+    if (!rt) return 0;
+    try {
+        const std::string s = rt->engine->snapshot(voice);
+        if (buf && cap) { const size_t k = s.size() < cap - 1 ? s.size() : cap - 1; std::memcpy(buf, s.data(), k); buf[k] = 0; }
+        return (int) s.size() + 1;
+    } catch (...) { return 0; }
+}
+
 int elem_b200_program_words(elem_b200_runtime* rt, int voice, uint32_t* buf, size_t cap) {
     if (!rt) return 0;
     try {

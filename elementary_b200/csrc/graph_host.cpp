@@ -250,6 +250,29 @@ std::string Engine::describe() const {
     return os.str();
 }
 
+std::string Engine::snapshot(int voice) const {
+    Lock lk(mu_);
+    std::string o = "{";
+    for (auto& g : groups_) {
+        if (voice < g->v0 || voice >= g->v0 + g->nv) continue;
+        std::map<int32_t, const Node*> sorted;
+        for (auto& kv : g->nodes) sorted[kv.first] = &kv.second;
+        bool first = true;
+        for (auto& kv : sorted) {
+            char key[24];
+            std::snprintf(key, sizeof key, "\"0x%08x\":", (unsigned) kv.first);    // nodeIdToHex, Types.h:16-27
+            if (!first) o += ',';
+            first = false;
+            o += key;
+            Value props = Value::object();
+            for (auto& p : kv.second->props) props.asObject()[p.first] = p.second;
+            writeJson(o, props);
+        }
+        break;
+    }
+    return o + "}";
+}
+
 long Engine::specializeDryRun(int voice, std::string& log) {
     Lock lk(mu_);
     for (auto& g : groups_) {
@@ -258,7 +281,7 @@ long Engine::specializeDryRun(int voice, std::string& log) {
         if (!p) { log = "no compiled program for this voice"; return -1; }
         if (p->stages.size() > 1) { log = "multi-stage programs (convolve) are not specialised"; return -1; }
         SpecKernel k;
-        if (!specialise_compile(p->code, g->tileWidth, opt_.niter, k, log)) return -1;
+        if (!specialise_compile(p->code, g->tileWidth, opt_.niter, customSource(), k, log)) return -1;
         return (long) k.cubin.size();
     }
     log = "voice out of range";
@@ -375,11 +398,52 @@ static bool toInt32(const Value& v, int32_t& out) {
     return true;
 }
 
+// builtin or registered: kind, fn (registered types: their index), state rows
+static bool lookupType(const std::string& name, const std::vector<std::pair<std::string, int>>& custom, TypeInfo& out) {
+    auto it = typeTable().find(name);
+    if (it != typeTable().end()) { out = it->second; return true; }
+    for (size_t i = 0; i < custom.size(); ++i)
+        if (custom[i].first == name) { out = TypeInfo{NodeKind::Custom, (uint32_t) i, custom[i].second, false}; return true; }
+    return false;
+}
+
+int Engine::registerNodeType(const char* type, int numInputs, int numState, const char* body) {
+    Lock lk(mu_);
+    if (!type || !body || numInputs < 0 || numInputs > 8 || numState < 0 || numState > 8) return fail(rc::BadArgument, "registerNodeType: 0..8 inputs, 0..8 state floats");
+    if (hasNodeType(type)) return rc::NodeTypeAlreadyExists;     // Runtime.h:482-483
+    customTypes_.push_back(CustomType{type, body, numInputs, numState});
+    return rc::Ok;
+}
+
+bool Engine::hasNodeType(const char* type) const {
+    Lock lk(mu_);
+    if (typeTable().count(type)) return true;
+    for (auto& c : customTypes_) if (c.name == type) return true;
+    return false;
+}
+
+std::string Engine::customSource() const {
+    if (customTypes_.empty()) return std::string();
+    std::ostringstream os;
+    os << "#define EB_CUSTOM_NODES 1\nnamespace eb {\n";
+    for (size_t i = 0; i < customTypes_.size(); ++i)
+        os << "// registered node type \"" << customTypes_[i].name << "\"\n__device__ __forceinline__ float eb_custom_" << i
+           << "(float* s, const float* in, const float sr) {\n" << customTypes_[i].body << "\n}\n";
+    os << "template <int ID> __device__ __forceinline__ float eb_custom_call(float* s, const float* in, const float sr) {\n";
+    for (size_t i = 0; i < customTypes_.size(); ++i) os << "    if constexpr (ID == " << i << ") return eb_custom_" << i << "(s, in, sr);\n";
+    os << "    return 0.0f;\n}\n}\n";
+    return os.str();
+}
+
 int Engine::createNode(Group& g, const Value& a1, const Value& a2) {   // Runtime.h:294-313
     int32_t id;
     if (!toInt32(a1, id) || !a2.isString()) return rc::InvalidInstructionFormat;
-    auto it = typeTable().find(a2.asString());
-    if (it == typeTable().end()) return rc::UnknownNodeType;
+    std::vector<std::pair<std::string, int>> custom;
+    for (auto& c : customTypes_) custom.push_back({c.name, c.nState});
+    TypeInfo ti;
+    if (!lookupType(a2.asString(), custom, ti)) return rc::UnknownNodeType;
+    struct { TypeInfo second; } holder{ti};
+    auto* it = &holder;
     if (g.nodes.count(id)) return rc::NodeAlreadyExists;
 
     Node n;
@@ -790,6 +854,7 @@ int Engine::splitGroupsAt(int v) {
             std::vector<char> isDoublePair((size_t) g.rowsUsed + 2, 0);
             for (auto& kv : g.nodes) {
                 const Node& n = kv.second;
+                if (n.kind == NodeKind::Custom) continue;     // registered types keep float state only
                 const auto& ti = typeTable().at(n.typeName);
                 if (ti.evenAlign && n.stateRow >= 0) for (int k = 0; k < ti.stateRows; k += 2) isDoublePair[(size_t) n.stateRow + k] = 1;
             }
@@ -870,6 +935,7 @@ int Engine::applyInstructions(int vb, int ve, const char* json, size_t len) {
     if (ve < 0 || ve > numVoices_) ve = numVoices_;
     if (vb >= ve) return fail(rc::BadArgument, "empty voice range");
     if (!parsed) return fail(rc::InvalidInstructionFormat, parseError);
+    lastError_.clear();
     if (!doc.isArray()) return fail(rc::InvalidInstructionFormat, "batch is not an array");
     auto& batch = doc.asArray();
 
@@ -882,7 +948,7 @@ int Engine::applyInstructions(int vb, int ve, const char* json, size_t len) {
         const int b = std::max(vb, g->v0), e = std::min(ve, g->v0 + g->nv);
         if (b >= e) continue;
         int r = applyToGroup(*g, batch, b - g->v0, e - g->v0);
-        if (r != rc::Ok) { if (lastError_.empty() || r > 0) lastError_ = "instruction failed"; return r; }
+        if (r != rc::Ok) { if (lastError_.empty()) lastError_ = "instruction failed"; return r; }
     }
     return rc::Ok;
 }
@@ -1098,6 +1164,13 @@ int Compiler::emitNode(Node& n, int rootIndex) {
             op.opcode = OP_BLEP; op.mode = n.fn; op.aux0 = fbits((float) E.sr_); take(1);
             break;
         case NodeKind::PassThrough: if (numCh < 1) { zeros(); break; } op.opcode = OP_COPY; take(1); break;
+        case NodeKind::Custom: {   // a registered device node type: missing inputs give zeros like every builtin
+            const auto& ct = E.customTypes_[n.fn];
+            if (numCh < ct.nIn) { zeros(); break; }
+            op.opcode = OP_CUSTOM; op.aux0 = n.fn; op.aux1 = (uint32_t) ct.nState; take(ct.nIn);
+            op.imm = {fbits((float) E.sr_)};
+            prog.hasCustom = true;
+        } break;
 
 
         // ---- sequencing / control nodes ----
@@ -1609,7 +1682,7 @@ int Engine::compile(Group& g, int nIn, std::shared_ptr<Program>& out) {
         if (n.stateRow < 0) return NO_STATE;
         auto it = smemIndexOfRow.find((uint32_t) n.stateRow);
         if (it != smemIndexOfRow.end()) return it->second;
-        const auto& ti = typeTable().at(n.typeName);
+        const TypeInfo ti = n.kind == NodeKind::Custom ? TypeInfo{NodeKind::Custom, n.fn, customTypes_[n.fn].nState, false} : typeTable().at(n.typeName);
         if (ti.evenAlign && (nStateRows & 1)) {   // keep doubles 8-byte aligned in shared memory
             prog->stateMap.push_back(STATE_PAD);
             nStateRows += 1;
@@ -1753,9 +1826,17 @@ int Engine::compile(Group& g, int nIn, std::shared_ptr<Program>& out) {
     }
     // Per-program specialisation of K1 (spec_host.h).  Not for groups that render through the batched many-groups launch (that
     // kernel is the interpreter by construction: one launch serves different programs), not for multi-stage programs.
-    const bool batched = groups_.size() > 1 && opt_.batchGroups;
-    if (opt_.specialize && !batched && prog->stages.size() <= 1 && (int) prog->code.size() <= opt_.specializeMaxWords) {
-        prog->specJob = specialise_request(prog->code, g.tileWidth, opt_.niter, device_);   // NVRTC on the compile-queue thread
+    const bool batched = groups_.size() > 1 && opt_.batchGroups && !prog->hasCustom;
+    if (prog->hasCustom) {
+        // Registered device node types exist only inside a kernel compiled for the program: specialisation is mandatory and
+        // synchronous, whatever the "specialize" option says, and a body that does not compile fails the COMMIT.
+        if (prog->stages.size() > 1) return fail(rc::InvariantViolation, "a registered node type cannot share a graph with convolve");
+        prog->specJob = specialise_request(prog->code, g.tileWidth, opt_.niter, device_, customSource());
+        specialise_wait(*prog->specJob);
+        if (prog->specJob->state.load(std::memory_order_acquire) < 0)
+            return fail(rc::InvariantViolation, "registered node type failed to compile: " + prog->specJob->log);
+    } else if (opt_.specialize && !batched && prog->stages.size() <= 1 && (int) prog->code.size() <= opt_.specializeMaxWords) {
+        prog->specJob = specialise_request(prog->code, g.tileWidth, opt_.niter, device_, std::string());   // NVRTC on the compile-queue thread
         if (opt_.specialize >= 2) {                                                          // synchronous mode: wait for the compiler here
             specialise_wait(*prog->specJob);
             if (prog->specJob->state.load(std::memory_order_acquire) < 0 && opt_.specializeStrict)
@@ -1940,7 +2021,7 @@ int Engine::enqueueBlock(size_t nIn, size_t nOut, size_t numSamples, bool perVoi
         while (wpc > 1 && perWarp * wpc > 200 * 1024) wpc >>= 1;
         if (perWarp > 220 * 1024) return fail(rc::InvariantViolation, "graph state does not fit in shared memory");
         const size_t nStages = std::max<size_t>(1, p.stages.size());
-        if (nStages == 1 && groups_.size() > 1 && opt_.batchGroups) {
+        if (nStages == 1 && groups_.size() > 1 && opt_.batchGroups && !p.hasCustom) {
             // heterogeneous voice groups: collect single-stage groups per tile geometry and launch each bucket once
             P.code = p.dCode + (p.stages.empty() ? 0 : p.stages[0].codeOffset);
             buckets[g.tileWidth].push_back(P);
@@ -1962,7 +2043,7 @@ int Engine::enqueueBlock(size_t nIn, size_t nOut, size_t numSamples, bool perVoi
                 if (p.specJob) {   // the cubin arrived: load it on this thread (its CUDA context is current), a matter of milliseconds
                     const int st = specialise_ensure_loaded(*p.specJob);
                     if (st == 2) spec = &p.specJob->kernel;
-                    else if (st < 0 && opt_.specializeStrict) return fail(rc::CudaError, "K1 specialisation failed: " + p.specJob->log);
+                    else if (st < 0 && (opt_.specializeStrict || p.hasCustom)) return fail(rc::CudaError, "K1 specialisation failed: " + p.specJob->log);
                 }
                 if (!dry && !cuda(launch_render_block(P, wpc, opt_.niter, stream_, spec), "render kernel launch")) return rc::CudaError;
                 ++launches_;

@@ -31,7 +31,8 @@ enum class NodeKind : uint8_t {
     Delay, SDelay, Z, Pole, Env, Biquad, Prewarp, MM1p, Svf, SvfShelf, TapIn, TapOut, Table, Blep, Convolve,
     PassThrough,  // analysis nodes whose events are not produced: audio passes through
     Once, Seq, Seq2, SparSeq, SparSeq2, Time, Metro,  // sequencing / control nodes
-    Meter, Snapshot, Scope, Capture, Fft              // analysis nodes feeding processQueuedEvents
+    Meter, Snapshot, Scope, Capture, Fft,             // analysis nodes feeding processQueuedEvents
+    Custom                                            // a device node type registered at run time (registerNodeType)
 };
 
 // A read-only device array owned jointly by the node that uploaded it and by every compiled program that points at it
@@ -135,6 +136,7 @@ struct Program {
     struct EvNode { int32_t node; int root; };
     std::vector<EvNode> evNodes;          // event-emitting nodes in render order (GraphRenderSequence.h:189-198 walks nodeList)
     std::vector<int32_t> dynNodes;        // LaunchParams::dyn[i] belongs to node dynNodes[i]
+    bool hasCustom = false;               // uses a registered device node type: only a specialised kernel can run it
     std::shared_ptr<SpecJob> specJob;     // K1 being / having been specialised for this program (option "specialize"); the interpreter runs until it is loaded
     const float* stagedTable = nullptr; int stagedTableFloats = 0;   // the wavetable K1 stages into shared memory with TMA (first `table` node that fits)
     ~Program();
@@ -195,6 +197,13 @@ public:
     int peerAttach(int rank, int world, const void* handles);
     int peerStatus();   // 0 = ok, 1 = a peer did not answer within the spin bound
     int setOption(const char* key, double value);
+    // Runtime::registerNodeType (Runtime.h:105-106,480-487) for a fused-kernel engine: a new node type is DEVICE code — the body of
+    //   float node(float* s /* numState persistent floats per voice, zero-initialised */, const float* in /* numInputs samples */, float sr)
+    // as CUDA C++ text, evaluated once per sample.  It is compiled (NVRTC) into the kernel specialised for every render program that
+    // uses the type; numState = 0 makes it element-wise (all lanes), otherwise it runs in the lane that owns the voice.  Returns
+    // NodeTypeAlreadyExists (4) for a builtin or already registered name, like the reference.
+    int registerNodeType(const char* type, int numInputs, int numState, const char* body);
+    bool hasNodeType(const char* type) const;
     void setStream(cudaStream_t s);
     float* mixDevicePtr() { return dMix_; }
     float* voiceOutDevicePtr() { return dOutVoice_; }
@@ -221,6 +230,9 @@ public:
     // A cross-GPU barrier on the render stream (K4 with an empty payload): returns once every rank's stream has reached it.
     int peerBarrier();
     std::string describe() const;
+    // Runtime::snapshot() (Runtime.h:110,490-499): {"0x<node id, 8 hex digits>": {props...}, ...} of the voice group containing `voice`
+    // (per-voice capable props report the value last set for the group's highest addressed voice, like any other prop the last write).
+    std::string snapshot(int voice) const;
     // The encoded render program (program.h) of the voice group containing `voice` — the newest compiled one.  Introspection:
     // tests, and the input of per-program kernel specialisation.
     std::vector<uint32_t> programWords(int voice) const;
@@ -244,6 +256,9 @@ private:
     EngineOptions opt_;
     std::vector<std::unique_ptr<Group>> groups_;
     std::map<std::string, std::shared_ptr<Resource>> resources_;
+    struct CustomType { std::string name, body; int nIn = 0, nState = 0; };
+    std::vector<CustomType> customTypes_;
+    std::string customSource() const;     // the generated device text of all registered types (part of the specialisation key)
     std::string lastError_;
     uint64_t launches_ = 0;
     int64_t sampleTime_ = 0;

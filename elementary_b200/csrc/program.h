@@ -67,6 +67,9 @@ enum Opcode : uint32_t {
     OP_SNAPSHOT,   // Analyzers.h:77-136   state: z, latest value, readouts pushed
     OP_SCOPE,      // Analyzers.h:146-255, wasm/FFT.h:17-139  ptr = ring [tile][aux1][SCOPE_RING][L]; aux0 = index of the write position in LaunchParams::dyn
     OP_CAPTURE,    // Capture.h:14-103     ptr = [tile][aux0 + CAPTURE_SCRATCH][L] (ring then scratch); state: lastIn, scratchSize, w, r, ready
+    // ---- device node types registered at run time (elem_b200_register_node_type; reference: Runtime::registerNodeType, Runtime.h:105-106) ----
+    OP_CUSTOM,     // aux0 = registered type index, aux1 = state floats; operands, then one immediate word: bits of float(sr).  Has a body
+                   // only in a kernel specialised for the program (spec_host.h): the body text is compiled by NVRTC
     OP_COUNT_
 };
 

@@ -128,7 +128,7 @@ void workerLoop(std::shared_ptr<Queue> q) {
             q->jobs.pop_front();
         }
         std::string log;
-        const bool ok = specialise_compile(job->code, job->tileWidth, job->niterOverride, job->kernel, log);
+        const bool ok = specialise_compile(job->code, job->tileWidth, job->niterOverride, job->customSource, job->kernel, log);
         {
             std::lock_guard<std::mutex> lk(q->m);
             job->log = log;
@@ -156,7 +156,7 @@ std::vector<uint32_t> specialise_key_words(const std::vector<uint32_t>& code) {
     return out;
 }
 
-bool specialise_compile(const std::vector<uint32_t>& codeIn, int tileWidth, int niterOverride, SpecKernel& out, std::string& log) {
+bool specialise_compile(const std::vector<uint32_t>& codeIn, int tileWidth, int niterOverride, const std::string& customSource, SpecKernel& out, std::string& log) {
     if (!loadNvrtc(log)) return false;
     Api& a = api();
     const std::vector<uint32_t> code = specialise_key_words(codeIn);
@@ -166,6 +166,7 @@ bool specialise_compile(const std::vector<uint32_t>& codeIn, int tileWidth, int 
     hdr << "#pragma once\n#include \"rtc_compat.h\"\nnamespace eb {\n__device__ constexpr uint32_t EB_SPEC_CODE[] = {";
     for (size_t i = 0; i < code.size(); ++i) hdr << (i ? "," : "") << "0x" << std::hex << code[i] << "u";
     hdr << "};\nconstexpr int EB_SPEC_CODE_LEN = " << std::dec << code.size() << ";\n}\n#define EB_SPEC_PROGRAM 1\n";
+    hdr << customSource;      // bodies of the registered node types (OP_CUSTOM), if any
     const std::string hdrText = hdr.str();
     const char* hdrSrc[] = {hdrText.c_str(), eb_src_render_ops_inc, eb_src_program_h, eb_src_kernels_h, eb_src_rtc_compat_h};
     const char* hdrNames[] = {"eb_spec_program.h", "render_ops.inc", "program.h", "kernels.h", "rtc_compat.h"};
@@ -216,16 +217,17 @@ bool specialise_load(SpecKernel& k, std::string& log) {
     return true;
 }
 
-std::shared_ptr<SpecJob> specialise_request(const std::vector<uint32_t>& code, int tileWidth, int niterOverride, int device) {
+std::shared_ptr<SpecJob> specialise_request(const std::vector<uint32_t>& code, int tileWidth, int niterOverride, int device, const std::string& customSource) {
     auto q = queue();
     const std::vector<uint32_t> key = specialise_key_words(code);
     std::string k(reinterpret_cast<const char*>(key.data()), key.size() * sizeof(uint32_t));
-    k += "|L" + std::to_string(tileWidth) + "|n" + std::to_string(render_niter_for(tileWidth, niterOverride)) + "|d" + std::to_string(device);
+    k += "|c" + customSource + "|L" + std::to_string(tileWidth) + "|n" + std::to_string(render_niter_for(tileWidth, niterOverride)) + "|d" + std::to_string(device);
     std::lock_guard<std::mutex> lk(q->m);
     auto it = q->cache.find(k);
     if (it != q->cache.end() && it->second->state.load(std::memory_order_acquire) >= 0) return it->second;
     auto job = std::make_shared<SpecJob>();
     job->code = key;
+    job->customSource = customSource;
     job->tileWidth = tileWidth;
     job->niterOverride = niterOverride;
     q->cache[k] = job;

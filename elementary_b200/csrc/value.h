@@ -7,6 +7,7 @@
 // (a ~150-line recursive-descent parser) instead of vendoring a JSON library.
 #pragma once
 #include <cmath>
+#include <cstdio>
 #include <cstdint>
 #include <cstdlib>
 #include <map>
@@ -228,5 +229,46 @@ private:
 };
 
 inline Value parseJson(const char* s, size_t n) { return JsonParser(s, n).parseDocument(); }
+
+
+// JSON text of a Value (what the reference's js::serialize does for the types an instruction batch can carry, JSON.h:160-248):
+// numbers in shortest round-trip form, undefined as null.
+inline void writeJson(std::string& o, const Value& v) {
+    switch (v.type()) {
+        case Value::Type::Undefined: case Value::Type::Null: o += "null"; break;
+        case Value::Type::Bool: o += v.asBool() ? "true" : "false"; break;
+        case Value::Type::Number: {
+            const double d = v.asNumber();
+            if (!std::isfinite(d)) { o += "null"; break; }
+            char b[40];
+            if (d == std::floor(d) && std::fabs(d) < 1e15) std::snprintf(b, sizeof b, "%.0f", d);
+            else std::snprintf(b, sizeof b, "%.17g", d);
+            o += b;
+        } break;
+        case Value::Type::String: {
+            o += '"';
+            for (unsigned char ch : v.asString()) {
+                if (ch == '"' || ch == '\\') { o += '\\'; o += (char) ch; }
+                else if (ch == '\n') o += "\\n";
+                else if (ch == '\t') o += "\\t";
+                else if (ch < 0x20) { char b[8]; std::snprintf(b, sizeof b, "\\u%04x", ch); o += b; }
+                else o += (char) ch;
+            }
+            o += '"';
+        } break;
+        case Value::Type::Array: {
+            o += '[';
+            bool first = true;
+            for (auto& e : v.asArray()) { if (!first) o += ','; first = false; writeJson(o, e); }
+            o += ']';
+        } break;
+        case Value::Type::Object: {
+            o += '{';
+            bool first = true;
+            for (auto& kv : v.asObject()) { if (!first) o += ','; first = false; writeJson(o, Value::string(kv.first)); o += ':'; writeJson(o, kv.second); }
+            o += '}';
+        } break;
+    }
+}
 
 } // namespace eb

@@ -96,6 +96,12 @@ def load_library() -> C.CDLL:
     lib.elem_b200_process_queued_events_range.argtypes = [C.c_void_p, C.c_int, C.c_int, EVENT_CB, C.c_void_p]
     lib.elem_b200_set_option.restype = C.c_int
     lib.elem_b200_set_option.argtypes = [C.c_void_p, C.c_char_p, C.c_double]
+    lib.elem_b200_register_node_type.restype = C.c_int
+    lib.elem_b200_register_node_type.argtypes = [C.c_void_p, C.c_char_p, C.c_int, C.c_int, C.c_char_p]
+    lib.elem_b200_has_node_type.restype = C.c_int
+    lib.elem_b200_has_node_type.argtypes = [C.c_void_p, C.c_char_p]
+    lib.elem_b200_snapshot.restype = C.c_int
+    lib.elem_b200_snapshot.argtypes = [C.c_void_p, C.c_int, C.c_char_p, C.c_size_t]
     lib.elem_b200_describe.restype = C.c_int
     lib.elem_b200_describe.argtypes = [C.c_void_p, C.c_char_p, C.c_size_t]
     lib.elem_b200_program_words.restype = C.c_int
@@ -326,6 +332,21 @@ class Runtime:
         n = self._lib.elem_b200_describe(self._h, None, 0)
         buf = C.create_string_buffer(n + 16)
         self._lib.elem_b200_describe(self._h, buf, len(buf))
+        return json.loads(buf.value.decode())
+
+    def register_node_type(self, type_name: str, num_inputs: int, num_state: int, cuda_body: str) -> int:
+        """Runtime::registerNodeType (Runtime.h:105-106) for device code: ``cuda_body`` is the body of
+        ``float node(float* s, const float* in, const float sr)``; returns the reference's codes (4 = name taken)."""
+        return self._lib.elem_b200_register_node_type(self._h, type_name.encode(), int(num_inputs), int(num_state), cuda_body.encode())
+
+    def has_node_type(self, type_name: str) -> bool:
+        return bool(self._lib.elem_b200_has_node_type(self._h, type_name.encode()))
+
+    def snapshot(self, voice: int = 0) -> dict:
+        """Runtime::snapshot() (Runtime.h:110,490-499): {"0x<hex node id>": props} of the voice group containing ``voice``."""
+        n = self._lib.elem_b200_snapshot(self._h, int(voice), None, 0)
+        buf = C.create_string_buffer(n + 16)
+        self._lib.elem_b200_snapshot(self._h, int(voice), buf, len(buf))
         return json.loads(buf.value.decode())
 
     def program_words(self, voice: int = 0) -> np.ndarray:

@@ -124,6 +124,23 @@ int elem_b200_process_queued_events_range(elem_b200_runtime* rt, int voiceBegin,
 /* Tuning and introspection (no reference equivalent). Keys: "tile_width" (1..32, 0 =
  * auto), "warps_per_cta", "target_tiles", "time_kernels" (0|1), "specialize" (0|1, experimental). Must be set before the first COMMIT of a voice group. */
 int elem_b200_set_option(elem_b200_runtime* rt, const char* key, double value);
+/* Runtime::registerNodeType(type, NodeFactoryFn) — Runtime.h:105-106,480-487 (the plug-in / operator interface of GraphNode.h:20-96).
+ * In a fused-kernel engine a new node type is DEVICE code: `cudaBody` is the body of
+ *     float node(float* s, const float* in, const float sr)
+ * as CUDA C++ text, evaluated once per sample: in[0..numInputs) are this sample's input values (children in order), s[0..numStateFloats)
+ * the node's persistent per-voice state (zero-initialised, GraphNode members in the reference), sr the sample rate; the return value is
+ * the node's output sample.  numStateFloats = 0 declares the node element-wise.  The body is compiled by NVRTC into the kernel
+ * specialised for every render program that uses the type (COMMIT returns 7 with the compiler log in elem_b200_last_error if it does
+ * not compile).  Like the reference: 4 (NodeTypeAlreadyExists) for a builtin or already registered name; nodes of the type lacking
+ * inputs render zeros; instructions naming an unregistered type return 1.  elem_b200_has_node_type: 1 if `type` is builtin or registered. */
+int elem_b200_register_node_type(elem_b200_runtime* rt, const char* type, int numInputs, int numStateFloats, const char* cudaBody);
+int elem_b200_has_node_type(elem_b200_runtime* rt, const char* type);
+
+/* Runtime::snapshot() — Runtime.h:110,490-499: the node table of the voice group containing `voice` as JSON text
+ * {"0x<node id as 8 hex digits>": {<props>}, ...} (nodeIdToHex, Types.h:16-27; props as they were last set, GraphNode.h:60-64,130).
+ * Returns the bytes needed including the terminating NUL; writes at most cap. */
+int elem_b200_snapshot(elem_b200_runtime* rt, int voice, char* buf, size_t cap);
+
 /* JSON description of voice groups and compiled programs; returns bytes needed. */
 int elem_b200_describe(elem_b200_runtime* rt, char* buf, size_t cap);
 /* The encoded render program (32-bit words, elementary_b200/csrc/program.h) of the voice group containing `voice`; writes up to

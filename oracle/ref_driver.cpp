@@ -41,6 +41,29 @@
 
 namespace {
 
+// Two node types registered through the REFERENCE's own plug-in interface (Runtime::registerNodeType, GraphNode.h:20-96) — test
+// fixtures for the device-side registration of the CUDA path (elem_b200_register_node_type): the same two types are registered there
+// as CUDA text and must render the same samples.
+//   "b200test.softclip": y = x / (1 + |x|)                      (stateless, 1 input)
+//   "b200test.leaky":    s = x + g * s; y = s   (g = 2nd input)   (one float of state, 2 inputs)
+template <typename F>
+struct SoftClipNode : public elem::GraphNode<F> {
+    using elem::GraphNode<F>::GraphNode;
+    void process(elem::BlockContext<F> const& ctx) override {
+        if (ctx.numInputChannels < 1) { std::fill_n(ctx.outputData[0], ctx.numSamples, F(0)); return; }
+        for (size_t i = 0; i < ctx.numSamples; ++i) { const F x = ctx.inputData[0][i]; ctx.outputData[0][i] = x / (F(1) + std::fabs(x)); }
+    }
+};
+template <typename F>
+struct LeakyNode : public elem::GraphNode<F> {
+    using elem::GraphNode<F>::GraphNode;
+    F s = 0;
+    void process(elem::BlockContext<F> const& ctx) override {
+        if (ctx.numInputChannels < 2) { std::fill_n(ctx.outputData[0], ctx.numSamples, F(0)); return; }
+        for (size_t i = 0; i < ctx.numSamples; ++i) { s = ctx.inputData[0][i] + ctx.inputData[1][i] * s; ctx.outputData[0][i] = s; }
+    }
+};
+
 struct RefRuntime {
     elem::Runtime<float> rt;
     int64_t sampleTime = 0;   // the host-kept clock handed to nodes as userData (wasm/Main.cpp:206-217)
@@ -58,6 +81,8 @@ struct RefRuntime {
         rt.registerNodeType("time", [](elem::NodeId const id, double fs, int const bs) {
             return std::make_shared<elem::SampleTimeNode<float>>(id, fs, bs);
         });
+        rt.registerNodeType("b200test.softclip", [](elem::NodeId const id, double fs, int const bs) { return std::make_shared<SoftClipNode<float>>(id, fs, bs); });
+        rt.registerNodeType("b200test.leaky", [](elem::NodeId const id, double fs, int const bs) { return std::make_shared<LeakyNode<float>>(id, fs, bs); });
     }
 };
 

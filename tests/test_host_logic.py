@@ -246,3 +246,41 @@ def test_specialisation_runs_in_the_background_or_on_demand():
     rt = plan(64, specialize=2, specialize_max_words=100)        # too long for the limit: the interpreter stays
     assert rt.apply_instructions(graphs.subsynth32()) == 0
     assert "spec_state" not in rt.describe()["groups"][0]
+
+
+# ---- Runtime::registerNodeType / snapshot (Runtime.h:105-110) at the boundary -------------------------------------------------
+SOFTCLIP = "const float x = in[0]; return x / (1.0f + fabsf(x));"
+LEAKY = "s[0] = in[0] + in[1] * s[0]; return s[0];"
+
+
+def test_register_node_type_return_codes_and_compile():
+    from elementary_b200 import el
+    rt = plan(8)
+    assert rt.has_node_type("svf") and not rt.has_node_type("b200test.softclip")
+    assert rt.apply_instructions([[0, 1, "b200test.softclip"]]) == 1            # UnknownNodeType before registration (Runtime.h:304-305)
+    assert rt.register_node_type("svf", 1, 0, SOFTCLIP) == 4                     # NodeTypeAlreadyExists for a builtin (Runtime.h:482-483)
+    assert rt.register_node_type("b200test.softclip", 1, 0, SOFTCLIP) == 0
+    assert rt.register_node_type("b200test.softclip", 1, 0, SOFTCLIP) == 4
+    assert rt.register_node_type("b200test.leaky", 2, 1, LEAKY) == 0
+    g = el.create_node("b200test.leaky", {}, [el.create_node("b200test.softclip", {}, [el.cycle(220.0)]), el.const(0.5, key="g")])
+    assert rt.apply_instructions(el.render(g)) == 0, rt.last_error()             # COMMIT compiles the bodies with NVRTC (no GPU needed)
+    d = rt.describe()["groups"][0]
+    assert d["spec_state"] == 1 and d["spec_cubin_bytes"] > 10000
+    # a body that does not compile fails the COMMIT with the compiler's message
+    rt2 = plan(8)
+    assert rt2.register_node_type("broken", 1, 0, "return in[0] +;") == 0
+    assert rt2.apply_instructions(el.render(el.create_node("broken", {}, [el.cycle(1.0)]))) == 7
+    assert "error" in rt2.last_error()
+
+
+def test_snapshot_lists_nodes_and_props_like_the_reference():
+    from elementary_b200 import el
+    rt = plan(4)
+    g = el.svf({"mode": "highpass"}, el.const(800.0, key="fc"), 1.0, el.cycle(220.0))
+    assert rt.apply_instructions(el.render(g)) == 0
+    snap = rt.snapshot()
+    fc = el.const(0, key="fc").id()
+    key = "0x%08x" % (fc & 0xFFFFFFFF)
+    assert key in snap and snap[key]["value"] == 800.0
+    assert any(v.get("mode") == "highpass" for v in snap.values())
+    assert all(k.startswith("0x") and len(k) == 10 for k in snap)

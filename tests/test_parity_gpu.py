@@ -540,3 +540,28 @@ def test_control_thread_edits_while_render_thread_processes(tmp_path):
     assert r.returncode == 0, (r.stdout[-500:], r.stderr[-2000:])
     stats = json.loads(r.stdout.strip().splitlines()[-1])
     assert stats["blocks"] > 100 and stats["edits"] > 10 and stats["failures"] == 0, stats
+
+
+@pytest.mark.parametrize("tile_width", [0, 2, 32])
+def test_registered_device_node_types_match_the_reference_plugin_nodes(tile_width):
+    """Runtime::registerNodeType (Runtime.h:105-106): two node types registered as CUDA text here and as GraphNode subclasses on the
+    reference (oracle/ref_driver.cpp, through the reference's own registerNodeType) render the same samples: a stateless one
+    (all lanes) and a stateful one (owner-lane recurrence whose state survives blocks)."""
+    from oracle import oracle as orc
+    if not orc.ref_available():
+        pytest.skip("needs the compiled reference (its plug-in interface is what is being mirrored)")
+    n_voices = 5 if tile_width != 32 else 37
+    soft = el.create_node("b200test.softclip", {}, [el.mul(3.0, IN0)])
+    g = el.add(el.create_node("b200test.leaky", {}, [soft, el.const(0.9, key="g")]), el.mul(0.1, el.cycle(330.0)))
+    batch = el.render(g)
+    opts = {"tile_width": tile_width} if tile_width else {}
+    rt = Runtime(SR, BS, n_voices, device=0, **opts)
+    assert rt.register_node_type("b200test.softclip", 1, 0, "const float x = in[0]; return x / (1.0f + fabsf(x));") == 0
+    assert rt.register_node_type("b200test.leaky", 2, 1, "s[0] = in[0] + in[1] * s[0]; return s[0];") == 0
+    assert rt.apply_instructions(batch) == 0, rt.last_error()
+    inputs = np.stack([np.stack([lcg_noise(4 * BS, 100 * v)]) for v in range(n_voices)])
+    got, mix = rt.render_voices(4, 1, inputs)
+    assert rt.describe()["groups"][0]["spec_state"] == 2
+    ref = oracle_render(batch, 4, 1, SR, BS, inputs, voice_batches=[None] * n_voices, cls=orc.RefRuntime)
+    ok, worst, ex = block_peak_tolerance_check(got, ref, BS)
+    assert ok, f"worst err/tol {worst:.3g}, bit-exact {ex:.4f}"
