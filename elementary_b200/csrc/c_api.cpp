@@ -59,6 +59,16 @@ int elem_b200_apply_instructions(elem_b200_runtime* rt, int voiceBegin, int voic
     GUARD(rt->engine->applyInstructions(voiceBegin, voiceEnd, json, len));
 }
 
+int elem_b200_apply_binary(elem_b200_runtime* rt, int voiceBegin, int voiceEnd, const void* data, size_t bytes) {
+    if (!data) return eb::rc::BadArgument;
+    GUARD(rt->engine->applyBinary(voiceBegin, voiceEnd, data, bytes));
+}
+
+int elem_b200_set_const_table(elem_b200_runtime* rt, const int32_t* nodeIds, int numProps, const float* values, int voiceBegin, int count) {
+    if (!nodeIds || !values) return eb::rc::BadArgument;
+    GUARD(rt->engine->setConstTable(nodeIds, numProps, values, voiceBegin, count));
+}
+
 int elem_b200_set_property_per_voice(elem_b200_runtime* rt, int32_t nodeId, const char* key, const double* values, int voiceBegin, int count) {
     if (!key || !values) return eb::rc::BadArgument;
     GUARD(rt->engine->setPropertyPerVoice(nodeId, key, values, voiceBegin, count));

@@ -71,9 +71,7 @@ void Engine::setStream(cudaStream_t s) {
 
 // ---------------------------------------------------------------------------------------------------------
 Program::~Program() {
-    if (dCode) rawFree(dCode, planOnly);
-    if (dStateMap) rawFree(dStateMap, planOnly);
-    if (dParamMap) rawFree(dParamMap, planOnly);
+    if (dCode) rawFree(dCode, planOnly);      // stateMap / paramMap live in the same allocation
     for (float* p : blockBuffers) rawFree(p, planOnly);
 }
 
@@ -329,9 +327,11 @@ int Engine::fillRowBits(Group& g, int row, int vb, int ve, uint32_t bits) {
     if (n <= 0) return rc::Ok;
     uint32_t* p = reinterpret_cast<uint32_t*>(g.dRows + (size_t) row * g.Vpad + vb);
     if (bits == 0) return cuda(dmemset(p, 0, sizeof(float) * n), "memset row") ? rc::Ok : rc::CudaError;
+    // cudaMemcpyAsync from PAGEABLE host memory returns once the source has been copied to the driver's staging buffer (CUDA runtime
+    // API, "API synchronization behavior"): tmp may die right after the call, no stream synchronisation needed — a graph with fifty
+    // consts used to cost fifty of them (config 5 set-up: 1250 graphs).
     std::vector<uint32_t> tmp((size_t) n, bits);
     if (!cuda(dmemcpy(p, tmp.data(), sizeof(uint32_t) * n, cudaMemcpyHostToDevice), "fill row")) return rc::CudaError;
-    dsync();   // tmp is pageable and dies here
     return rc::Ok;
 }
 
@@ -937,8 +937,10 @@ int Engine::applyInstructions(int vb, int ve, const char* json, size_t len) {
     if (!parsed) return fail(rc::InvalidInstructionFormat, parseError);
     lastError_.clear();
     if (!doc.isArray()) return fail(rc::InvalidInstructionFormat, "batch is not an array");
-    auto& batch = doc.asArray();
+    return applyBatch(vb, ve, doc.asArray());
+}
 
+int Engine::applyBatch(int vb, int ve, const std::vector<Value>& batch) {
     if (!isValueOnlyBatch(batch, vb, ve)) {
         int r = splitGroupsAt(vb);
         if (r != rc::Ok) return r;
@@ -949,6 +951,82 @@ int Engine::applyInstructions(int vb, int ve, const char* json, size_t len) {
         if (b >= e) continue;
         int r = applyToGroup(*g, batch, b - g->v0, e - g->v0);
         if (r != rc::Ok) { if (lastError_.empty()) lastError_ = "instruction failed"; return r; }
+    }
+    return rc::Ok;
+}
+
+// Binary instruction batch (include/elem_b200.h "binary batch format"): little-endian, unaligned.
+namespace {
+struct BinReader {
+    const unsigned char* p; const unsigned char* end; bool ok = true;
+    template <typename T> T get() { T v{}; if ((size_t) (end - p) < sizeof(T)) { ok = false; return v; } std::memcpy(&v, p, sizeof(T)); p += sizeof(T); return v; }
+    std::string str(size_t n) { if ((size_t) (end - p) < n) { ok = false; return std::string(); } std::string s(reinterpret_cast<const char*>(p), n); p += n; return s; }
+};
+}
+
+int Engine::applyBinary(int vb, int ve, const void* data, size_t bytes) {
+    BinReader r{static_cast<const unsigned char*>(data), static_cast<const unsigned char*>(data) + bytes};
+    if (r.get<uint32_t>() != 0x49324245u /* "EB2I" */ || r.get<uint32_t>() != 1u) { Lock lk(mu_); return fail(rc::InvalidInstructionFormat, "binary batch: bad magic or version"); }
+    const uint32_t count = r.get<uint32_t>();
+    std::vector<Value> batch;
+    batch.reserve(count);
+    for (uint32_t i = 0; i < count && r.ok; ++i) {          // decoded outside the lock, like the JSON text
+        Value ins = Value::array();
+        auto& a = ins.asArray();
+        const uint8_t op = r.get<uint8_t>();
+        a.push_back(Value::number(op));
+        switch (op) {
+            case 0: { const int32_t id = r.get<int32_t>(); const uint16_t n = r.get<uint16_t>(); a.push_back(Value::number(id)); a.push_back(Value::string(r.str(n))); } break;
+            case 2: { for (int k = 0; k < 3; ++k) a.push_back(Value::number(r.get<int32_t>())); } break;
+            case 3: {
+                const int32_t id = r.get<int32_t>(); const uint16_t n = r.get<uint16_t>();
+                a.push_back(Value::number(id)); a.push_back(Value::string(r.str(n)));
+                const uint8_t vt = r.get<uint8_t>();
+                switch (vt) {
+                    case 0: a.push_back(Value::null()); break;
+                    case 1: a.push_back(Value::boolean(r.get<uint8_t>() != 0)); break;
+                    case 2: a.push_back(Value::number(r.get<double>())); break;
+                    case 3: { const uint32_t len = r.get<uint32_t>(); a.push_back(Value::string(r.str(len))); } break;
+                    case 4: { const uint32_t len = r.get<uint32_t>(); Value arr = Value::array(); arr.asArray().reserve(len);
+                              for (uint32_t k = 0; k < len && r.ok; ++k) arr.asArray().push_back(Value::number(r.get<float>())); a.push_back(arr); } break;
+                    case 5: { const uint32_t len = r.get<uint32_t>(); const std::string js = r.str(len);      // anything else travels as JSON text
+                              try { a.push_back(parseJson(js.data(), js.size())); } catch (const std::exception&) { r.ok = false; } } break;
+                    default: r.ok = false; break;
+                }
+            } break;
+            case 4: { const uint32_t n = r.get<uint32_t>(); Value roots = Value::array(); for (uint32_t k = 0; k < n && r.ok; ++k) roots.asArray().push_back(Value::number(r.get<int32_t>())); a.push_back(roots); } break;
+            case 5: break;
+            default: r.ok = false; break;
+        }
+        batch.push_back(std::move(ins));
+    }
+    Lock lk(mu_);
+    dsetdev();
+    if (!r.ok) return fail(rc::InvalidInstructionFormat, "binary batch: truncated or malformed");
+    if (vb < 0) vb = 0;
+    if (ve < 0 || ve > numVoices_) ve = numVoices_;
+    if (vb >= ve) return fail(rc::BadArgument, "empty voice range");
+    lastError_.clear();
+    return applyBatch(vb, ve, batch);
+}
+
+int Engine::setConstTable(const int32_t* nodeIds, int nProps, const float* values, int vb, int count) {
+    Lock lk(mu_);
+    dsetdev();
+    if (vb < 0 || count < 0 || vb + count > numVoices_ || nProps < 0) return fail(rc::BadArgument, "voice range out of bounds");
+    for (auto& gp : groups_) {
+        Group& g = *gp;
+        const int b = std::max(vb, g.v0), e = std::min(vb + count, g.v0 + g.nv);
+        if (b >= e) continue;
+        for (int p = 0; p < nProps; ++p) {
+            auto it = g.nodes.find(nodeIds[p]);
+            if (it == g.nodes.end()) return rc::NodeNotFound;
+            Node& n = it->second;
+            if (n.kind != NodeKind::Const) return fail(rc::InvalidPropertyType, "property table rows must address const nodes");
+            const float* src = values + (size_t) p * count + (b - vb);
+            if (!cuda(dmemcpy(g.dRows + (size_t) n.paramRow * g.Vpad + (b - g.v0), src, sizeof(float) * (size_t) (e - b), cudaMemcpyHostToDevice), "property table upload")) return rc::CudaError;
+            n.props["value"] = Value::number(src[e - b - 1]);
+        }
     }
     return rc::Ok;
 }
@@ -976,8 +1054,7 @@ int Engine::setPropertyPerVoice(int32_t nodeId, const char* key, const double* v
             row = n.stateRow;
             for (int v = b; v < e; ++v) bits[v - b] = static_cast<uint32_t>(values[v - vb]);
         } else return fail(rc::InvalidPropertyType, "property is not per-voice capable");
-        if (!cuda(dmemcpy(g.dRows + (size_t) row * g.Vpad + (b - g.v0), bits.data(), sizeof(uint32_t) * bits.size(), cudaMemcpyHostToDevice), "per-voice prop upload")) return rc::CudaError;
-        dsync();
+        if (!cuda(dmemcpy(g.dRows + (size_t) row * g.Vpad + (b - g.v0), bits.data(), sizeof(uint32_t) * bits.size(), cudaMemcpyHostToDevice), "per-voice prop upload")) return rc::CudaError;   // pageable source: staged before the call returns
         n.props[k] = Value::number(values[e - 1 - vb]);
     }
     return rc::Ok;
@@ -1813,16 +1890,20 @@ int Engine::compile(Group& g, int nIn, std::shared_ptr<Program>& out) {
     prog->nStateRows = (nStateRows + 1) & ~1;
     prog->nSlots = nSlotsMax;
 
-    // ---- upload ----
-    if (!cuda(dmalloc((void**) &prog->dCode, sizeof(uint32_t) * prog->code.size()), "cudaMalloc code")) return rc::CudaError;
-    if (!cuda(dmemcpySync(prog->dCode, prog->code.data(), sizeof(uint32_t) * prog->code.size(), cudaMemcpyHostToDevice), "upload code")) return rc::CudaError;
-    if (!prog->stateMap.empty()) {
-        if (!cuda(dmalloc((void**) &prog->dStateMap, sizeof(uint32_t) * prog->stateMap.size()), "cudaMalloc stateMap")) return rc::CudaError;
-        if (!cuda(dmemcpySync(prog->dStateMap, prog->stateMap.data(), sizeof(uint32_t) * prog->stateMap.size(), cudaMemcpyHostToDevice), "upload stateMap")) return rc::CudaError;
-    }
-    if (!prog->paramMap.empty()) {
-        if (!cuda(dmalloc((void**) &prog->dParamMap, sizeof(uint32_t) * prog->paramMap.size()), "cudaMalloc paramMap")) return rc::CudaError;
-        if (!cuda(dmemcpySync(prog->dParamMap, prog->paramMap.data(), sizeof(uint32_t) * prog->paramMap.size(), cudaMemcpyHostToDevice), "upload paramMap")) return rc::CudaError;
+    // ---- upload: code, stateMap and paramMap in ONE allocation; the copies are stream-ordered in front of the first launch and their
+    // sources are members of the Program, so nothing has to be waited for here ----
+    {
+        const size_t codeW = (prog->code.size() + 3) & ~(size_t) 3, smW = (prog->stateMap.size() + 3) & ~(size_t) 3, pmW = prog->paramMap.size();
+        if (!cuda(dmalloc((void**) &prog->dCode, sizeof(uint32_t) * (codeW + smW + pmW + 4)), "cudaMalloc program")) return rc::CudaError;
+        if (!cuda(dmemcpy(prog->dCode, prog->code.data(), sizeof(uint32_t) * prog->code.size(), cudaMemcpyHostToDevice), "upload code")) return rc::CudaError;
+        if (!prog->stateMap.empty()) {
+            prog->dStateMap = prog->dCode + codeW;
+            if (!cuda(dmemcpy(prog->dStateMap, prog->stateMap.data(), sizeof(uint32_t) * prog->stateMap.size(), cudaMemcpyHostToDevice), "upload stateMap")) return rc::CudaError;
+        }
+        if (!prog->paramMap.empty()) {
+            prog->dParamMap = prog->dCode + codeW + smW;
+            if (!cuda(dmemcpy(prog->dParamMap, prog->paramMap.data(), sizeof(uint32_t) * prog->paramMap.size(), cudaMemcpyHostToDevice), "upload paramMap")) return rc::CudaError;
+        }
     }
     // Per-program specialisation of K1 (spec_host.h).  Not for groups that render through the batched many-groups launch (that
     // kernel is the interpreter by construction: one launch serves different programs), not for multi-stage programs.

@@ -176,6 +176,13 @@ public:
 
     int applyInstructions(int voiceBegin, int voiceEnd, const char* json, size_t len);
     int setPropertyPerVoice(int32_t nodeId, const char* key, const double* values, int voiceBegin, int count);
+    // Instruction-stream ingestion at scale.  applyBinary: the SAME instruction stream in the binary encoding
+    // documented in include/elem_b200.h (no text to parse: ids are int32, numbers float64, strings length-prefixed), decoded into the
+    // same in-memory batch and run through the same interpreter — identical semantics and return codes.  setConstTable: a per-voice
+    // property TABLE, values[p][count] float32 row-major -> `value` of const node nodeIds[p] for voices [voiceBegin, voiceBegin +
+    // count): nProps copies straight from the caller's table, no per-value conversion, no JSON.
+    int applyBinary(int voiceBegin, int voiceEnd, const void* data, size_t bytes);
+    int setConstTable(const int32_t* nodeIds, int nProps, const float* values, int voiceBegin, int count);
     int addSharedResource(const char* name, const float* const* chans, size_t nCh, size_t nSamples);
     void pruneSharedResources();
     std::vector<std::string> listSharedResources() const;
@@ -299,6 +306,7 @@ private:
 
     // instruction interpreter (Runtime.h:170-433)
     int applyToGroup(Group& g, const std::vector<Value>& batch, int vb, int ve);
+    int applyBatch(int vb, int ve, const std::vector<Value>& batch);
     int createNode(Group& g, const Value& id, const Value& type);
     int appendChild(Group& g, const Value& parent, const Value& child, const Value& chan);
     int setProperty(Group& g, const Value& id, const Value& key, const Value& val, int vb, int ve);

@@ -370,3 +370,45 @@ def render(*graphs: ElemNode) -> List[list]:
 
 def to_json(batch: List[list]) -> str:
     return json.dumps(batch)
+
+
+def encode_binary(batch) -> bytes:
+    """The instruction batch (list form, Appendix B of SURVEY.md) in the binary encoding of include/elem_b200.h ('EB2I' v1)."""
+    import json as _json
+    import struct
+    out = [struct.pack("<III", 0x49324245, 1, len(batch))]
+    for ins in batch:
+        op = int(ins[0])
+        out.append(struct.pack("<B", op))
+        if op == 0:
+            t = str(ins[2]).encode()
+            out.append(struct.pack("<iH", int(ins[1]), len(t)) + t)
+        elif op == 2:
+            out.append(struct.pack("<iii", int(ins[1]), int(ins[2]), int(ins[3])))
+        elif op == 3:
+            k = str(ins[2]).encode()
+            out.append(struct.pack("<iH", int(ins[1]), len(k)) + k)
+            v = ins[3]
+            if v is None:
+                out.append(struct.pack("<B", 0))
+            elif isinstance(v, bool):
+                out.append(struct.pack("<BB", 1, 1 if v else 0))
+            elif isinstance(v, (int, float)):
+                out.append(struct.pack("<Bd", 2, float(v)))
+            elif isinstance(v, str):
+                b = v.encode()
+                out.append(struct.pack("<BI", 3, len(b)) + b)
+            elif isinstance(v, (list, tuple)) and all(isinstance(x, (int, float)) and not isinstance(x, bool) for x in v) and \
+                    all(struct.unpack("<f", struct.pack("<f", float(x)))[0] == float(x) for x in v):
+                out.append(struct.pack("<BI", 4, len(v)) + struct.pack("<%df" % len(v), *[float(x) for x in v]))
+            else:
+                b = _json.dumps(v).encode()
+                out.append(struct.pack("<BI", 5, len(b)) + b)
+        elif op == 4:
+            ids = [int(x) for x in ins[1]]
+            out.append(struct.pack("<I", len(ids)) + struct.pack("<%di" % len(ids), *ids))
+        elif op == 5:
+            pass
+        else:
+            raise ValueError(f"unknown opcode {op}")
+    return b"".join(out)

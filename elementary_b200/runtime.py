@@ -54,6 +54,10 @@ def load_library() -> C.CDLL:
     lib.elem_b200_destroy.argtypes = [C.c_void_p]
     lib.elem_b200_apply_instructions.restype = C.c_int
     lib.elem_b200_apply_instructions.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_char_p, C.c_size_t]
+    lib.elem_b200_apply_binary.restype = C.c_int
+    lib.elem_b200_apply_binary.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_char_p, C.c_size_t]
+    lib.elem_b200_set_const_table.restype = C.c_int
+    lib.elem_b200_set_const_table.argtypes = [C.c_void_p, C.POINTER(C.c_int32), C.c_int, _f32p, C.c_int, C.c_int]
     lib.elem_b200_set_property_per_voice.restype = C.c_int
     lib.elem_b200_set_property_per_voice.argtypes = [C.c_void_p, C.c_int32, C.c_char_p, C.POINTER(C.c_double), C.c_int, C.c_int]
     lib.elem_b200_process.restype = C.c_int
@@ -178,6 +182,19 @@ class Runtime:
         b = s.encode() if isinstance(s, str) else s
         vb, ve = (0, -1) if voices is None else (int(voices[0]), int(voices[1]))
         return self._lib.elem_b200_apply_instructions(self._h, vb, ve, b, len(b))
+
+    def apply_binary(self, data: bytes, voices: Optional[Sequence[int]] = None) -> int:
+        """Apply an instruction batch in the binary encoding (include/elem_b200.h; ``el.encode_binary`` writes it)."""
+        vb, ve = (0, -1) if voices is None else (int(voices[0]), int(voices[1]))
+        return self._lib.elem_b200_apply_binary(self._h, vb, ve, data, len(data))
+
+    def set_const_table(self, node_ids, values, voice_begin: int = 0) -> int:
+        """values[p][i] -> ``value`` of const node ``node_ids[p]`` for voice ``voice_begin + i`` (float32 table, one copy per row)."""
+        ids = np.ascontiguousarray(np.asarray(node_ids, dtype=np.int32))
+        v = np.ascontiguousarray(np.asarray(values, dtype=np.float32))
+        assert v.ndim == 2 and v.shape[0] == ids.size
+        return self._lib.elem_b200_set_const_table(self._h, ids.ctypes.data_as(C.POINTER(C.c_int32)), ids.size,
+                                                   v.ctypes.data_as(_f32p), int(voice_begin), v.shape[1])
 
     def set_property_per_voice(self, node_id: int, key: str, values, voice_begin: int = 0) -> int:
         v = np.ascontiguousarray(np.asarray(values, dtype=np.float64))

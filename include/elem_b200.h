@@ -42,6 +42,23 @@ void elem_b200_destroy(elem_b200_runtime* rt);
  * per-voice capable props (const.value, rand.seed) may address any sub-range. */
 int elem_b200_apply_instructions(elem_b200_runtime* rt, int voiceBegin, int voiceEnd, const char* json, size_t len);
 
+/* Instruction-stream ingestion at scale (what runtime/elem/JSON.h:17-156 costs when there are a million voices).
+ * BINARY BATCH FORMAT — the same instruction stream (core/index.ts:43-49, Runtime.h:115-121), same semantics, same return codes:
+ *   little-endian, unaligned:  u32 magic 'EB2I' (0x49324245)  u32 version = 1  u32 numInstructions, then per instruction  u8 opcode:
+ *     0 CREATE_NODE     i32 id, u16 len, type bytes
+ *     2 APPEND_CHILD    i32 parent, i32 child, i32 childOutputChannel
+ *     3 SET_PROPERTY    i32 id, u16 len, key bytes, u8 valueType: 0 null | 1 bool (u8) | 2 number (f64) | 3 string (u32 len, bytes)
+ *                                                         | 4 float array (u32 n, f32[n]) | 5 any other value as JSON text (u32 len, bytes)
+ *     4 ACTIVATE_ROOTS  u32 n, i32 ids[n]
+ *     5 COMMIT_UPDATES
+ * elementary_b200.el.encode_binary() writes it from the list form. */
+int elem_b200_apply_binary(elem_b200_runtime* rt, int voiceBegin, int voiceEnd, const void* data, size_t bytes);
+
+/* Per-voice property TABLE: values[p][i] (float32, row-major, numProps rows of `count`) -> the `value` prop of const node nodeIds[p]
+ * for voice voiceBegin+i.  One device copy per row straight from the caller's table: a million voices x a dozen per-voice constants
+ * are a dozen copies, not a dozen million JSON numbers.  Equivalent to the [[3,nodeIds[p],"value",values[p][i]]] batches. */
+int elem_b200_set_const_table(elem_b200_runtime* rt, const int32_t* nodeIds, int numProps, const float* values, int voiceBegin, int count);
+
 /* Vectorised SET_PROPERTY: values[i] -> voice voiceBegin+i; equivalent to `count` single-voice
  * [[3,nodeId,key,values[i]]] batches (Runtime.h:316-333) without `count` JSON parses. */
 int elem_b200_set_property_per_voice(elem_b200_runtime* rt, int32_t nodeId, const char* key,
