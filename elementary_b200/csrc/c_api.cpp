@@ -85,6 +85,10 @@ int elem_b200_process_voices(elem_b200_runtime* rt, const float* in, size_t nIn,
     GUARD(rt->engine->processVoices(in, nIn, outVoices, mix, nOut, numSamples));
 }
 
+int elem_b200_render_offline(elem_b200_runtime* rt, size_t nOut, size_t numBlocks, float* hostOut, size_t chunkBlocks) {
+    GUARD(rt->engine->renderOffline(nOut, numBlocks, hostOut, chunkBlocks));
+}
+
 int elem_b200_enqueue_block(elem_b200_runtime* rt, size_t nIn, size_t nOut, size_t numSamples, int flags) {
     GUARD(rt->engine->enqueueBlock(nIn, nOut, numSamples, (flags & 1) != 0, (flags & 2) != 0, (flags & 4) != 0, (flags & 8) != 0));
 }

@@ -198,6 +198,7 @@ bool Engine::cuda(cudaError_t e, const char* what) {
 
 int Engine::setOption(const char* key, double value) {
     Lock lk(mu_);
+    steadyValid_ = false;
     const std::string k(key);
     if (k == "tile_width") { opt_.tileWidth = (int) value; }
     else if (k == "warps_per_cta") { opt_.warpsPerCta = (int) value; }
@@ -941,6 +942,7 @@ int Engine::applyInstructions(int vb, int ve, const char* json, size_t len) {
 }
 
 int Engine::applyBatch(int vb, int ve, const std::vector<Value>& batch) {
+    steadyValid_ = false;
     if (!isValueOnlyBatch(batch, vb, ve)) {
         int r = splitGroupsAt(vb);
         if (r != rc::Ok) return r;
@@ -1941,7 +1943,7 @@ int Engine::ensureBuffers(size_t nIn, size_t nOut, bool perVoiceIn, bool materia
         dmemset(dPartial_, 0, sizeof(float) * pf);
         partialFloats_ = pf;
     }
-    if (materialise) {
+    if (materialise && !offlineOut_) {
         const size_t of = (size_t) numVoices_ * nOut * blockSize_;
         if (of > outVoiceFloats_) {
             dsync();
@@ -1992,6 +1994,28 @@ int Engine::enqueueBlock(size_t nIn, size_t nOut, size_t numSamples, bool perVoi
     dsetdev();
     if (numSamples > (size_t) blockSize_ || nOut > (size_t) MAX_OUT_CHANNELS) return fail(rc::BadArgument, "numSamples > blockSize or too many output channels");
 
+    const size_t key[6] = {nIn, nOut, numSamples, (size_t) perVoiceIn, (size_t) materialise | ((size_t) (uintptr_t) offlineOut_ << 1), (size_t) mix | ((size_t) offlineStride_ << 1)};
+    if (steadyValid_ && !dry && std::memcmp(key, steadyKey_, sizeof key) == 0) {
+        for (auto& sb : steadyBuckets_) {
+            BatchBuffers& bb = batch_[sb.L];
+            auto ev = timedBegin();
+            if (!cuda(launch_render_groups(bb.dDescs, bb.dTileStart, sb.nGroups, sb.totalTiles, sb.L, sb.maxSlots, (int) nOut, sb.maxState, sb.maxParams, sb.wpc, sampleTime_, offlineOut_ ? offlineOffset_ : 0, stream_),
+                      "render groups kernel launch")) return rc::CudaError;
+            if (timeKernels_) { cudaEventRecord(ev.second, stream_); timedEvents_.push_back(ev); }
+            ++launches_;
+        }
+        if (mix) {
+            auto ev = timedBegin();
+            if (!cuda(launch_mix_reduce(dPartial_, dMix_, dMixScratch_, dMixTickets_, steadyTiles_, (int) nOut, blockSize_, (int) numSamples, stream_), "mix reduce launch")) return rc::CudaError;
+            if (timeKernels_) { cudaEventRecord(ev.second, stream_); timedMixEvents_.push_back(ev); }
+            ++launches_;
+        }
+        curNOut_ = nOut;
+        sampleTime_ += (int64_t) numSamples;
+        return rc::Ok;
+    }
+    bool allSteady = !(allReduce && peerAttached_ && peer_.world > 1), allBatched = true;
+
     // Runtime::process: swap in the newest render sequence (Runtime.h:277-285); recompile when the number of
     // host input channels a leaf node sees has changed.
     for (auto& gp : groups_) {
@@ -2023,11 +2047,12 @@ int Engine::enqueueBlock(size_t nIn, size_t nOut, size_t numSamples, bool perVoi
     for (auto& gp : groups_) {
         Group& g = *gp;
         const int nTiles = g.nTiles();
+        if (!g.active || nTiles == 0) { allSteady = false; }
         if (!g.active || nTiles == 0) {
             // no render sequence yet: outputs are silence (Runtime.h:287-289 leaves the host buffers untouched;
             // we define the voice's contribution as zero)
             if (nTiles && mix) dmemset(dPartial_ + (size_t) tileBase * nOut * blockSize_, 0, sizeof(float) * (size_t) nTiles * nOut * blockSize_);
-            if (materialise && dOutVoice_) dmemset(dOutVoice_ + (size_t) g.v0 * nOut * blockSize_, 0, sizeof(float) * (size_t) g.nv * nOut * blockSize_);
+            if (materialise && dOutVoice_ && !offlineOut_) dmemset(dOutVoice_ + (size_t) g.v0 * nOut * blockSize_, 0, sizeof(float) * (size_t) g.nv * nOut * blockSize_);
             tileBase += nTiles;
             continue;
         }
@@ -2040,7 +2065,8 @@ int Engine::enqueueBlock(size_t nIn, size_t nOut, size_t numSamples, bool perVoi
         P.rows = g.dRows;
         P.inShared = (!perVoiceIn && nIn) ? dInShared_ : nullptr;
         P.inVoice = (perVoiceIn && nIn) ? dInVoice_ : nullptr;
-        P.outVoice = materialise ? dOutVoice_ : nullptr;
+        float* const voiceOut = offlineOut_ ? offlineOut_ : dOutVoice_;
+        P.outVoice = materialise ? voiceOut : nullptr;
         P.mixPartial = mix ? dPartial_ : nullptr;
         P.nStateEntries = (int) p.stateMap.size();
         P.nStateRows = p.nStateRows;
@@ -2054,7 +2080,7 @@ int Engine::enqueueBlock(size_t nIn, size_t nOut, size_t numSamples, bool perVoi
         P.nIn = (int) nIn;
         P.nOut = (int) nOut;
         P.inStride = blockSize_;
-        P.outStride = blockSize_;
+        P.outStride = offlineOut_ ? offlineStride_ : blockSize_;
         P.tileBase = tileBase;
         uint32_t runMask = 0;
         for (size_t ri = 0; ri < p.rootIds.size(); ++ri) {
@@ -2066,7 +2092,9 @@ int Engine::enqueueBlock(size_t nIn, size_t nOut, size_t numSamples, bool perVoi
             if (stillRunning && chanOk) runMask |= (1u << ri);
             if (rn.fade.on()) runMask |= (1u << (16 + ri));                                   // promoteTapBuffers: :200-205
             P.roots[ri] = RootDyn{rn.fade.current, rn.fade.step, rn.fade.target, rn.channel};
+            if (rn.fade.current != rn.fade.target) allSteady = false;        // the descriptor changes while a root fades
         }
+        if (!p.evNodes.empty() || !p.dynNodes.empty() || g.codeDirty || g.pending) allSteady = false;
         P.runMask = runMask;
         P.sampleTime = sampleTime_;
         P.tableSrc = p.stagedTable; P.tableFloats = p.stagedTableFloats; P.tableSmem = -1;   // the launcher places it (single-group launches)
@@ -2106,11 +2134,13 @@ int Engine::enqueueBlock(size_t nIn, size_t nOut, size_t numSamples, bool perVoi
             // heterogeneous voice groups: collect single-stage groups per tile geometry and launch each bucket once
             P.code = p.dCode + (p.stages.empty() ? 0 : p.stages[0].codeOffset);
             buckets[g.tileWidth].push_back(P);
+            buckets[g.tileWidth].back().sampleTime = 0;      // the many-groups kernel takes the clock as an argument: descriptors stay equal block to block
         } else
         for (size_t stg = 0; stg < nStages; ++stg) {
+            allBatched = false;
             const bool last = stg + 1 == nStages;
             P.code = p.dCode + (p.stages.empty() ? 0 : p.stages[stg].codeOffset);
-            P.outVoice = (last && materialise) ? dOutVoice_ : nullptr;   // outputs and taps belong to the last stage
+            P.outVoice = (last && materialise) ? voiceOut + (offlineOut_ ? offlineOffset_ : 0) : nullptr;   // outputs and taps belong to the last stage
             P.mixPartial = (last && mix) ? dPartial_ : nullptr;
             std::pair<cudaEvent_t, cudaEvent_t> ev{nullptr, nullptr};
             if (timeKernels_) {
@@ -2169,6 +2199,7 @@ int Engine::enqueueBlock(size_t nIn, size_t nOut, size_t numSamples, bool perVoi
         }
         tileBase += nTiles;
     }
+    steadyBuckets_.clear();
     for (auto& kv : buckets) {
         auto& descs = kv.second;
         const int L = kv.first;
@@ -2207,7 +2238,8 @@ int Engine::enqueueBlock(size_t nIn, size_t nOut, size_t numSamples, bool perVoi
             else { cudaEventCreate(&ev.first); cudaEventCreate(&ev.second); }
             cudaEventRecord(ev.first, stream_);
         }
-        if (!dry && !cuda(launch_render_groups(bb.dDescs, bb.dTileStart, (int) descs.size(), total, L, maxSlots, (int) nOut, maxState, maxParams, wpc, stream_),
+        steadyBuckets_.push_back(SteadyBucket{L, (int) descs.size(), total, maxSlots, maxState, maxParams, wpc});
+        if (!dry && !cuda(launch_render_groups(bb.dDescs, bb.dTileStart, (int) descs.size(), total, L, maxSlots, (int) nOut, maxState, maxParams, wpc, sampleTime_, offlineOut_ ? offlineOffset_ : 0, stream_),
                   "render groups kernel launch")) return rc::CudaError;
         if (timeKernels_) { cudaEventRecord(ev.second, stream_); timedEvents_.push_back(ev); }
         ++launches_;
@@ -2236,6 +2268,9 @@ int Engine::enqueueBlock(size_t nIn, size_t nOut, size_t numSamples, bool perVoi
         if (timeKernels_) { cudaEventRecord(ev.second, stream_); timedXchgEvents_.push_back(ev); }
         ++launches_;
     }
+    steadyValid_ = allSteady && allBatched && !buckets.empty() && !dry;
+    std::memcpy(steadyKey_, key, sizeof key);
+    steadyTiles_ = tileBase;
     curNOut_ = nOut;
     sampleTime_ += (int64_t) numSamples;   // wasm/Main.cpp:217
     return rc::Ok;
@@ -2275,6 +2310,52 @@ double Engine::takeKernelTimeMs(uint64_t* count) {
     lastConvMs_ = lastKindMs_[2]; lastConvCount_ = lastKindCount_[2];
     if (count) *count = lastKindCount_[0];
     return lastKindMs_[0];
+}
+
+int Engine::renderOffline(size_t nOut, size_t numBlocks, float* hostOut, size_t chunkBlocks) {
+    Lock lk(mu_);
+    if (planOnly_) return fail(rc::CudaError, "plan-only runtime (no CUDA device): rendering is impossible, there is no CPU fallback");
+    if (!hostOut || nOut == 0 || nOut > (size_t) MAX_OUT_CHANNELS) return fail(rc::BadArgument, "renderOffline: bad arguments");
+    dsetdev();
+    const size_t bs = (size_t) blockSize_, rows = (size_t) numVoices_ * nOut;
+    size_t C = chunkBlocks ? chunkBlocks : 32;
+    while (C > 1 && rows * C * bs * sizeof(float) > ((size_t) 512 << 20)) C >>= 1;          // two chunk buffers of at most 512 MiB each
+    if (C > numBlocks) C = std::max<size_t>(1, numBlocks);
+    float* buf[2] = {nullptr, nullptr};
+    cudaStream_t copyStream = nullptr;
+    cudaEvent_t rendered[2] = {nullptr, nullptr}, copied[2] = {nullptr, nullptr};
+    int rcode = rc::Ok;
+    auto cleanup = [&]() {
+        offlineOut_ = nullptr; offlineStride_ = 0; offlineOffset_ = 0; steadyValid_ = false;
+        cudaStreamSynchronize(stream_);
+        if (copyStream) { cudaStreamSynchronize(copyStream); cudaStreamDestroy(copyStream); }
+        for (int i = 0; i < 2; ++i) { if (buf[i]) cudaFree(buf[i]); if (rendered[i]) cudaEventDestroy(rendered[i]); if (copied[i]) cudaEventDestroy(copied[i]); }
+    };
+    for (int i = 0; i < 2; ++i) {
+        if (!cuda(cudaMalloc((void**) &buf[i], rows * C * bs * sizeof(float)), "cudaMalloc offline chunk")) { cleanup(); return rc::CudaError; }
+        cudaMemsetAsync(buf[i], 0, rows * C * bs * sizeof(float), stream_);                    // voices without a render sequence stay silent
+        cudaEventCreateWithFlags(&rendered[i], cudaEventDisableTiming);
+        cudaEventCreateWithFlags(&copied[i], cudaEventDisableTiming);
+    }
+    cudaStreamCreateWithFlags(&copyStream, cudaStreamNonBlocking);
+    steadyValid_ = false;
+    for (size_t b = 0; b < numBlocks && rcode == rc::Ok; ++b) {
+        const size_t chunk = b / C, slot = chunk & 1, inChunk = b % C;
+        if (inChunk == 0 && chunk >= 2) cudaStreamWaitEvent(stream_, copied[slot], 0);          // the chunk two back has left this buffer
+        offlineOut_ = buf[slot]; offlineStride_ = (int) (C * bs); offlineOffset_ = (int) (inChunk * bs);
+        rcode = enqueueBlock(0, nOut, bs, false, true, false);
+        const bool lastOfChunk = inChunk + 1 == C || b + 1 == numBlocks;
+        if (rcode == rc::Ok && lastOfChunk) {
+            cudaEventRecord(rendered[slot], stream_);
+            cudaStreamWaitEvent(copyStream, rendered[slot], 0);
+            const size_t width = (inChunk + 1) * bs * sizeof(float);
+            if (!cuda(cudaMemcpy2DAsync(hostOut + chunk * C * bs, numBlocks * bs * sizeof(float), buf[slot], C * bs * sizeof(float), width, rows,
+                                        cudaMemcpyDeviceToHost, copyStream), "D2H offline chunk")) rcode = rc::CudaError;
+            cudaEventRecord(copied[slot], copyStream);
+        }
+    }
+    cleanup();
+    return rcode;
 }
 
 int Engine::synchronize() {

@@ -196,6 +196,11 @@ public:
     // Device-resident: no host I/O, no synchronisation; used for throughput timing and by processVoices/process.
     int enqueueBlock(size_t nIn, size_t nOut, size_t numSamples, bool perVoiceIn, bool materialise, bool mix, bool allReduce = false);
     int synchronize();
+    // Offline rendering (BASELINE config 5: minutes of audio per graph, nobody listening): numBlocks blocks of every voice, per-voice
+    // output, no mix bus, no host round trip per block — blocks are enqueued back to back, the kernels write straight into chunk buffers
+    // of `chunkBlocks` blocks ([voice][nOut][chunk] on the device), and finished chunks travel to hostOut[voice][nOut][numBlocks *
+    // blockSize] on a copy stream while the next chunk renders.  The reference does the same job with OfflineRenderer.process in a loop.
+    int renderOffline(size_t nOut, size_t numBlocks, float* hostOut, size_t chunkBlocks);
 
     // Cross-GPU mix bus: peerExport() allocates this rank's exchange buffer and returns its CUDA IPC handle
     // (64 bytes); peerAttach() maps the buffers of all ranks (handles = world x 64 bytes, in rank order).  Afterwards
@@ -287,6 +292,16 @@ private:
     size_t curNOut_ = 0;
     struct BatchBuffers { LaunchParams* dDescs = nullptr; int* dTileStart = nullptr; size_t capGroups = 0; std::vector<char> lastDescs; };
     std::map<int, BatchBuffers> batch_;   // per tile width
+    // Steady-state fast path for engines made of many batched voice groups (BASELINE config 5: 1250 graphs): when the last block found
+    // every group steady — no queued program, nothing dirty, all root fades settled, no event mirrors to advance — and the call has the
+    // same shape, the next block re-launches the cached buckets (the descriptors on the device are still right; the sample clock is a
+    // kernel argument) without walking the groups.  Any instruction batch, gc, option or resource change invalidates it.
+    struct SteadyBucket { int L, nGroups, totalTiles, maxSlots, maxState, maxParams, wpc; };
+    std::vector<SteadyBucket> steadyBuckets_;
+    bool steadyValid_ = false;
+    size_t steadyKey_[6] = {0, 0, 0, 0, 0, 0};
+    int steadyTiles_ = 0;
+    float* offlineOut_ = nullptr; int offlineStride_ = 0, offlineOffset_ = 0;   // renderOffline: where materialised outputs go instead of dOutVoice_
 
     // K4 state
     void* dExchange_ = nullptr; size_t exchangeBytes_ = 0; size_t exchangeFlagOffset_ = 0;

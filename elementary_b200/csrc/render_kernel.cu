@@ -477,7 +477,7 @@ __device__ __noinline__ void ctl_capture(const CtlCtx& c) {
 // =========================================================================================================
 // The whole per-tile interpreter; instantiated by the two thin __global__ wrappers at the end of this section.
 template <int NITER, int LOGL>
-__device__ __forceinline__ void render_tile(const LaunchParams& P, const int tile, const int perWarp) {
+__device__ __forceinline__ void render_tile(const LaunchParams& P, const int tile, const int perWarp, const long long sampleTime, const int outOffset) {
     constexpr int L = 1 << LOGL;          // voices per warp
     constexpr int E = 32 * NITER;         // elements per sample tile
     constexpr int T = E >> LOGL;          // samples per tile
@@ -630,7 +630,7 @@ __device__ __forceinline__ void render_tile(const LaunchParams& P, const int til
                     const int v = qq >> LOGT, t = qq & (T - 1);
                     const int vv = tile * L + v;
                     if (t < cnt && vv < P.nv)
-                        P.outVoice[((size_t) (P.voice0 + vv) * P.nOut + ch) * P.outStride + s0 + t] = a[t * L + v];
+                        P.outVoice[((size_t) (P.voice0 + vv) * P.nOut + ch) * P.outStride + outOffset + s0 + t] = a[t * L + v];
                 }
             }
         }
@@ -710,7 +710,7 @@ __global__ void EB_BOUNDS render_block_kernel(const __grid_constant__ LaunchPara
         stage_table_tma(P.tableSrc, P.tableFloats, g_smem + P.tableSmem, reinterpret_cast<uint64_t*>(g_smem + P.tableSmem + P.tableFloats));
     const int tile = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (tile >= ((P.nv + (1 << LOGL) - 1) >> LOGL)) return;   // whole warp leaves together
-    render_tile<NITER, LOGL>(P, tile, perWarp);
+    render_tile<NITER, LOGL>(P, tile, perWarp, P.sampleTime, 0);
 }
 
 // Many voice groups (different graphs) of the same tile geometry in ONE launch: warp w finds its group by binary
@@ -718,7 +718,7 @@ __global__ void EB_BOUNDS render_block_kernel(const __grid_constant__ LaunchPara
 // thousands of small heterogeneous graphs (BASELINE config 5) run concurrently instead of one launch each.
 template <int NITER, int LOGL>
 __global__ void EB_BOUNDS render_groups_kernel(const LaunchParams* __restrict__ descs, const int* __restrict__ tileStart,
-                                                const int nGroups, const int totalTiles, const int perWarp) {
+                                                const int nGroups, const int totalTiles, const int perWarp, const long long sampleTime, const int outOffset) {
     const int w = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (w >= totalTiles) return;
     int lo = 0, hi = nGroups - 1;                      // largest g with tileStart[g] <= w
@@ -726,7 +726,7 @@ __global__ void EB_BOUNDS render_groups_kernel(const LaunchParams* __restrict__ 
         const int mid = (lo + hi + 1) >> 1;
         if (__ldg(tileStart + mid) <= w) lo = mid; else hi = mid - 1;
     }
-    render_tile<NITER, LOGL>(descs[lo], w - __ldg(tileStart + lo), perWarp);
+    render_tile<NITER, LOGL>(descs[lo], w - __ldg(tileStart + lo), perWarp, sampleTime, outOffset);   // the sample clock travels as an argument: the descriptors of a steady engine never change
 }
 
 #ifndef __CUDACC_RTC__   // K2, K4 and the host launchers are not needed by a run-time compiled specialisation of K1
@@ -815,11 +815,11 @@ static cudaError_t launch_render_block_geometry(const LaunchParams& P, int L, in
 
 template <int NITER, int LOGL>
 static cudaError_t launch_groups_impl(const LaunchParams* descs, const int* tileStart, int nGroups, int totalTiles,
-                                      int grid, int threads, size_t smem, cudaStream_t stream) {
+                                      int grid, int threads, size_t smem, long long sampleTime, int outOffset, cudaStream_t stream) {
     cudaError_t e = cudaFuncSetAttribute(render_groups_kernel<NITER, LOGL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
     if (e != cudaSuccess) return e;
     render_groups_kernel<NITER, LOGL><<<grid, threads, smem, stream>>>(descs, tileStart, nGroups, totalTiles,
-                                                                          (int) (smem / sizeof(float) / (threads / 32)));
+                                                                          (int) (smem / sizeof(float) / (threads / 32)), sampleTime, outOffset);
     return cudaGetLastError();
 }
 
@@ -855,18 +855,18 @@ static cudaError_t launch_render_block_geometry(const LaunchParams& P, int L, in
 
 // descs / tileStart are DEVICE pointers; maxSlots etc. are the maxima over the groups (uniform shared-memory carve-up).
 cudaError_t launch_render_groups(const LaunchParams* descs, const int* tileStart, int nGroups, int totalTiles, int tileWidth,
-                                 int maxSlots, int nOut, int maxStateRows, int maxParams, int warpsPerCta, cudaStream_t stream) {
+                                 int maxSlots, int nOut, int maxStateRows, int maxParams, int warpsPerCta, long long sampleTime, int outOffset, cudaStream_t stream) {
     if (totalTiles <= 0) return cudaSuccess;
     const int grid = (totalTiles + warpsPerCta - 1) / warpsPerCta;
     const int threads = warpsPerCta * 32;
     const size_t smem = render_smem_bytes(maxSlots, nOut, maxStateRows, maxParams, warpsPerCta, tileWidth, 0);
     switch (tileWidth) {
-        case 32: return launch_groups_impl<8, 5>(descs, tileStart, nGroups, totalTiles, grid, threads, smem, stream);
-        case 16: return launch_groups_impl<8, 4>(descs, tileStart, nGroups, totalTiles, grid, threads, smem, stream);
-        case 8:  return launch_groups_impl<8, 3>(descs, tileStart, nGroups, totalTiles, grid, threads, smem, stream);
-        case 4:  return launch_groups_impl<4, 2>(descs, tileStart, nGroups, totalTiles, grid, threads, smem, stream);
-        case 2:  return launch_groups_impl<4, 1>(descs, tileStart, nGroups, totalTiles, grid, threads, smem, stream);
-        default: return launch_groups_impl<1, 0>(descs, tileStart, nGroups, totalTiles, grid, threads, smem, stream);
+        case 32: return launch_groups_impl<8, 5>(descs, tileStart, nGroups, totalTiles, grid, threads, smem, sampleTime, outOffset, stream);
+        case 16: return launch_groups_impl<8, 4>(descs, tileStart, nGroups, totalTiles, grid, threads, smem, sampleTime, outOffset, stream);
+        case 8:  return launch_groups_impl<8, 3>(descs, tileStart, nGroups, totalTiles, grid, threads, smem, sampleTime, outOffset, stream);
+        case 4:  return launch_groups_impl<4, 2>(descs, tileStart, nGroups, totalTiles, grid, threads, smem, sampleTime, outOffset, stream);
+        case 2:  return launch_groups_impl<4, 1>(descs, tileStart, nGroups, totalTiles, grid, threads, smem, sampleTime, outOffset, stream);
+        default: return launch_groups_impl<1, 0>(descs, tileStart, nGroups, totalTiles, grid, threads, smem, sampleTime, outOffset, stream);
     }
 }
 

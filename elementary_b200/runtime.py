@@ -67,6 +67,8 @@ def load_library() -> C.CDLL:
     lib.elem_b200_current_time.argtypes = [C.c_void_p]
     lib.elem_b200_process_voices.restype = C.c_int
     lib.elem_b200_process_voices.argtypes = [C.c_void_p, _f32p, C.c_size_t, _f32p, _f32p, C.c_size_t, C.c_size_t]
+    lib.elem_b200_render_offline.restype = C.c_int
+    lib.elem_b200_render_offline.argtypes = [C.c_void_p, C.c_size_t, C.c_size_t, _f32p, C.c_size_t]
     lib.elem_b200_enqueue_block.restype = C.c_int
     lib.elem_b200_enqueue_block.argtypes = [C.c_void_p, C.c_size_t, C.c_size_t, C.c_size_t, C.c_int]
     lib.elem_b200_peer_export.restype = C.c_int
@@ -249,6 +251,14 @@ class Runtime:
             vs.append(v)
             ms.append(m)
         return np.concatenate(vs, axis=2), np.concatenate(ms, axis=1)
+
+    def render_offline(self, n_blocks: int, num_outputs: int = 1, chunk_blocks: int = 0, out: Optional[np.ndarray] = None) -> np.ndarray:
+        """Offline render: ``n_blocks`` blocks of every voice with no host round trip per block; returns [voice, n_out, n_blocks*bs]."""
+        if out is None:
+            out = np.empty((self.num_voices, num_outputs, n_blocks * self.block_size), dtype=np.float32)
+        assert out.flags["C_CONTIGUOUS"] and out.dtype == np.float32 and out.shape == (self.num_voices, num_outputs, n_blocks * self.block_size)
+        self._check(self._lib.elem_b200_render_offline(self._h, num_outputs, n_blocks, out.ctypes.data_as(_f32p), chunk_blocks), "render_offline")
+        return out
 
     # -- device-resident stepping -----------------------------------------------------------------------------
     def enqueue_block(self, n_in: int = 0, n_out: int = 1, num_samples: Optional[int] = None, flags: int = FLAG_MIX) -> None:

@@ -82,6 +82,12 @@ int64_t elem_b200_current_time(elem_b200_runtime* rt);
 int elem_b200_process_voices(elem_b200_runtime* rt, const float* in, size_t nIn,
                              float* outVoices, float* mix, size_t nOut, size_t numSamples);
 
+/* Offline rendering (what js/packages/offline-renderer does with process() in a loop; BASELINE config 5): numBlocks full blocks of every
+ * voice, per-voice output hostOut[voice][nOut][numBlocks * blockSize] (host memory), no inputs, no mix bus.  Blocks are enqueued back to
+ * back with no host synchronisation in between; outputs are written by the kernels into device chunk buffers of chunkBlocks blocks
+ * (0 = default 32) and copied out on a second stream while the next chunk renders. */
+int elem_b200_render_offline(elem_b200_runtime* rt, size_t nOut, size_t numBlocks, float* hostOut, size_t chunkBlocks);
+
 /* Device-resident stepping for throughput measurement and pipelines that keep audio in HBM: enqueue one block
  * on the engine's stream (no host copies, no synchronisation).  flags: 1 = read per-voice inputs from
  * elem_b200_voice_in_device(), 2 = materialise per-voice outputs, 4 = produce the mix bus, 8 = (with 4, after

@@ -284,3 +284,53 @@ def test_snapshot_lists_nodes_and_props_like_the_reference():
     assert key in snap and snap[key]["value"] == 800.0
     assert any(v.get("mode") == "highpass" for v in snap.values())
     assert all(k.startswith("0x") and len(k) == 10 for k in snap)
+
+
+# ---- ingestion at scale: binary batch + property table ---------------------------------------------------
+def test_binary_batch_is_the_same_instruction_stream():
+    from elementary_b200 import el, graphs
+    import numpy as np
+    for batch in (graphs.subsynth32(), graphs.random_graph(7, 48), el.render(el.seq({"seq": [1, 2, 3.5], "hold": True, "loop": False}, el.train(5.0))),
+                  el.render(el.sparseq({"seq": [{"value": 1, "tickTime": 0}, {"value": 2, "tickTime": 4}], "loop": [0, 8]}, el.train(9.0)))):
+        a, b = plan(8), plan(8)
+        assert a.apply_instructions(batch) == 0
+        blob = el.encode_binary(batch)
+        assert b.apply_binary(blob) == 0, b.last_error()
+        def masked(w):                       # the device-pointer words of the op headers differ between two runtimes
+            w = w.copy(); pc = 0
+            while pc + 8 <= len(w):
+                n = 8 + ((int(w[pc]) >> 8) & 0xFF); w[pc + 4:pc + 6] = 0
+                if (int(w[pc]) & 0xFF) == 0: break
+                pc += n
+            return w[:pc + 8]
+        assert np.array_equal(masked(a.program_words(0)), masked(b.program_words(0)))          # same render program, word for word
+        assert a.snapshot() == b.snapshot()
+    rt = plan(4)
+    assert rt.apply_binary(b"nope") == 8                                       # InvalidInstructionFormat
+    assert rt.apply_binary(el.encode_binary([[0, 1, "no_such_type"]])) == 1     # same return codes as the text form
+    assert rt.apply_binary(el.encode_binary(graphs.subsynth32())[:-3]) == 8    # truncated
+
+
+def test_binary_batch_is_smaller_and_faster_to_ingest_than_json():
+    import json, time
+    from elementary_b200 import el, graphs
+    batch = graphs.additive64(110.0, 64)
+    text, blob = json.dumps(batch).encode(), el.encode_binary(batch)
+    assert len(blob) < len(text)
+    rt = plan(1)
+    t0 = time.perf_counter(); assert rt.apply_binary(blob) == 0; t_bin = time.perf_counter() - t0
+    rt = plan(1)
+    t0 = time.perf_counter(); assert rt.apply_instructions(text) == 0; t_txt = time.perf_counter() - t0
+    print(f"additive64: json {len(text)} B {t_txt * 1e3:.2f} ms, binary {len(blob)} B {t_bin * 1e3:.2f} ms")
+
+
+def test_const_table_return_codes():
+    import numpy as np
+    from elementary_b200 import el, graphs
+    rt = plan(64)
+    assert rt.apply_instructions(graphs.subsynth32()) == 0
+    ida, idb = graphs.subsynth32_param_ids()
+    tab = np.stack([55.0 * np.arange(1, 65), 55.0 * 1.007 * np.arange(1, 65)]).astype(np.float32)
+    assert rt.set_const_table([ida, idb], tab) == 0
+    assert rt.set_const_table([ida, 123456], tab) == 2                         # NodeNotFound
+    assert rt.snapshot()["0x%08x" % (ida & 0xFFFFFFFF)]["value"] == float(tab[0, -1])

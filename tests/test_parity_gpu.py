@@ -565,3 +565,109 @@ def test_registered_device_node_types_match_the_reference_plugin_nodes(tile_widt
     ref = oracle_render(batch, 4, 1, SR, BS, inputs, voice_batches=[None] * n_voices, cls=orc.RefRuntime)
     ok, worst, ex = block_peak_tolerance_check(got, ref, BS)
     assert ok, f"worst err/tol {worst:.3g}, bit-exact {ex:.4f}"
+
+
+def test_binary_batch_and_const_table_render_like_the_json_path():
+    """the binary instruction batch and the per-voice property table are the same stream in another encoding —
+    the rendered samples must be identical bit for bit to the JSON + per-voice SET_PROPERTY path."""
+    n_voices = 96
+    ida, idb = graphs.subsynth32_param_ids()
+    f0 = np.array([graphs.subsynth32_f0(v) for v in range(n_voices)])
+    a = Runtime(SR, BS, n_voices, device=0)
+    assert a.apply_instructions(graphs.subsynth32()) == 0
+    assert a.set_property_per_voice(ida, "value", f0) == 0 and a.set_property_per_voice(idb, "value", f0 * 1.007) == 0
+    b = Runtime(SR, BS, n_voices, device=0)
+    assert b.apply_binary(el.encode_binary(graphs.subsynth32())) == 0, b.last_error()
+    assert b.set_const_table([ida, idb], np.stack([f0, f0 * 1.007]).astype(np.float32)) == 0
+    ga, _ = a.render_voices(4, 1)
+    gb, _ = b.render_voices(4, 1)
+    assert np.array_equal(ga, gb)
+
+
+@pytest.mark.parametrize("tile_width", [0, 4])
+def test_split_keeps_sequencer_and_analysis_state(tile_width):
+    """SURVEY.md §8f N1 for the control / analysis nodes (VERDICT r01 missing #8): a live cut of a voice group carries the seq
+    position, the sparseq tick state, the capture ring / scratch, the scope ring and the meter readout of the moving voices along;
+    audio AND events of every voice match per-voice reference instances across the cut."""
+    from helpers import oracle_cls
+    from events_common import canon, same
+    n_voices, bs = 8, BS
+    clock = el.train(el.const(40.0, key="rate"))
+    sq = el.seq({"seq": [0.1, 0.2, 0.3, 0.4, 0.5], "hold": True, "loop": True, "key": "sq"}, clock)
+    sp = el.sparseq({"seq": [{"value": 1.0, "tickTime": 0}, {"value": 0.5, "tickTime": 3}, {"value": 0.25, "tickTime": 5}], "loop": [0, 7], "key": "sp"}, clock)
+    sig = el.mul(el.add(sq, sp), el.cycle(el.const(220.0, key="f")))
+    g1 = el.add(el.meter({"name": "m"}, sig), el.mul(0.0, el.scope({"name": "s", "size": 512}, sig)),
+                el.mul(0.0, el.capture({"name": "c"}, el.le(el.phasor(3.0), 0.5), sig)))
+    g2 = el.tanh(el.add(g1, el.mul(0.1, el.cycle(el.const(330.0, key="f2")))))
+    fid, rid = el.const(0, key="f").id(), el.const(0, key="rate").id()
+    freqs, rates = 110.0 * (1 + np.arange(n_voices)), 30.0 + 7.0 * np.arange(n_voices)
+    opts = {"tile_width": tile_width} if tile_width else {}
+    rt = Runtime(SR, bs, n_voices, device=0, **opts)
+    rg = el.Renderer()
+    a, b = rg.render(g1), rg.render(g2)
+    assert rt.apply_instructions(a) == 0, rt.last_error()
+    assert rt.set_property_per_voice(fid, "value", freqs) == 0 and rt.set_property_per_voice(rid, "value", rates) == 0
+    oracles = []
+    for v in range(n_voices):
+        o = oracle_cls()(SR, bs)
+        assert o.apply(a) == 0 and o.apply([[3, fid, "value", float(freqs[v])], [3, rid, "value", float(rates[v])]]) == 0
+        oracles.append(o)
+    seen = 0
+    for blk in range(14):
+        if blk == 6:
+            assert rt.apply_instructions(b, voices=(4, 8)) == 0, rt.last_error()
+            for o in oracles[4:]:
+                assert o.apply(b) == 0
+            assert len(rt.describe()["groups"]) == 2
+        got = rt.process_voices(None, 1, bs)[0]
+        ref = np.stack([o.process(None, 1, bs) for o in oracles])
+        ok, worst, ex = block_peak_tolerance_check(got, ref, bs)
+        assert ok, f"block {blk}: worst err/tol {worst:.3g}"
+        if blk % 3 == 2:
+            events = rt.process_queued_events()
+            for v, o in enumerate(oracles):
+                want = canon(o.process_queued_events())
+                have = canon([e for e in events if e["event"]["voice"] == v])
+                assert same(have, want), f"block {blk} voice {v}: {str(have)[:300]} != {str(want)[:300]}"
+                seen += len(want)
+    assert seen > 0
+
+
+def test_offline_render_equals_block_by_block_and_many_groups_stay_correct_in_steady_state():
+    """elem_b200_render_offline (no host round trip per block, chunked device buffers, copy stream) gives the same samples as
+    process_voices block by block — on a single voice group and on many batched groups, where after the root fade-in the steady-state
+    fast path (cached descriptors, sample clock as a kernel argument) takes over; a live edit in between must be picked up."""
+    n_blocks = 21                                     # not a multiple of the chunk size
+    # one group
+    a = Runtime(SR, BS, 37, device=0)
+    b = Runtime(SR, BS, 37, device=0)
+    for rt in (a, b):
+        assert rt.apply_instructions(graphs.subsynth32()) == 0
+    ref, _ = a.render_voices(n_blocks, 1)
+    got = b.render_offline(n_blocks, 1, chunk_blocks=8)
+    assert np.array_equal(got, ref)
+    # many groups, with a `time` node in one of them (the sample clock is an argument of the many-groups kernel)
+    batches = [graphs.random_graph(2000 + i, 32) for i in range(6)] + [el.render(el.mul(el.cycle(100.0), el.le(el.mod(el.time(), 4096.0), 2048.0)))]
+    a = Runtime(SR, BS, 14, device=0)
+    b = Runtime(SR, BS, 14, device=0)
+    for rt in (a, b):
+        for i, bt in enumerate(batches):
+            assert rt.apply_instructions(bt, voices=(2 * i, 2 * i + 2)) == 0, rt.last_error()
+    ref, _ = a.render_voices(n_blocks, 1)
+    got = b.render_offline(n_blocks, 1, chunk_blocks=4)
+    assert np.array_equal(got, ref)
+    for i, bt in enumerate(batches):
+        o = oracle_render(bt, n_blocks, 1, SR, BS)
+        ok, worst, ex = block_peak_tolerance_check(got[2 * i], o[0], BS)
+        assert ok, f"graph {i}: worst err/tol {worst:.3g}"
+    # a live edit after the engine went steady: the next blocks must show it
+    edit = [[3, el.const(0, key="zz").id(), "value", 1.0]]
+    g = el.mul(el.const(0.0, key="zz"), el.cycle(50.0))
+    c = Runtime(SR, BS, 4, device=0)
+    assert c.apply_instructions(el.render(g), voices=(0, 2)) == 0 and c.apply_instructions(el.render(el.cycle(60.0)), voices=(2, 4)) == 0
+    for _ in range(6):
+        v, _ = c.process_voices(None, 1, BS)
+    assert not v[0].any()
+    assert c.apply_instructions(edit, voices=(0, 2)) == 0
+    v, _ = c.process_voices(None, 1, BS)
+    assert np.abs(v[0]).max() > 0.1
