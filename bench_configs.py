@@ -143,8 +143,34 @@ def config5(quick):
         assert rt.apply_instructions(batch, voices=(i, i + 1)) == 0, rt.last_error()
     build_s = time.perf_counter() - t0
     ms, k1, k3, launches = timed_blocks(rt, 0, FLAG_MIX, 10 if quick else 30, 5)
+    # the offline path the config is about: per-graph output, blocks back to back, chunked D2H on a copy stream (host wall clock, D2H included)
+    nb_off = 32 if quick else 128
+    out = np.empty((n_graphs, 1, nb_off * BS), dtype=np.float32)
+    rt.render_offline(8, 1, out=out[:, :, :8 * BS].copy())                      # warm-up (allocations, page faults of the driver)
+    t0 = time.perf_counter()
+    rt.render_offline(nb_off, 1, out=out)
+    off_s = time.perf_counter() - t0
+    offline = {"blocks": nb_off, "seconds": off_s, "ms_per_block": off_s / nb_off * 1e3, "msamples_per_s": n_graphs * BS * nb_off / off_s / 1e6,
+               "realtime_x": (nb_off * BS / SR) / off_s, "note": "elem_b200_render_offline: per-graph outputs copied to host memory, wall clock"}
+    # parity at this scale: a sample of the graphs against the reference over the offline output (blocks after the timed_blocks run are
+    # not comparable from block 0, so a fresh small runtime renders the same graphs from the start)
+    parity = None
     cpu = None
     from oracle import oracle as orc
+    if orc.ref_available():
+        chk = Runtime(SR, BS, 16, device=0)
+        pick = [int(i * (n_graphs - 1) / 15) for i in range(16)]
+        for j, gi in enumerate(pick):
+            assert chk.apply_instructions(batches[gi], voices=(j, j + 1)) == 0
+        got = chk.render_offline(12, 1)
+        worst = 0.0
+        for j, gi in enumerate(pick):
+            o = orc.RefRuntime(SR, BS); assert o.apply(batches[gi]) == 0
+            ref = o.render(12, 1)
+            g = got[j, 0].reshape(12, BS).astype(np.float64); r = ref[0].reshape(12, BS).astype(np.float64)
+            tol = 1e-5 * np.abs(r).max(axis=1, keepdims=True) + 1e-7
+            worst = max(worst, float((np.abs(g - r) / tol).max()))
+        parity = {"parity_checked": True, "graphs_checked": pick, "blocks": 12, "worst_err_over_tol": worst}
     if orc.ref_available():
         # CPU: time 64 of the graphs, one Runtime each, on all host threads (distinct graphs => one bench call per graph is
         # too slow to set up; use graph 0..63 sequentially on one thread each via the multi-instance harness per graph)
@@ -157,7 +183,7 @@ def config5(quick):
         cpu = {"msamples_per_s_per_core": ng * BS * 200 / tot / 1e6, "cores_used": 1, "sample": f"{ng} graphs x 200 blocks, one thread"}
     return {"config": f"5: {n_graphs} independent random 64-node graphs on one GPU (10000 over 8), one voice group each",
             "ms_per_block": ms, "k1_ms_sum": k1, "msamples_per_s": n_graphs * BS / ms / 1e3, "realtime_x": BS / (ms * 1e-3) / SR,
-            "launches_per_block": launches, "graph_setup_s": build_s, "cpu_reference": cpu}
+            "launches_per_block": launches, "graph_setup_s": build_s, "offline": offline, "parity": parity, "cpu_reference": cpu}
 
 
 def main():
