@@ -173,6 +173,14 @@ def host_description():
             "loadavg_1m_before": load1, "cpu_model": model}
 
 
+def bench_config(voices_per_gpu, world):
+    """The workload description — the SAME dict in both arms (`--impl b200` and `--impl reference`), so that the driver's
+    same-config check compares like with like; everything engine specific lives in the line's "engine" key."""
+    return {"workload": f"{voices_per_gpu} SUBSYNTH32 voices per GPU (BASELINE.json configs[1]: 32-node subtractive synth), 512-sample blocks, 48 kHz",
+            "voices_per_gpu": voices_per_gpu, "voices_total": world * voices_per_gpu, "block": BS, "sample_rate": SR,
+            "l2": "GPU arm: L2 flushed between steps (256 MiB memset outside the timed events); CPU arm: the voices' state exceeds the host caches"}
+
+
 def run_reference(args, rank, world, emit=print):
     if rank != 0:
         return
@@ -191,8 +199,8 @@ def run_reference(args, rank, world, emit=print):
         "impl": "reference", "metric": METRIC, "value": rall["msamples_per_s"], "unit": "Msamples/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"{VOICES_PER_GPU} SUBSYNTH32 voices per GPU x {world} (BASELINE.json configs[1]), 512-sample blocks, 48 kHz",
-                   "engine": "elem::Runtime<float> (unmodified reference, oracle/_ref), one instance per voice, round-robin per thread"},
+        "config": bench_config(VOICES_PER_GPU, world),
+        "engine": {"name": "elem::Runtime<float> (unmodified reference, oracle/_ref), one instance per voice, round-robin per thread"},
         "voice_blocks_per_s": rall["voice_blocks_per_s"],
         "cpu_baseline": {"value": rall["msamples_per_s"], "unit": "Msamples/s", "cores": cores, "kind": "reference", "sample": sample,
                          "t1": None if r1 is None else {"value": r1["msamples_per_s"], "unit": "Msamples/s", "cores": 1,
@@ -309,8 +317,8 @@ def measure(args, voices, steps, warmup, rank, local_rank, world, stream, flush,
         line_up()
         torch.cuda.synchronize()
         t0 = time.perf_counter()
-        if world == 1:
-            rt.process(None, 1, BS)
+        if world == 1 or fused:
+            rt.process(None, 1, BS)      # with peers attached process() returns the mix of ALL ranks on every rank (K4 inside)
             blocks_done += 1
         else:
             step_device()
@@ -442,9 +450,8 @@ def run_b200(args, rank, local_rank, world, emit=print):
         "metric": METRIC, "value": value, "unit": "Msamples/s", "n_gpus": world, "steps": steps, "warmup": max(3, args.warmup),
         "ms_per_step": dev_ms / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"{voices} SUBSYNTH32 voices per GPU (BASELINE.json configs[1]: 32-node subtractive synth), 512-sample blocks, 48 kHz",
-                   "voices_total": world * voices, "block": BS, "sample_rate": SR,
-                   "l2": "flushed between steps (256 MiB memset outside the timed events)",
+        "config": bench_config(voices, world),
+        "engine": {"name": "elementary_b200 (libelem_b200.so through the C ABI)",
                    "tile_width": desc["tile_width"], "slots": desc["slots"], "state_rows": desc["state_rows"],
                    "k1": ("specialised per program (NVRTC, option specialize=%d)" % args.specialize) if specialised else "interpreter",
                    "spec": {k: desc[k] for k in ("spec_state", "spec_regs", "spec_local_bytes", "spec_cubin_bytes", "spec_log") if k in desc},
@@ -456,8 +463,8 @@ def run_b200(args, rank, local_rank, world, emit=print):
         "realtime_factor": value * 1e6 / (world * voices * SR),
         "wall_ms_per_step_incl_flush": m["t_wall"] / steps * 1e3,
         "e2e": {"value": e2e_value, "unit": "Msamples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 4 * BS,
-                "ms_per_step": e2e_ms / steps, "api": "elem_b200_process (host out buffers)" if world == 1 else
-                       ("elem_b200_enqueue_block (render + K4 cross-GPU mix) + D2H of the mix bus" if fused else "elem_b200_enqueue_block + NCCL all_reduce + D2H of the mix bus")},
+                "ms_per_step": e2e_ms / steps, "api": "elem_b200_process (host out buffers; the kernel that finishes the mix bus stores it into mapped host memory)" if world == 1 else
+                       ("elem_b200_process on every rank (render + K4 cross-GPU mix, delivered to host memory by K4)" if fused else "elem_b200_enqueue_block + NCCL all_reduce + D2H of the mix bus")},
         "gpu_launches": m["launches"],
         "kernel_ms": {"K1_render": k1_avg_ms, "K2_mix_reduce": m["k2_ms"] / max(1, m["k2_n"]),
                       "K4_mix_exchange": (m["k4_ms"] / m["k4_n"]) if m["k4_n"] else None,

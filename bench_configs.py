@@ -136,6 +136,8 @@ def config5(quick):
     from elementary_b200 import Runtime, graphs
     from elementary_b200.runtime import FLAG_MIX
     n_graphs = 200 if quick else 1250   # 10000 graphs / 8 GPUs
+    if "--graphs" in sys.argv:
+        n_graphs = int(sys.argv[sys.argv.index("--graphs") + 1])
     rt = Runtime(SR, BS, n_graphs, device=0, time_kernels=1)
     batches = [graphs.random_graph(i, 64) for i in range(n_graphs)]     # the Python generator is not part of the engine's setup cost
     t0 = time.perf_counter()

@@ -3,6 +3,8 @@
 #include "graph_host.h"
 
 #include <algorithm>
+#include <atomic>
+#include <chrono>
 #include <cmath>
 #include <cstring>
 #include <functional>
@@ -15,6 +17,14 @@
 #include "spec_host.h"
 
 namespace eb {
+
+static inline void cpuRelax() {
+#if defined(__x86_64__) || defined(__i386__)
+    __builtin_ia32_pause();
+#elif defined(__aarch64__)
+    asm volatile("yield" ::: "memory");
+#endif
+}
 
 // ---------------------------------------------------------------------------------------------------------
 // GainFade mirror (helpers/GainFade.h)
@@ -154,6 +164,18 @@ Engine::Engine(double sampleRate, int blockSize, int numVoices, int device)
         cuda(cudaMalloc((void**) &dMixScratch_, sizeof(float) * MIX_REDUCE_MAX_GROUPS * MAX_OUT_CHANNELS * blockSize_), "cudaMalloc mix scratch");
         cuda(cudaMalloc((void**) &dMixTickets_, sizeof(unsigned int) * tick), "cudaMalloc mix tickets");
         if (dMixTickets_) cuda(cudaMemsetAsync(dMixTickets_, 0, sizeof(unsigned int) * tick, stream_), "memset mix tickets");
+        // mapped pinned mix bus + sequence word (HostDeliver); a failure here only disables the fast hand-over
+        const size_t mixFloats = (size_t) MAX_OUT_CHANNELS * blockSize_;
+        if (cudaHostAlloc((void**) &hMixHost_, sizeof(float) * mixFloats + 64, cudaHostAllocMapped) == cudaSuccess) {
+            std::memset(hMixHost_, 0, sizeof(float) * mixFloats + 64);
+            hMixFlag_ = reinterpret_cast<volatile uint32_t*>(hMixHost_ + mixFloats);
+            void* d = nullptr;
+            if (cudaHostGetDevicePointer(&d, hMixHost_, 0) == cudaSuccess && cudaMalloc((void**) &dDeliverDone_, sizeof(unsigned int)) == cudaSuccess) {
+                dMixHostAlias_ = static_cast<float*>(d);
+                dMixFlagAlias_ = reinterpret_cast<uint32_t*>(dMixHostAlias_ + mixFloats);
+                cudaMemsetAsync(dDeliverDone_, 0, sizeof(unsigned int), stream_);
+            } else { cudaFreeHost(hMixHost_); hMixHost_ = nullptr; hMixFlag_ = nullptr; }
+        } else { hMixHost_ = nullptr; cudaGetLastError(); }
     }
 }
 
@@ -183,6 +205,8 @@ Engine::~Engine() {
     if (dInVoice_) dfree(dInVoice_);
     if (dInShared_) dfree(dInShared_);
     if (hPinned_ && !planOnly_) cudaFreeHost(hPinned_);
+    if (hMixHost_) cudaFreeHost(hMixHost_);
+    if (dDeliverDone_) cudaFree(dDeliverDone_);
     for (auto& kv : batch_) { if (kv.second.dDescs) dfree(kv.second.dDescs); if (kv.second.dTileStart) dfree(kv.second.dTileStart); }
     for (auto* l : {&timedEvents_, &timedMixEvents_, &timedConvEvents_, &timedXchgEvents_})
         for (auto& ev : *l) { cudaEventDestroy(ev.first); cudaEventDestroy(ev.second); }
@@ -210,6 +234,8 @@ int Engine::setOption(const char* key, double value) {
     else if (k == "specialize_max_words") { opt_.specializeMaxWords = (int) value; }
     else if (k == "specialize_strict") { opt_.specializeStrict = value != 0; }
     else if (k == "time_kernels") { timeKernels_ = value != 0 && !planOnly_; }
+    else if (k == "host_deliver") { hostDeliver_ = value != 0; }
+    else if (k == "process_allreduce") { processAllReduce_ = value != 0; }
     else if (k == "plan_dry_run") { planDryRun_ = value != 0 && planOnly_; }
     else return rc::BadArgument;
     return rc::Ok;
@@ -2006,7 +2032,7 @@ int Engine::enqueueBlock(size_t nIn, size_t nOut, size_t numSamples, bool perVoi
         }
         if (mix) {
             auto ev = timedBegin();
-            if (!cuda(launch_mix_reduce(dPartial_, dMix_, dMixScratch_, dMixTickets_, steadyTiles_, (int) nOut, blockSize_, (int) numSamples, stream_), "mix reduce launch")) return rc::CudaError;
+            if (!cuda(launch_mix_reduce(dPartial_, dMix_, dMixScratch_, dMixTickets_, steadyTiles_, (int) nOut, blockSize_, (int) numSamples, stream_, takeDeliver()), "mix reduce launch")) return rc::CudaError;
             if (timeKernels_) { cudaEventRecord(ev.second, stream_); timedMixEvents_.push_back(ev); }
             ++launches_;
         }
@@ -2255,7 +2281,7 @@ int Engine::enqueueBlock(size_t nIn, size_t nOut, size_t numSamples, bool perVoi
     if (mix) {
         if (tileBase > 0) {
             auto ev = timedBegin();
-            if (!dry && !cuda(launch_mix_reduce(dPartial_, mixOut, dMixScratch_, dMixTickets_, tileBase, (int) nOut, blockSize_, (int) numSamples, stream_), "mix reduce launch")) return rc::CudaError;
+            if (!dry && !cuda(launch_mix_reduce(dPartial_, mixOut, dMixScratch_, dMixTickets_, tileBase, (int) nOut, blockSize_, (int) numSamples, stream_, exchange ? HostDeliver{} : takeDeliver()), "mix reduce launch")) return rc::CudaError;
             if (timeKernels_) { cudaEventRecord(ev.second, stream_); timedMixEvents_.push_back(ev); }
             ++launches_;
         } else {
@@ -2264,7 +2290,7 @@ int Engine::enqueueBlock(size_t nIn, size_t nOut, size_t numSamples, bool perVoi
     }
     if (exchange) {   // K4: the cross-GPU sum of the mix bus, in the same stream
         auto ev = timedBegin();
-        if (!cuda(launch_mix_exchange(peer_, dMix_, (int) (nOut * blockSize_), peerEpoch_, dPeerStatus_, stream_), "mix exchange launch")) return rc::CudaError;
+        if (!cuda(launch_mix_exchange(peer_, dMix_, (int) (nOut * blockSize_), peerEpoch_, dPeerStatus_, stream_, takeDeliver()), "mix exchange launch")) return rc::CudaError;
         if (timeKernels_) { cudaEventRecord(ev.second, stream_); timedXchgEvents_.push_back(ev); }
         ++launches_;
     }
@@ -2274,6 +2300,15 @@ int Engine::enqueueBlock(size_t nIn, size_t nOut, size_t numSamples, bool perVoi
     curNOut_ = nOut;
     sampleTime_ += (int64_t) numSamples;   // wasm/Main.cpp:217
     return rc::Ok;
+}
+
+HostDeliver Engine::takeDeliver() {
+    HostDeliver hd;
+    if (!deliverArmed_ || !hMixHost_ || planOnly_) return hd;
+    deliverArmed_ = false;
+    deliverLaunched_ = true;
+    hd.out = dMixHostAlias_; hd.flag = dMixFlagAlias_; hd.done = dDeliverDone_; hd.seq = ++deliverSeq_;
+    return hd;
 }
 
 std::pair<cudaEvent_t, cudaEvent_t> Engine::timedBegin() {
@@ -2369,6 +2404,8 @@ int Engine::synchronize() {
 
 int Engine::process(const float* const* in, size_t nIn, float* const* out, size_t nOut, size_t numSamples, const int64_t* sampleTime) {
     float* hOut = nullptr;
+    uint32_t waitSeq = 0;
+    bool polled = false;
     {
         Lock lk(mu_);   // held while the block is ENQUEUED; the wait for the GPU below runs without it (the control thread may work meanwhile)
         if (planOnly_) return fail(rc::CudaError, "plan-only runtime (no CUDA device): rendering is impossible, there is no CPU fallback");
@@ -2387,15 +2424,48 @@ int Engine::process(const float* const* in, size_t nIn, float* const* out, size_
             for (size_t c = 0; c < nIn; ++c) std::memcpy(hPinned_ + c * blockSize_, in[c], sizeof(float) * numSamples);
             if (!cuda(dmemcpy(d, hPinned_, sizeof(float) * nIn * blockSize_, cudaMemcpyHostToDevice), "H2D inputs")) return rc::CudaError;
         }
-        int r = enqueueBlock(nIn, nOut, numSamples, false, false, true);
+        // With peers attached every rank's process() returns the mix of ALL ranks (K4), like one Runtime over all the voices would.
+        deliverArmed_ = hostDeliver_ && nOut > 0 && hMixHost_ != nullptr;
+        deliverLaunched_ = false;
+        int r = enqueueBlock(nIn, nOut, numSamples, false, false, true, processAllReduce_ && peerAttached_ && peer_.world > 1);
+        deliverArmed_ = false;
         if (r != rc::Ok) return r;
-        hOut = hPinned_ + nIn * blockSize_;
-        if (nOut) {
-            if (!cuda(dmemcpy(hOut, dMix_, sizeof(float) * nOut * blockSize_, cudaMemcpyDeviceToHost), "D2H mix")) return rc::CudaError;
+        if (deliverLaunched_) {
+            hOut = hMixHost_;
+            waitSeq = deliverSeq_;
+            polled = true;
+        } else {
+            hOut = hPinned_ + nIn * blockSize_;
+            if (nOut) {
+                if (!cuda(dmemcpy(hOut, dMix_, sizeof(float) * nOut * blockSize_, cudaMemcpyDeviceToHost), "D2H mix")) return rc::CudaError;
+            }
         }
     }
-    int r = synchronize();
-    if (r != rc::Ok) return r;
+    if (polled) {
+        // The kernel that finishes the mix bus has stored it into mapped host memory and raises the sequence word behind it: poll that
+        // word (no D2H copy launch, no stream synchronize wake-up).  A failed launch never raises it — the stream is queried every
+        // ~20 us so that an error (or a finished stream) ends the wait.
+        using clk = std::chrono::steady_clock;
+        auto lastQuery = clk::now();
+        for (;;) {
+            if (*hMixFlag_ == waitSeq) break;
+            for (int k = 0; k < 32; ++k) cpuRelax();
+            const auto now = clk::now();
+            if (now - lastQuery > std::chrono::microseconds(20)) {
+                lastQuery = now;
+                const cudaError_t q = cudaStreamQuery(stream_);
+                if (q == cudaErrorNotReady) continue;
+                if (q != cudaSuccess) { Lock lk(mu_); cuda(q, "stream query while waiting for the mix bus"); return rc::CudaError; }
+                if (*hMixFlag_ == waitSeq) break;
+                Lock lk(mu_);
+                return fail(rc::CudaError, "the render stream finished without delivering the mix bus");
+            }
+        }
+        std::atomic_thread_fence(std::memory_order_acquire);
+    } else {
+        int r = synchronize();
+        if (r != rc::Ok) return r;
+    }
     // hPinned_ belongs to the render thread: only process() (re)allocates it
     for (size_t c = 0; c < nOut; ++c) std::memcpy(out[c], hOut + c * blockSize_, sizeof(float) * numSamples);
     return rc::Ok;

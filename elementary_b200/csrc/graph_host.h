@@ -289,6 +289,15 @@ private:
     float* dInVoice_ = nullptr; size_t inVoiceFloats_ = 0;
     float* dInShared_ = nullptr; size_t inSharedFloats_ = 0;
     float* hPinned_ = nullptr; size_t pinnedFloats_ = 0;
+    // Host delivery of the mix bus (kernels.h HostDeliver): mapped pinned [MAX_OUT][blockSize] floats + the sequence word behind them.
+    // process() arms it for the block it enqueues and polls the word instead of D2H copy + stream synchronize.
+    float* hMixHost_ = nullptr; float* dMixHostAlias_ = nullptr;
+    volatile uint32_t* hMixFlag_ = nullptr; uint32_t* dMixFlagAlias_ = nullptr;
+    unsigned int* dDeliverDone_ = nullptr;
+    uint32_t deliverSeq_ = 0;
+    bool hostDeliver_ = true, processAllReduce_ = true;   // options "host_deliver", "process_allreduce"
+    bool deliverArmed_ = false, deliverLaunched_ = false;
+    HostDeliver takeDeliver();
     size_t curNOut_ = 0;
     struct BatchBuffers { LaunchParams* dDescs = nullptr; int* dTileStart = nullptr; size_t capGroups = 0; std::vector<char> lastDescs; };
     std::map<int, BatchBuffers> batch_;   // per tile width

@@ -20,8 +20,17 @@ cudaError_t launch_render_groups(const LaunchParams* descs, const int* tileStart
 // scratch: [MIX_REDUCE_MAX_GROUPS][nOut][blockSize] floats, tickets: [nOut * ceil(blockSize/32)] zeroed counters (both may be null:
 // single-pass reduction).
 constexpr int MIX_REDUCE_MAX_GROUPS = 16;
+// Host delivery of the finished mix bus: the kernel that writes the FINAL mix (K2 on one GPU, K4 across GPUs) also stores it into a
+// mapped pinned host buffer and, once every CTA has done so (`done` counter), raises `flag = seq` there — Runtime::process polls that
+// word instead of paying a D2H copy launch + stream synchronize per block.  out == nullptr: no host delivery.
+struct HostDeliver {
+    float* out = nullptr;            // device alias of the mapped host buffer [nOut][blockSize]
+    uint32_t* flag = nullptr;        // device alias of the host sequence word
+    unsigned int* done = nullptr;    // device counter, zero between launches
+    uint32_t seq = 0;
+};
 cudaError_t launch_mix_reduce(const float* partial, float* out, float* scratch, unsigned int* tickets, int nTiles, int nOut, int blockSize,
-                              int numSamples, cudaStream_t stream);
+                              int numSamples, cudaStream_t stream, HostDeliver hd = HostDeliver{});
 
 // K4: the one collective of the path as our own kernel over NVLink/NVSwitch peer memory: K2 leaves this rank's
 // partial mix bus in the rank's own slot of its exchange buffer; world-1 CTAs each push it into one peer's buffer, raise a flag there,
@@ -33,7 +42,7 @@ struct PeerMix {
     uint32_t* flag[MAX_PEERS];    // flag[p]: rank p's flags [2][MAX_PEERS]
     int rank, world, stride;
 };
-cudaError_t launch_mix_exchange(const PeerMix& pm, float* mix, int count, uint32_t epoch, int* status, cudaStream_t stream);
+cudaError_t launch_mix_exchange(const PeerMix& pm, float* mix, int count, uint32_t epoch, int* status, cudaStream_t stream, HostDeliver hd = HostDeliver{});
 
 } // namespace eb
 #endif   // __CUDACC_RTC__

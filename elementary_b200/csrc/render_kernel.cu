@@ -738,8 +738,25 @@ namespace eb {
 // interleaved accumulators per lane so that independent loads are in flight), leaves its result in scratch[g]; the block that
 // arrives last at the chunk's ticket counter adds the G group sums in group order.  The summation order is a function of
 // (nTiles, G) only — never of which block happens to be last — so the mix is reproducible run to run.
+__device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v) { asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
+
+// Called by every CTA that has just written its part of the FINAL mix bus (all threads of the CTA): the part is already in hd.out;
+// the CTA that arrives last at the `done` counter raises the host flag (data first: system-scope fences on both sides of the counter).
+__device__ __forceinline__ void host_deliver_arrive(const HostDeliver& hd, unsigned int nCtas) {
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned int d = atomicAdd(hd.done, 1u);
+        if (d == nCtas - 1) {
+            *hd.done = 0;                                     // ready for the next block of audio
+            __threadfence_system();
+            st_release_sys(hd.flag, hd.seq);
+        }
+    }
+}
+
 __global__ void __launch_bounds__(1024) mix_reduce_kernel(const float* __restrict__ partial, float* __restrict__ out, float* __restrict__ scratch,
-                                                          unsigned int* __restrict__ tickets, int nTiles, int nOut, int blockSize, int numSamples) {
+                                                          unsigned int* __restrict__ tickets, int nTiles, int nOut, int blockSize, int numSamples, const HostDeliver hd) {
     __shared__ float red[32][33];
     __shared__ bool last;
     const int sx = threadIdx.x & 31, gy = threadIdx.x >> 5;       // 32 samples x 32 tile lanes
@@ -762,10 +779,13 @@ __global__ void __launch_bounds__(1024) mix_reduce_kernel(const float* __restric
     if (gy == 0) {
         float v = 0.0f;
         for (int k = 0; k < 32; ++k) v += red[k][sx];
-        if (G == 1) { if (s < numSamples) out[(size_t) ch * blockSize + s] = v; }
+        if (G == 1) { if (s < numSamples) { out[(size_t) ch * blockSize + s] = v; if (hd.out) hd.out[(size_t) ch * blockSize + s] = v; } }
         else if (s < numSamples) scratch[((size_t) g * nOut + ch) * blockSize + s] = v;
     }
-    if (G == 1) return;
+    if (G == 1) {
+        if (hd.out) host_deliver_arrive(hd, gridDim.x);
+        return;
+    }
     __threadfence();
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -779,7 +799,9 @@ __global__ void __launch_bounds__(1024) mix_reduce_kernel(const float* __restric
         float v = 0.0f;
         for (int k = 0; k < G; ++k) v += __ldcg(scratch + ((size_t) k * nOut + ch) * blockSize + s);
         out[(size_t) ch * blockSize + s] = v;
+        if (hd.out) hd.out[(size_t) ch * blockSize + s] = v;
     }
+    if (last && hd.out) host_deliver_arrive(hd, gridDim.x);   // `last` is uniform over the CTA: one finishing CTA per chunk
 }
 
 // =========================================================================================================
@@ -871,17 +893,16 @@ cudaError_t launch_render_groups(const LaunchParams* descs, const int* tileStart
 }
 
 cudaError_t launch_mix_reduce(const float* partial, float* out, float* scratch, unsigned int* tickets, int nTiles, int nOut, int blockSize,
-                              int numSamples, cudaStream_t stream) {
+                              int numSamples, cudaStream_t stream, HostDeliver hd) {
     const int chunksPerCh = (blockSize + 31) / 32;
     int G = (nTiles + 255) / 256;                 // ~8 tiles per lane per group; 4096 voices at L = 2 -> 8 groups x 16 chunks = 128 CTAs
     if (G > MIX_REDUCE_MAX_GROUPS) G = MIX_REDUCE_MAX_GROUPS;
     if (G < 1 || !scratch || !tickets) G = 1;
-    mix_reduce_kernel<<<dim3(nOut * chunksPerCh, G), 1024, 0, stream>>>(partial, out, scratch, tickets, nTiles, nOut, blockSize, numSamples);
+    mix_reduce_kernel<<<dim3(nOut * chunksPerCh, G), 1024, 0, stream>>>(partial, out, scratch, tickets, nTiles, nOut, blockSize, numSamples, hd);
     return cudaGetLastError();
 }
 
 // ---- K4: cross-GPU all-reduce of the mix bus over peer memory (see kernels.h) -------------------------------------------
-__device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v) { asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
 __device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) { uint32_t v; asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory"); return v; }
 __device__ __forceinline__ float ld_volatile_f32(const float* p) { float v; asm volatile("ld.volatile.global.f32 %0, [%1];" : "=f"(v) : "l"(p) : "memory"); return v; }
 
@@ -892,7 +913,7 @@ __device__ __forceinline__ float ld_volatile_f32(const float* p) { float v; asm 
 // over the slots in rank order — every rank computes the bit-identical float sum — into the mix bus.  Two parities: a rank can be
 // one epoch ahead of a slow peer, never two (it needs the peer's flag of epoch e+1, which the peer raises after finishing e).
 // count = 0 is a pure barrier.
-__global__ void __launch_bounds__(256) mix_exchange_kernel(const PeerMix pm, float* __restrict__ mix, int count, uint32_t epoch, int* status) {
+__global__ void __launch_bounds__(256) mix_exchange_kernel(const PeerMix pm, float* __restrict__ mix, int count, uint32_t epoch, int* status, const HostDeliver hd) {
     const int tid = threadIdx.x, b = blockIdx.x, nb = gridDim.x;
     const int parity = (int) (epoch & 1u);
     const float* own = pm.slot[pm.rank] + (size_t) parity * MAX_PEERS * pm.stride;             // [src rank][stride] in OUR buffer
@@ -926,12 +947,14 @@ __global__ void __launch_bounds__(256) mix_exchange_kernel(const PeerMix pm, flo
         float s = 0.0f;
         for (int src = 0; src < pm.world; ++src) s += ld_volatile_f32(own + (size_t) src * pm.stride + i);
         mix[i] = s;
+        if (hd.out) hd.out[i] = s;
     }
+    if (hd.out) host_deliver_arrive(hd, nb);
 }
 
-cudaError_t launch_mix_exchange(const PeerMix& pm, float* mix, int count, uint32_t epoch, int* status, cudaStream_t stream) {
+cudaError_t launch_mix_exchange(const PeerMix& pm, float* mix, int count, uint32_t epoch, int* status, cudaStream_t stream, HostDeliver hd) {
     if (pm.world < 2) return cudaSuccess;
-    mix_exchange_kernel<<<pm.world - 1, 256, 0, stream>>>(pm, mix, count, epoch, status);
+    mix_exchange_kernel<<<pm.world - 1, 256, 0, stream>>>(pm, mix, count, epoch, status, hd);
     return cudaGetLastError();
 }
 

@@ -595,7 +595,9 @@ def test_split_keeps_sequencer_and_analysis_state(tile_width):
     clock = el.train(el.const(40.0, key="rate"))
     sq = el.seq({"seq": [0.1, 0.2, 0.3, 0.4, 0.5], "hold": True, "loop": True, "key": "sq"}, clock)
     sp = el.sparseq({"seq": [{"value": 1.0, "tickTime": 0}, {"value": 0.5, "tickTime": 3}, {"value": 0.25, "tickTime": 5}], "loop": [0, 7], "key": "sp"}, clock)
-    sig = el.mul(el.add(sq, sp), el.cycle(el.const(220.0, key="f")))
+    # the carrier is a phasor-built saw, not el.cycle: events are compared EXACTLY (events_common.same) and only transcendental-free
+    # signals are bit-exact between CUDA's libm and glibc's (numerics)
+    sig = el.mul(el.add(sq, sp), el.sub(el.mul(2.0, el.phasor(el.const(220.0, key="f"))), 1.0))
     g1 = el.add(el.meter({"name": "m"}, sig), el.mul(0.0, el.scope({"name": "s", "size": 512}, sig)),
                 el.mul(0.0, el.capture({"name": "c"}, el.le(el.phasor(3.0), 0.5), sig)))
     g2 = el.tanh(el.add(g1, el.mul(0.1, el.cycle(el.const(330.0, key="f2")))))
@@ -671,3 +673,20 @@ def test_offline_render_equals_block_by_block_and_many_groups_stay_correct_in_st
     assert c.apply_instructions(edit, voices=(0, 2)) == 0
     v, _ = c.process_voices(None, 1, BS)
     assert np.abs(v[0]).max() > 0.1
+
+
+@pytest.mark.parametrize("n_voices,n_out", [(4096, 1), (33, 2), (1, 1)])
+def test_process_host_delivery_equals_the_copy_path(n_voices, n_out):
+    """Runtime::process hands the mix bus over through mapped host memory + a sequence word written by the kernel that finishes the
+    mix (K2; kernels.h HostDeliver) instead of a D2H copy + stream synchronize.  Same samples, bit for bit, as with the option off —
+    full blocks, short blocks, two output channels, the multi-group reduction (4096 voices: G > 1) and the single-pass one."""
+    sig = graphs.subsynth32_graph(110.0)
+    batch = el.render(sig) if n_out == 1 else el.render(sig, el.mul(-0.5, sig))
+    a = Runtime(SR, BS, n_voices, device=0)
+    b = Runtime(SR, BS, n_voices, device=0, host_deliver=0)
+    for rt in (a, b):
+        assert rt.apply_instructions(batch) == 0, rt.last_error()
+    for n in (BS, BS, 100, 37, BS, 1, BS):
+        oa, ob = a.process(None, n_out, n), b.process(None, n_out, n)
+        assert oa.shape == (n_out, n) and np.array_equal(oa, ob)
+        assert np.abs(oa).max() > 0 or n == 1

@@ -15,6 +15,6 @@ print("# voices  L  ms/step  K1_ms  Msamples/s  realtime_x  hbm_frac")
 for v in (4096, 8192, 16384, 32768, 65536, 131072, 262144):
     f = "gpurun_out/final_bench_n1.json" if v == 4096 else f"gpurun_out/final_v{v}.json"
     d = json.load(open(f))
-    print(v, d["config"]["tile_width"], round(d["ms_per_step"], 4), round(d["roofline"]["kernel_ms"], 4), round(d["value"], 1), round(d["realtime_factor"], 2), round(d["roofline"]["frac"], 5))
+    print(v, d["engine"]["tile_width"], round(d["ms_per_step"], 4), round(d["roofline"]["kernel_ms"], 4), round(d["value"], 1), round(d["realtime_factor"], 2), round(d["roofline"]["frac"], 5))
 PY
 python bench_configs.py 3 4 5 > gpurun_out/final_configs.jsonl 2>/dev/null; cut -c1-260 gpurun_out/final_configs.jsonl

@@ -8,6 +8,6 @@ for c in fused nccl; do
   python - <<PY
 import json
 d = json.load(open("gpurun_out/peer_n${N}_$c.json"))
-print("N=$N $c: Msamples/s", round(d["value"]), "ms/step", round(d["ms_per_step"], 4), "e2e", round(d["e2e"]["value"]), "|", d["config"]["collective"][:70])
+print("N=$N $c: Msamples/s", round(d["value"]), "ms/step", round(d["ms_per_step"], 4), "e2e", round(d["e2e"]["value"]), "|", d["engine"]["collective"][:70])
 PY
 done

@@ -19,7 +19,7 @@ for v in (4096, 131072):
     for k in ("interp", "spec"):
         try:
             d = json.load(open(f"gpurun_out/r02a_{k}_v{v}.json"))
-            print(k, v, "L", d["config"]["tile_width"], "ms/step", round(d["ms_per_step"], 4), "K1 ms", round(d["roofline"]["kernel_ms"], 4), "Msamples/s", round(d["value"], 1), d["config"].get("spec"))
+            print(k, v, "L", d["engine"]["tile_width"], "ms/step", round(d["ms_per_step"], 4), "K1 ms", round(d["roofline"]["kernel_ms"], 4), "Msamples/s", round(d["value"], 1), d["engine"].get("spec"))
         except Exception as e:
             print(k, v, "FAILED", e)
 PY

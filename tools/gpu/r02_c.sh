@@ -18,7 +18,7 @@ import json, glob
 for f in sorted(glob.glob("gpurun_out/r02c_*_L*.json")):
     try:
         d = json.load(open(f))
-        print(f.split("/")[-1], "L", d["config"]["tile_width"], "ms/step", round(d["ms_per_step"], 4), "K1", round(d["roofline"]["kernel_ms"], 4), "parity", d.get("worst_err_over_tol"), d["config"].get("spec", {}).get("spec_regs"))
+        print(f.split("/")[-1], "L", d["engine"]["tile_width"], "ms/step", round(d["ms_per_step"], 4), "K1", round(d["roofline"]["kernel_ms"], 4), "parity", d.get("worst_err_over_tol"), d["engine"].get("spec", {}).get("spec_regs"))
     except Exception as e:
         print(f, "FAILED", e)
 PY
