@@ -488,7 +488,26 @@ def run_b200(args, rank, local_rank, world, emit=print):
             "k1": "specialised" if t1["desc"].get("spec_state") == 2 else "interpreter",
             "hbm_frac": (ALGO_BYTES_PER_VOICE_BLOCK_MIX_ONLY * T1_VOICES_PER_GPU / (t1["k1_ms"] / max(1, t1["k1_n"]) * 1e-3) / 1e9) / peak,
             "steps": t1["steps"], **t1["parity"]}
+    if world == 1 and not args.no_configs:
+        line["other_configs"] = other_configs()
     emit(json.dumps(line))
+
+
+def other_configs():
+    """BASELINE.json configs 3, 4 and 5 at their per-GPU share (bench_configs.py), so that they are driver-run numbers too: ms per block
+    (device resident), Msamples/s, the kernel's algorithmic-bytes roofline fraction (K3 for config 4), a bounded CPU reference sample
+    and — config 5 — the parity check of a sample of the graphs.  Short runs: the whole leg takes well under a minute."""
+    import bench_configs
+    out = {}
+    for key, fn, quick in (("3_additive64_8192_voices", bench_configs.config3, True), ("4_convolve_16384_taps_1024_channels", bench_configs.config4, True),
+                           ("5_random_graphs_1250", bench_configs.config5, False)):
+        try:
+            r = fn(quick)
+            r.pop("program", None)
+            out[key] = r
+        except Exception as e:      # reported, never silent
+            out[key] = {"failed": repr(e)[:300]}
+    return out
 
 
 def main():
@@ -501,6 +520,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-parity", action="store_true", help="skip the parity check of the timed runtime (exploration only)")
     ap.add_argument("--no-t1", action="store_true", help="skip the extra 131072-voices-per-GPU measurement")
+    ap.add_argument("--no-configs", action="store_true", help="skip the BASELINE configs 3/4/5 leg (N = 1 only)")
     ap.add_argument("--specialize", type=int, default=2, help="K1 per-program specialisation: 0 interpreter, 2 NVRTC at COMMIT (default)")
     ap.add_argument("--collective", default="fused", choices=["fused", "nccl"], help="N > 1: K4 peer-memory kernel (default) or NCCL all_reduce")
     ap.add_argument("--tile-width", type=int, default=0, help="override the voices-per-warp heuristic (exploration only)")

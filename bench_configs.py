@@ -138,7 +138,10 @@ def config5(quick):
     n_graphs = 200 if quick else 1250   # 10000 graphs / 8 GPUs
     if "--graphs" in sys.argv:
         n_graphs = int(sys.argv[sys.argv.index("--graphs") + 1])
-    rt = Runtime(SR, BS, n_graphs, device=0, time_kernels=1)
+    extra = {}
+    if "--stages" in sys.argv:
+        extra["pipeline_stages"] = int(sys.argv[sys.argv.index("--stages") + 1])
+    rt = Runtime(SR, BS, n_graphs, device=0, time_kernels=1, **extra)
     batches = [graphs.random_graph(i, 64) for i in range(n_graphs)]     # the Python generator is not part of the engine's setup cost
     t0 = time.perf_counter()
     for i, batch in enumerate(batches):
@@ -183,7 +186,8 @@ def config5(quick):
             secs, _ = orc.ref_bench(SR, BS, graphs.random_graph(i, 64), None, 1, 1, 0, 1, 3, 200)
             tot += secs
         cpu = {"msamples_per_s_per_core": ng * BS * 200 / tot / 1e6, "cores_used": 1, "sample": f"{ng} graphs x 200 blocks, one thread"}
-    return {"config": f"5: {n_graphs} independent random 64-node graphs on one GPU (10000 over 8), one voice group each",
+    stages = sorted({g.get("pipeline_stages", 1) for g in rt.describe()["groups"]})
+    return {"config": f"5: {n_graphs} independent random 64-node graphs on one GPU (10000 over 8), one voice group each", "pipeline_stages": stages,
             "ms_per_block": ms, "k1_ms_sum": k1, "msamples_per_s": n_graphs * BS / ms / 1e3, "realtime_x": BS / (ms * 1e-3) / SR,
             "launches_per_block": launches, "graph_setup_s": build_s, "offline": offline, "parity": parity, "cpu_reference": cpu}
 

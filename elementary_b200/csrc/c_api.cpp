@@ -8,6 +8,7 @@
 #include <vector>
 
 #include "graph_host.h"
+#include "kernels.h"
 
 struct elem_b200_runtime {
     eb::Engine* engine;
@@ -188,6 +189,12 @@ int elem_b200_snapshot(elem_b200_runtime* rt, int voice, char* buf, size_t cap) 
         if (buf && cap) { const size_t k = s.size() < cap - 1 ? s.size() : cap - 1; std::memcpy(buf, s.data(), k); buf[k] = 0; }
         return (int) s.size() + 1;
     } catch (...) { return 0; }
+}
+
+int elem_b200_debug_opprof(elem_b200_runtime* rt, unsigned long long* out128, int reset) {
+    if (!rt || !out128) return -1;
+    rt->engine->synchronize();
+    return eb::debug_opprof_read(out128, reset != 0) == cudaSuccess ? 0 : -1;
 }
 
 int elem_b200_program_words(elem_b200_runtime* rt, int voice, uint32_t* buf, size_t cap) {

@@ -44,9 +44,27 @@ bool convolver_init(ConvolverState& st, const float* ir, size_t irLen, int nv, b
 // Copy of channels [c0, c0+n) of `src` (same IR, same position in the partition cycle) — used when a voice group is cut.
 bool convolver_clone_range(const ConvolverState& src, int c0, int n, ConvolverState& dst, cudaStream_t stream, std::string& err);
 
+// Root + mix fused behind the inverse transform (graph_host.cpp sets it when the convolver's output feeds nothing but the graph's root,
+// the `convolve -> root` shape of a reverb send: BASELINE config 4).  The kernel then applies the root's gain fade exactly like K1's
+// OP_ROOT does (Core.h:66-78, GainFade.h:56-72: g = clamp(gain0 + step * sampleIndex) while fading, the target otherwise), writes the
+// per-voice output and this channel's row of the per-tile partial mix (one-voice tiles: row = channel) — the K1 launch that would only
+// have re-read the block and multiplied it disappears, and the convolver's own output buffer is not written at all.
+struct ConvEpilogue {
+    bool active = false;
+    bool running = true;             // the root's sub-sequence runs this block (else: silence, like the skipped segment in K1)
+    float gain0 = 1.0f, step = 0.0f, target = 1.0f;
+    int channel = 0;                 // the root's output channel
+    int nOut = 1, blockSize = 512;
+    float* mixPartial = nullptr;     // [tileBase + channel][nOut][blockSize] or null
+    int tileBase = 0;
+    float* outVoice = nullptr;       // [voice0 + channel][nOut][outStride] (+ outOffset) or null
+    int voice0 = 0, outStride = 512, outOffset = 0;
+};
+
 // Convolve `n` more samples (n <= 512 - st.fill) of every channel: in is [channel][inStride] (inStride 0 = one input shared by
 // all channels), out is [channel][outStride]; the samples of this call start at `offset`.  Advances st.fill / st.cur.
-cudaError_t convolver_process_chunk(ConvolverState& st, const float* in, int inStride, float* out, int outStride, int offset, int n, cudaStream_t stream);
+cudaError_t convolver_process_chunk(ConvolverState& st, const float* in, int inStride, float* out, int outStride, int offset, int n, cudaStream_t stream,
+                                    const ConvEpilogue& epi = ConvEpilogue{});
 
 // Algorithmic HBM bytes of one full 512-sample block for one channel.
 inline size_t convolver_algorithmic_bytes_per_channel_block(int partitions) {

@@ -116,7 +116,7 @@ __device__ __forceinline__ void fft512_t(float2 (*a)[N2], float2 (*b)[N2], const
 __global__ void __launch_bounds__(TM_THREADS, TM_CTAS_PER_SM) convolve_chunk_tm_kernel(
     const float* __restrict__ in, int inStride, float* __restrict__ out, int stride, int offset, int n, int fill, int cur, int S, int nv,
     const float2* __restrict__ H, float2* __restrict__ fdl, float2* __restrict__ ypre,
-    float* __restrict__ overlap, float* __restrict__ inbuf, const float2* __restrict__ twg) {
+    float* __restrict__ overlap, float* __restrict__ inbuf, const float2* __restrict__ twg, const ConvEpilogue epi) {
     extern __shared__ __align__(128) unsigned char smemRaw[];
     float2 (*stX)[CH][N2] = reinterpret_cast<float2 (*)[CH][N2]>(smemRaw);                                        // [TM_STAGES][CH][512]
     float2 (*stH)[N2] = reinterpret_cast<float2 (*)[N2]>(smemRaw + (size_t) TM_STAGES * CH * ROW_BYTES);          // [TM_STAGES][512]
@@ -358,9 +358,33 @@ __global__ void __launch_bounds__(TM_THREADS, TM_CTAS_PER_SM) convolve_chunk_tm_
             const int ch = ch0 + c;
             if (ch >= nv) continue;
             const float* y = reinterpret_cast<const float*>(&Sc[c][0]);
-            float* o = out + (size_t) ch * stride + offset;
+            if (!epi.active) {
+                float* o = out + (size_t) ch * stride + offset;
 #pragma unroll
-            for (int q = 0; q < 4; ++q) { const int i = t + q * TM_GROUP; if (i < n) o[i] = y[fill + i] * scale + ovv[c][q]; }
+                for (int q = 0; q < 4; ++q) { const int i = t + q * TM_GROUP; if (i < n) o[i] = y[fill + i] * scale + ovv[c][q]; }
+            } else {
+                // root + mix epilogue (ConvEpilogue): the same arithmetic as K1's OP_ROOT, sample index = position in the block
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const int i = t + q * TM_GROUP;
+                    if (i >= n) continue;
+                    const float v = y[fill + i] * scale + ovv[c][q];
+                    float r = 0.0f;
+                    if (epi.running) {
+                        if (epi.gain0 == epi.target) r = v * epi.target;
+                        else {
+                            const float gr = epi.gain0 + epi.step * (float) (offset + i);
+                            r = v * ((gr < 0.0f) ? 0.0f : ((1.0f < gr) ? 1.0f : gr));
+                        }
+                        r = 0.0f + r;                                   // K1 accumulates into a zeroed output row
+                    }
+                    for (int oc = 0; oc < epi.nOut; ++oc) {
+                        const float w = (oc == epi.channel) ? r : 0.0f;
+                        if (epi.mixPartial) epi.mixPartial[((size_t) (epi.tileBase + ch) * epi.nOut + oc) * epi.blockSize + offset + i] = w;
+                        if (epi.outVoice) epi.outVoice[((size_t) (epi.voice0 + ch) * epi.nOut + oc) * epi.outStride + epi.outOffset + offset + i] = w;
+                    }
+                }
+            }
         }
         if (fill + n == CONV_BLOCK) {
 #pragma unroll
@@ -385,9 +409,16 @@ __global__ void __launch_bounds__(TM_THREADS, TM_CTAS_PER_SM) convolve_chunk_tm_
     if (prevU >= 0) inverse(prevU, nloc - 1);
 }
 
-cudaError_t convolver_process_chunk(ConvolverState& st, const float* in, int inStride, float* out, int stride, int offset, int n, cudaStream_t stream) {
+cudaError_t convolver_process_chunk(ConvolverState& st, const float* in, int inStride, float* out, int stride, int offset, int n, cudaStream_t stream,
+                                    const ConvEpilogue& epi) {
     if (st.planOnly) return cudaErrorNotSupported;
     if (st.partitions == 0) {   // empty (fully trimmed) IR: silence (FFTConvolver.cpp:149-153)
+        if (epi.active) {
+            cudaError_t e = cudaSuccess;
+            if (epi.mixPartial) e = cudaMemset2DAsync(epi.mixPartial + (size_t) epi.tileBase * epi.nOut * epi.blockSize + offset, sizeof(float) * epi.blockSize, 0, sizeof(float) * n, (size_t) st.nv * epi.nOut, stream);
+            if (e == cudaSuccess && epi.outVoice) e = cudaMemset2DAsync(epi.outVoice + (size_t) epi.voice0 * epi.nOut * epi.outStride + epi.outOffset + offset, sizeof(float) * epi.outStride, 0, sizeof(float) * n, (size_t) st.nv * epi.nOut, stream);
+            return e;
+        }
         return cudaMemset2DAsync(out + offset, sizeof(float) * stride, 0, sizeof(float) * n, st.nv, stream);
     }
     const int units = (st.nv + CONV_CH_PER_CTA - 1) / CONV_CH_PER_CTA;
@@ -404,7 +435,7 @@ cudaError_t convolver_process_chunk(ConvolverState& st, const float* in, int inS
     const int persistent = smCount * TM_CTAS_PER_SM;                   // a multiple of the SM count: one resident wave
     const int grid = units < persistent ? units : persistent;
     convolve_chunk_tm_kernel<<<grid, TM_THREADS, smem, stream>>>(in, inStride, out, stride, offset, n, st.fill, st.cur, st.partitions, st.nv,
-                                                                st.dH, st.dFdl, st.dYpre, st.dOverlap, st.dInBuf, st.dTw);
+                                                                st.dH, st.dFdl, st.dYpre, st.dOverlap, st.dInBuf, st.dTw, epi);
     st.fill += n;
     if (st.fill == CONV_BLOCK) {
         st.fill = 0;

@@ -206,6 +206,7 @@ Engine::~Engine() {
     if (dInShared_) dfree(dInShared_);
     if (hPinned_ && !planOnly_) cudaFreeHost(hPinned_);
     if (hMixHost_) cudaFreeHost(hMixHost_);
+    for (int i = 0; i < 2; ++i) { if (offlineDev_[i]) cudaFree(offlineDev_[i]); if (offlinePinned_[i]) cudaFreeHost(offlinePinned_[i]); }
     if (dDeliverDone_) cudaFree(dDeliverDone_);
     for (auto& kv : batch_) { if (kv.second.dDescs) dfree(kv.second.dDescs); if (kv.second.dTileStart) dfree(kv.second.dTileStart); }
     for (auto* l : {&timedEvents_, &timedMixEvents_, &timedConvEvents_, &timedXchgEvents_})
@@ -234,6 +235,8 @@ int Engine::setOption(const char* key, double value) {
     else if (k == "specialize_max_words") { opt_.specializeMaxWords = (int) value; }
     else if (k == "specialize_strict") { opt_.specializeStrict = value != 0; }
     else if (k == "time_kernels") { timeKernels_ = value != 0 && !planOnly_; }
+    else if (k == "fuse_conv_root") { opt_.fuseConvRoot = value != 0; }
+    else if (k == "pipeline_stages") { opt_.pipelineStages = std::max(0, std::min((int) value, (int) MAX_PIPE)); }
     else if (k == "host_deliver") { hostDeliver_ = value != 0; }
     else if (k == "process_allreduce") { processAllReduce_ = value != 0; }
     else if (k == "plan_dry_run") { planDryRun_ = value != 0 && planOnly_; }
@@ -253,7 +256,7 @@ std::string Engine::describe() const {
         if (g->pending || g->active) {
             auto& p = g->pending ? g->pending : g->active;
             os << ",\"slots\":" << p->nSlots << ",\"state_rows\":" << p->nStateRows << ",\"params\":" << p->paramMap.size() << ",\"ops\":" << p->nOps << ",\"code_words\":" << p->code.size()
-               << ",\"roots\":" << p->rootIds.size();
+               << ",\"roots\":" << p->rootIds.size() << ",\"pipeline_stages\":" << p->pipeW;
             if (p->specJob) {
                 const int st = p->specJob->state.load(std::memory_order_acquire);
                 os << ",\"spec_state\":" << st << ",\"spec_cubin_bytes\":" << (st > 0 ? p->specJob->kernel.cubin.size() : 0);
@@ -1777,6 +1780,120 @@ int Engine::compile(Group& g, int nIn, std::shared_ptr<Program>& out) {
             for (auto& op : out) if (!op.isSeg) anyWork = true;
             prog->stages[st].empty = !anyWork;
         }
+        // `convolve -> root` (a reverb send, BASELINE config 4): the last stage is [LOADBUF conv.out][ROOT of it] and nothing else
+        if (opt_.fuseConvRoot && g.tileWidth == 1 && nStages >= 2 && prog->rootIds.size() == 1 && C.promotes.empty()) {
+            const auto& lastOps = stageOps[nStages - 1];
+            std::vector<const Compiler::PendingOp*> body;
+            for (auto& op : lastOps) if (!op.isSeg) body.push_back(&op);
+            if (body.size() == 2 && body[0]->opcode == OP_LOADBUF && body[1]->opcode == OP_ROOT && body[1]->operands.size() == 1 &&
+                body[1]->operands[0].first == K_SLOT && body[1]->operands[0].second == body[0]->outNode) {
+                for (int st = 0; st < nStages - 1 && prog->fusedConvStage < 0; ++st)
+                    for (size_t ci = 0; ci < prog->stages[st].convolves.size(); ++ci)
+                        if ((uint64_t) (uintptr_t) prog->stages[st].convolves[ci].out == body[0]->ptr) {
+                            prog->fusedConvStage = st; prog->fusedConvIndex = (int) ci; prog->fusedRoot = (int) body[1]->aux0;
+                            break;
+                        }
+            }
+        }
+    }
+
+    // ---- warp pipeline for one-voice groups (BASELINE config 5: thousands of different graphs, one voice each) ----------------
+    // With one voice per warp every recurrence owns a single lane and the warp is latency bound.  The op list (one root sub-sequence,
+    // already in its final order) is cut into W contiguous stages of about equal cost; render_groups_pipe_kernel gives each stage its
+    // own warp, and the warps work on consecutive sample tiles of the same graph at the same time.  A value that crosses a cut lives in
+    // a ring slot with W buffers (tile index mod W), everything else in slots private to its stage.  Same ops, same order of evaluation
+    // per value: bit-identical output (tests/test_parity_gpu.py::test_pipelined_groups_equal_the_unpipelined_path).
+    std::vector<int> pipeStageOf;            // per op of stageOps[0]; empty = not pipelined
+    {
+        const bool batchedGroup = groups_.size() > 1 && opt_.batchGroups;
+        int W = std::min(opt_.pipelineStages, (int) MAX_PIPE);
+        bool ok = W > 1 && batchedGroup && g.tileWidth == 1 && stageOps.size() == 1 && prog->rootIds.size() == 1 && C.promotes.empty() &&
+                  prog->evNodes.empty() && prog->dynNodes.empty() && !prog->hasCustom;
+        auto& sops = stageOps[0];
+        auto costOf = [](const Compiler::PendingOp& op) -> long {     // rough latency of one 32-sample tile at L = 1, in cycles
+            const long dispatch = 150;
+            switch (op.opcode) {
+                case OP_CHAIN: {
+                    long c = 30;
+                    for (auto& st : op.steps) {
+                        const uint32_t fn = st.fn & 0xFF;
+                        if (fn <= F_EXP && fn != F_CEIL && fn != F_FLOOR && fn != F_ROUND && fn != F_SQRT) c += 80;
+                        else if (fn == F_DIV || fn == F_MOD || fn == F_POW) c += 40;
+                        else c += 8;
+                    }
+                    return dispatch + c;
+                }
+                case OP_PHASOR: return op.mode == 1 ? 0 : dispatch + 450;          // a run costs what its leader costs
+                case OP_SPHASOR: return dispatch + 600;
+                case OP_COUNTER: case OP_ACCUM: case OP_LATCH: case OP_MAXHOLD: return dispatch + 400;
+                case OP_RAND: return dispatch + 500;
+                case OP_POLE: return dispatch + 500;
+                case OP_ENV: return dispatch + 700;
+                case OP_BIQUAD: return dispatch + 900;
+                case OP_PREWARP: return dispatch + 250;
+                case OP_MM1P: return dispatch + 700;
+                case OP_SVF: return dispatch + 900;
+                case OP_SVFSHELF: return dispatch + 1200;
+                case OP_BLEP: return dispatch + 500;
+                case OP_DELAY: return dispatch + 150;
+                case OP_SDELAY: case OP_TABLE: return dispatch + 70;
+                default: return dispatch + 30;
+            }
+        };
+        if (ok) {
+            for (size_t i = 0; i < sops.size() && ok; ++i) {
+                const auto& op = sops[i];
+                if (op.isSeg) { ok = (i == 0); continue; }
+                switch (op.opcode) {
+                    case OP_FILL0: case OP_COPY: case OP_CHAIN: case OP_PHASOR: case OP_SPHASOR: case OP_COUNTER: case OP_ACCUM: case OP_LATCH:
+                    case OP_MAXHOLD: case OP_RAND: case OP_POLE: case OP_ENV: case OP_BIQUAD: case OP_PREWARP: case OP_MM1P: case OP_SVF:
+                    case OP_SVFSHELF: case OP_Z: case OP_DELAY: case OP_SDELAY: case OP_TABLE: case OP_BLEP: case OP_ROOT: break;
+                    default: ok = false;
+                }
+            }
+        }
+        if (ok) {
+            // units: an op, or a phasor run (leader + its followers), which must stay together
+            std::vector<std::pair<size_t, size_t>> units;     // [first op, one past the last op)
+            std::vector<long> ucost;
+            for (size_t i = 1; i < sops.size();) {
+                size_t j = i + 1;
+                if (sops[i].opcode == OP_PHASOR && sops[i].aux1 > 1) j = i + sops[i].aux1;
+                long c = 0;
+                for (size_t k = i; k < j && k < sops.size(); ++k) c += costOf(sops[k]);
+                units.push_back({i, std::min(j, sops.size())});
+                ucost.push_back(c);
+                i = j;
+            }
+            const int n = (int) units.size();
+            if (n < 2 * W) ok = false;
+            if (ok) {
+                // linear partition: minimise the most expensive stage (O(n^2 W), n <= a few hundred)
+                std::vector<long> pre(n + 1, 0);
+                for (int i = 0; i < n; ++i) pre[i + 1] = pre[i] + ucost[i];
+                const long INF = (long) 1 << 60;
+                std::vector<std::vector<long>> best(W + 1, std::vector<long>(n + 1, INF));
+                std::vector<std::vector<int>> cut(W + 1, std::vector<int>(n + 1, 0));
+                best[0][0] = 0;
+                for (int w = 1; w <= W; ++w)
+                    for (int i = w; i <= n; ++i)
+                        for (int j = w - 1; j < i; ++j) {
+                            if (best[w - 1][j] >= INF) continue;
+                            const long c = std::max(best[w - 1][j], pre[i] - pre[j]);
+                            if (c < best[w][i]) { best[w][i] = c; cut[w][i] = j; }
+                        }
+                std::vector<int> bounds(W + 1, 0);
+                bounds[W] = n;
+                for (int w = W; w >= 1; --w) bounds[w - 1] = cut[w][bounds[w]];
+                pipeStageOf.assign(sops.size(), 0);
+                for (int w = 0; w < W; ++w)
+                    for (int u = bounds[w]; u < bounds[w + 1]; ++u)
+                        for (size_t k = units[u].first; k < units[u].second; ++k) pipeStageOf[k] = w;
+                for (size_t i = 1; i < sops.size(); ++i)          // roots write the graph's output accumulator: last stage only
+                    if (sops[i].opcode == OP_ROOT && pipeStageOf[i] != W - 1) { pipeStageOf.clear(); break; }
+                if (!pipeStageOf.empty()) { prog->pipeW = W; prog->pipeDepth = W; }
+            }
+        }
     }
 
     // ---- per stage: slot allocation by liveness (an output slot is never the slot of one of its own inputs),
@@ -1810,13 +1927,72 @@ int Engine::compile(Group& g, int nIn, std::shared_ptr<Program>& out) {
         auto& sops = stageOps[stg];
         prog->stages[stg].codeOffset = (uint32_t) prog->code.size();
 
+        std::vector<int> outSlot(sops.size(), 0);
+        int nSlots = 0;
+        bool piped = !pipeStageOf.empty() && stg == 0;
+        if (piped) {
+            // ring values: read in a later pipeline stage than the one that produces them
+            const int W = prog->pipeW;
+            std::unordered_map<int32_t, int> prodStage, ringOf;
+            for (size_t i = 0; i < sops.size(); ++i) if (!sops[i].isSeg) prodStage[sops[i].outNode] = pipeStageOf[i];
+            int nRing = 0;
+            for (size_t i = 0; i < sops.size(); ++i) {
+                if (sops[i].isSeg) continue;
+                forEachSlotUse(sops[i], [&](int32_t id) {
+                    auto ps = prodStage.find(id);
+                    if (ps != prodStage.end() && ps->second < pipeStageOf[i] && !ringOf.count(id)) ringOf[id] = nRing++;
+                });
+            }
+            // private slots: liveness inside each stage, every stage in its own index range
+            int privBase = 0;
+            for (int w = 0; w < W; ++w) {
+                std::unordered_map<int32_t, size_t> lastUse;
+                for (size_t i = 0; i < sops.size(); ++i)
+                    if (!sops[i].isSeg && pipeStageOf[i] == w) forEachSlotUse(sops[i], [&](int32_t id) { lastUse[id] = i; });
+                std::unordered_map<int32_t, int> slotOf;
+                std::vector<int> freeSlots;
+                int local = 0;
+                for (size_t i = 0; i < sops.size(); ++i) {
+                    auto& op = sops[i];
+                    if (op.isSeg || pipeStageOf[i] != w) continue;
+                    auto rg = ringOf.find(op.outNode);
+                    if (rg != ringOf.end()) {
+                        outSlot[i] = -(rg->second + 1);                      // placed behind the private ranges below
+                    } else {
+                        int sl;
+                        if (!freeSlots.empty()) { sl = freeSlots.back(); freeSlots.pop_back(); }
+                        else sl = local++;
+                        outSlot[i] = privBase + sl;
+                        slotOf[op.outNode] = sl;
+                    }
+                    forEachSlotUse(op, [&](int32_t id) {
+                        auto lu = lastUse.find(id);
+                        auto so = slotOf.find(id);
+                        if (lu != lastUse.end() && lu->second == i && so != slotOf.end()) { freeSlots.push_back(so->second); slotOf.erase(so); }
+                    });
+                    if (rg == ringOf.end() && !lastUse.count(op.outNode)) {
+                        auto so = slotOf.find(op.outNode);
+                        if (so != slotOf.end()) { freeSlots.push_back(so->second); slotOf.erase(so); }
+                    }
+                }
+                privBase += local;
+            }
+            const int ringBase = std::max(privBase, 1);
+            nSlots = ringBase + nRing * prog->pipeDepth;
+            if (nSlots >= MAX_SLOTS) {                                       // does not fit the 8-bit slot field: keep the program in one piece
+                piped = false; pipeStageOf.clear(); prog->pipeW = 1; prog->pipeDepth = 1;
+            } else {
+                for (size_t i = 0; i < sops.size(); ++i) if (outSlot[i] < 0) outSlot[i] = ringBase + (-outSlot[i] - 1) * prog->pipeDepth;
+                prog->pipeRingBase = ringBase;
+            }
+        }
+        if (!piped) {
         std::unordered_map<int32_t, size_t> lastUse;
         for (size_t i = 0; i < sops.size(); ++i)
             if (!sops[i].isSeg) forEachSlotUse(sops[i], [&](int32_t id) { lastUse[id] = i; });
         std::unordered_map<int32_t, int> slotOf;
         std::vector<int> freeSlots;
-        int nSlots = 0;
-        std::vector<int> outSlot(sops.size(), 0);
+        nSlots = 0;
         for (size_t i = 0; i < sops.size(); ++i) {
             auto& op = sops[i];
             if (op.isSeg) continue;
@@ -1836,6 +2012,7 @@ int Engine::compile(Group& g, int nIn, std::shared_ptr<Program>& out) {
             });
             // an output nobody reads (root buffers, dangling nodes) is dead immediately
             if (!lastUse.count(op.outNode)) { freeSlots.push_back(s); slotOf.erase(op.outNode); }
+        }
         }
         nSlotsMax = std::max(nSlotsMax, nSlots);
 
@@ -1862,18 +2039,14 @@ int Engine::compile(Group& g, int nIn, std::shared_ptr<Program>& out) {
             size_t n = op.operands.size() + 2 * op.steps.size() + op.imm.size();
             return OP_HEADER_WORDS + ((n + 3) & ~(size_t) 3);
         };
-        std::vector<size_t> wordOffset(sops.size() + 1, 0);
-        for (size_t i = 0; i < sops.size(); ++i) wordOffset[i + 1] = wordOffset[i] + opWords(sops[i]);
-        for (size_t i = 0; i < sops.size(); ++i) {
-            auto& op = sops[i];
-            if (op.isSeg) {
-                prog->code.push_back(make_w0(OP_SEG, 0, 0, 0));
-                prog->code.push_back(NO_STATE);
-                prog->code.push_back((uint32_t) op.segRoot);
-                prog->code.push_back((uint32_t) (wordOffset[op.segEndOp] - wordOffset[i + 1]));
-                for (int k = 0; k < 4; ++k) prog->code.push_back(0);
-                continue;
-            }
+        auto emitSeg = [&](int segRoot, size_t skipWords) {
+            prog->code.push_back(make_w0(OP_SEG, 0, 0, 0));
+            prog->code.push_back(NO_STATE);
+            prog->code.push_back((uint32_t) segRoot);
+            prog->code.push_back((uint32_t) skipWords);
+            for (int k = 0; k < 4; ++k) prog->code.push_back(0);
+        };
+        auto emitOp = [&](const Compiler::PendingOp& op, int slot) -> int {
             ++prog->nOps;
             uint32_t st = NO_STATE;
             if (op.state != NO_STATE) {
@@ -1882,7 +2055,7 @@ int Engine::compile(Group& g, int nIn, std::shared_ptr<Program>& out) {
             }
             const size_t nOperandWords = opWords(op) - OP_HEADER_WORDS;
             if (nOperandWords > 255) return fail(rc::InvariantViolation, "operand block of one op exceeds 255 words");
-            prog->code.push_back(make_w0(op.opcode, (uint32_t) nOperandWords, (uint32_t) outSlot[i], op.mode));
+            prog->code.push_back(make_w0(op.opcode, (uint32_t) nOperandWords, (uint32_t) slot, op.mode));
             prog->code.push_back(st);
             prog->code.push_back(op.aux0);
             prog->code.push_back(op.aux1);
@@ -1899,6 +2072,35 @@ int Engine::compile(Group& g, int nIn, std::shared_ptr<Program>& out) {
             }
             for (uint32_t w : op.imm) { prog->code.push_back(w); ++written; }
             for (; written < nOperandWords; ++written) prog->code.push_back(0);
+            return rc::Ok;
+        };
+        if (piped) {
+            // one code section per pipeline stage: [SEG header][the stage's ops][END]; state rows in stage order
+            const uint32_t base = prog->stages[stg].codeOffset;
+            for (int w = 0; w < prog->pipeW; ++w) {
+                prog->pipeCode[w] = (uint32_t) prog->code.size() - base;
+                prog->pipeState[w] = (unsigned short) prog->stateMap.size();
+                prog->pipeSrow[w] = (unsigned short) nStateRows;
+                size_t words = 0;
+                for (size_t i = 1; i < sops.size(); ++i) if (pipeStageOf[i] == w) words += opWords(sops[i]);
+                emitSeg(sops[0].segRoot, words);
+                for (size_t i = 1; i < sops.size(); ++i) {
+                    if (pipeStageOf[i] != w) continue;
+                    int r = emitOp(sops[i], outSlot[i]);
+                    if (r != rc::Ok) return r;
+                }
+                for (int k = 0; k < 8; ++k) prog->code.push_back(k == 0 ? make_w0(OP_END, 0, 0, 0) : 0u);
+            }
+            for (int w = prog->pipeW; w <= MAX_PIPE; ++w) prog->pipeState[w] = (unsigned short) prog->stateMap.size();
+        } else {
+        std::vector<size_t> wordOffset(sops.size() + 1, 0);
+        for (size_t i = 0; i < sops.size(); ++i) wordOffset[i + 1] = wordOffset[i] + opWords(sops[i]);
+        for (size_t i = 0; i < sops.size(); ++i) {
+            auto& op = sops[i];
+            if (op.isSeg) { emitSeg(op.segRoot, wordOffset[op.segEndOp] - wordOffset[i + 1]); continue; }
+            int r = emitOp(op, outSlot[i]);
+            if (r != rc::Ok) return r;
+        }
         }
         for (int k = 0; k < 8; ++k) prog->code.push_back(k == 0 ? make_w0(OP_END, 0, 0, 0) : 0u);
         if (stg + 1 == stageOps.size()) {   // tap promotion records live behind the last stage only
@@ -2023,9 +2225,11 @@ int Engine::enqueueBlock(size_t nIn, size_t nOut, size_t numSamples, bool perVoi
     const size_t key[6] = {nIn, nOut, numSamples, (size_t) perVoiceIn, (size_t) materialise | ((size_t) (uintptr_t) offlineOut_ << 1), (size_t) mix | ((size_t) offlineStride_ << 1)};
     if (steadyValid_ && !dry && std::memcmp(key, steadyKey_, sizeof key) == 0) {
         for (auto& sb : steadyBuckets_) {
-            BatchBuffers& bb = batch_[sb.L];
+            BatchBuffers& bb = batch_[sb.key];
             auto ev = timedBegin();
-            if (!cuda(launch_render_groups(bb.dDescs, bb.dTileStart, sb.nGroups, sb.totalTiles, sb.L, sb.maxSlots, (int) nOut, sb.maxState, sb.maxParams, sb.wpc, sampleTime_, offlineOut_ ? offlineOffset_ : 0, stream_),
+            if (!cuda(sb.pipeStages > 1
+                          ? launch_render_groups_pipe(bb.dDescs, bb.dTileStart, sb.nGroups, sb.totalTiles, sb.pipeStages, sb.maxSlots, (int) nOut, sb.maxState, sb.maxParams, sampleTime_, offlineOut_ ? offlineOffset_ : 0, stream_)
+                          : launch_render_groups(bb.dDescs, bb.dTileStart, sb.nGroups, sb.totalTiles, sb.L, sb.maxSlots, (int) nOut, sb.maxState, sb.maxParams, sb.wpc, sampleTime_, offlineOut_ ? offlineOffset_ : 0, stream_),
                       "render groups kernel launch")) return rc::CudaError;
             if (timeKernels_) { cudaEventRecord(ev.second, stream_); timedEvents_.push_back(ev); }
             ++launches_;
@@ -2124,6 +2328,9 @@ int Engine::enqueueBlock(size_t nIn, size_t nOut, size_t numSamples, bool perVoi
         P.runMask = runMask;
         P.sampleTime = sampleTime_;
         P.tableSrc = p.stagedTable; P.tableFloats = p.stagedTableFloats; P.tableSmem = -1;   // the launcher places it (single-group launches)
+        P.pipeW = p.pipeW; P.pipeRingBase = p.pipeRingBase; P.pipeDepth = p.pipeDepth;
+        for (int w = 0; w < MAX_PIPE; ++w) { P.pipeCode[w] = p.pipeCode[w]; P.pipeSrow[w] = p.pipeSrow[w]; }
+        for (int w = 0; w <= MAX_PIPE; ++w) P.pipeState[w] = p.pipeState[w];
         for (size_t di = 0; di < p.dynNodes.size(); ++di) {
             auto it = g.nodes.find(p.dynNodes[di]);
             if (it != g.nodes.end()) P.dyn[di] = it->second.scopeW;
@@ -2159,8 +2366,9 @@ int Engine::enqueueBlock(size_t nIn, size_t nOut, size_t numSamples, bool perVoi
         if (nStages == 1 && groups_.size() > 1 && opt_.batchGroups && !p.hasCustom) {
             // heterogeneous voice groups: collect single-stage groups per tile geometry and launch each bucket once
             P.code = p.dCode + (p.stages.empty() ? 0 : p.stages[0].codeOffset);
-            buckets[g.tileWidth].push_back(P);
-            buckets[g.tileWidth].back().sampleTime = 0;      // the many-groups kernel takes the clock as an argument: descriptors stay equal block to block
+            const int bkey = g.tileWidth + (p.pipeW > 1 ? PIPE_BUCKET : 0);      // pipelined one-voice programs launch through their own kernel
+            buckets[bkey].push_back(P);
+            buckets[bkey].back().sampleTime = 0;      // the many-groups kernel takes the clock as an argument: descriptors stay equal block to block
         } else
         for (size_t stg = 0; stg < nStages; ++stg) {
             allBatched = false;
@@ -2174,7 +2382,7 @@ int Engine::enqueueBlock(size_t nIn, size_t nOut, size_t numSamples, bool perVoi
                 else { cudaEventCreate(&ev.first); cudaEventCreate(&ev.second); }
                 cudaEventRecord(ev.first, stream_);
             }
-            const bool emptyStage = !p.stages.empty() && p.stages[stg].empty && !last;
+            const bool emptyStage = !p.stages.empty() && ((p.stages[stg].empty && !last) || (last && p.fusedConvStage >= 0));   // fused: K3's epilogue did the root
             if (!emptyStage) {
                 const SpecKernel* spec = nullptr;
                 if (p.specJob) {   // the cubin arrived: load it on this thread (its CUDA context is current), a matter of milliseconds
@@ -2189,10 +2397,22 @@ int Engine::enqueueBlock(size_t nIn, size_t nOut, size_t numSamples, bool perVoi
             if (p.stages.empty()) continue;
             // K3: the convolvers fed by this stage (ConvolutionNode::process, wasm/Convolve.h:58-85); a call longer
             // than what is left of the current 512-sample partition is cut like FFTConvolver.cpp:155-203 does
-            for (auto& cv : p.stages[stg].convolves) {
+            for (size_t cvi = 0; cvi < p.stages[stg].convolves.size(); ++cvi) {
+                auto& cv = p.stages[stg].convolves[cvi];
                 auto it = g.nodes.find(cv.node);
                 if (it == g.nodes.end() || !it->second.conv) continue;
                 ConvolverState& cs = *it->second.conv;
+                ConvEpilogue epi;
+                if (p.fusedConvStage == (int) stg && p.fusedConvIndex == (int) cvi) {
+                    const RootDyn& rd = P.roots[p.fusedRoot];
+                    epi.active = true;
+                    epi.running = ((runMask >> p.fusedRoot) & 1u) != 0;
+                    epi.gain0 = rd.gain0; epi.step = rd.step; epi.target = rd.target; epi.channel = rd.channel;
+                    epi.nOut = (int) nOut; epi.blockSize = blockSize_;
+                    epi.mixPartial = mix ? dPartial_ : nullptr; epi.tileBase = tileBase;
+                    epi.outVoice = materialise ? voiceOut + (offlineOut_ ? offlineOffset_ : 0) : nullptr;
+                    epi.voice0 = g.v0; epi.outStride = P.outStride; epi.outOffset = 0;
+                }
                 int offset = 0;
                 while (offset < (int) numSamples) {
                     const int n = cs.partitions == 0 ? (int) numSamples - offset
@@ -2209,7 +2429,7 @@ int Engine::enqueueBlock(size_t nIn, size_t nOut, size_t numSamples, bool perVoi
                         if (perVoiceIn) { cin = dInVoice_ + ((size_t) g.v0 * nIn + cv.inChannel) * blockSize_; cinStride = (int) nIn * blockSize_; }
                         else { cin = dInShared_ + (size_t) cv.inChannel * blockSize_; cinStride = 0; }
                     }
-                    if (!dry && !cuda(convolver_process_chunk(cs, cin, cinStride, cv.out, blockSize_, offset, n, stream_), "convolver launch")) return rc::CudaError;
+                    if (!dry && !cuda(convolver_process_chunk(cs, cin, cinStride, cv.out, blockSize_, offset, n, stream_, epi), "convolver launch")) return rc::CudaError;
                     if (dry) { offset += n; continue; }
                     if (timeKernels_) { cudaEventRecord(ev3.second, stream_); timedConvEvents_.push_back(ev3); }
                     ++launches_;
@@ -2228,18 +2448,19 @@ int Engine::enqueueBlock(size_t nIn, size_t nOut, size_t numSamples, bool perVoi
     steadyBuckets_.clear();
     for (auto& kv : buckets) {
         auto& descs = kv.second;
-        const int L = kv.first;
+        const int L = kv.first % PIPE_BUCKET;
         std::vector<int> tileStart(descs.size());
-        int total = 0, maxSlots = 1, maxState = 0, maxParams = 0;
+        int total = 0, maxSlots = 1, maxState = 0, maxParams = 0, pipeStages = 0;
         for (size_t i = 0; i < descs.size(); ++i) {
             tileStart[i] = total;
             total += (descs[i].nv + L - 1) / L;
             maxSlots = std::max(maxSlots, descs[i].nSlots);
             maxState = std::max(maxState, descs[i].nStateRows);
             maxParams = std::max(maxParams, descs[i].nParams);
+            if (kv.first >= PIPE_BUCKET) pipeStages = std::max(pipeStages, descs[i].pipeW);
         }
         // descriptors change only while roots fade or when graphs change: re-upload only then
-        BatchBuffers& bb = batch_[L];
+        BatchBuffers& bb = batch_[kv.first];
         const size_t dbytes = descs.size() * sizeof(LaunchParams), tbytes = tileStart.size() * sizeof(int);
         if (bb.capGroups < descs.size()) {
             dsync();
@@ -2264,8 +2485,10 @@ int Engine::enqueueBlock(size_t nIn, size_t nOut, size_t numSamples, bool perVoi
             else { cudaEventCreate(&ev.first); cudaEventCreate(&ev.second); }
             cudaEventRecord(ev.first, stream_);
         }
-        steadyBuckets_.push_back(SteadyBucket{L, (int) descs.size(), total, maxSlots, maxState, maxParams, wpc});
-        if (!dry && !cuda(launch_render_groups(bb.dDescs, bb.dTileStart, (int) descs.size(), total, L, maxSlots, (int) nOut, maxState, maxParams, wpc, sampleTime_, offlineOut_ ? offlineOffset_ : 0, stream_),
+        steadyBuckets_.push_back(SteadyBucket{L, (int) descs.size(), total, maxSlots, maxState, maxParams, wpc, pipeStages, kv.first});
+        if (!dry && !cuda(pipeStages > 1
+                              ? launch_render_groups_pipe(bb.dDescs, bb.dTileStart, (int) descs.size(), total, pipeStages, maxSlots, (int) nOut, maxState, maxParams, sampleTime_, offlineOut_ ? offlineOffset_ : 0, stream_)
+                              : launch_render_groups(bb.dDescs, bb.dTileStart, (int) descs.size(), total, L, maxSlots, (int) nOut, maxState, maxParams, wpc, sampleTime_, offlineOut_ ? offlineOffset_ : 0, stream_),
                   "render groups kernel launch")) return rc::CudaError;
         if (timeKernels_) { cudaEventRecord(ev.second, stream_); timedEvents_.push_back(ev); }
         ++launches_;
@@ -2353,43 +2576,69 @@ int Engine::renderOffline(size_t nOut, size_t numBlocks, float* hostOut, size_t 
     if (!hostOut || nOut == 0 || nOut > (size_t) MAX_OUT_CHANNELS) return fail(rc::BadArgument, "renderOffline: bad arguments");
     dsetdev();
     const size_t bs = (size_t) blockSize_, rows = (size_t) numVoices_ * nOut;
-    size_t C = chunkBlocks ? chunkBlocks : 32;
-    while (C > 1 && rows * C * bs * sizeof(float) > ((size_t) 512 << 20)) C >>= 1;          // two chunk buffers of at most 512 MiB each
+    size_t C = chunkBlocks ? chunkBlocks : 8;
+    while (C > 1 && rows * C * bs * sizeof(float) > ((size_t) 256 << 20)) C >>= 1;          // two chunk buffers of at most 256 MiB each
     if (C > numBlocks) C = std::max<size_t>(1, numBlocks);
-    float* buf[2] = {nullptr, nullptr};
+    // Chunk buffers: two on the device (rendered into back to back) and two PINNED on the host.  The user's buffer is pageable and
+    // strided ([row][numBlocks * bs]); a 2-D copy straight into it would be staged by the driver row by row, synchronously.  So a chunk
+    // leaves the device as ONE contiguous async copy into pinned memory on the copy stream, and this thread scatters the previous
+    // chunk's rows into the user's buffer while the GPU renders the next one.  The buffers are kept across calls.
+    const size_t chunkFloats = rows * C * bs;
+    if (chunkFloats > offlineChunkFloats_) {
+        dsync();
+        for (int i = 0; i < 2; ++i) {
+            if (offlineDev_[i]) cudaFree(offlineDev_[i]);
+            if (offlinePinned_[i]) cudaFreeHost(offlinePinned_[i]);
+            offlineDev_[i] = nullptr; offlinePinned_[i] = nullptr;
+        }
+        offlineChunkFloats_ = 0;
+        for (int i = 0; i < 2; ++i) {
+            if (!cuda(cudaMalloc((void**) &offlineDev_[i], chunkFloats * sizeof(float)), "cudaMalloc offline chunk")) return rc::CudaError;
+            if (!cuda(cudaMallocHost((void**) &offlinePinned_[i], chunkFloats * sizeof(float)), "cudaMallocHost offline chunk")) return rc::CudaError;
+        }
+        offlineChunkFloats_ = chunkFloats;
+    }
     cudaStream_t copyStream = nullptr;
     cudaEvent_t rendered[2] = {nullptr, nullptr}, copied[2] = {nullptr, nullptr};
     int rcode = rc::Ok;
-    auto cleanup = [&]() {
-        offlineOut_ = nullptr; offlineStride_ = 0; offlineOffset_ = 0; steadyValid_ = false;
-        cudaStreamSynchronize(stream_);
-        if (copyStream) { cudaStreamSynchronize(copyStream); cudaStreamDestroy(copyStream); }
-        for (int i = 0; i < 2; ++i) { if (buf[i]) cudaFree(buf[i]); if (rendered[i]) cudaEventDestroy(rendered[i]); if (copied[i]) cudaEventDestroy(copied[i]); }
-    };
     for (int i = 0; i < 2; ++i) {
-        if (!cuda(cudaMalloc((void**) &buf[i], rows * C * bs * sizeof(float)), "cudaMalloc offline chunk")) { cleanup(); return rc::CudaError; }
-        cudaMemsetAsync(buf[i], 0, rows * C * bs * sizeof(float), stream_);                    // voices without a render sequence stay silent
+        cudaMemsetAsync(offlineDev_[i], 0, chunkFloats * sizeof(float), stream_);               // voices without a render sequence stay silent
         cudaEventCreateWithFlags(&rendered[i], cudaEventDisableTiming);
         cudaEventCreateWithFlags(&copied[i], cudaEventDisableTiming);
     }
     cudaStreamCreateWithFlags(&copyStream, cudaStreamNonBlocking);
     steadyValid_ = false;
+    struct Pending { bool valid = false; size_t chunk = 0, blocks = 0; int slot = 0; } prev;
+    auto scatter = [&](const Pending& pc) {          // pinned chunk [row][C * bs] -> user rows
+        if (!pc.valid) return;
+        if (!cuda(cudaEventSynchronize(copied[pc.slot]), "wait for an offline chunk")) { rcode = rc::CudaError; return; }
+        const size_t width = pc.blocks * bs;
+        for (size_t r = 0; r < rows; ++r)
+            std::memcpy(hostOut + r * numBlocks * bs + pc.chunk * C * bs, offlinePinned_[pc.slot] + r * C * bs, width * sizeof(float));
+    };
     for (size_t b = 0; b < numBlocks && rcode == rc::Ok; ++b) {
-        const size_t chunk = b / C, slot = chunk & 1, inChunk = b % C;
-        if (inChunk == 0 && chunk >= 2) cudaStreamWaitEvent(stream_, copied[slot], 0);          // the chunk two back has left this buffer
-        offlineOut_ = buf[slot]; offlineStride_ = (int) (C * bs); offlineOffset_ = (int) (inChunk * bs);
+        const size_t chunk = b / C, inChunk = b % C;
+        const int slot = (int) (chunk & 1);
+        if (inChunk == 0 && chunk >= 2) cudaStreamWaitEvent(stream_, copied[slot], 0);          // the chunk two back has left this device buffer
+        offlineOut_ = offlineDev_[slot]; offlineStride_ = (int) (C * bs); offlineOffset_ = (int) (inChunk * bs);
         rcode = enqueueBlock(0, nOut, bs, false, true, false);
         const bool lastOfChunk = inChunk + 1 == C || b + 1 == numBlocks;
         if (rcode == rc::Ok && lastOfChunk) {
+            // the pinned buffer of this slot was scattered when chunk - 1 was enqueued (below), i.e. before this copy is issued
             cudaEventRecord(rendered[slot], stream_);
             cudaStreamWaitEvent(copyStream, rendered[slot], 0);
-            const size_t width = (inChunk + 1) * bs * sizeof(float);
-            if (!cuda(cudaMemcpy2DAsync(hostOut + chunk * C * bs, numBlocks * bs * sizeof(float), buf[slot], C * bs * sizeof(float), width, rows,
-                                        cudaMemcpyDeviceToHost, copyStream), "D2H offline chunk")) rcode = rc::CudaError;
+            if (!cuda(cudaMemcpyAsync(offlinePinned_[slot], offlineDev_[slot], chunkFloats * sizeof(float), cudaMemcpyDeviceToHost, copyStream), "D2H offline chunk")) rcode = rc::CudaError;
             cudaEventRecord(copied[slot], copyStream);
+            Pending cur; cur.valid = true; cur.chunk = chunk; cur.blocks = inChunk + 1; cur.slot = slot;
+            scatter(prev);                                                                      // overlaps with the GPU rendering what was just enqueued
+            prev = cur;
         }
     }
-    cleanup();
+    scatter(prev);
+    offlineOut_ = nullptr; offlineStride_ = 0; offlineOffset_ = 0; steadyValid_ = false;
+    cudaStreamSynchronize(stream_);
+    if (copyStream) { cudaStreamSynchronize(copyStream); cudaStreamDestroy(copyStream); }
+    for (int i = 0; i < 2; ++i) { if (rendered[i]) cudaEventDestroy(rendered[i]); if (copied[i]) cudaEventDestroy(copied[i]); }
     return rcode;
 }
 

@@ -127,10 +127,17 @@ struct Program {
     uint32_t* dStateMap = nullptr;
     uint32_t* dParamMap = nullptr;
     bool planOnly = false;
+    // warp pipeline of a one-voice program (LaunchParams::pipeW ...): filled by compile() when the program was cut
+    int pipeW = 1, pipeRingBase = 0, pipeDepth = 1;
+    uint32_t pipeCode[MAX_PIPE] = {0, 0, 0, 0};
+    unsigned short pipeState[MAX_PIPE + 1] = {0, 0, 0, 0, 0}, pipeSrow[MAX_PIPE] = {0, 0, 0, 0};
     // K1 stages: stage k interprets code[stages[k].codeOffset ...]; after it the convolvers of that stage run (K3)
     struct Conv { int32_t node; float* in; float* out; int inChannel; };   // inChannel >= 0: K3 reads host input channel inChannel directly (no staging copy)
     struct Stage { uint32_t codeOffset = 0; std::vector<Conv> convolves; bool empty = false; };   // empty: no K1 work in this stage
     std::vector<Stage> stages;
+    // `convolve -> root`: the last stage would only reload the convolver's output and apply the root — K3 does that in its epilogue
+    // (convolve.h ConvEpilogue) and the stage's K1 launch is skipped.  fusedConvStage < 0: not fused.
+    int fusedConvStage = -1, fusedConvIndex = 0, fusedRoot = 0;
     std::vector<float*> blockBuffers;     // [Vpad][blockSize] HBM buffers carrying values across stages
     std::vector<std::shared_ptr<DeviceArray>> pinned;   // device arrays the code points at
     struct EvNode { int32_t node; int root; };
@@ -166,6 +173,9 @@ struct EngineOptions {
     int specialize = 0;           // spec_host.h: NVRTC-compile K1 against each small single-stage program; 1 = on the compile-queue thread
                                   // (the interpreter serves meanwhile), 2 = wait for the compiler at COMMIT (benchmarks, parity runs)
     int specializeMaxWords = 512; // programs longer than this keep the interpreter (compile time grows with the unrolled program)
+    bool fuseConvRoot = true;     // `convolve -> root`: root gain + per-voice output + partial mix in K3's epilogue, no K1 launch for the last stage
+    int pipelineStages = 3;       // one-voice groups in the many-groups launch: cut the program into this many pipeline stages, one warp each
+                                  // (render_groups_pipe_kernel; 0 / 1 = off).  3 x 1250 graphs still fit one resident wave on 148 SMs at 64 registers
     bool specializeStrict = false; // a failed specialisation is an error (COMMIT returns 7 / process -1) instead of a silent stay on the interpreter
 };
 
@@ -298,6 +308,7 @@ private:
     bool hostDeliver_ = true, processAllReduce_ = true;   // options "host_deliver", "process_allreduce"
     bool deliverArmed_ = false, deliverLaunched_ = false;
     HostDeliver takeDeliver();
+    float* offlineDev_[2] = {nullptr, nullptr}; float* offlinePinned_[2] = {nullptr, nullptr}; size_t offlineChunkFloats_ = 0;   // renderOffline chunk buffers, kept across calls
     size_t curNOut_ = 0;
     struct BatchBuffers { LaunchParams* dDescs = nullptr; int* dTileStart = nullptr; size_t capGroups = 0; std::vector<char> lastDescs; };
     std::map<int, BatchBuffers> batch_;   // per tile width
@@ -305,7 +316,8 @@ private:
     // every group steady — no queued program, nothing dirty, all root fades settled, no event mirrors to advance — and the call has the
     // same shape, the next block re-launches the cached buckets (the descriptors on the device are still right; the sample clock is a
     // kernel argument) without walking the groups.  Any instruction batch, gc, option or resource change invalidates it.
-    struct SteadyBucket { int L, nGroups, totalTiles, maxSlots, maxState, maxParams, wpc; };
+    struct SteadyBucket { int L, nGroups, totalTiles, maxSlots, maxState, maxParams, wpc, pipeStages, key; };
+    static constexpr int PIPE_BUCKET = 1000;   // bucket key = tile width (+ PIPE_BUCKET for pipelined one-voice programs)
     std::vector<SteadyBucket> steadyBuckets_;
     bool steadyValid_ = false;
     size_t steadyKey_[6] = {0, 0, 0, 0, 0, 0};

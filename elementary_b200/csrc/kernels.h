@@ -16,6 +16,10 @@ cudaError_t launch_render_block(const LaunchParams& P, int warpsPerCta, int nite
 cudaError_t launch_render_groups(const LaunchParams* descs, const int* tileStart, int nGroups, int totalTiles, int tileWidth,
                                  int maxSlots, int nOut, int maxStateRows, int maxParams, int warpsPerCta, long long sampleTime, int outOffset, cudaStream_t stream);
 
+// K1 for many ONE-VOICE graphs whose programs were cut into pipeline stages (LaunchParams::pipeW): one CTA of `stages` warps per graph.
+cudaError_t launch_render_groups_pipe(const LaunchParams* descs, const int* tileStart, int nGroups, int totalTiles, int stages,
+                                      int maxSlots, int nOut, int maxStateRows, int maxParams, long long sampleTime, int outOffset, cudaStream_t stream);
+
 // K2: deterministic reduction of per-tile partial mixes into the [nOut][blockSize] mix bus.
 // scratch: [MIX_REDUCE_MAX_GROUPS][nOut][blockSize] floats, tickets: [nOut * ceil(blockSize/32)] zeroed counters (both may be null:
 // single-pass reduction).
@@ -43,6 +47,9 @@ struct PeerMix {
     int rank, world, stride;
 };
 cudaError_t launch_mix_exchange(const PeerMix& pm, float* mix, int count, uint32_t epoch, int* status, cudaStream_t stream, HostDeliver hd = HostDeliver{});
+
+// A/B builds (-DEB_OPPROF): cycles / dispatches per opcode of the interpreter; zeros in the product library.
+cudaError_t debug_opprof_read(unsigned long long* out128, bool reset);
 
 } // namespace eb
 #endif   // __CUDACC_RTC__

@@ -94,6 +94,7 @@ constexpr uint32_t STATE_PAD = 0x7FFFFFFFu;           // stateMap entry: one unu
 constexpr int MAX_ROOTS = 16;
 constexpr int MAX_OUT_CHANNELS = 8;
 constexpr int MAX_SLOTS = 255;
+constexpr int MAX_PIPE = 4;                 // stages of the warp pipeline of one graph (LaunchParams::pipeW)
 constexpr int MAX_DYN = 16;                 // per-launch dynamic scalars (ring positions the host mirrors)
 constexpr int SCOPE_RING = 8192;            // MultiChannelRingBuffer default capacity (MultiChannelRingBuffer.h:17), 4 channels (Analyzers.h:149)
 constexpr int SCOPE_CHANNELS = 4;
@@ -150,6 +151,15 @@ struct LaunchParams {
     const float* tableSrc;       // device copy of the resource (16-byte aligned, padded to a multiple of 16 bytes), or null
     int tableFloats;             // padded length in floats
     int tableSmem;               // float index of the staged copy in the CTA's dynamic shared memory, or -1
+    // Stage pipeline (render_groups_pipe_kernel; one-voice groups, BASELINE config 5): the host cut the program into pipeW contiguous
+    // stages; pipeW warps of ONE CTA share the graph's shared-memory area, warp w runs stage w, one sample tile behind warp w - 1.
+    // Values crossing a stage boundary live in ring slots (pipeDepth buffers, buffer = tile index mod pipeDepth).  0 / 1 = not pipelined.
+    int pipeW;
+    int pipeRingBase;            // slot indices >= pipeRingBase are ring slots
+    int pipeDepth;
+    uint32_t pipeCode[MAX_PIPE];            // word offset of stage w's code behind `code`
+    unsigned short pipeState[MAX_PIPE + 1]; // stage w owns stateMap entries [pipeState[w], pipeState[w + 1])
+    unsigned short pipeSrow[MAX_PIPE];      // first shared-memory state row of stage w
 };
 constexpr int TABLE_SMEM_MAX_FLOATS = 8192;   // tables up to 32 KB are staged
 

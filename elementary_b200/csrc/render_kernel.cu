@@ -474,10 +474,19 @@ __device__ __noinline__ void ctl_capture(const CtlCtx& c) {
 #undef STU
 #undef STI
 
+// A/B builds only (-DEB_OPPROF, tools/gpu/opprof.sh): cycles and dispatch count per opcode, accumulated by lane 0 of every warp of
+// the interpreter — what the host's pipeline cost model (graph_host.cpp) is calibrated against.  Not compiled into the product library.
+#ifdef EB_OPPROF
+__device__ unsigned long long g_opprof[2 * 64];
+#endif
+
 // =========================================================================================================
 // The whole per-tile interpreter; instantiated by the two thin __global__ wrappers at the end of this section.
-template <int NITER, int LOGL>
-__device__ __forceinline__ void render_tile(const LaunchParams& P, const int tile, const int perWarp, const long long sampleTime, const int outOffset) {
+// PIPE (many-groups launch of one-voice graphs only): this warp is stage `stage` of the P.pipeW-stage pipeline of ONE graph — the
+// warps of the CTA share the graph's shared-memory area and hand sample tiles on through progress counters (see LaunchParams).
+template <int NITER, int LOGL, bool PIPE = false>
+__device__ __forceinline__ void render_tile(const LaunchParams& P, const int tile, const int perWarp, const long long sampleTime, const int outOffset,
+                                            const int stage = 0) {
     constexpr int L = 1 << LOGL;          // voices per warp
     constexpr int E = 32 * NITER;         // elements per sample tile
     constexpr int T = E >> LOGL;          // samples per tile
@@ -493,23 +502,37 @@ __device__ __forceinline__ void render_tile(const LaunchParams& P, const int til
     const bool owner = lane < L;          // this lane runs the recurrences of `voice`
     const int tlane = lane >> LOGL;       // sample index of this lane's element inside slice 0
 
-    const SP slots{warpInCta * perWarp};
+    const SP slots{PIPE ? 0 : warpInCta * perWarp};
     const SP outacc = slots + P.nSlots * E;
     const SP sst = outacc + P.nOut * E;
     const SP spar = sst + P.nStateRows * L;   // [nParams + 1][L], row 0 = zeros
 
+    // pipeline bookkeeping (all constants when !PIPE)
+    const int pipeW = PIPE ? max(1, P.pipeW) : 1;
+    const bool firstStage = !PIPE || stage == 0, lastStage = !PIPE || stage == pipeW - 1;
+    const int ringBase = PIPE ? P.pipeRingBase : 0x7FFFFFFF, pipeDepth = PIPE ? max(1, P.pipeDepth) : 1;
+    volatile int* const progress = PIPE ? reinterpret_cast<volatile int*>(g_smem + perWarp) : nullptr;   // [MAX_PIPE] tiles finished per stage
+    int ringOff = 0;                          // ring buffer of the current tile: tile index mod pipeDepth
+    auto SLOTI = [&](int idx) -> int { if constexpr (PIPE) return idx + ((idx >= ringBase) ? ringOff : 0); else return idx; };
+    (void) firstStage; (void) lastStage; (void) ringBase; (void) pipeDepth; (void) progress;
+
     auto decode = [&](uint32_t w) -> Opnd {
         Opnd o;
         const uint32_t idx = w & 0x3FFFFFFFu;
-        if ((w >> 30) == K_SLOT) { o.p = slots + ((int) idx * E + lane); o.stride = 32; o.tstride = L; }
+        if ((w >> 30) == K_SLOT) { o.p = slots + (SLOTI((int) idx) * E + lane); o.stride = 32; o.tstride = L; }
         else { o.p = spar + ((int) idx * L + vlane); o.stride = 0; o.tstride = 0; }
         return o;
     };
 
     // ---- state and parameter rows HBM -> shared memory (once per block), by the owner lanes ----
+    // (a pipeline stage stages the state rows of ITS ops only; stage 0 also stages the parameters — the later stages read them after
+    // their first hand-over from the stage before, which orders them behind these stores)
+    const int stateBegin = (PIPE && pipeW > 1) ? (int) P.pipeState[stage] : 0;
+    const int stateEnd = (PIPE && pipeW > 1) ? (int) P.pipeState[stage + 1] : P.nStateEntries;
+    const int srowBegin = (PIPE && pipeW > 1) ? (int) P.pipeSrow[stage] : 0;
     if (owner) {
-        int srow = 0;
-        for (int i = 0; i < P.nStateEntries; ++i) {
+        int srow = srowBegin;
+        for (int i = stateBegin; i < stateEnd; ++i) {
             const uint32_t m = __ldg(P.stateMap + i);
             if (m == STATE_PAD) { srow += 1; continue; }
             const size_t row = m & ~STATE_DOUBLE_FLAG;
@@ -522,9 +545,11 @@ __device__ __forceinline__ void render_tile(const LaunchParams& P, const int til
                 srow += 1;
             }
         }
-        spar[lane] = 0.0f;
-        for (int i = 0; i < P.nParams; ++i)
-            spar[(i + 1) * L + lane] = __ldg(P.rows + (size_t) __ldg(P.paramMap + i) * P.Vpad + voice);
+        if (firstStage) {
+            spar[lane] = 0.0f;
+            for (int i = 0; i < P.nParams; ++i)
+                spar[(i + 1) * L + lane] = __ldg(P.rows + (size_t) __ldg(P.paramMap + i) * P.Vpad + voice);
+        }
     }
     __syncwarp();
 
@@ -532,11 +557,26 @@ __device__ __forceinline__ void render_tile(const LaunchParams& P, const int til
 #define T_OF(k) (tlane + (k) * PER)                       /* sample index of this lane's element in slice k */
 #define FOR_OWNER(t) _Pragma("unroll 4") for (int t = 0; t < cnt; ++t)
 
+#ifdef EB_OPPROF
+    const long long prof_tile0 = clock64();
+#endif
     const int numSamples = P.numSamples;
-    for (int s0 = 0; s0 < numSamples; s0 += T) {
+    int tileIdx = 0;
+    for (int s0 = 0; s0 < numSamples; s0 += T, ++tileIdx) {
         const int cnt = min(T, numSamples - s0);          // samples in this tile
 
-        for (int i = lane; i < P.nOut * E; i += 32) outacc[i] = 0.0f;
+        if constexpr (PIPE) {
+            if (pipeW > 1) {
+                // RAW: the stage before has finished this tile (transitively: every earlier stage has).  WAR: the ring buffer this tile
+                // writes was last used pipeDepth tiles ago — the LAST stage must be through with that tile.  Bounded spins: a protocol
+                // bug must end in wrong samples (the parity tests say so), never in a hung GPU.
+                ringOff = tileIdx % pipeDepth;
+                if (stage > 0) { for (int spins = 0; progress[stage - 1] <= tileIdx && spins < (1 << 22); ++spins) __nanosleep(20); }
+                if (!lastStage && tileIdx >= pipeDepth) { for (int spins = 0; progress[pipeW - 1] <= tileIdx - pipeDepth && spins < (1 << 22); ++spins) __nanosleep(20); }
+                __threadfence_block();
+            }
+        }
+        if (lastStage) for (int i = lane; i < P.nOut * E; i += 32) outacc[i] = 0.0f;
 
 #ifdef EB_SPEC_PROGRAM
         // ---- per-program specialisation (compiled only when a generated header defines the program as the
@@ -588,7 +628,7 @@ __device__ __forceinline__ void render_tile(const LaunchParams& P, const int til
             run.template operator()<0, EB_SPEC_CODE_LEN>(run);
         }
 #else
-        const uint32_t* pc = P.code;
+        const uint32_t* pc = P.code + ((PIPE && pipeW > 1) ? P.pipeCode[stage] : 0u);
         for (;;) {
             __syncwarp();   // slot / state traffic of the previous op is visible to every lane
             const uint4 h0 = __ldg(reinterpret_cast<const uint4*>(pc));
@@ -596,7 +636,7 @@ __device__ __forceinline__ void render_tile(const LaunchParams& P, const int til
             if (opcode == OP_END) break;
             const uint4 h1 = __ldg(reinterpret_cast<const uint4*>(pc + 4));
             const uint32_t nwords = (h0.x >> 8) & 0xFF, mode = h0.x >> 24;
-            const SP out = slots + ((int) ((h0.x >> 16) & 0xFF) * E + lane);    // element k of this lane: out[k * 32]
+            const SP out = slots + (SLOTI((int) ((h0.x >> 16) & 0xFF)) * E + lane);    // element k of this lane: out[k * 32]
             const SP outT = out;                                         // owner lane, sample t: outT[t * L]
             const uint32_t sidx = h0.y, aux0 = h0.z, aux1 = h0.w;
             const uint64_t ptrbits = (uint64_t) h1.x | ((uint64_t) h1.y << 32);
@@ -611,7 +651,14 @@ __device__ __forceinline__ void render_tile(const LaunchParams& P, const int til
 #define CHAIN_OPND_WORD(s) __ldg(sp + 1)
 #define PC_ADVANCE(n) pc += (n)
 #define PC_SKIP_SEGMENT_IF(cond, n) if (cond) pc += (n)
+#ifdef EB_OPPROF
+            const long long prof_t0 = clock64();
+#endif
 #include "render_ops.inc"
+#ifdef EB_OPPROF
+            __syncwarp();
+            if (lane == 0) { atomicAdd(&g_opprof[2 * (opcode & 63)], (unsigned long long) (clock64() - prof_t0)); atomicAdd(&g_opprof[2 * (opcode & 63) + 1], 1ull); }
+#endif
 #undef OPWORD
 #undef CHAIN_FOR_STEPS
 #undef CHAIN_FN_WORD
@@ -621,6 +668,14 @@ __device__ __forceinline__ void render_tile(const LaunchParams& P, const int til
         }
 #endif   // EB_SPEC_PROGRAM
 
+        if constexpr (PIPE) {
+            if (pipeW > 1) {   // hand the tile on: slot / state stores first, then the counter
+                __syncwarp();
+                __threadfence_block();
+                if (lane == 0) progress[stage] = tileIdx + 1;
+            }
+            if (!lastStage) continue;
+        }
         // ---- tile epilogue: per-voice output and per-tile partial mix ----
         if (P.outVoice) {
             for (int ch = 0; ch < P.nOut; ++ch) {
@@ -650,10 +705,13 @@ __device__ __forceinline__ void render_tile(const LaunchParams& P, const int til
     }
     __syncwarp();
 
+#ifdef EB_OPPROF
+    if (lane == 0) { atomicAdd(&g_opprof[2 * 63], (unsigned long long) (clock64() - prof_tile0)); atomicAdd(&g_opprof[2 * 63 + 1], 1ull); }   // whole sample loop of one warp
+#endif
     // ---- state rows shared memory -> HBM ----
     if (owner) {
-        int srow = 0;
-        for (int i = 0; i < P.nStateEntries; ++i) {
+        int srow = srowBegin;
+        for (int i = stateBegin; i < stateEnd; ++i) {
             const uint32_t m = __ldg(P.stateMap + i);
             if (m == STATE_PAD) { srow += 1; continue; }
             const size_t row = m & ~STATE_DOUBLE_FLAG;
@@ -669,7 +727,7 @@ __device__ __forceinline__ void render_tile(const LaunchParams& P, const int til
     }
 
     // ---- tap promotion (GraphRenderSequence.h:200-210,306-308): OP_PROMOTE records after the first OP_END ----
-    {
+    if (!(PIPE && pipeW > 1)) {    // (the host never pipelines a program with taps)
         const uint32_t* pc = P.code;
         for (;;) {   // skip the main program
             const uint32_t w0 = __ldg(pc);
@@ -701,7 +759,10 @@ __device__ __forceinline__ void render_tile(const LaunchParams& P, const int til
 #ifndef EB_L32_MINBLOCKS
 #define EB_L32_MINBLOCKS 8
 #endif
-#define EB_BOUNDS __launch_bounds__(128, (LOGL == 5) ? EB_L32_MINBLOCKS : 4)
+#ifndef EB_L1_MINBLOCKS
+#define EB_L1_MINBLOCKS 4
+#endif
+#define EB_BOUNDS __launch_bounds__(128, (LOGL == 5) ? EB_L32_MINBLOCKS : ((LOGL == 0) ? EB_L1_MINBLOCKS : 4))
 
 // One voice group per launch: the descriptor travels in the constant bank.
 template <int NITER, int LOGL>
@@ -727,6 +788,28 @@ __global__ void EB_BOUNDS render_groups_kernel(const LaunchParams* __restrict__ 
         if (__ldg(tileStart + mid) <= w) lo = mid; else hi = mid - 1;
     }
     render_tile<NITER, LOGL>(descs[lo], w - __ldg(tileStart + lo), perWarp, sampleTime, outOffset);   // the sample clock travels as an argument: the descriptors of a steady engine never change
+}
+
+// The same for one-voice graphs whose programs the host cut into pipeline stages (LaunchParams::pipeW): ONE CTA per graph, warp w of
+// the CTA runs stage w.  A graph's recurrences are serial per sample and own a single lane, so one warp per graph is latency bound
+// (profiles/r02_f_groups_ncu.txt: 0.08 instructions per cycle and warp at 8 warps per SM); with W stages W warps work on W different
+// sample tiles of the same graph at once.  Programs that were not cut (pipeW <= 1) simply use warp 0.
+__global__ void __launch_bounds__(32 * MAX_PIPE, 8) render_groups_pipe_kernel(const LaunchParams* __restrict__ descs, const int* __restrict__ tileStart,
+                                                                              const int nGroups, const int totalTiles, const int perGraph,
+                                                                              const long long sampleTime, const int outOffset) {
+    const int w = blockIdx.x;                          // one-voice tiles: tile index == CTA index
+    const int stage = threadIdx.x >> 5;
+    if (threadIdx.x < MAX_PIPE) reinterpret_cast<volatile int*>(g_smem + perGraph)[threadIdx.x] = 0;   // progress counters
+    __syncthreads();
+    if (w >= totalTiles) return;
+    int lo = 0, hi = nGroups - 1;                      // largest g with tileStart[g] <= w
+    while (lo < hi) {
+        const int mid = (lo + hi + 1) >> 1;
+        if (__ldg(tileStart + mid) <= w) lo = mid; else hi = mid - 1;
+    }
+    const LaunchParams& P = descs[lo];
+    if (stage >= max(1, P.pipeW)) return;              // (whole warps leave; no CTA-wide barrier follows)
+    render_tile<1, 0, true>(P, w - __ldg(tileStart + lo), perGraph, sampleTime, outOffset, stage);
 }
 
 #ifndef __CUDACC_RTC__   // K2, K4 and the host launchers are not needed by a run-time compiled specialisation of K1
@@ -892,6 +975,20 @@ cudaError_t launch_render_groups(const LaunchParams* descs, const int* tileStart
     }
 }
 
+// One CTA of `stages` warps per one-voice graph (descs / tileStart are DEVICE pointers; the maxima size the per-graph shared memory).
+cudaError_t launch_render_groups_pipe(const LaunchParams* descs, const int* tileStart, int nGroups, int totalTiles, int stages,
+                                      int maxSlots, int nOut, int maxStateRows, int maxParams, long long sampleTime, int outOffset, cudaStream_t stream) {
+    if (totalTiles <= 0) return cudaSuccess;
+    if (stages < 1) stages = 1;
+    if (stages > MAX_PIPE) stages = MAX_PIPE;
+    const size_t graphBytes = render_smem_bytes(maxSlots, nOut, maxStateRows, maxParams, 1, 1, 0);
+    const size_t smem = graphBytes + sizeof(int) * 8;              // + the progress counters
+    cudaError_t e = cudaFuncSetAttribute(render_groups_pipe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
+    if (e != cudaSuccess) return e;
+    render_groups_pipe_kernel<<<totalTiles, 32 * stages, smem, stream>>>(descs, tileStart, nGroups, totalTiles, (int) (graphBytes / sizeof(float)), sampleTime, outOffset);
+    return cudaGetLastError();
+}
+
 cudaError_t launch_mix_reduce(const float* partial, float* out, float* scratch, unsigned int* tickets, int nTiles, int nOut, int blockSize,
                               int numSamples, cudaStream_t stream, HostDeliver hd) {
     const int chunksPerCh = (blockSize + 31) / 32;
@@ -950,6 +1047,19 @@ __global__ void __launch_bounds__(256) mix_exchange_kernel(const PeerMix pm, flo
         if (hd.out) hd.out[i] = s;
     }
     if (hd.out) host_deliver_arrive(hd, nb);
+}
+
+// Per-opcode profile of an -DEB_OPPROF build: out[2 * opcode] = cycles, out[2 * opcode + 1] = dispatches; zeros in the product build.
+cudaError_t debug_opprof_read(unsigned long long* out128, bool reset) {
+#ifdef EB_OPPROF
+    cudaError_t e = cudaMemcpyFromSymbol(out128, g_opprof, sizeof(unsigned long long) * 128);
+    if (e == cudaSuccess && reset) { static const unsigned long long z[128] = {}; e = cudaMemcpyToSymbol(g_opprof, z, sizeof z); }
+    return e;
+#else
+    for (int i = 0; i < 128; ++i) out128[i] = 0;
+    (void) reset;
+    return cudaSuccess;
+#endif
 }
 
 cudaError_t launch_mix_exchange(const PeerMix& pm, float* mix, int count, uint32_t epoch, int* status, cudaStream_t stream, HostDeliver hd) {

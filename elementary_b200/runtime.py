@@ -376,6 +376,14 @@ class Runtime:
         self._lib.elem_b200_snapshot(self._h, int(voice), buf, len(buf))
         return json.loads(buf.value.decode())
 
+    def debug_opprof(self, reset: bool = True) -> np.ndarray:
+        """A/B builds with -DEB_OPPROF only: [64, 2] uint64 (cycles, dispatches) per opcode of the K1 interpreter; zeros otherwise."""
+        buf = np.zeros(128, dtype=np.uint64)
+        self._lib.elem_b200_debug_opprof.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
+        rc = self._lib.elem_b200_debug_opprof(self._h, buf.ctypes.data_as(C.c_void_p), 1 if reset else 0)
+        self._check(rc, "debug_opprof")
+        return buf.reshape(64, 2)
+
     def program_words(self, voice: int = 0) -> np.ndarray:
         """The encoded render program of the voice group containing ``voice`` (uint32 words, csrc/program.h)."""
         n = self._lib.elem_b200_program_words(self._h, int(voice), None, 0)

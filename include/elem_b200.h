@@ -173,6 +173,10 @@ int elem_b200_program_words(elem_b200_runtime* rt, int voice, uint32_t* buf, siz
  * program of a voice group as a compile-time constant.  This entry point only COMPILES the specialised kernel of the group
  * containing `voice` (no GPU needed) and returns the cubin size, or -1 with the compiler log in logBuf. */
 long elem_b200_specialize_dry_run(elem_b200_runtime* rt, int voice, char* logBuf, size_t cap);
+/* A/B builds of the library compiled with -DEB_OPPROF (tools/gpu/opprof.sh) only: cycles (out128[2*op]) and dispatch counts
+ * (out128[2*op+1]) per opcode of the K1 interpreter since the last reset; the product library writes zeros.  No reference counterpart:
+ * this is what the pipeline cost model of the host compiler is calibrated against.  Returns 0, or -1 on a CUDA error. */
+int elem_b200_debug_opprof(elem_b200_runtime* rt, unsigned long long* out128, int reset);
 /* Number of CUDA kernels this runtime has launched so far. */
 uint64_t elem_b200_kernel_launches(elem_b200_runtime* rt);
 /* With option "time_kernels" = 1 every K1 render-kernel launch is bracketed by CUDA events on the launching

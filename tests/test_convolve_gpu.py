@@ -97,3 +97,41 @@ def test_convolve_varying_call_lengths():
         outs_g.append(rt.process_voices(x[None], 1, n)[0][0]); outs_r.append(o.process(x, 1, n))
     g, r = np.concatenate(outs_g, axis=1), np.concatenate(outs_r, axis=1)
     check(g, r)
+
+
+@pytest.mark.parametrize("n_out", [1, 2])
+def test_convolve_root_epilogue_equals_the_k1_stage(n_out):
+    """`convolve -> root` (BASELINE config 4): K3 applies the root's gain fade and writes the per-voice output and the partial mix
+    itself (convolve.h ConvEpilogue); with the option off a K1 stage does it.  Same bits — through the 20 ms root fade-in, with ragged
+    call lengths (partition fill / wrap inside one call), per-voice outputs AND the mix bus, a silent second output channel, a fully
+    trimmed IR, and a graph update (root cross-fade: the old root fades out on the K1 path) — and the same bits as before the update."""
+    bs = 512
+    ir = np.asarray(graphs.lcg_ir(3000), dtype=np.float32)
+    sizes = [512, 512, 100, 412, 37, 512, 1, 474, 512, 512]
+    n_voices = 5
+    x = np.stack([noise(sum(sizes), 17 * v + 3)[None, :] for v in range(n_voices)])
+    outs = {}
+    for fuse in (1, 0):
+        rt = Runtime(SR, bs, n_voices, device=0, fuse_conv_root=fuse)
+        assert rt.add_shared_resource("ir", ir) and rt.add_shared_resource("zero", np.zeros(64, dtype=np.float32))
+        assert rt.apply_instructions(graphs.convolve_channel("ir")) == 0, rt.last_error()
+        vs, ms, pos = [], [], 0
+        for k, n in enumerate(sizes):
+            if k == 7:       # live edit: the same graph behind a gain (new root, old one fades out; not the fused shape any more)
+                rg = el.Renderer()
+                rg.render(el.convolve({"path": "ir"}, el.in_(0)))
+                assert rt.apply_instructions(rg.render(el.mul(0.5, el.convolve({"path": "ir"}, el.in_(0))))) == 0, rt.last_error()
+            v, m = rt.process_voices(x[:, :, pos:pos + n], n_out, n)
+            vs.append(v); ms.append(m); pos += n
+        outs[fuse] = (np.concatenate(vs, axis=2), np.concatenate(ms, axis=1))
+        z = Runtime(SR, bs, 3, device=0, fuse_conv_root=fuse)
+        assert z.add_shared_resource("ir", np.zeros(64, dtype=np.float32))
+        assert z.apply_instructions(graphs.convolve_channel("ir")) == 0
+        v, m = z.process_voices(x[:3, :, :bs], n_out, bs)
+        assert not v.any() and not m.any()
+    assert np.array_equal(outs[1][0], outs[0][0]) and np.array_equal(outs[1][1], outs[0][1])
+    assert np.abs(outs[1][0][:, 0]).max() > 0
+    if n_out == 2:
+        assert not outs[1][0][:, 1].any() and not outs[1][1][1].any()
+    ref = oracle_render(graphs.convolve_channel("ir"), 2, 1, SR, bs, x[:, :, :1024], voice_batches=[None] * n_voices, resources={"ir": ir})
+    check(outs[1][0][:, 0:1, :1024], ref)

@@ -334,3 +334,46 @@ def test_const_table_return_codes():
     assert rt.set_const_table([ida, idb], tab) == 0
     assert rt.set_const_table([ida, 123456], tab) == 2                         # NodeNotFound
     assert rt.snapshot()["0x%08x" % (ida & 0xFFFFFFFF)]["value"] == float(tab[0, -1])
+
+
+def test_pipeline_cut_of_one_voice_groups_plan_only():
+    """The host side of the warp pipeline (render_groups_pipe_kernel): one-voice groups in a many-groups engine get
+    their program cut into pipeline stages; single-group engines, wide tiles and pipeline_stages = 0 do not; the program words of a cut
+    program are one [SEG ... END] section per stage whose ring slots are only ever written in one stage and read in later ones."""
+    from elementary_b200 import graphs
+    n = 6
+    rt = Runtime(SR, BS, n, device=-1)
+    for i in range(n):
+        assert rt.apply_instructions(graphs.random_graph(300 + i, 64), voices=(i, i + 1)) == 0, rt.last_error()
+    groups = rt.describe()["groups"]
+    assert len(groups) == n and all(g["pipeline_stages"] == 3 for g in groups), groups
+    off = Runtime(SR, BS, n, device=-1, pipeline_stages=0)
+    for i in range(n):
+        assert off.apply_instructions(graphs.random_graph(300 + i, 64), voices=(i, i + 1)) == 0
+    assert all(g["pipeline_stages"] == 1 for g in off.describe()["groups"])
+    assert all(a["ops"] == b["ops"] and a["state_rows"] == b["state_rows"] for a, b in zip(groups, off.describe()["groups"]))
+    single = Runtime(SR, BS, 4, device=-1)
+    assert single.apply_instructions(graphs.random_graph(300, 64)) == 0
+    assert single.describe()["groups"][0]["pipeline_stages"] == 1
+    # structure of the cut program: sections [SEG][ops][END], outputs of a section never collide with another section's private slots
+    words = rt.program_words(0)
+    HDR = 8
+    sections, pc, cur = [], 0, None
+    while pc < len(words):
+        w0 = words[pc]
+        opcode, nwords, out_slot = w0 & 0xFF, (w0 >> 8) & 0xFF, (w0 >> 16) & 0xFF
+        if opcode == 1:                       # OP_SEG opens a section
+            cur = {"outs": [], "skip": words[pc + 3], "start": pc}
+        elif opcode == 0:                     # OP_END closes it
+            if cur is None:
+                break
+            assert pc - cur["start"] - HDR == cur["skip"], "the SEG header skips exactly its own section"
+            sections.append(cur)
+            cur = None
+        else:
+            cur["outs"].append(out_slot)
+        pc += HDR + nwords
+    assert len(sections) == 3 and all(s["outs"] for s in sections)
+    for i in range(3):
+        for j in range(i + 1, 3):
+            assert not (set(sections[i]["outs"]) & set(sections[j]["outs"])), "stages never share an output slot"

@@ -690,3 +690,40 @@ def test_process_host_delivery_equals_the_copy_path(n_voices, n_out):
         oa, ob = a.process(None, n_out, n), b.process(None, n_out, n)
         assert oa.shape == (n_out, n) and np.array_equal(oa, ob)
         assert np.abs(oa).max() > 0 or n == 1
+
+
+@pytest.mark.parametrize("stages", [2, 3, 4])
+def test_pipelined_groups_equal_the_unpipelined_path(stages):
+    """BASELINE config 5 shape: one-voice groups of different random 64-node graphs.  The host cuts every program into `stages` pipeline
+    stages (one warp each, render_groups_pipe_kernel); the samples must be the SAME BITS as with one warp running the whole program
+    (pipeline_stages = 0) — same ops, same order per value — through the root fade-in, short blocks and into the steady state; and a
+    sample of the graphs is checked against the reference."""
+    n = 40
+    batches = [graphs.random_graph(2000 + i, 64) for i in range(n)]
+    a = Runtime(SR, BS, n, device=0, pipeline_stages=stages)
+    b = Runtime(SR, BS, n, device=0, pipeline_stages=0)
+    for rt in (a, b):
+        for i, bt in enumerate(batches):
+            assert rt.apply_instructions(bt, voices=(i, i + 1)) == 0, rt.last_error()
+    blocks = [BS, BS, 100, BS, 33, BS, BS, BS]
+    outs_a, outs_b = [], []
+    for nsmp in blocks:
+        va, ma = a.process_voices(None, 1, nsmp)
+        vb, mb = b.process_voices(None, 1, nsmp)
+        assert np.array_equal(va, vb) and np.array_equal(ma, mb)
+        outs_a.append(va)
+    da, db = a.describe()["groups"], b.describe()["groups"]
+    assert sum(1 for g in da if g.get("pipeline_stages") == stages) >= n * 3 // 4, [g.get("pipeline_stages") for g in da]
+    assert all(g.get("pipeline_stages") == 1 for g in db)
+    # offline path (per-graph outputs, steady-state descriptors) on the pipelined engine == block by block
+    c = Runtime(SR, BS, n, device=0, pipeline_stages=stages)
+    d = Runtime(SR, BS, n, device=0, pipeline_stages=0)
+    for rt in (c, d):
+        for i, bt in enumerate(batches):
+            assert rt.apply_instructions(bt, voices=(i, i + 1)) == 0
+    oc, od = c.render_offline(11, 1), d.render_offline(11, 1)
+    assert np.array_equal(oc, od)
+    for i in (0, 7, 19, 39):
+        ref = oracle_render(batches[i], 11, 1, SR, BS)
+        ok, worst, ex = block_peak_tolerance_check(oc[i], ref[0], BS)
+        assert ok, f"graph {i}: worst err/tol {worst:.3g}"

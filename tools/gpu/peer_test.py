@@ -46,6 +46,20 @@ def main():
         if not torch.equal(mix_a, want):
             bad += 1
             print(f"rank {rank} block {blk}: max diff {(mix_a - want).abs().max().item()}")
+    # Runtime::process with peers attached: every rank's host buffers receive the mix of ALL ranks, written into mapped host memory
+    # by K4 itself (kernels.h HostDeliver) — must be the same bits as the rank-ordered sum of the partial mixes
+    for blk in range(6):
+        host = a.process(None, 2, BS)
+        b.enqueue_block(0, 2, BS, FLAG_MIX)
+        b.synchronize()
+        parts = [torch.empty_like(mix_b) for _ in range(world)]
+        dist.all_gather(parts, mix_b.clone())
+        want = torch.zeros_like(mix_b)
+        for p in parts:
+            want = want + p
+        if not np.array_equal(host, want[:2].cpu().numpy()):
+            bad += 1
+            print(f"rank {rank} process() block {blk}: max diff {np.abs(host - want[:2].cpu().numpy()).max()}")
     st = a.peer_status()
     t = torch.tensor([bad, st], device=f"cuda:{local_rank}")
     dist.all_reduce(t)

@@ -3,7 +3,7 @@
 mkdir -p gpurun_out
 timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -6 | tee gpurun_out/r02f_pytest.txt
 python bench.py --steps 100 --warmup 10 > gpurun_out/r02f_bench.json 2> gpurun_out/r02f_bench.err; tail -2 gpurun_out/r02f_bench.err
-python bench.py --steps 100 --warmup 10 --no-cpu-baseline --no-t1 --opt host_deliver=0 > gpurun_out/r02f_bench_copy_path.json 2>/dev/null
+python bench.py --steps 100 --warmup 10 --no-cpu-baseline --no-t1 --no-configs --opt host_deliver=0 > gpurun_out/r02f_bench_copy_path.json 2>/dev/null
 python - <<'PY'
 import json
 for f in ("r02f_bench", "r02f_bench_copy_path"):
