@@ -84,11 +84,63 @@ constexpr int TM_CTAS_PER_SM = EB_CONV_TM_CTAS;
 
 __device__ __forceinline__ void tgroup_sync() { asm volatile("bar.sync 2, %0;" ::"n"(TM_GROUP) : "memory"); }
 
-// 9 Stockham radix-2 stages, 128 threads: two butterflies per thread per channel per stage.  Result lands in `b`.
+// Complex FFT 512 (Stockham autosort, out of place between two shared-memory buffers), 128 threads: four radix-4 stages — one
+// butterfly per thread and channel, sub-transform length p = 1, 4, 16, 64 — and a final radix-2 stage (p = 256, two butterflies per
+// thread): 5 group barriers instead of the 9 of a pure radix-2 transform.  tw[m] = exp(-2 pi i m / 1024), m < 512.  Result in `b`.
+#ifndef EB_CONV_RADIX4
+#define EB_CONV_RADIX4 1      /* 0 = the radix-2 transform of round 1 (A/B: profiles/r02_n_k3_radix4_ab.txt) */
+#endif
 template <bool INVERSE>
 __device__ __forceinline__ void fft512_t(float2 (*a)[N2], float2 (*b)[N2], const float2* tw, int t) {
     float2 (*src)[N2] = a;
     float2 (*dst)[N2] = b;
+#if EB_CONV_RADIX4
+#pragma unroll 1
+    for (int p = 1; p < N2 / 2; p <<= 2) {
+        const int k = t & (p - 1);
+        const int m = k * (N2 / 2 / p);                  // exp(-2 pi i k / (4 p)) = tw[k * 256 / p]
+        float2 w1 = tw[m], w2 = tw[2 * m];
+        float2 w3 = (3 * m < N2) ? tw[3 * m] : tw[3 * m - N2];
+        if (3 * m >= N2) { w3.x = -w3.x; w3.y = -w3.y; }   // exp(-i (pi + x)) = -exp(-i x)
+        if (INVERSE) { w1.y = -w1.y; w2.y = -w2.y; w3.y = -w3.y; }
+        const int j0 = ((t - k) << 2) + k;
+#pragma unroll
+        for (int c = 0; c < CH; ++c) {
+            const float2 x0 = src[c][t];
+            const float2 a1 = cmul(w1, src[c][t + N2 / 4]);
+            const float2 a2 = cmul(w2, src[c][t + N2 / 2]);
+            const float2 a3 = cmul(w3, src[c][t + 3 * N2 / 4]);
+            const float2 b0 = cadd(x0, a2), b1 = csub(x0, a2), b2 = cadd(a1, a3);
+            const float2 d = csub(a1, a3);
+            const float2 b3 = INVERSE ? make_float2(-d.y, d.x) : make_float2(d.y, -d.x);   // (a1 - a3) * (+-i)
+            dst[c][j0] = cadd(b0, b2);
+            dst[c][j0 + p] = cadd(b1, b3);
+            dst[c][j0 + 2 * p] = csub(b0, b2);
+            dst[c][j0 + 3 * p] = csub(b1, b3);
+        }
+        tgroup_sync();
+        float2 (*tmp)[N2] = src; src = dst; dst = tmp;
+    }
+    {
+        constexpr int ns = N2 / 2;
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int bi = t + h * TM_GROUP;                 // butterfly index 0..255
+            const int k = bi & (ns - 1);
+            float2 w = tw[k * (N2 / ns)];
+            if (INVERSE) w.y = -w.y;
+            const int j0 = ((bi - k) << 1) + k;
+#pragma unroll
+            for (int c = 0; c < CH; ++c) {
+                const float2 u = src[c][bi];
+                const float2 v = cmul(w, src[c][bi + N2 / 2]);
+                dst[c][j0] = cadd(u, v);
+                dst[c][j0 + ns] = csub(u, v);
+            }
+        }
+        tgroup_sync();
+    }
+#else
 #pragma unroll 1
     for (int ns = 1; ns < N2; ns <<= 1) {
 #pragma unroll
@@ -109,6 +161,7 @@ __device__ __forceinline__ void fft512_t(float2 (*a)[N2], float2 (*b)[N2], const
         tgroup_sync();
         float2 (*tmp)[N2] = src; src = dst; dst = tmp;
     }
+#endif
 }
 
 } // namespace

@@ -1810,34 +1810,35 @@ int Engine::compile(Group& g, int nIn, std::shared_ptr<Program>& out) {
         bool ok = W > 1 && batchedGroup && g.tileWidth == 1 && stageOps.size() == 1 && prog->rootIds.size() == 1 && C.promotes.empty() &&
                   prog->evNodes.empty() && prog->dynNodes.empty() && !prog->hasCustom;
         auto& sops = stageOps[0];
-        auto costOf = [](const Compiler::PendingOp& op) -> long {     // rough latency of one 32-sample tile at L = 1, in cycles
-            const long dispatch = 150;
-            switch (op.opcode) {
+        auto costOf = [](const Compiler::PendingOp& op) -> long {     // cycles of one 32-sample tile at L = 1, dispatch included: measured per
+            switch (op.opcode) {                                          // opcode with the cycle-counter build (profiles/r02_k_opprof_config5.txt)
                 case OP_CHAIN: {
-                    long c = 30;
+                    long c = 350;
                     for (auto& st : op.steps) {
                         const uint32_t fn = st.fn & 0xFF;
-                        if (fn <= F_EXP && fn != F_CEIL && fn != F_FLOOR && fn != F_ROUND && fn != F_SQRT) c += 80;
-                        else if (fn == F_DIV || fn == F_MOD || fn == F_POW) c += 40;
-                        else c += 8;
+                        if (fn <= F_EXP && fn != F_CEIL && fn != F_FLOOR && fn != F_ROUND && fn != F_SQRT && fn != F_ABS) c += 450;
+                        else if (fn == F_DIV || fn == F_MOD || fn == F_POW) c += 150;
+                        else c += 60;
                     }
-                    return dispatch + c;
+                    return c;
                 }
-                case OP_PHASOR: return op.mode == 1 ? 0 : dispatch + 450;          // a run costs what its leader costs
-                case OP_SPHASOR: return dispatch + 600;
-                case OP_COUNTER: case OP_ACCUM: case OP_LATCH: case OP_MAXHOLD: return dispatch + 400;
-                case OP_RAND: return dispatch + 500;
-                case OP_POLE: return dispatch + 500;
-                case OP_ENV: return dispatch + 700;
-                case OP_BIQUAD: return dispatch + 900;
-                case OP_PREWARP: return dispatch + 250;
-                case OP_MM1P: return dispatch + 700;
-                case OP_SVF: return dispatch + 900;
-                case OP_SVFSHELF: return dispatch + 1200;
-                case OP_BLEP: return dispatch + 500;
-                case OP_DELAY: return dispatch + 150;
-                case OP_SDELAY: case OP_TABLE: return dispatch + 70;
-                default: return dispatch + 30;
+                case OP_PHASOR: return op.mode == 1 ? 0 : 1850;          // a run costs what its leader costs
+                case OP_SPHASOR: return 2200;
+                case OP_COUNTER: case OP_ACCUM: case OP_LATCH: case OP_MAXHOLD: return 1500;
+                case OP_RAND: return 450;
+                case OP_POLE: return 1850;
+                case OP_ENV: return 2000;
+                case OP_BIQUAD: return 2600;
+                case OP_PREWARP: return 1350;
+                case OP_MM1P: return 6800;
+                case OP_SVF: return 3450;
+                case OP_SVFSHELF: return 4500;
+                case OP_BLEP: return 2500;
+                case OP_DELAY: return 3300;
+                case OP_SDELAY: case OP_TABLE: return 800;
+                case OP_Z: return 700;
+                case OP_ROOT: return 1100;
+                default: return 300;
             }
         };
         if (ok) {
@@ -2228,8 +2229,8 @@ int Engine::enqueueBlock(size_t nIn, size_t nOut, size_t numSamples, bool perVoi
             BatchBuffers& bb = batch_[sb.key];
             auto ev = timedBegin();
             if (!cuda(sb.pipeStages > 1
-                          ? launch_render_groups_pipe(bb.dDescs, bb.dTileStart, sb.nGroups, sb.totalTiles, sb.pipeStages, sb.maxSlots, (int) nOut, sb.maxState, sb.maxParams, sampleTime_, offlineOut_ ? offlineOffset_ : 0, stream_)
-                          : launch_render_groups(bb.dDescs, bb.dTileStart, sb.nGroups, sb.totalTiles, sb.L, sb.maxSlots, (int) nOut, sb.maxState, sb.maxParams, sb.wpc, sampleTime_, offlineOut_ ? offlineOffset_ : 0, stream_),
+                          ? launch_render_groups_pipe(bb.dDescs, bb.dTileStart, sb.nGroups, sb.totalTiles, sb.pipeStages, sb.maxSlots, (int) nOut, sb.maxState, sb.maxParams, sampleTime_, offlineOut_ ? offlineOffset_ : 0, stream_, opt_.niter)
+                          : launch_render_groups(bb.dDescs, bb.dTileStart, sb.nGroups, sb.totalTiles, sb.L, sb.maxSlots, (int) nOut, sb.maxState, sb.maxParams, sb.wpc, sampleTime_, offlineOut_ ? offlineOffset_ : 0, stream_, opt_.niter),
                       "render groups kernel launch")) return rc::CudaError;
             if (timeKernels_) { cudaEventRecord(ev.second, stream_); timedEvents_.push_back(ev); }
             ++launches_;
@@ -2478,7 +2479,7 @@ int Engine::enqueueBlock(size_t nIn, size_t nOut, size_t numSamples, bool perVoi
         }
         int wpc = opt_.warpsPerCta;
         if (wpc <= 0) wpc = total >= 148 * 8 ? 4 : (total >= 148 * 4 ? 2 : 1);
-        while (wpc > 1 && render_smem_bytes(maxSlots, (int) nOut, maxState, maxParams, wpc, L, 0) > 200 * 1024) wpc >>= 1;
+        while (wpc > 1 && render_smem_bytes(maxSlots, (int) nOut, maxState, maxParams, wpc, L, L == 1 ? opt_.niter : 0) > 200 * 1024) wpc >>= 1;
         std::pair<cudaEvent_t, cudaEvent_t> ev{nullptr, nullptr};
         if (timeKernels_) {
             if (!eventPool_.empty()) { ev = eventPool_.back(); eventPool_.pop_back(); }
@@ -2487,8 +2488,8 @@ int Engine::enqueueBlock(size_t nIn, size_t nOut, size_t numSamples, bool perVoi
         }
         steadyBuckets_.push_back(SteadyBucket{L, (int) descs.size(), total, maxSlots, maxState, maxParams, wpc, pipeStages, kv.first});
         if (!dry && !cuda(pipeStages > 1
-                              ? launch_render_groups_pipe(bb.dDescs, bb.dTileStart, (int) descs.size(), total, pipeStages, maxSlots, (int) nOut, maxState, maxParams, sampleTime_, offlineOut_ ? offlineOffset_ : 0, stream_)
-                              : launch_render_groups(bb.dDescs, bb.dTileStart, (int) descs.size(), total, L, maxSlots, (int) nOut, maxState, maxParams, wpc, sampleTime_, offlineOut_ ? offlineOffset_ : 0, stream_),
+                              ? launch_render_groups_pipe(bb.dDescs, bb.dTileStart, (int) descs.size(), total, pipeStages, maxSlots, (int) nOut, maxState, maxParams, sampleTime_, offlineOut_ ? offlineOffset_ : 0, stream_, opt_.niter)
+                              : launch_render_groups(bb.dDescs, bb.dTileStart, (int) descs.size(), total, L, maxSlots, (int) nOut, maxState, maxParams, wpc, sampleTime_, offlineOut_ ? offlineOffset_ : 0, stream_, opt_.niter),
                   "render groups kernel launch")) return rc::CudaError;
         if (timeKernels_) { cudaEventRecord(ev.second, stream_); timedEvents_.push_back(ev); }
         ++launches_;

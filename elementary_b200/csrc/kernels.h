@@ -14,11 +14,13 @@ cudaError_t launch_render_block(const LaunchParams& P, int warpsPerCta, int nite
 
 // K1 for many voice groups of one tile geometry in one launch (descs / tileStart are device pointers).
 cudaError_t launch_render_groups(const LaunchParams* descs, const int* tileStart, int nGroups, int totalTiles, int tileWidth,
-                                 int maxSlots, int nOut, int maxStateRows, int maxParams, int warpsPerCta, long long sampleTime, int outOffset, cudaStream_t stream);
+                                 int maxSlots, int nOut, int maxStateRows, int maxParams, int warpsPerCta, long long sampleTime, int outOffset, cudaStream_t stream,
+                                 int niterOverride = 0);
 
 // K1 for many ONE-VOICE graphs whose programs were cut into pipeline stages (LaunchParams::pipeW): one CTA of `stages` warps per graph.
 cudaError_t launch_render_groups_pipe(const LaunchParams* descs, const int* tileStart, int nGroups, int totalTiles, int stages,
-                                      int maxSlots, int nOut, int maxStateRows, int maxParams, long long sampleTime, int outOffset, cudaStream_t stream);
+                                      int maxSlots, int nOut, int maxStateRows, int maxParams, long long sampleTime, int outOffset, cudaStream_t stream,
+                                      int niterOverride = 0);
 
 // K2: deterministic reduction of per-tile partial mixes into the [nOut][blockSize] mix bus.
 // scratch: [MIX_REDUCE_MAX_GROUPS][nOut][blockSize] floats, tickets: [nOut * ceil(blockSize/32)] zeroed counters (both may be null:

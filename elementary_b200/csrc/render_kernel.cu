@@ -90,6 +90,15 @@ struct Opnd {
 
 #define LDE(o, k) ((o).p[(k) * (o).stride])
 #define LDT(o, t) ((o).p[(t) * (o).tstride])
+// the same read by ANY lane of the voice column (an operand pointer is set up for the owner lane = lane vlane of the column;
+// parameter operands, stride 0, already point at the column)
+#define LDC(o, t) ((o).p[(t) * (o).tstride + ((o).stride ? (vlane - lane) : 0)])
+#ifndef EB_RECUR_BROADCAST
+#define EB_RECUR_BROADCAST 0      /* narrow-tile recurrences: 0 = operands by shuffle from the lane that holds them, 1 = broadcast reads of the slots (A/B: profiles/r02_m_*) */
+#endif
+#ifndef EB_INTERP_PREFETCH
+#define EB_INTERP_PREFETCH 0      /* interpreter loop: 1 = next op's header + operand words loaded while the current op runs (A/B: profiles/r02_m_*) */
+#endif
 
 __device__ __forceinline__ float clampf(float v, float lo, float hi) { return (v < lo) ? lo : ((hi < v) ? hi : v); }
 __device__ __forceinline__ double clampd(double v, double lo, double hi) { return (v < lo) ? lo : ((hi < v) ? hi : v); }
@@ -121,6 +130,13 @@ __device__ __noinline__ float log2_f32(float x) { return log2f(x); }
 __device__ __noinline__ float exp_f32(float x) { return expf(x); }
 __device__ __noinline__ float pow_f32(float x, float y) { return powf(x, y); }
 __device__ __noinline__ float fmod_f32(float x, float y) { return fmodf(x, y); }
+// Out-of-line twins of the math that is inline in the hot geometries, for the 128-sample one-voice tiles (NITER = 4, L = 1): there a
+// FOR_K loop is four unrolled copies of its body, and the many-graphs launch is bound by instruction FETCH (about one instruction per
+// clock and SM once the interpreter's hot set has outgrown the 32 KB L1.5 instruction cache) — four calls to one copy of sinf fetch
+// a quarter of the instructions of four inlined copies.
+__device__ __noinline__ float sin_f32_ool(float x) { return sinf(x); }
+__device__ __noinline__ float tanh_f32_ool(float x) { return tanhf(x); }
+__device__ __noinline__ double ddiv_ool(double a, double b) { return a / b; }
 
 // 1/b and a/b in double to ~1 ulp: MUFU.RCP64H seed (rcp.approx.ftz.f64, >= 20 good bits) + two Newton steps (+ one residual
 // correction for the quotient), 6-9 instructions instead of the ~30 of the IEEE-exact division sequence with its slow path.
@@ -165,6 +181,12 @@ __device__ __forceinline__ double tan_quarter_wave(double x) {
     c = fma(c, y2, -0.5);
     c = fma(c, y2, 1.0);
     return big ? div_fast(c, s) : div_fast(s, c);
+}
+
+// svf coefficients of one sample (SVF.h:72-80) out of line, for the 128-sample one-voice tiles (see sin_f32_ool): g, a1 = 1/(1 + g (g + k))
+__device__ __noinline__ void svf_coefs_ool(double x, double kq, double& g, double& a1) {
+    g = tan_quarter_wave(x);
+    a1 = rcp_fast(fma(g, g + kq, 1.0));
 }
 
 // Math.h:30-57,128-188 — fn(x, y) for the binary and reducing node families
@@ -493,6 +515,7 @@ __device__ __forceinline__ void render_tile(const LaunchParams& P, const int til
     constexpr int LOGT = ilog2(T);
     constexpr int PER = 32 >> LOGL;       // samples of one voice inside one 32-element slice
 
+    constexpr bool OOLM = (NITER == 4 && LOGL == 0);    // 128-sample one-voice tiles: heavy math through out-of-line copies (sin_f32_ool)
     const int warpInCta = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
 
@@ -556,6 +579,12 @@ __device__ __forceinline__ void render_tile(const LaunchParams& P, const int til
 #define FOR_K(k) _Pragma("unroll") for (int k = 0; k < NITER; ++k)
 #define T_OF(k) (tlane + (k) * PER)                       /* sample index of this lane's element in slice k */
 #define FOR_OWNER(t) _Pragma("unroll 4") for (int t = 0; t < cnt; ++t)
+    // recurrences walked by every lane of a voice column (narrow tiles, render_ops.inc OP_POLE): sample t = k * PER + j of the column
+    // lives in register k of lane j * L + vlane
+    // (the j loop stays ROLLED: the interpreter is instruction-fetch bound, 32 unrolled steps of shuffles run 3x slower than a rolled
+    // loop that stays in the instruction cache — profiles/r02_j_opprof_config5_unrolled.txt)
+#define FOR_TJ(k, j) _Pragma("unroll") for (int k = 0; k < NITER; ++k) _Pragma("unroll 4") for (int j = 0, jn_ = min(PER, cnt - k * PER); j < jn_; ++j)
+#define FETCH_T(reg, j) __shfl_sync(FULL, (reg), (j) * L + vlane)
 
 #ifdef EB_OPPROF
     const long long prof_tile0 = clock64();
@@ -610,9 +639,11 @@ __device__ __forceinline__ void render_tile(const LaunchParams& P, const int til
 #define CHAIN_FOR_STEPS(s) _Pragma("unroll") for (uint32_t s = 0; s < count6; ++s)
 #define CHAIN_FN_WORD(s) (EB_SPEC_CODE[PC + (int) OP_HEADER_WORDS + 1 + 2 * (int) (s)])
 #define CHAIN_OPND_WORD(s) (EB_SPEC_CODE[PC + (int) OP_HEADER_WORDS + 2 + 2 * (int) (s)])
+#define CHAIN_NEXT(s) ((void) 0)
 #define PC_ADVANCE(n) ((void) 0)
 #define PC_SKIP_SEGMENT_IF(cond, n) ((void) 0)
 #include "render_ops.inc"
+#undef CHAIN_NEXT
 #undef OPWORD
 #undef CHAIN_FOR_STEPS
 #undef CHAIN_FN_WORD
@@ -626,6 +657,63 @@ __device__ __forceinline__ void render_tile(const LaunchParams& P, const int til
                 }
             };
             run.template operator()<0, EB_SPEC_CODE_LEN>(run);
+        }
+#else
+#if EB_INTERP_PREFETCH
+        // The interpreter loop is software-pipelined: the header (two 128-bit words) and the first four operand words of the NEXT op are
+        // loaded while the current op executes, so that a dispatch does not begin with three dependent trips to memory (header ->
+        // operand word -> slot).  Ops that move the program counter themselves (phasor runs, skipped segments) just reload.
+        const uint32_t* pc = P.code + ((PIPE && pipeW > 1) ? P.pipeCode[stage] : 0u);
+        uint4 h0 = __ldg(reinterpret_cast<const uint4*>(pc));
+        uint4 h1 = __ldg(reinterpret_cast<const uint4*>(pc + 4));
+        uint4 ow4 = __ldg(reinterpret_cast<const uint4*>(pc + 8));      // (behind the last op lie the END header's zero words: always readable)
+        for (;;) {
+            __syncwarp();   // slot / state traffic of the previous op is visible to every lane
+            const uint32_t opcode = h0.x & 0xFF;
+            if (opcode == OP_END) break;
+            const uint32_t nwords = (h0.x >> 8) & 0xFF, mode = h0.x >> 24;
+            const SP out = slots + (SLOTI((int) ((h0.x >> 16) & 0xFF)) * E + lane);    // element k of this lane: out[k * 32]
+            const SP outT = out;                                         // owner lane, sample t: outT[t * L]
+            const uint32_t sidx = h0.y, aux0 = h0.z, aux1 = h0.w;
+            const uint64_t ptrbits = (uint64_t) h1.x | ((uint64_t) h1.y << 32);
+            const uint32_t count6 = h1.z;
+            const uint32_t* opnds = pc + OP_HEADER_WORDS;
+            const uint4 ow = ow4;
+            pc += OP_HEADER_WORDS + nwords;
+            const uint32_t* const pcPrefetched = pc;
+            const uint4 h0n = __ldg(reinterpret_cast<const uint4*>(pc));
+            const uint4 h1n = __ldg(reinterpret_cast<const uint4*>(pc + 4));
+            const uint4 ow4n = __ldg(reinterpret_cast<const uint4*>(pc + 8));
+
+            // program-word access of the interpreter (render_ops.inc explains the contract)
+#define OPWORD(i) (((i) == 0) ? ow.x : ((i) == 1) ? ow.y : ((i) == 2) ? ow.z : ((i) == 3) ? ow.w : __ldg(opnds + (i)))
+#define CHAIN_FOR_STEPS(s) const uint32_t* sp = opnds + 1; uint32_t cfw_ = ow.y, cow_ = ow.z; for (uint32_t s = 0; s < count6; ++s, sp += 2)
+#define CHAIN_FN_WORD(s) cfw_
+#define CHAIN_OPND_WORD(s) cow_
+#define CHAIN_NEXT(s) do { cfw_ = __ldg(sp + 2); cow_ = __ldg(sp + 3); } while (0)
+#define PC_ADVANCE(n) pc += (n)
+#define PC_SKIP_SEGMENT_IF(cond, n) if (cond) pc += (n)
+#ifdef EB_OPPROF
+            const long long prof_t0 = clock64();
+#endif
+#include "render_ops.inc"
+#ifdef EB_OPPROF
+            __syncwarp();
+            if (lane == 0) { atomicAdd(&g_opprof[2 * (opcode & 63)], (unsigned long long) (clock64() - prof_t0)); atomicAdd(&g_opprof[2 * (opcode & 63) + 1], 1ull); }
+#endif
+#undef OPWORD
+#undef CHAIN_FOR_STEPS
+#undef CHAIN_FN_WORD
+#undef CHAIN_OPND_WORD
+#undef CHAIN_NEXT
+#undef PC_ADVANCE
+#undef PC_SKIP_SEGMENT_IF
+            if (pc == pcPrefetched) { h0 = h0n; h1 = h1n; ow4 = ow4n; }
+            else {
+                h0 = __ldg(reinterpret_cast<const uint4*>(pc));
+                h1 = __ldg(reinterpret_cast<const uint4*>(pc + 4));
+                ow4 = __ldg(reinterpret_cast<const uint4*>(pc + 8));
+            }
         }
 #else
         const uint32_t* pc = P.code + ((PIPE && pipeW > 1) ? P.pipeCode[stage] : 0u);
@@ -646,9 +734,10 @@ __device__ __forceinline__ void render_tile(const LaunchParams& P, const int til
 
             // program-word access of the interpreter (render_ops.inc explains the contract)
 #define OPWORD(i) __ldg(opnds + (i))
-#define CHAIN_FOR_STEPS(s) const uint32_t* sp = opnds + 1; for (uint32_t s = 0; s < count6; ++s, sp += 2)
-#define CHAIN_FN_WORD(s) __ldg(sp)
-#define CHAIN_OPND_WORD(s) __ldg(sp + 1)
+#define CHAIN_FOR_STEPS(s) const uint32_t* sp = opnds + 1; uint32_t cfw_ = __ldg(sp), cow_ = __ldg(sp + 1); for (uint32_t s = 0; s < count6; ++s, sp += 2)
+#define CHAIN_FN_WORD(s) cfw_
+#define CHAIN_OPND_WORD(s) cow_
+#define CHAIN_NEXT(s) do { cfw_ = __ldg(sp + 2); cow_ = __ldg(sp + 3); } while (0)
 #define PC_ADVANCE(n) pc += (n)
 #define PC_SKIP_SEGMENT_IF(cond, n) if (cond) pc += (n)
 #ifdef EB_OPPROF
@@ -663,9 +752,11 @@ __device__ __forceinline__ void render_tile(const LaunchParams& P, const int til
 #undef CHAIN_FOR_STEPS
 #undef CHAIN_FN_WORD
 #undef CHAIN_OPND_WORD
+#undef CHAIN_NEXT
 #undef PC_ADVANCE
 #undef PC_SKIP_SEGMENT_IF
         }
+#endif   // EB_INTERP_PREFETCH
 #endif   // EB_SPEC_PROGRAM
 
         if constexpr (PIPE) {
@@ -751,6 +842,8 @@ __device__ __forceinline__ void render_tile(const LaunchParams& P, const int til
 #undef FOR_K
 #undef T_OF
 #undef FOR_OWNER
+#undef FOR_TJ
+#undef FETCH_T
 }
 
 // Occupancy target (measured, profiles/r01_d_occupancy_ab.txt): the full-width geometry (L = 32, every lane a voice)
@@ -794,6 +887,7 @@ __global__ void EB_BOUNDS render_groups_kernel(const LaunchParams* __restrict__ 
 // the CTA runs stage w.  A graph's recurrences are serial per sample and own a single lane, so one warp per graph is latency bound
 // (profiles/r02_f_groups_ncu.txt: 0.08 instructions per cycle and warp at 8 warps per SM); with W stages W warps work on W different
 // sample tiles of the same graph at once.  Programs that were not cut (pipeW <= 1) simply use warp 0.
+template <int NITER>
 __global__ void __launch_bounds__(32 * MAX_PIPE, 8) render_groups_pipe_kernel(const LaunchParams* __restrict__ descs, const int* __restrict__ tileStart,
                                                                               const int nGroups, const int totalTiles, const int perGraph,
                                                                               const long long sampleTime, const int outOffset) {
@@ -809,7 +903,7 @@ __global__ void __launch_bounds__(32 * MAX_PIPE, 8) render_groups_pipe_kernel(co
     }
     const LaunchParams& P = descs[lo];
     if (stage >= max(1, P.pipeW)) return;              // (whole warps leave; no CTA-wide barrier follows)
-    render_tile<1, 0, true>(P, w - __ldg(tileStart + lo), perGraph, sampleTime, outOffset, stage);
+    render_tile<NITER, 0, true>(P, w - __ldg(tileStart + lo), perGraph, sampleTime, outOffset, stage);
 }
 
 #ifndef __CUDACC_RTC__   // K2, K4 and the host launchers are not needed by a run-time compiled specialisation of K1
@@ -895,6 +989,7 @@ int render_niter_for(int tileWidth, int niterOverride) {
     //   L >= 8 : E = 256 (T = 256/L);  L = 4 : T = 32;  L = 2 : T = 64 (fewer op dispatches per sample);  L = 1 : T = 32
     // L = 32 may also run with NITER = 4 (T = 4) for A/B runs.
     if (tileWidth == 32 && niterOverride == 4) return 4;
+    if (tileWidth == 1 && niterOverride == 4) return 4;       // L = 1, T = 128: four times fewer op dispatches per sample (A/B: profiles/r02_k_*)
     if (tileWidth >= 8) return 8;
     if (tileWidth == 4) return 4;
     return tileWidth == 2 ? 4 : 1;   // L = 1 keeps T = 32: with one voice per warp longer tiles push delay lines off their fast path (config 5)
@@ -954,17 +1049,22 @@ static cudaError_t launch_render_block_geometry(const LaunchParams& P, int L, in
         case 8:  return launch_impl<8, 3>(P, grid, threads, smem, stream);
         case 4:  return launch_impl<4, 2>(P, grid, threads, smem, stream);
         case 2:  return launch_impl<4, 1>(P, grid, threads, smem, stream);
-        default: return launch_impl<1, 0>(P, grid, threads, smem, stream);
+        default: return render_niter_for(1, niterOverride) == 4 ? launch_impl<4, 0>(P, grid, threads, smem, stream)
+                                                                : launch_impl<1, 0>(P, grid, threads, smem, stream);
     }
 }
 
 // descs / tileStart are DEVICE pointers; maxSlots etc. are the maxima over the groups (uniform shared-memory carve-up).
 cudaError_t launch_render_groups(const LaunchParams* descs, const int* tileStart, int nGroups, int totalTiles, int tileWidth,
-                                 int maxSlots, int nOut, int maxStateRows, int maxParams, int warpsPerCta, long long sampleTime, int outOffset, cudaStream_t stream) {
+                                 int maxSlots, int nOut, int maxStateRows, int maxParams, int warpsPerCta, long long sampleTime, int outOffset, cudaStream_t stream,
+                                 int niterOverride) {
     if (totalTiles <= 0) return cudaSuccess;
     const int grid = (totalTiles + warpsPerCta - 1) / warpsPerCta;
     const int threads = warpsPerCta * 32;
-    const size_t smem = render_smem_bytes(maxSlots, nOut, maxStateRows, maxParams, warpsPerCta, tileWidth, 0);
+    if (tileWidth != 1) niterOverride = 0;       // the many-groups launch has the T = 128 variant for one-voice tiles only
+    const size_t smem = render_smem_bytes(maxSlots, nOut, maxStateRows, maxParams, warpsPerCta, tileWidth, niterOverride);
+    if (tileWidth == 1 && render_niter_for(1, niterOverride) == 4)
+        return launch_groups_impl<4, 0>(descs, tileStart, nGroups, totalTiles, grid, threads, smem, sampleTime, outOffset, stream);
     switch (tileWidth) {
         case 32: return launch_groups_impl<8, 5>(descs, tileStart, nGroups, totalTiles, grid, threads, smem, sampleTime, outOffset, stream);
         case 16: return launch_groups_impl<8, 4>(descs, tileStart, nGroups, totalTiles, grid, threads, smem, sampleTime, outOffset, stream);
@@ -977,15 +1077,19 @@ cudaError_t launch_render_groups(const LaunchParams* descs, const int* tileStart
 
 // One CTA of `stages` warps per one-voice graph (descs / tileStart are DEVICE pointers; the maxima size the per-graph shared memory).
 cudaError_t launch_render_groups_pipe(const LaunchParams* descs, const int* tileStart, int nGroups, int totalTiles, int stages,
-                                      int maxSlots, int nOut, int maxStateRows, int maxParams, long long sampleTime, int outOffset, cudaStream_t stream) {
+                                      int maxSlots, int nOut, int maxStateRows, int maxParams, long long sampleTime, int outOffset, cudaStream_t stream,
+                                      int niterOverride) {
     if (totalTiles <= 0) return cudaSuccess;
     if (stages < 1) stages = 1;
     if (stages > MAX_PIPE) stages = MAX_PIPE;
-    const size_t graphBytes = render_smem_bytes(maxSlots, nOut, maxStateRows, maxParams, 1, 1, 0);
+    const size_t graphBytes = render_smem_bytes(maxSlots, nOut, maxStateRows, maxParams, 1, 1, niterOverride);
     const size_t smem = graphBytes + sizeof(int) * 8;              // + the progress counters
-    cudaError_t e = cudaFuncSetAttribute(render_groups_pipe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
+    const bool wide = render_niter_for(1, niterOverride) == 4;
+    cudaError_t e = wide ? cudaFuncSetAttribute(render_groups_pipe_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem)
+                         : cudaFuncSetAttribute(render_groups_pipe_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
     if (e != cudaSuccess) return e;
-    render_groups_pipe_kernel<<<totalTiles, 32 * stages, smem, stream>>>(descs, tileStart, nGroups, totalTiles, (int) (graphBytes / sizeof(float)), sampleTime, outOffset);
+    if (wide) render_groups_pipe_kernel<4><<<totalTiles, 32 * stages, smem, stream>>>(descs, tileStart, nGroups, totalTiles, (int) (graphBytes / sizeof(float)), sampleTime, outOffset);
+    else render_groups_pipe_kernel<1><<<totalTiles, 32 * stages, smem, stream>>>(descs, tileStart, nGroups, totalTiles, (int) (graphBytes / sizeof(float)), sampleTime, outOffset);
     return cudaGetLastError();
 }
 

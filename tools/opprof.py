@@ -11,7 +11,8 @@ NAMES = ["END", "SEG", "FILL0", "COPY", "LOADIN", "CHAIN", "PHASOR", "SPHASOR", 
          "PREWARP", "MM1P", "SVF", "SVFSHELF", "Z", "DELAY", "SDELAY", "TABLE", "BLEP", "TAPIN", "TAPOUT", "ROOT", "STOREBUF", "LOADBUF", "PROMOTE"]
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 1250
 stages = int(sys.argv[2]) if len(sys.argv) > 2 else 0
-rt = Runtime(48000.0, 512, n, device=0, pipeline_stages=stages)
+niter = int(sys.argv[3]) if len(sys.argv) > 3 else 0
+rt = Runtime(48000.0, 512, n, device=0, pipeline_stages=stages, **({"niter": niter} if niter else {}))
 for i in range(n):
     assert rt.apply_instructions(graphs.random_graph(i, 64), voices=(i, i + 1)) == 0
 from elementary_b200.runtime import FLAG_MIX
@@ -26,7 +27,7 @@ rt.synchronize()
 p = rt.debug_opprof(True).astype(np.float64)
 tot_ops = p[:63, 0].sum()
 whole = p[63, 0]
-print(json.dumps({"graphs": n, "pipeline_stages": stages, "blocks": B, "warp_cycles_total": whole, "cycles_in_op_bodies": tot_ops, "share_in_bodies": tot_ops / max(1.0, whole),
+print(json.dumps({"graphs": n, "pipeline_stages": stages, "niter": niter, "blocks": B, "warp_cycles_total": whole, "cycles_in_op_bodies": tot_ops, "share_in_bodies": tot_ops / max(1.0, whole),
                   "warps": p[63, 1] / B, "cycles_per_warp_block": whole / max(1.0, p[63, 1])}))
 rows = []
 for op in range(63):
