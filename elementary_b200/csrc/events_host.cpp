@@ -20,8 +20,10 @@ int Engine::peerExport(void* handleOut64) {
     dsetdev();
     if (!dExchange_) {
         const size_t stride = (size_t) MAX_OUT_CHANNELS * blockSize_;
-        exchangeFlagOffset_ = sizeof(float) * 2 * MAX_PEERS * stride;
-        exchangeBytes_ = exchangeFlagOffset_ + sizeof(uint32_t) * 2 * MAX_PEERS;
+        exchangeFlagOffset_ = sizeof(uint2) * 2 * MAX_PEERS * stride;                       // (sample, epoch) pairs: [2][MAX_PEERS][stride]
+        exchangeOwnOffset_ = exchangeFlagOffset_ + sizeof(uint32_t) * 2 * MAX_PEERS + 64;    // then the flags, then this rank's own partial mix
+        exchangeOwnOffset_ = (exchangeOwnOffset_ + 255) & ~(size_t) 255;
+        exchangeBytes_ = exchangeOwnOffset_ + sizeof(float) * stride;
         if (!cuda(cudaMalloc(&dExchange_, exchangeBytes_), "cudaMalloc exchange buffer")) return rc::CudaError;
         if (!cuda(cudaMemset(dExchange_, 0, exchangeBytes_), "memset exchange buffer")) return rc::CudaError;
         if (!cuda(cudaMalloc((void**) &dPeerStatus_, sizeof(int)), "cudaMalloc peer status")) return rc::CudaError;
@@ -49,8 +51,9 @@ int Engine::peerAttach(int rank, int world, const void* handles) {
             if (!cuda(cudaIpcOpenMemHandle(&base, h, cudaIpcMemLazyEnablePeerAccess), "cudaIpcOpenMemHandle (is peer access available between the GPUs?)")) return rc::CudaError;
             peerMapped_.push_back(base);
         }
-        peer_.slot[p] = static_cast<float*>(base);
+        peer_.slot[p] = static_cast<uint2*>(base);
         peer_.flag[p] = reinterpret_cast<uint32_t*>(static_cast<char*>(base) + exchangeFlagOffset_);
+        if (p == rank) peer_.own = reinterpret_cast<float*>(static_cast<char*>(base) + exchangeOwnOffset_);
     }
     peerAttached_ = true;
     peerEpoch_ = 0;

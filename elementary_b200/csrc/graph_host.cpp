@@ -2494,13 +2494,13 @@ int Engine::enqueueBlock(size_t nIn, size_t nOut, size_t numSamples, bool perVoi
         if (timeKernels_) { cudaEventRecord(ev.second, stream_); timedEvents_.push_back(ev); }
         ++launches_;
     }
-    // With the cross-GPU sum behind it, K2 leaves this rank's partial mix directly in its own slot of the exchange buffer (K4 pushes
-    // it to the peers from there and writes the total to the mix bus): no staging copy, no in-place hazard between K4's CTAs.
+    // With the cross-GPU sum behind it, K2 leaves this rank's partial mix in PeerMix::own (K4 pushes it to the peers from there and
+    // writes the total to the mix bus): no staging copy, no in-place hazard between K4's CTAs.
     const bool exchange = mix && allReduce && peerAttached_ && peer_.world > 1;
     float* mixOut = dMix_;
     if (exchange) {
         ++peerEpoch_;
-        mixOut = peer_.slot[peer_.rank] + (size_t) ((peerEpoch_ & 1u) * MAX_PEERS + peer_.rank) * peer_.stride;
+        mixOut = peer_.own;
     }
     if (mix) {
         if (tileBase > 0) {

@@ -174,8 +174,9 @@ struct EngineOptions {
                                   // (the interpreter serves meanwhile), 2 = wait for the compiler at COMMIT (benchmarks, parity runs)
     int specializeMaxWords = 512; // programs longer than this keep the interpreter (compile time grows with the unrolled program)
     bool fuseConvRoot = true;     // `convolve -> root`: root gain + per-voice output + partial mix in K3's epilogue, no K1 launch for the last stage
-    int pipelineStages = 3;       // one-voice groups in the many-groups launch: cut the program into this many pipeline stages, one warp each
-                                  // (render_groups_pipe_kernel; 0 / 1 = off).  3 x 1250 graphs still fit one resident wave on 148 SMs at 64 registers
+    int pipelineStages = 0;       // one-voice groups in the many-groups launch: cut the program into this many pipeline stages, one warp each
+                                  // (render_groups_pipe_kernel; 0 / 1 = off, the default: bit-identical but measured no faster — per-op time grows
+                                  // with the number of resident warps, DESIGN.md section 4, profiles/r02_m_*, r02_o_*)
     bool specializeStrict = false; // a failed specialisation is an error (COMMIT returns 7 / process -1) instead of a silent stay on the interpreter
 };
 
@@ -325,7 +326,7 @@ private:
     float* offlineOut_ = nullptr; int offlineStride_ = 0, offlineOffset_ = 0;   // renderOffline: where materialised outputs go instead of dOutVoice_
 
     // K4 state
-    void* dExchange_ = nullptr; size_t exchangeBytes_ = 0; size_t exchangeFlagOffset_ = 0;
+    void* dExchange_ = nullptr; size_t exchangeBytes_ = 0; size_t exchangeFlagOffset_ = 0, exchangeOwnOffset_ = 0;
     PeerMix peer_{}; bool peerAttached_ = false; uint32_t peerEpoch_ = 0; int* dPeerStatus_ = nullptr;
     std::vector<void*> peerMapped_;
 

@@ -39,13 +39,17 @@ cudaError_t launch_mix_reduce(const float* partial, float* out, float* scratch, 
                               int numSamples, cudaStream_t stream, HostDeliver hd = HostDeliver{});
 
 // K4: the one collective of the path as our own kernel over NVLink/NVSwitch peer memory: K2 leaves this rank's
-// partial mix bus in the rank's own slot of its exchange buffer; world-1 CTAs each push it into one peer's buffer, raise a flag there,
-// wait for the flags of all sources in their own buffer and sum a share of the samples over the slots in rank order — one launch,
-// deterministic, no NCCL call on the data path.  count = 0 makes it a cross-GPU stream barrier.
+// partial mix bus in PeerMix::own; world-1 CTAs each push it into one peer's buffer as (sample, epoch) pairs, then every CTA waits for the
+// pairs of all sources to arrive in its OWN buffer and sums a share of the samples in rank order — one launch, deterministic, no NCCL
+// call on the data path, one NVLink one-way latency between "my partial is ready" and "the peer can use it".  count = 0 makes it a
+// cross-GPU stream barrier (flags).
 constexpr int MAX_PEERS = 8;
 struct PeerMix {
-    float* slot[MAX_PEERS];       // slot[p]: rank p's exchange buffer [2][MAX_PEERS][stride] (peer-mapped for p != rank)
-    uint32_t* flag[MAX_PEERS];    // flag[p]: rank p's flags [2][MAX_PEERS]
+    uint2* slot[MAX_PEERS];       // slot[p]: rank p's exchange buffer [2 parities][MAX_PEERS sources][stride] of (sample bits, epoch) pairs
+                                  // (peer-mapped for p != rank): every 8-byte store carries its own arrival flag, so the data needs no
+                                  // fence and no separate flag store behind it (the "LL" form NCCL uses for small messages)
+    uint32_t* flag[MAX_PEERS];    // flag[p]: rank p's flags [2][MAX_PEERS] — used by the pure barrier (count = 0) only
+    float* own;                   // this rank's partial mix bus [stride] (local; K2 leaves it here)
     int rank, world, stride;
 };
 cudaError_t launch_mix_exchange(const PeerMix& pm, float* mix, int count, uint32_t epoch, int* status, cudaStream_t stream, HostDeliver hd = HostDeliver{});

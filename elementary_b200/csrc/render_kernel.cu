@@ -989,7 +989,8 @@ int render_niter_for(int tileWidth, int niterOverride) {
     //   L >= 8 : E = 256 (T = 256/L);  L = 4 : T = 32;  L = 2 : T = 64 (fewer op dispatches per sample);  L = 1 : T = 32
     // L = 32 may also run with NITER = 4 (T = 4) for A/B runs.
     if (tileWidth == 32 && niterOverride == 4) return 4;
-    if (tileWidth == 1 && niterOverride == 4) return 4;       // L = 1, T = 128: four times fewer op dispatches per sample (A/B: profiles/r02_k_*)
+    if (tileWidth == 1 && niterOverride == 4) return 4;
+    if (tileWidth == 2 && niterOverride == 8) return 8;       // L = 2, T = 128 (A/B: profiles/r02_q_*)       // L = 1, T = 128: four times fewer op dispatches per sample (A/B: profiles/r02_k_*)
     if (tileWidth >= 8) return 8;
     if (tileWidth == 4) return 4;
     return tileWidth == 2 ? 4 : 1;   // L = 1 keeps T = 32: with one voice per warp longer tiles push delay lines off their fast path (config 5)
@@ -1048,7 +1049,8 @@ static cudaError_t launch_render_block_geometry(const LaunchParams& P, int L, in
         case 16: return launch_impl<8, 4>(P, grid, threads, smem, stream);
         case 8:  return launch_impl<8, 3>(P, grid, threads, smem, stream);
         case 4:  return launch_impl<4, 2>(P, grid, threads, smem, stream);
-        case 2:  return launch_impl<4, 1>(P, grid, threads, smem, stream);
+        case 2:  return render_niter_for(2, niterOverride) == 8 ? launch_impl<8, 1>(P, grid, threads, smem, stream)
+                                                                 : launch_impl<4, 1>(P, grid, threads, smem, stream);
         default: return render_niter_for(1, niterOverride) == 4 ? launch_impl<4, 0>(P, grid, threads, smem, stream)
                                                                 : launch_impl<1, 0>(P, grid, threads, smem, stream);
     }
@@ -1107,46 +1109,57 @@ cudaError_t launch_mix_reduce(const float* partial, float* out, float* scratch, 
 __device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) { uint32_t v; asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory"); return v; }
 __device__ __forceinline__ float ld_volatile_f32(const float* p) { float v; asm volatile("ld.volatile.global.f32 %0, [%1];" : "=f"(v) : "l"(p) : "memory"); return v; }
 
-// grid = world - 1 CTAs.  CTA b PUSHES this rank's partial mix (left in the rank's own slot [parity][rank] of its exchange buffer by
-// K2) into the same slot of ONE peer — peer (rank + 1 + b) mod world, so at any moment every link carries one stream — fences and
-// raises flag[parity][rank] there; then every CTA waits (bounded) until the flags of all remote sources show this epoch in its OWN
-// buffer (local polling: the peers' stores come to us, we never read over the link) and sums its 1/(world-1) share of the samples
-// over the slots in rank order — every rank computes the bit-identical float sum — into the mix bus.  Two parities: a rank can be
-// one epoch ahead of a slow peer, never two (it needs the peer's flag of epoch e+1, which the peer raises after finishing e).
-// count = 0 is a pure barrier.
+// grid = world - 1 CTAs.  CTA b PUSHES this rank's partial mix (PeerMix::own, left there by K2) into slot [parity][rank] of ONE peer —
+// peer (rank + 1 + b) mod world, so at any moment every link carries one stream — as 8-byte (sample bits, epoch) pairs: a pair is its
+// own arrival flag (8-byte stores are single transactions), so there is no fence and no flag store behind the data.  Then every CTA
+// sums its 1/(world-1) share of the samples over the sources in rank order — its own partial from local memory, a remote one by
+// polling the pair in its OWN buffer until it shows this epoch (bounded: a dead peer must not hang the GPU) — so every rank computes
+// the bit-identical float sum.  Two parities: a rank can be one epoch ahead of a slow peer, never two (it needs the peer's pairs of
+// epoch e+1, which the peer sends after finishing e).  count = 0 is a pure barrier through the flag words.
+__device__ __forceinline__ void st_volatile_v2(uint2* p, uint32_t x, uint32_t y) { asm volatile("st.volatile.global.v2.u32 [%0], {%1, %2};" ::"l"(p), "r"(x), "r"(y) : "memory"); }
+__device__ __forceinline__ uint2 ld_volatile_v2(const uint2* p) { uint2 v; asm volatile("ld.volatile.global.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(p) : "memory"); return v; }
+
 __global__ void __launch_bounds__(256) mix_exchange_kernel(const PeerMix pm, float* __restrict__ mix, int count, uint32_t epoch, int* status, const HostDeliver hd) {
     const int tid = threadIdx.x, b = blockIdx.x, nb = gridDim.x;
     const int parity = (int) (epoch & 1u);
-    const float* own = pm.slot[pm.rank] + (size_t) parity * MAX_PEERS * pm.stride;             // [src rank][stride] in OUR buffer
-    {   // 1. push
+    if (count == 0) {   // barrier: raise my flag on one peer, wait for every peer's flag here
         const int p = (pm.rank + 1 + b) % pm.world;
-        const float* src = own + (size_t) pm.rank * pm.stride;
-        float* dst = pm.slot[p] + (size_t) (parity * MAX_PEERS + pm.rank) * pm.stride;
-        if ((count & 3) == 0) {
-            for (int i = tid; i < (count >> 2); i += blockDim.x) reinterpret_cast<float4*>(dst)[i] = reinterpret_cast<const float4*>(src)[i];
-        } else {
-            for (int i = tid; i < count; i += blockDim.x) dst[i] = src[i];
-        }
-        __threadfence_system();
-        __syncthreads();
         if (tid == 0) st_release_sys(pm.flag[p] + parity * MAX_PEERS + pm.rank, epoch);
-    }
-    // 2. wait until every remote source has published this epoch into OUR buffer (bounded spin: a dead peer must not hang the GPU)
-    if (tid < pm.world && tid != pm.rank) {
-        const uint32_t* f = pm.flag[pm.rank] + parity * MAX_PEERS + tid;
-        const long long t0 = clock64();
-        while (ld_acquire_sys(f) != epoch) {
-            if (clock64() - t0 > 2000000000ll) { if (status) *status = 1; break; }   // ~1 s
-            __nanosleep(32);
+        if (tid < pm.world && tid != pm.rank) {
+            const uint32_t* f = pm.flag[pm.rank] + parity * MAX_PEERS + tid;
+            const long long t0 = clock64();
+            while (ld_acquire_sys(f) != epoch) {
+                if (clock64() - t0 > 2000000000ll) { if (status) *status = 1; break; }   // ~1 s
+                __nanosleep(32);
+            }
         }
+        return;
     }
-    __syncthreads();
-    // 3. sum this CTA's share of the samples over the slots in rank order
+    {   // 1. push (value, epoch) pairs
+        const int p = (pm.rank + 1 + b) % pm.world;
+        uint2* dst = pm.slot[p] + (size_t) (parity * MAX_PEERS + pm.rank) * pm.stride;
+        for (int i = tid; i < count; i += blockDim.x) st_volatile_v2(dst + i, __float_as_uint(pm.own[i]), epoch);
+    }
+    // 2. sum this CTA's share of the samples over the sources in rank order
+    const uint2* mine = pm.slot[pm.rank] + (size_t) parity * MAX_PEERS * pm.stride;               // [src rank][stride] in OUR buffer
     const int per = (count + nb - 1) / nb;
     const int i1 = min(count, (b + 1) * per);
     for (int i = b * per + tid; i < i1; i += blockDim.x) {
         float s = 0.0f;
-        for (int src = 0; src < pm.world; ++src) s += ld_volatile_f32(own + (size_t) src * pm.stride + i);
+        for (int src = 0; src < pm.world; ++src) {
+            if (src == pm.rank) { s += pm.own[i]; continue; }
+            const uint2* q = mine + (size_t) src * pm.stride + i;
+            uint2 v = ld_volatile_v2(q);
+            if (v.y != epoch) {
+                const long long t0 = clock64();
+                do {
+                    if (clock64() - t0 > 2000000000ll) { if (status) *status = 1; break; }       // ~1 s
+                    __nanosleep(20);
+                    v = ld_volatile_v2(q);
+                } while (v.y != epoch);
+            }
+            s += __uint_as_float(v.x);
+        }
         mix[i] = s;
         if (hd.out) hd.out[i] = s;
     }

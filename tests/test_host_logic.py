@@ -342,17 +342,17 @@ def test_pipeline_cut_of_one_voice_groups_plan_only():
     program are one [SEG ... END] section per stage whose ring slots are only ever written in one stage and read in later ones."""
     from elementary_b200 import graphs
     n = 6
-    rt = Runtime(SR, BS, n, device=-1)
+    rt = Runtime(SR, BS, n, device=-1, pipeline_stages=3)
     for i in range(n):
         assert rt.apply_instructions(graphs.random_graph(300 + i, 64), voices=(i, i + 1)) == 0, rt.last_error()
     groups = rt.describe()["groups"]
     assert len(groups) == n and all(g["pipeline_stages"] == 3 for g in groups), groups
-    off = Runtime(SR, BS, n, device=-1, pipeline_stages=0)
+    off = Runtime(SR, BS, n, device=-1)                     # the default is off (option pipeline_stages)
     for i in range(n):
         assert off.apply_instructions(graphs.random_graph(300 + i, 64), voices=(i, i + 1)) == 0
     assert all(g["pipeline_stages"] == 1 for g in off.describe()["groups"])
     assert all(a["ops"] == b["ops"] and a["state_rows"] == b["state_rows"] for a, b in zip(groups, off.describe()["groups"]))
-    single = Runtime(SR, BS, 4, device=-1)
+    single = Runtime(SR, BS, 4, device=-1, pipeline_stages=3)
     assert single.apply_instructions(graphs.random_graph(300, 64)) == 0
     assert single.describe()["groups"][0]["pipeline_stages"] == 1
     # structure of the cut program: sections [SEG][ops][END], outputs of a section never collide with another section's private slots
