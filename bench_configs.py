@@ -143,6 +143,8 @@ def config5(quick):
         extra["pipeline_stages"] = int(sys.argv[sys.argv.index("--stages") + 1])
     if "--niter" in sys.argv:
         extra["niter"] = int(sys.argv[sys.argv.index("--niter") + 1])
+    if "--wpc" in sys.argv:
+        extra["warps_per_cta"] = int(sys.argv[sys.argv.index("--wpc") + 1])
     rt = Runtime(SR, BS, n_graphs, device=0, time_kernels=1, **extra)
     batches = [graphs.random_graph(i, 64) for i in range(n_graphs)]     # the Python generator is not part of the engine's setup cost
     t0 = time.perf_counter()
@@ -196,7 +198,7 @@ def config5(quick):
 
 def main():
     quick = "--quick" in sys.argv
-    which = [a for i, a in enumerate(sys.argv[1:], 1) if a in ("1", "3", "4", "5") and sys.argv[i - 1] not in ("--stages", "--graphs", "--niter")] or ["1", "3", "4", "5"]
+    which = [a for i, a in enumerate(sys.argv[1:], 1) if a in ("1", "3", "4", "5") and sys.argv[i - 1] not in ("--stages", "--graphs", "--niter", "--wpc")] or ["1", "3", "4", "5"]
     for w in which:
         r = {"1": config1, "3": config3, "4": config4, "5": config5}[w](quick)
         print(json.dumps(r))

@@ -2228,7 +2228,7 @@ int Engine::enqueueBlock(size_t nIn, size_t nOut, size_t numSamples, bool perVoi
         for (auto& sb : steadyBuckets_) {
             BatchBuffers& bb = batch_[sb.key];
             auto ev = timedBegin();
-            if (!cuda(sb.pipeStages > 1
+            if (!cuda(sb.pipeStages >= 1
                           ? launch_render_groups_pipe(bb.dDescs, bb.dTileStart, sb.nGroups, sb.totalTiles, sb.pipeStages, sb.maxSlots, (int) nOut, sb.maxState, sb.maxParams, sampleTime_, offlineOut_ ? offlineOffset_ : 0, stream_, opt_.niter)
                           : launch_render_groups(bb.dDescs, bb.dTileStart, sb.nGroups, sb.totalTiles, sb.L, sb.maxSlots, (int) nOut, sb.maxState, sb.maxParams, sb.wpc, sampleTime_, offlineOut_ ? offlineOffset_ : 0, stream_, opt_.niter),
                       "render groups kernel launch")) return rc::CudaError;
@@ -2367,7 +2367,9 @@ int Engine::enqueueBlock(size_t nIn, size_t nOut, size_t numSamples, bool perVoi
         if (nStages == 1 && groups_.size() > 1 && opt_.batchGroups && !p.hasCustom) {
             // heterogeneous voice groups: collect single-stage groups per tile geometry and launch each bucket once
             P.code = p.dCode + (p.stages.empty() ? 0 : p.stages[0].codeOffset);
-            const int bkey = g.tileWidth + (p.pipeW > 1 ? PIPE_BUCKET : 0);      // pipelined one-voice programs launch through their own kernel
+            // one-voice groups launch through the pipeline kernel (programs that were not cut simply use warp 0 of their CTA): one
+            // launch for all of them whether or not every program could be cut
+            const int bkey = g.tileWidth + ((p.pipeW > 1 || (g.tileWidth == 1 && opt_.pipelineStages > 1)) ? PIPE_BUCKET : 0);
             buckets[bkey].push_back(P);
             buckets[bkey].back().sampleTime = 0;      // the many-groups kernel takes the clock as an argument: descriptors stay equal block to block
         } else
@@ -2458,7 +2460,7 @@ int Engine::enqueueBlock(size_t nIn, size_t nOut, size_t numSamples, bool perVoi
             maxSlots = std::max(maxSlots, descs[i].nSlots);
             maxState = std::max(maxState, descs[i].nStateRows);
             maxParams = std::max(maxParams, descs[i].nParams);
-            if (kv.first >= PIPE_BUCKET) pipeStages = std::max(pipeStages, descs[i].pipeW);
+            if (kv.first >= PIPE_BUCKET) pipeStages = std::max(pipeStages, std::max(1, descs[i].pipeW));
         }
         // descriptors change only while roots fade or when graphs change: re-upload only then
         BatchBuffers& bb = batch_[kv.first];
@@ -2487,7 +2489,7 @@ int Engine::enqueueBlock(size_t nIn, size_t nOut, size_t numSamples, bool perVoi
             cudaEventRecord(ev.first, stream_);
         }
         steadyBuckets_.push_back(SteadyBucket{L, (int) descs.size(), total, maxSlots, maxState, maxParams, wpc, pipeStages, kv.first});
-        if (!dry && !cuda(pipeStages > 1
+        if (!dry && !cuda(pipeStages >= 1
                               ? launch_render_groups_pipe(bb.dDescs, bb.dTileStart, (int) descs.size(), total, pipeStages, maxSlots, (int) nOut, maxState, maxParams, sampleTime_, offlineOut_ ? offlineOffset_ : 0, stream_, opt_.niter)
                               : launch_render_groups(bb.dDescs, bb.dTileStart, (int) descs.size(), total, L, maxSlots, (int) nOut, maxState, maxParams, wpc, sampleTime_, offlineOut_ ? offlineOffset_ : 0, stream_, opt_.niter),
                   "render groups kernel launch")) return rc::CudaError;

@@ -174,9 +174,10 @@ struct EngineOptions {
                                   // (the interpreter serves meanwhile), 2 = wait for the compiler at COMMIT (benchmarks, parity runs)
     int specializeMaxWords = 512; // programs longer than this keep the interpreter (compile time grows with the unrolled program)
     bool fuseConvRoot = true;     // `convolve -> root`: root gain + per-voice output + partial mix in K3's epilogue, no K1 launch for the last stage
-    int pipelineStages = 0;       // one-voice groups in the many-groups launch: cut the program into this many pipeline stages, one warp each
-                                  // (render_groups_pipe_kernel; 0 / 1 = off, the default: bit-identical but measured no faster — per-op time grows
-                                  // with the number of resident warps, DESIGN.md section 4, profiles/r02_m_*, r02_o_*)
+    int pipelineStages = 4;       // one-voice groups in the many-groups launch: cut the program into this many pipeline stages, one warp each
+                                  // (render_groups_pipe_kernel; 0 / 1 = off).  Bit-identical to one warp per graph; worth 7 % on BASELINE
+                                  // config 5 (0.77 against 0.83 ms per block, profiles/r02_o_*, r02_s_*) — per-op time grows with the number
+                                  // of resident warps, so the gain is far from the stage count
     bool specializeStrict = false; // a failed specialisation is an error (COMMIT returns 7 / process -1) instead of a silent stay on the interpreter
 };
 

@@ -533,7 +533,7 @@ __device__ __forceinline__ void render_tile(const LaunchParams& P, const int til
     // pipeline bookkeeping (all constants when !PIPE)
     const int pipeW = PIPE ? max(1, P.pipeW) : 1;
     const bool firstStage = !PIPE || stage == 0, lastStage = !PIPE || stage == pipeW - 1;
-    const int ringBase = PIPE ? P.pipeRingBase : 0x7FFFFFFF, pipeDepth = PIPE ? max(1, P.pipeDepth) : 1;
+    const int ringBase = (PIPE && pipeW > 1) ? P.pipeRingBase : 0x7FFFFFFF, pipeDepth = PIPE ? max(1, P.pipeDepth) : 1;
     volatile int* const progress = PIPE ? reinterpret_cast<volatile int*>(g_smem + perWarp) : nullptr;   // [MAX_PIPE] tiles finished per stage
     int ringOff = 0;                          // ring buffer of the current tile: tile index mod pipeDepth
     auto SLOTI = [&](int idx) -> int { if constexpr (PIPE) return idx + ((idx >= ringBase) ? ringOff : 0); else return idx; };

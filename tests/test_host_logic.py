@@ -336,6 +336,14 @@ def test_const_table_return_codes():
     assert rt.snapshot()["0x%08x" % (ida & 0xFFFFFFFF)]["value"] == float(tab[0, -1])
 
 
+def Runtime_with_graphs(n):
+    from elementary_b200 import graphs
+    rt = Runtime(SR, BS, n, device=-1)
+    for i in range(n):
+        assert rt.apply_instructions(graphs.random_graph(300 + i, 64), voices=(i, i + 1)) == 0, rt.last_error()
+    return rt
+
+
 def test_pipeline_cut_of_one_voice_groups_plan_only():
     """The host side of the warp pipeline (render_groups_pipe_kernel): one-voice groups in a many-groups engine get
     their program cut into pipeline stages; single-group engines, wide tiles and pipeline_stages = 0 do not; the program words of a cut
@@ -347,7 +355,8 @@ def test_pipeline_cut_of_one_voice_groups_plan_only():
         assert rt.apply_instructions(graphs.random_graph(300 + i, 64), voices=(i, i + 1)) == 0, rt.last_error()
     groups = rt.describe()["groups"]
     assert len(groups) == n and all(g["pipeline_stages"] == 3 for g in groups), groups
-    off = Runtime(SR, BS, n, device=-1)                     # the default is off (option pipeline_stages)
+    assert all(g["pipeline_stages"] == 4 for g in Runtime_with_graphs(n).describe()["groups"])       # the default (option pipeline_stages)
+    off = Runtime(SR, BS, n, device=-1, pipeline_stages=0)
     for i in range(n):
         assert off.apply_instructions(graphs.random_graph(300 + i, 64), voices=(i, i + 1)) == 0
     assert all(g["pipeline_stages"] == 1 for g in off.describe()["groups"])
