@@ -486,7 +486,16 @@ cudaError_t convolver_process_chunk(ConvolverState& st, const float* in, int inS
         if (smCount <= 0) smCount = 148;
     }
     const int persistent = smCount * TM_CTAS_PER_SM;                   // a multiple of the SM count: one resident wave
-    const int grid = units < persistent ? units : persistent;
+#ifndef EB_CONV_BALANCED
+#define EB_CONV_BALANCED 1      /* 0 = always the full resident wave (A/B: profiles/r02_w_k3_balanced_grid_ab.txt) */
+#endif
+    // Every CTA walks the same number of channel pairs: 512 pairs on 296 resident CTAs would leave 80 CTAs idle for the second half of
+    // the kernel (216 CTAs hold two pairs, 80 hold one); 256 CTAs with two pairs each keep the HBM stream full until the end.
+    int grid = units < persistent ? units : persistent;
+    if (EB_CONV_BALANCED && units > persistent) {
+        const int rounds = (units + persistent - 1) / persistent;
+        grid = (units + rounds - 1) / rounds;
+    }
     convolve_chunk_tm_kernel<<<grid, TM_THREADS, smem, stream>>>(in, inStride, out, stride, offset, n, st.fill, st.cur, st.partitions, st.nv,
                                                                 st.dH, st.dFdl, st.dYpre, st.dOverlap, st.dInBuf, st.dTw, epi);
     st.fill += n;
