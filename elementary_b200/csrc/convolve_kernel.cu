@@ -74,7 +74,7 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
 constexpr int TM_GROUP = 128;                       // threads per worker group
 constexpr int TM_THREADS = 2 * TM_GROUP + 32;       // T + M + producer warp
 #ifndef EB_CONV_TM_STAGES
-#define EB_CONV_TM_STAGES 4   /* A/B: profiles/r01_n_k3_persistent_ab.txt */
+#define EB_CONV_TM_STAGES 5   /* 5 x 12 KB + 44 KB = 104 KB per CTA, two CTAs per SM still fit; A/B: profiles/r01_n_k3_persistent_ab.txt, r02_x_k3_ring_depth_ab.txt */
 #endif
 #ifndef EB_CONV_TM_CTAS
 #define EB_CONV_TM_CTAS 2
@@ -186,33 +186,44 @@ __global__ void __launch_bounds__(TM_THREADS, TM_CTAS_PER_SM) convolve_chunk_tm_
 
     const int tid = threadIdx.x;
     const int numUnits = (nv + CH - 1) / CH;
-    if (tid == 0) {
+#ifndef EB_CONV_EARLY_PRODUCER
+#define EB_CONV_EARLY_PRODUCER 1   /* 0 = the producer starts behind the CTA barrier like everyone else (A/B: profiles/r02_y_*) */
+#endif
+    // The producer thread initialises the barriers itself and fills the first ring stages BEFORE the CTA-wide barrier: the delay line
+    // is on its way from HBM while the other warps still fetch the twiddle table (cold after an L2 flush).  Its first TM_STAGES
+    // stages need no `empty` wait (fresh barriers pass the parity-1 wait), so nothing it touches depends on the other warps yet.
+    const bool producerThread = (tid == 2 * TM_GROUP);
+    uint32_t pit = 0;                    // producer: stages issued so far
+    int pu = blockIdx.x, pi = 1;         // producer: next (unit, partition) to issue
+    auto produceOne = [&]() {
+        const int stg = pit % TM_STAGES;
+        mbar_wait_b(&empty[stg], ((pit / TM_STAGES) & 1) ^ 1);
+        int slotIdx = cur + pi;
+        if (slotIdx >= S) slotIdx -= S;
+        const int ch0 = pu * CH;
+        mbar_expect_tx(&full[stg], (CH + 1) * ROW_BYTES);
+#pragma unroll
+        for (int c = 0; c < CH; ++c)
+            tma_load_1d(&stX[stg][c][0], fdl + ((size_t) min(ch0 + c, nv - 1) * S + slotIdx) * NB, ROW_BYTES, &full[stg]);
+        tma_load_1d(&stH[stg][0], H + (size_t) pi * NB, ROW_BYTES, &full[stg]);
+        ++pit;
+        if (++pi >= S) { pi = 1; pu += gridDim.x; }
+    };
+    if (EB_CONV_EARLY_PRODUCER ? producerThread : (tid == 0)) {
         for (int i = 0; i < TM_STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], TM_GROUP / 32); }
         for (int i = 0; i < 2; ++i) { mbar_init(&xfull[i], 1); mbar_init(&xempty[i], TM_GROUP / 32); mbar_init(&yfull[i], TM_GROUP / 32); mbar_init(&yempty[i], 1); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         fence_proxy_async();
+        if (EB_CONV_EARLY_PRODUCER && fill == 0 && S > 1)
+            for (int k = 0; k < TM_STAGES && pu < numUnits; ++k) produceOne();
     }
     for (int i = tid; i < N2; i += TM_THREADS) tw[i] = twg[i];
     __syncthreads();
 
     if (tid >= 2 * TM_GROUP) {
         // ---------------- producer warp ----------------
-        if (tid == 2 * TM_GROUP && fill == 0) {
-            uint32_t it = 0;
-            for (int u = blockIdx.x; u < numUnits; u += gridDim.x) {
-                const int ch0 = u * CH;
-                for (int i = 1; i < S; ++i, ++it) {
-                    const int stg = it % TM_STAGES;
-                    mbar_wait_b(&empty[stg], ((it / TM_STAGES) & 1) ^ 1);
-                    int slotIdx = cur + i;
-                    if (slotIdx >= S) slotIdx -= S;
-                    mbar_expect_tx(&full[stg], (CH + 1) * ROW_BYTES);
-#pragma unroll
-                    for (int c = 0; c < CH; ++c)
-                        tma_load_1d(&stX[stg][c][0], fdl + ((size_t) min(ch0 + c, nv - 1) * S + slotIdx) * NB, ROW_BYTES, &full[stg]);
-                    tma_load_1d(&stH[stg][0], H + (size_t) i * NB, ROW_BYTES, &full[stg]);
-                }
-            }
+        if (producerThread && fill == 0 && S > 1) {
+            while (pu < numUnits) produceOne();
         }
         return;
     }
