@@ -66,7 +66,10 @@ int elem_b200_set_property_per_voice(elem_b200_runtime* rt, int32_t nodeId, cons
 
 /* Runtime::process(in, nIn, out, nOut, numSamples, userData) — Runtime.h:51-57,275-290.
  * `in` channels are broadcast to every voice; out[c] receives the MIX BUS: the sum over all voices of what
- * each voice's Runtime would have written to its out[c].  Host buffers; H2D/D2H copies are inside the call.
+ * each voice's Runtime would have written to its out[c].  Host buffers; the H2D copy of the inputs and the hand-over of the
+ * result (stored into mapped host memory by the kernel that finishes the mix bus; the call returns when its sequence word
+ * arrives) are inside the call.  With peers attached (elem_b200_peer_attach) the sum runs over the voices of ALL ranks and every
+ * rank must make the call for every block.
  * userData: NULL, or — as every reference host passes it (wasm/Main.cpp:206-215) — a pointer to the int64 sample
  * time of the block's first sample, read by the `time` and `metro` nodes (wasm/SampleTime.h:19, Metro.h:44).
  * With NULL the engine keeps the clock itself (+= numSamples per call, like wasm/Main.cpp:217). */
@@ -144,8 +147,14 @@ void elem_b200_process_queued_events(elem_b200_runtime* rt, elem_b200_event_cb c
  * voice), so a poll that reaches a group consumes that window for the whole group. */
 int elem_b200_process_queued_events_range(elem_b200_runtime* rt, int voiceBegin, int voiceEnd, elem_b200_event_cb cb, void* user);
 
-/* Tuning and introspection (no reference equivalent). Keys: "tile_width" (1..32, 0 =
- * auto), "warps_per_cta", "target_tiles", "time_kernels" (0|1), "specialize" (0|1, experimental). Must be set before the first COMMIT of a voice group. */
+/* Tuning and introspection (no reference equivalent).  Keys: "tile_width" (1..32 voices per warp, 0 = auto), "warps_per_cta",
+ * "target_tiles", "niter" (sample-tile variant: 4 = 128-sample one-voice tiles), "batch_groups", "fuse_chains",
+ * "specialize" (per-program NVRTC kernels: 0 off, 1 compile in the background while the interpreter serves, 2 wait at COMMIT),
+ * "specialize_max_words", "specialize_strict", "pipeline_stages" (warp pipeline of one-voice groups, default 4, 0 = off),
+ * "fuse_conv_root" (root + mix in the convolver's epilogue, default 1), "host_deliver" (process(): the finishing kernel stores the
+ * mix bus into mapped host memory, default 1), "process_allreduce" (process() sums over the attached peers, default 1),
+ * "time_kernels" (event pairs around every kernel launch), "plan_dry_run" (plan-only engines).  Geometry options must be set before
+ * the first COMMIT of a voice group.  Returns -2 for an unknown key. */
 int elem_b200_set_option(elem_b200_runtime* rt, const char* key, double value);
 /* Runtime::registerNodeType(type, NodeFactoryFn) — Runtime.h:105-106,480-487 (the plug-in / operator interface of GraphNode.h:20-96).
  * In a fused-kernel engine a new node type is DEVICE code: `cudaBody` is the body of
