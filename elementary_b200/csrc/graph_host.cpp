@@ -227,13 +227,14 @@ int Engine::setOption(const char* key, double value) {
     const std::string k(key);
     if (k == "tile_width") { opt_.tileWidth = (int) value; }
     else if (k == "warps_per_cta") { opt_.warpsPerCta = (int) value; }
-    else if (k == "target_tiles") { opt_.targetTiles = (int) value; }
+    else if (k == "target_tiles") { opt_.targetTiles = (int) value; opt_.targetTilesSet = true; }
     else if (k == "niter") { opt_.niter = (int) value; }
     else if (k == "batch_groups") { opt_.batchGroups = value != 0; }
     else if (k == "fuse_chains") { opt_.fuseChains = value != 0; }
     else if (k == "specialize") { opt_.specialize = (int) value; }
     else if (k == "specialize_max_words") { opt_.specializeMaxWords = (int) value; }
     else if (k == "specialize_strict") { opt_.specializeStrict = value != 0; }
+    else if (k == "spec_minblocks") { opt_.specMinBlocks = (int) value; }
     else if (k == "time_kernels") { timeKernels_ = value != 0 && !planOnly_; }
     else if (k == "fuse_conv_root") { opt_.fuseConvRoot = value != 0; }
     else if (k == "pipeline_stages") { opt_.pipelineStages = std::max(0, std::min((int) value, (int) MAX_PIPE)); }
@@ -309,7 +310,7 @@ long Engine::specializeDryRun(int voice, std::string& log) {
         if (!p) { log = "no compiled program for this voice"; return -1; }
         if (p->stages.size() > 1) { log = "multi-stage programs (convolve) are not specialised"; return -1; }
         SpecKernel k;
-        if (!specialise_compile(p->code, g->tileWidth, opt_.niter, customSource(), k, log)) return -1;
+        if (!specialise_compile(p->code, g->tileWidth, opt_.niter, customSource(), k, log, opt_.specMinBlocks)) return -1;
         return (long) k.cubin.size();
     }
     log = "voice out of range";
@@ -1128,8 +1129,9 @@ int Engine::chooseTileWidth(int nv) const {
         while (L * 2 <= std::min(32, opt_.tileWidth)) L *= 2;
         return L;
     }
+    const int target = midRangeDense(nv) ? 4096 : opt_.targetTiles;
     int L = 32;
-    while (L > 1 && (nv + L - 1) / L < opt_.targetTiles) L >>= 1;
+    while (L > 1 && (nv + L - 1) / L < target) L >>= 1;
     return L;
 }
 
@@ -2148,7 +2150,7 @@ int Engine::compile(Group& g, int nIn, std::shared_ptr<Program>& out) {
         if (prog->specJob->state.load(std::memory_order_acquire) < 0)
             return fail(rc::InvariantViolation, "registered node type failed to compile: " + prog->specJob->log);
     } else if (opt_.specialize && !batched && prog->stages.size() <= 1 && (int) prog->code.size() <= opt_.specializeMaxWords) {
-        prog->specJob = specialise_request(prog->code, g.tileWidth, opt_.niter, device_, std::string());   // NVRTC on the compile-queue thread
+        prog->specJob = specialise_request(prog->code, g.tileWidth, opt_.niter, device_, std::string(), midRangeDense(g.nv) ? 8 : opt_.specMinBlocks);   // NVRTC on the compile-queue thread
         if (opt_.specialize >= 2) {                                                          // synchronous mode: wait for the compiler here
             specialise_wait(*prog->specJob);
             if (prog->specJob->state.load(std::memory_order_acquire) < 0 && opt_.specializeStrict)

@@ -167,6 +167,7 @@ struct EngineOptions {
     int tileWidth = 0;            // 0 = choose per group from the voice count
     int warpsPerCta = 0;          // 0 = choose
     int targetTiles = 2048;       // shrink the tile width until about this many warps exist (measured optimum, profiles/)
+    bool targetTilesSet = false;  // the option was given explicitly: no automatic choice (see Engine::midRangeDense)
     int niter = 0;                // 0 = default elements-per-lane per tile; 4 selects the T = 4 variant for L = 32
     bool batchGroups = true;      // launch all single-stage voice groups of one tile geometry together
     bool fuseChains = true;       // fold runs of element-wise nodes into one OP_CHAIN
@@ -178,6 +179,7 @@ struct EngineOptions {
                                   // (render_groups_pipe_kernel; 0 / 1 = off).  Bit-identical to one warp per graph; worth 7 % on BASELINE
                                   // config 5 (0.77 against 0.83 ms per block, profiles/r02_o_*, r02_s_*) — per-op time grows with the number
                                   // of resident warps, so the gain is far from the stage count
+    int specMinBlocks = 0;        // > 0: specialised kernels of the narrow geometries (1 < L < 32) are compiled for this many CTAs per SM (8 = 64 registers)
     bool specializeStrict = false; // a failed specialisation is an error (COMMIT returns 7 / process -1) instead of a silent stay on the interpreter
 };
 
@@ -352,6 +354,9 @@ private:
     int nodeSetProperty(Group& g, Node& n, const std::string& key, const Value& val, int vb, int ve);
     bool isValueOnlyBatch(const std::vector<Value>& batch, int vb, int ve);
     int splitGroupsAt(int v);
+    // 8192 <= voices < 131072 with specialised kernels: twice the warps (about 4096) from narrow-geometry kernels compiled for 8 CTAs per
+    // SM (64 registers) — 6-18 % faster than ~2048 warps at 110 registers (profiles/r02_aa_midrange_voices_ab.txt)
+    bool midRangeDense(int nv) const { return opt_.specialize > 0 && !opt_.targetTilesSet && opt_.tileWidth == 0 && opt_.specMinBlocks == 0 && nv >= 8192; }
 
     // storage
     int allocRows(Group& g, int count, bool evenAlign, int& row);

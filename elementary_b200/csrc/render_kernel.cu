@@ -855,7 +855,10 @@ __device__ __forceinline__ void render_tile(const LaunchParams& P, const int til
 #ifndef EB_L1_MINBLOCKS
 #define EB_L1_MINBLOCKS 4
 #endif
-#define EB_BOUNDS __launch_bounds__(128, (LOGL == 5) ? EB_L32_MINBLOCKS : ((LOGL == 0) ? EB_L1_MINBLOCKS : 4))
+#ifndef EB_NARROW_MINBLOCKS
+#define EB_NARROW_MINBLOCKS 4      /* 1 < L < 32; a specialised kernel may be compiled for 8 (64 registers): engine option "spec_minblocks" */
+#endif
+#define EB_BOUNDS __launch_bounds__(128, (LOGL == 5) ? EB_L32_MINBLOCKS : ((LOGL == 0) ? EB_L1_MINBLOCKS : EB_NARROW_MINBLOCKS))
 
 // One voice group per launch: the descriptor travels in the constant bank.
 template <int NITER, int LOGL>

@@ -128,7 +128,7 @@ void workerLoop(std::shared_ptr<Queue> q) {
             q->jobs.pop_front();
         }
         std::string log;
-        const bool ok = specialise_compile(job->code, job->tileWidth, job->niterOverride, job->customSource, job->kernel, log);
+        const bool ok = specialise_compile(job->code, job->tileWidth, job->niterOverride, job->customSource, job->kernel, log, job->minBlocks);
         {
             std::lock_guard<std::mutex> lk(q->m);
             job->log = log;
@@ -156,7 +156,8 @@ std::vector<uint32_t> specialise_key_words(const std::vector<uint32_t>& code) {
     return out;
 }
 
-bool specialise_compile(const std::vector<uint32_t>& codeIn, int tileWidth, int niterOverride, const std::string& customSource, SpecKernel& out, std::string& log) {
+bool specialise_compile(const std::vector<uint32_t>& codeIn, int tileWidth, int niterOverride, const std::string& customSource, SpecKernel& out, std::string& log,
+                        int minBlocks) {
     if (!loadNvrtc(log)) return false;
     Api& a = api();
     const std::vector<uint32_t> code = specialise_key_words(codeIn);
@@ -178,8 +179,9 @@ bool specialise_compile(const std::vector<uint32_t>& codeIn, int tileWidth, int 
     const int niter = render_niter_for(tileWidth, niterOverride);
     const std::string name = "eb::render_block_kernel<" + std::to_string(niter) + ", " + std::to_string(logl) + ">";
     a.addNameExpression(prog, name.c_str());
+    const std::string mb = "-DEB_NARROW_MINBLOCKS=" + std::to_string(minBlocks > 0 ? minBlocks : 4);
     const char* opts[] = {"--std=c++20", "--gpu-architecture=sm_100a", "--fmad=false", "-lineinfo", "-default-device",
-                          "--pre-include=eb_spec_program.h", "-diag-suppress=186,68,179,177"};
+                          "--pre-include=eb_spec_program.h", "-diag-suppress=186,68,179,177", mb.c_str()};
     const nvrtcResult rc = a.compileProgram(prog, (int) (sizeof(opts) / sizeof(opts[0])), opts);
     size_t n = 0;
     a.getLogSize(prog, &n);
@@ -217,11 +219,12 @@ bool specialise_load(SpecKernel& k, std::string& log) {
     return true;
 }
 
-std::shared_ptr<SpecJob> specialise_request(const std::vector<uint32_t>& code, int tileWidth, int niterOverride, int device, const std::string& customSource) {
+std::shared_ptr<SpecJob> specialise_request(const std::vector<uint32_t>& code, int tileWidth, int niterOverride, int device, const std::string& customSource,
+                                            int minBlocks) {
     auto q = queue();
     const std::vector<uint32_t> key = specialise_key_words(code);
     std::string k(reinterpret_cast<const char*>(key.data()), key.size() * sizeof(uint32_t));
-    k += "|c" + customSource + "|L" + std::to_string(tileWidth) + "|n" + std::to_string(render_niter_for(tileWidth, niterOverride)) + "|d" + std::to_string(device);
+    k += "|c" + customSource + "|L" + std::to_string(tileWidth) + "|n" + std::to_string(render_niter_for(tileWidth, niterOverride)) + "|d" + std::to_string(device) + "|b" + std::to_string(minBlocks);
     std::lock_guard<std::mutex> lk(q->m);
     auto it = q->cache.find(k);
     if (it != q->cache.end() && it->second->state.load(std::memory_order_acquire) >= 0) return it->second;
@@ -230,6 +233,7 @@ std::shared_ptr<SpecJob> specialise_request(const std::vector<uint32_t>& code, i
     job->customSource = customSource;
     job->tileWidth = tileWidth;
     job->niterOverride = niterOverride;
+    job->minBlocks = minBlocks;
     q->cache[k] = job;
     q->jobs.push_back(job);
     if (!q->workerStarted) {

@@ -35,7 +35,8 @@ struct SpecKernel {
 
 // Step 1 — pure compilation (NVRTC only; thread safe, needs no CUDA context, works without a GPU): K1 for (tileWidth,
 // niterOverride) against `code` (one single-stage program).  Fills out.cubin / out.loweredName.
-bool specialise_compile(const std::vector<uint32_t>& code, int tileWidth, int niterOverride, const std::string& customSource, SpecKernel& out, std::string& log);
+bool specialise_compile(const std::vector<uint32_t>& code, int tileWidth, int niterOverride, const std::string& customSource, SpecKernel& out, std::string& log,
+                        int minBlocks = 0);   // minBlocks > 0: CTAs per SM the narrow geometries (1 < L < 32) are compiled for (8 = 64 registers)
 // Step 2 — on a thread whose CUDA context is current: load the cubin and resolve the kernel (milliseconds).
 bool specialise_load(SpecKernel& k, std::string& log);
 
@@ -47,11 +48,12 @@ struct SpecJob {
     std::mutex loadMutex;        // two engines sharing a cached job must not both load it
     std::vector<uint32_t> code;
     std::string customSource;
-    int tileWidth = 0, niterOverride = 0;
+    int tileWidth = 0, niterOverride = 0, minBlocks = 0;
 };
 // Queue (or find in the cache) the specialisation of `code` for a tile geometry on `device`.  Never blocks on the compiler.
 // customSource: device text of the registered node types the program may use (Engine::customSource; empty = none) — compiled in front of the kernel.
-std::shared_ptr<SpecJob> specialise_request(const std::vector<uint32_t>& code, int tileWidth, int niterOverride, int device, const std::string& customSource);
+std::shared_ptr<SpecJob> specialise_request(const std::vector<uint32_t>& code, int tileWidth, int niterOverride, int device, const std::string& customSource,
+                                            int minBlocks = 0);
 // Block until the job has left state 0 (used by option "specialize" = 2 and by tests).
 void specialise_wait(SpecJob& job);
 // Render thread: load a compiled job (state 1 -> 2 / -1).  Returns the state afterwards.
