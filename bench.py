@@ -14,7 +14,8 @@ owns its own 4096 voices; the only data-path collective is the mix-bus sum (SURV
            D2H of the mix bus and the synchronisation inside the timed region; the graph has no audio inputs,
            so h2d_bytes_per_step is 0).
   roofline: K1 only — algorithmic bytes per launch / mean launch duration measured with CUDA events
-           around every K1 launch on its own stream, against MEASURED_PEAKS.json hbm_gbs; beside it the issue-slot
+           around every K1 launch on its own stream (a second pass of the same steps: the event pairs sit between the
+           kernels of a step and would cost `value` a few microseconds of launch gap), against MEASURED_PEAKS.json hbm_gbs; beside it the issue-slot
            roofline (K1's real bound): warp instructions per launch (ncu capture of the SAME K1 sources, else null)
            / duration against SMs x 4 schedulers x the SM clock sampled during the run.
   parity : after the timed loops the SAME runtime renders one more block with per-voice outputs; every voice and the
@@ -289,6 +290,10 @@ def measure(args, voices, steps, warmup, rank, local_rank, world, stream, flush,
     rt.take_kernel_time_ms()
 
     # ---- value: device-resident, per-step CUDA events, L2 flushed between steps ----
+    # The engine's own per-kernel event pairs are OFF in this loop: they sit between the kernels of a step and cost a few microseconds
+    # of launch gap per step (at N > 1 they made `value` slower than `e2e`).  The per-kernel durations the roofline needs come from a
+    # second pass of the same steps right below, with the pairs on.
+    rt.set_option("time_kernels", 0)
     sampler = ClockSampler(local_rank) if with_clocks and rank == 0 else None
     if sampler:
         sampler.start()
@@ -305,9 +310,18 @@ def measure(args, voices, steps, warmup, rank, local_rank, world, stream, flush,
     barrier()
     t_wall = time.perf_counter() - t_wall0
     dev_ms = sum(a.elapsed_time(b) for a, b in evs)
+    launches = rt.kernel_launches - launches0      # K1 + K2 (+ K4) per step; the line-up barriers are not counted by the engine
+
+    # ---- per-kernel durations (roofline, kernel_ms): the same steps once more, event pairs around every launch ----
+    rt.set_option("time_kernels", 1)
+    barrier()
+    for _ in range(min(steps, 100)):
+        flush.zero_()
+        line_up()
+        step_device()
+    barrier()
     k1_ms, k1_n = rt.take_kernel_time_ms()
     kinds = rt.last_kernel_times()
-    launches = rt.kernel_launches - launches0      # K1 + K2 (+ K4) per step; the line-up barriers are not counted by the engine
 
     # ---- e2e: the public call with host buffers (D2H + sync inside) ----
     # (per-kernel event pairs are a measurement device of the loop above, not part of what a caller of process() pays: off here)
@@ -469,7 +483,7 @@ def run_b200(args, rank, local_rank, world, emit=print):
         "gpu_launches": m["launches"],
         "kernel_ms": {"K1_render": k1_avg_ms, "K2_mix_reduce": m["k2_ms"] / max(1, m["k2_n"]),
                       "K4_mix_exchange": (m["k4_ms"] / m["k4_n"]) if m["k4_n"] else None,
-                      "note": "mean device time per launch, CUDA events around each launch on the render stream, max over ranks"},
+                      "note": "mean device time per launch, CUDA events around each launch on the render stream, max over ranks; measured in a second pass of the same steps (the timed loop of `value` runs without these event pairs)"},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": traffic, "peak_kind": f"of {peak_kind}", "kernel": "render_block_kernel<NITER,LOGL> (K1)" + (" specialised" if specialised else ""),
                      "kernel_ms": k1_avg_ms, "kernel_launches_timed": m["k1_n"], "ncu": ncu, "k1_source_sha16": sha,
