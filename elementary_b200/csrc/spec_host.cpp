@@ -62,6 +62,7 @@ Api& api() {
     return a;
 }
 std::once_flag g_nvrtcOnce, g_driverOnce;
+void waitForCompilerAtExit();   // below: registered with atexit once NVRTC is loaded
 
 bool loadNvrtc(std::string& log) {
     Api& a = api();
@@ -78,6 +79,10 @@ bool loadNvrtc(std::string& log) {
                     sym(h, "nvrtcGetCUBINSize", a.getCubinSize) && sym(h, "nvrtcGetCUBIN", a.getCubin) &&
                     sym(h, "nvrtcGetLoweredName", a.getLoweredName);
         if (!a.nvrtcOk) { a.nvrtcErr = "libnvrtc lacks a required entry point"; dlclose(h); }
+        // A process that exits while the (detached) compile-queue thread is inside nvrtcCompileProgram tears NVRTC's own statics down
+        // under it (segfault / "realloc(): invalid pointer" at exit).  Registered HERE — after NVRTC's static initialisers have run —
+        // the handler runs BEFORE their destructors and simply waits for the compile in flight; no further job is started.
+        else std::atexit(waitForCompilerAtExit);
     });
     if (!a.nvrtcOk) log = a.nvrtcErr;
     return a.nvrtcOk;
@@ -112,6 +117,8 @@ struct Queue {
     std::deque<std::shared_ptr<SpecJob>> jobs;
     std::map<std::string, std::shared_ptr<SpecJob>> cache;
     bool workerStarted = false;
+    bool busy = false;          // the worker is inside specialise_compile
+    bool quitting = false;      // the process is exiting: the worker starts nothing new
 };
 std::shared_ptr<Queue> queue() {
     static std::shared_ptr<Queue> q = std::make_shared<Queue>();
@@ -123,9 +130,11 @@ void workerLoop(std::shared_ptr<Queue> q) {
         std::shared_ptr<SpecJob> job;
         {
             std::unique_lock<std::mutex> lk(q->m);
-            q->cv.wait(lk, [&] { return !q->jobs.empty(); });
+            q->cv.wait(lk, [&] { return !q->jobs.empty() || q->quitting; });
+            if (q->quitting) return;
             job = q->jobs.front();
             q->jobs.pop_front();
+            q->busy = true;
         }
         std::string log;
         const bool ok = specialise_compile(job->code, job->tileWidth, job->niterOverride, job->customSource, job->kernel, log, job->minBlocks);
@@ -133,9 +142,18 @@ void workerLoop(std::shared_ptr<Queue> q) {
             std::lock_guard<std::mutex> lk(q->m);
             job->log = log;
             job->state.store(ok ? 1 : -1, std::memory_order_release);
+            q->busy = false;
         }
         q->done.notify_all();
     }
+}
+
+void waitForCompilerAtExit() {
+    auto q = queue();
+    std::unique_lock<std::mutex> lk(q->m);
+    q->quitting = true;
+    q->cv.notify_all();
+    q->done.wait(lk, [&] { return !q->busy; });
 }
 
 }  // namespace

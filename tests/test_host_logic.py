@@ -386,3 +386,30 @@ def test_pipeline_cut_of_one_voice_groups_plan_only():
     for i in range(3):
         for j in range(i + 1, 3):
             assert not (set(sections[i]["outs"]) & set(sections[j]["outs"])), "stages never share an output slot"
+
+
+def test_tile_width_choice_dense_mid_range_with_specialised_kernels():
+    """Engine::chooseTileWidth: ~2048 warps by default; from 8192 voices up, WITH specialised kernels (64-register narrow geometries),
+    ~4096 warps (profiles/r02_aa_midrange_voices_ab.txt); an explicit target_tiles or tile_width always wins."""
+    from elementary_b200 import graphs
+
+    def tw(nv, **opts):
+        rt = Runtime(SR, BS, nv, device=-1, **opts)
+        assert rt.apply_instructions(graphs.plumbing() if hasattr(graphs, "plumbing") else graphs.subsynth32()) == 0, rt.last_error()
+        return rt.describe()["groups"][0]["tile_width"]
+
+    assert [tw(v) for v in (45, 4096, 8192, 65536, 131072)] == [1, 2, 4, 32, 32]
+    assert [tw(v, specialize=1) for v in (4096, 8192, 16384, 32768, 65536, 131072)] == [2, 2, 4, 8, 16, 32]
+    assert tw(65536, specialize=1, target_tiles=2048) == 32 and tw(65536, specialize=1, tile_width=8) == 8
+
+
+def test_bench_arms_describe_the_same_workload():
+    """bench.py: `config` is one dict for both arms (--impl b200 and --impl reference) — the driver compares them."""
+    import importlib, sys, os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sys.path.insert(0, root)
+    bench = importlib.import_module("bench")
+    a, b = bench.bench_config(4096, 1), bench.bench_config(4096, 1)
+    assert a == b and a["voices_total"] == 4096 and "SUBSYNTH32" in a["workload"] and "l2" in a
+    assert bench.bench_config(4096, 8)["voices_total"] == 32768
+    assert "Msamples/s" in bench.METRIC
