@@ -413,3 +413,19 @@ def test_bench_arms_describe_the_same_workload():
     assert a == b and a["voices_total"] == 4096 and "SUBSYNTH32" in a["workload"] and "l2" in a
     assert bench.bench_config(4096, 8)["voices_total"] == 32768
     assert "Msamples/s" in bench.METRIC
+
+
+def test_process_exit_during_a_background_compile_is_clean():
+    """A process that ends while the compile-queue thread is inside NVRTC must exit with code 0 (spec_host.cpp waitForCompilerAtExit:
+    the handler registered behind NVRTC's statics waits for the compile in flight).  It used to die at exit, intermittently, with a
+    segmentation fault or "realloc(): invalid pointer"."""
+    import os, subprocess, sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = ("import sys; sys.path.insert(0, %r)\n"
+            "from elementary_b200 import Runtime, graphs\n"
+            "rt = Runtime(48000.0, 512, 64, device=-1, specialize=1)\n"
+            "assert rt.apply_instructions(graphs.subsynth32()) == 0\n"
+            "print('queued', flush=True)\n" % root)
+    for _ in range(3):
+        p = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300)
+        assert p.returncode == 0 and "queued" in p.stdout, (p.returncode, p.stderr[-500:])
